@@ -1,0 +1,262 @@
+"""Generate tests/golden/*.npz by running THE REFERENCE ITSELF (build container only).
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  Run:  python -m oracle.make_golden
+
+The reference (/root/reference, read-only, python) is imported unmodified under import
+shims for the packages missing from this image (pytorch_lightning, omegaconf, torchmetrics,
+speechbrain, fairseq, ...).  ``Wav2Vec2Model.from_pretrained`` cannot reach the
+network, so it is patched to build the same architecture from ``Wav2Vec2Config`` and the
+parameters are then overwritten with ``oracle.params.make_params(seed)`` -- the very
+parameters the oracle and the CUDA engine are tested with.  The reference's own classes do
+the arithmetic:
+    Wav2vec2FCModule.compute_speaker_embedding / compute_speaker_prediction
+        (R:src/lightning_modules/speaker/wav2vec2_fc.py:414-438)
+    Wav2Vec2WrapperModule.forward (R:src/models/wav2vec2.py:126-146)
+    MeanStatPool1D / MeanStdStatPool1D / AttentiveStatPool1D (R:src/layers/pooling.py)
+    CrossEntropyLoss / AngularAdditiveMarginSoftMaxLoss (R:src/optim/loss/*.py)
+speechbrain's AttentiveStatisticsPooling is absent offline; the shim provides a torch.nn
+restatement of the published module (the only part of these fixtures not produced by
+reference/HF code).
+
+Fixtures are small: full tensors for embeddings / logits / last hidden state, and
+(norm, mean, strided sample) summaries for the big intermediates.
+"""
+from __future__ import annotations
+
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+STUB_PREFIXES = ("pytorch_lightning", "omegaconf", "torchmetrics", "speechbrain", "fairseq", "hurry",
+                 "webdataset", "comet_ml", "pl_bolts", "jiwer", "librosa", "yaspin", "hydra", "dotenv",
+                 "torchaudio", "augment", "seaborn", "matplotlib", "pytorch_model_summary", "bob",
+                 "wget", "tqdm_joblib", "optuna")
+
+
+class _Anything:
+    """Permissive placeholder: subclassable, callable, attribute-able."""
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+    def __getattr__(self, n):
+        if n.startswith("__"):
+            raise AttributeError(n)
+        return _Anything()
+
+
+class _StubModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        cls = type(name, (_Anything,), {})
+        setattr(self, name, cls)
+        return cls
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split(".")[0] in STUB_PREFIXES:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StubModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+class _LightningModule(nn.Module):
+    """pytorch_lightning.LightningModule stand-in: nn.Module + freeze/unfreeze semantics
+    (all params requires_grad False + eval / True + train)."""
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+
+    def unfreeze(self):
+        for p in self.parameters():
+            p.requires_grad = True
+        self.train()
+
+    def log(self, *a, **k):
+        pass
+
+    def save_hyperparameters(self, *a, **k):
+        pass
+
+
+class _ASP(nn.Module):
+    """speechbrain.lobes.models.ECAPA_TDNN.AttentiveStatisticsPooling(channels) restated with
+    torch.nn modules and speechbrain's parameter names (see oracle.w2v2_oracle.attentive_stat_pool)."""
+    def __init__(self, channels, attention_channels=128, global_context=True):
+        super().__init__()
+        self.eps = 1e-12
+
+        class _Wrap(nn.Module):
+            def __init__(self, name, mod):
+                super().__init__()
+                setattr(self, name, mod)
+        self.tdnn = nn.Module()
+        self.tdnn.conv = _Wrap("conv", nn.Conv1d(channels * 3, attention_channels, 1))
+        self.tdnn.norm = _Wrap("norm", nn.BatchNorm1d(attention_channels))
+        self.conv = _Wrap("conv", nn.Conv1d(attention_channels, channels, 1))
+
+    def forward(self, x, lengths=None):
+        L = x.shape[-1]
+
+        def stats(x, m, dim=2, eps=self.eps):
+            mean = (m * x).sum(dim)
+            std = torch.sqrt((m * (x - mean.unsqueeze(dim)).pow(2)).sum(dim).clamp(eps))
+            return mean, std
+        mask = torch.ones(x.shape[0], 1, L, dtype=x.dtype)
+        total = mask.sum(dim=2, keepdim=True).float()
+        mean, std = stats(x, mask / total)
+        attn = torch.cat([x, mean.unsqueeze(2).repeat(1, 1, L), std.unsqueeze(2).repeat(1, 1, L)], dim=1)
+        attn = self.tdnn.norm.norm(torch.relu(self.tdnn.conv.conv(attn)))
+        attn = self.conv.conv(torch.tanh(attn))
+        attn = attn.masked_fill(mask == 0, float("-inf"))
+        attn = torch.softmax(attn, dim=2)
+        mean, std = stats(x, attn)
+        return torch.cat((mean, std), dim=1).unsqueeze(2)
+
+
+def install_shims():
+    # import transformers first: its optional-dependency probes must not see the stubs
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+    import transformers.models.wav2vec2.modeling_wav2vec2  # noqa: F401
+    sys.meta_path.insert(0, _StubFinder())
+    import pytorch_lightning as pl
+    pl.LightningModule = _LightningModule
+    import pytorch_lightning.core.decorators as dec
+    dec.auto_move_data = lambda f: f
+    import omegaconf
+    omegaconf.DictConfig = dict
+    omegaconf.OmegaConf.to_container = staticmethod(lambda c, *a, **k: dict(c))
+    import speechbrain.lobes.models.ECAPA_TDNN as ecapa
+    ecapa.AttentiveStatisticsPooling = _ASP
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    # random-init instead of from_pretrained (no network / no HF cache)
+
+    def _from_pretrained(cls_or_id, *args, **kw):
+        hid = cls_or_id if isinstance(cls_or_id, str) else args[0]
+        kw.pop("gradient_checkpointing", None)
+        size = {}
+        if "large" in hid:
+            size = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096)
+        cfg = Wav2Vec2Config(**size, **kw)
+        cfg._attn_implementation = "eager"
+        return Wav2Vec2Model(cfg)
+    Wav2Vec2Model.from_pretrained = staticmethod(_from_pretrained)
+
+
+def build_reference_module(pooling: str, loss: str, num_speakers: int = 5994):
+    """Construct the reference's Wav2vec2FCModule as R:src/main.py:223-285 would (network cfg
+    R:config/network/wav2vec2_fc.yaml), with all stochastic regularisation at 0."""
+    from src.lightning_modules.speaker.wav2vec2_fc import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    from src.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
+    cfg = Wav2vec2FCModuleConfig(
+        wav2vec_hunggingface_id="facebook/wav2vec2-base", reset_weights=False,
+        wav2vec_feature_encoder_only=False, wav2vec_initially_frozen=False, num_frozen_steps=None,
+        completely_freeze_feature_extractor=True, hidden_fc_layers_out=[], embedding_layer_idx=-1,
+        stat_pooling_type=pooling, test_stat_pooling_type=pooling,
+        activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0,
+        layerdrop=0.0, mask_feature_length=10, mask_feature_prob=0.0, mask_time_length=10, mask_time_prob=0.0,
+        final_channel_mask_prob=0.0, final_channel_mask_width=5,
+        explicit_stat_pool_embedding_size=None, explicit_num_speakers=None)
+    if loss == "aam":
+        ctor = lambda: AngularAdditiveMarginSoftMaxLoss(input_features=1, output_features=1, margin=0.2, scale=30)
+    else:
+        ctor = lambda: CrossEntropyLoss()
+
+    class _Eval:
+        max_num_training_samples = 0
+    m = Wav2vec2FCModule(hyperparameters_to_save={}, cfg=cfg, num_speakers=num_speakers,
+                         loss_fn_constructor=ctor, validation_pairs=[], test_pairs=[], evaluator=_Eval())
+    return m
+
+
+def summarise(name: str, t: torch.Tensor, out: dict):
+    t = t.detach().float()
+    out[name + ".shape"] = np.array(t.shape, dtype=np.int64)
+    out[name + ".norm"] = np.array(t.double().norm().item())
+    out[name + ".mean"] = np.array(t.double().mean().item())
+    flat = t.reshape(-1)
+    step = max(1, flat.numel() // 4096)
+    out[name + ".sample"] = flat[::step][:4096].numpy().copy()
+
+
+def main():
+    install_shims()
+    from oracle.params import BASE, make_asp_params, make_head_params, make_inputs, make_params
+    torch.set_num_threads(8)
+    os.makedirs(OUT, exist_ok=True)
+    S = 5994
+    params = make_params(BASE, seed=0)
+    for tag, B, N in (("cfg0_b2_1s", 2, 16000), ("b3_ragged_0p7s", 3, 11283)):
+        wav, labels = make_inputs(B, N, S, seed=1234)
+        out = {"B": np.array(B), "N": np.array(N), "labels": labels.numpy(),
+               "wav.sample": wav.reshape(-1)[::97][:2048].numpy().copy()}
+        for pooling, loss in (("mean", "ce"), ("mean+std", "aam"), ("attentive", "aam")):
+            E = 768 if pooling == "mean" else 1536
+            m = build_reference_module(pooling, loss, S)
+            res = m.wav2vec.model.load_state_dict(params, strict=False)
+            # masked_spec_embed only exists when mask_time_prob > 0 (HF:1258-1262)
+            assert not res.missing_keys and set(res.unexpected_keys) <= {"masked_spec_embed"}, res
+            head = make_head_params(E, S, seed=1)
+            if loss == "ce":
+                m.fc_list[-1][0].weight.data.copy_(head["fc.weight"])
+                m.fc_list[-1][0].bias.data.copy_(head["fc.bias"])
+            else:
+                m.loss_fn.fc_weights.data.copy_(head["aam.fc_weights"])
+            if pooling == "attentive":
+                asp = make_asp_params(768, seed=2)
+                m.stat_pooling.pooling_layer.load_state_dict(asp, strict=False)
+                sd = m.stat_pooling.pooling_layer.state_dict()
+                for k, v in asp.items():
+                    assert torch.equal(sd[k], v), k
+            m.eval()
+            with torch.no_grad():
+                # the reference hands [B,1,N] batches (R:.../training_batch_speaker.py:44-75)
+                emb = m.compute_speaker_embedding(wav[:, None, :])
+                pred = m.compute_speaker_prediction(emb)
+                loss_v, softmax = m.loss_fn(pred, labels)
+                key = f"{pooling}.{loss}"
+                out[key + ".embedding"] = emb.numpy()
+                out[key + ".loss"] = np.array(loss_v.item())
+                out[key + ".argmax"] = softmax.argmax(1).numpy()
+                summarise(key + ".softmax", softmax, out)
+                if loss == "ce":
+                    out[key + ".logits"] = pred.numpy()
+                    hf = m.wav2vec.model(wav, output_hidden_states=True)
+                    out["last_hidden_state"] = hf.last_hidden_state.numpy()
+                    for i, hs in enumerate(hf.hidden_states):
+                        summarise(f"hidden_states.{i}", hs, out)
+                    feat = m.wav2vec.model.feature_extractor(wav)
+                    summarise("feature_extractor", feat, out)
+                    h = wav[:, None, :]
+                    for i, layer in enumerate(m.wav2vec.model.feature_extractor.conv_layers):
+                        h = layer(h)
+                        summarise(f"conv.{i}", h, out)
+            print(tag, key, "emb", tuple(emb.shape), "loss", float(loss_v))
+        np.savez_compressed(os.path.join(OUT, f"ref_{tag}.npz"), **out)
+        print("wrote", tag, sum(v.nbytes for v in out.values()) / 1e6, "MB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""Pins the CPU oracle (oracle/w2v2_oracle.py) to outputs of the reference itself
+(tests/golden/ref_*.npz, produced by oracle/make_golden.py from /root/reference's own
+Wav2vec2FCModule) and, where transformers is importable, to the live HF Wav2Vec2Model."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import w2v2_oracle as O
+from oracle.params import BASE, make_asp_params, make_head_params, make_inputs
+
+CASES = [("ref_cfg0_b2_1s.npz", 2, 16000), ("ref_b3_ragged_0p7s.npz", 3, 11283)]
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double(); b = torch.as_tensor(b).double()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def check_summary(name, t, g, tol=2e-5):
+    t = t.detach().float()
+    assert list(t.shape) == list(g[name + ".shape"])
+    flat = t.reshape(-1)
+    step = max(1, flat.numel() // 4096)
+    assert rel(flat[::step][:4096], g[name + ".sample"]) < tol, name
+    assert abs(t.double().norm().item() - float(g[name + ".norm"])) / float(g[name + ".norm"]) < tol, name
+
+
+@pytest.mark.parametrize("fname,B,N", CASES)
+def test_oracle_matches_reference_fixtures(fname, B, N, base_params):
+    torch.set_num_threads(8)
+    g = golden(fname)
+    wav, labels = make_inputs(B, N, 5994, seed=1234)
+    assert np.array_equal(labels.numpy(), g["labels"])
+    assert np.allclose(wav.reshape(-1)[::97][:2048].numpy(), g["wav.sample"])
+    trace = {}
+    with torch.no_grad():
+        h = O.wav2vec2_forward(wav, base_params, BASE, trace)
+        assert rel(h, g["last_hidden_state"]) < 2e-5
+        for i, c in enumerate(trace["conv"]):
+            check_summary(f"conv.{i}", c, g)
+        for i, hs in enumerate(trace["hidden_states"]):
+            check_summary(f"hidden_states.{i}", hs, g)
+        # mean + CE
+        emb = O.mean_pool(h)
+        assert rel(emb, g["mean.ce.embedding"]) < 2e-5
+        hp = make_head_params(768, 5994, seed=1)
+        logits, loss, sm = O.cross_entropy_head(emb, hp["fc.weight"], hp["fc.bias"], labels)
+        assert rel(logits, g["mean.ce.logits"]) < 2e-5
+        assert abs(loss.item() - float(g["mean.ce.loss"])) < 1e-4
+        assert np.array_equal(sm.argmax(1).numpy(), g["mean.ce.argmax"])
+        check_summary("mean.ce.softmax", sm, g, tol=1e-4)
+        # mean+std + AAM
+        emb = O.mean_std_pool(h)
+        assert rel(emb, g["mean+std.aam.embedding"]) < 2e-5
+        hp = make_head_params(1536, 5994, seed=1)
+        _, loss, sm = O.aam_softmax(emb, hp["aam.fc_weights"], labels, 0.2, 30.0)
+        assert abs(loss.item() - float(g["mean+std.aam.loss"])) < 1e-4
+        assert np.array_equal(sm.argmax(1).numpy(), g["mean+std.aam.argmax"])
+        # attentive + AAM
+        emb = O.attentive_stat_pool(h, make_asp_params(768, seed=2))
+        assert rel(emb, g["attentive.aam.embedding"]) < 2e-5
+        _, loss, sm = O.aam_softmax(emb, hp["aam.fc_weights"], labels, 0.2, 30.0)
+        assert abs(loss.item() - float(g["attentive.aam.loss"])) < 1e-4
+        assert np.array_equal(sm.argmax(1).numpy(), g["attentive.aam.argmax"])
+
+
+def test_oracle_matches_live_hf_model(base_params):
+    """The encoder arithmetic lives in transformers (not in /root/reference): check the
+    restatement against the installed HF Wav2Vec2Model directly (eager attention)."""
+    tr = pytest.importorskip("transformers")
+    torch.set_num_threads(8)
+    cfg = tr.Wav2Vec2Config(mask_time_prob=0.0)
+    cfg._attn_implementation = "eager"
+    m = tr.Wav2Vec2Model(cfg).eval()
+    res = m.load_state_dict(base_params, strict=False)
+    assert not res.missing_keys
+    wav, _ = make_inputs(2, 8000, seed=7)
+    with torch.no_grad():
+        ref = m(wav).last_hidden_state
+        got = O.wav2vec2_forward(wav, base_params, BASE)
+    assert rel(got, ref) < 1e-5
+
+
+def test_pos_conv_weight_norm_formula(base_params):
+    w = O.pos_conv_weight(base_params)
+    v = base_params["encoder.pos_conv_embed.conv.parametrizations.weight.original1"]
+    g = base_params["encoder.pos_conv_embed.conv.parametrizations.weight.original0"]
+    ref = torch._weight_norm(v, g, 2)
+    assert rel(w, ref) < 1e-6
