@@ -1,0 +1,126 @@
+/* w2v2_b200.h -- C ABI of the B200-native wav2vec2 speaker hot path (libw2v2_b200.so).
+ *
+ * The reference (nikvaessen/w2v2-speaker) is pure Python: its hot path dispatches to
+ * torch / cuDNN / cuBLAS through `torch.nn` modules, there is no FFI of its own.  Each entry
+ * point below therefore replaces the torch op sequence of one reference call site (cited as
+ * R:<file>:<line> = /root/reference/..., HF:<line> = transformers/models/wav2vec2/
+ * modeling_wav2vec2.py 5.5.0, the third-party file that holds the encoder arithmetic the
+ * reference calls at R:src/models/wav2vec2.py:71).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *   - the CALLER owns every buffer (kernels never allocate); `stream` is a cudaStream_t;
+ *     all work is asynchronous on that stream;
+ *   - return value 0 = ok, negative = error (message via w2v2_last_error()); no exceptions;
+ *   - activations are channels-last: conv stack [B, L, C], transformer [B*T, H] row-major;
+ *   - "f16" buffers hold IEEE binary16 (GEMM operands, RNE-rounded by the producer), "f32"
+ *     buffers hold the residual stream / statistics / outputs.
+ */
+#ifndef W2V2_B200_H_
+#define W2V2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* w2v2_last_error(void);          /* thread-local, valid until the next failing call */
+int w2v2_abi_version(void);                 /* bump on any signature change */
+int w2v2_sm_count(void);                    /* SM count of the current device (grid sizing) */
+
+/* ---- dense contractions (tcgen05) ---------------------------------------------------------- */
+/* out[b,r,n] = act(sum_{tap,c} A[b][r*a_row_stride + tap*a_tap_stride + c] * W[n][tap*cin + c] + bias[n])
+ * A, W fp16; accumulation fp32; out fp16 (out_dtype 0) or fp32 (1).  All strides in ELEMENTS.
+ * Replaces: Conv1d k=3/2,s=2 + GELU (HF:254-272; ntaps = kernel size, a_row_stride = 2*C,
+ * a_tap_stride = C), nn.Linear (+GELU) of HF:429-434 / HF:524-549 / HF:566-573, the ASP 1x1
+ * convs and the classifier GEMMs (R:src/lightning_modules/speaker/wav2vec2_fc.py:199-210,
+ * R:src/optim/loss/aam_softmax.py:55).   act: 0 = none, 1 = exact-erf GELU.  bias may be NULL.
+ * Requirements: cin % 64 == 0; row pitches (bytes) multiples of 16; bases 16-byte aligned. */
+int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,
+                  int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N,
+                  const float* bias, int act, void* out, int out_dtype, int64_t ldo, int64_t out_batch_stride,
+                  void* stream);
+
+/* ---- feature extractor layer 0 -------------------------------------------------------------- */
+/* Conv1d(1->C,k=10,s=5,no bias) + GroupNorm(C groups == per-(b,c) instance norm over time, eps,
+ * affine) + exact GELU  (HF:302-323).  wav f32 [B,N]; w f32 [C,10]; gamma/beta f32 [C];
+ * stats f32 workspace of w2v2_conv0_stats_floats(B,C) floats ([B,C,2] mean/rstd + fp64 moments); out f16 channels-last [B,L0,C],
+ * L0 = (N-10)/5+1.  Two fused passes (statistics, then normalise+GELU), the conv is recomputed
+ * in both so the [B,C,L0] pre-norm tensor never touches HBM. */
+int64_t w2v2_conv0_stats_floats(int B, int C);   /* size of `stats` in floats (incl. fp64 moment scratch) */
+int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta,
+                       float eps, float* stats, void* out_f16, int C, void* stream);
+
+/* ---- normalisation --------------------------------------------------------------------------- */
+/* y = LayerNorm(x (+ bias) (+ residual)) * gamma + beta over the last dim (HF:429-431, 690-693,
+ * 596-607).  x: f32 or f16 [rows, H] (x_dtype 1/0); bias f32 [H] or NULL; residual f32 [rows,H]
+ * or NULL; outputs: y32 (f32, may be NULL) and y16 (f16, may be NULL). */
+int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
+                   const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, void* stream);
+
+/* ---- positional conv embedding --------------------------------------------------------------- */
+/* Fold weight_norm (HF:340-358): w[o,i,k] = g[k] * v[o,i,k] / ||v[:,:,k]||, and re-lay it out as
+ * fp16 [G][K][I/8][O][8] (per (group, tap): an [O x I] K-major block in UMMA core-matrix order).  w16 must have room
+ * for H*(H/groups)*K halfs followed by K floats of scratch (the per-tap norms). */
+int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, void* stream);
+/* y[b,t,:] = GELU(conv1d(x, w, bias, pad=K/2, groups)[.., :T]) (HF:360-379); x f16 [B,T,H];
+ * out f32 [B,T,H] (the encoder then does LN(h + y), fused in w2v2_layernorm via `residual`). */
+int w2v2_posconv(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H, int groups,
+                 int K, void* stream);
+
+/* ---- self-attention core ---------------------------------------------------------------------- */
+/* o = softmax(q k^T) v per (batch, head), no mask (HF:438-463; the 1/sqrt(d) scale is folded
+ * into the q projection).  qkv f16 [B*T, 3H] (q | k | v blocks); out f16 [B*T, H]. */
+int w2v2_attention(const void* qkv16, void* out16, int B, int T, int H, int heads, void* stream);
+
+/* ---- pooling (R:src/layers/pooling.py) -------------------------------------------------------- */
+/* mode 0: mean -> [B,H] (:24-30); mode 1: [std_unbiased || mean] -> [B,2H] (:38-44);
+ * mode 2: max -> [B,H] (:74-80).  x f32 [B,T,H]. */
+int w2v2_stat_pool(const float* x, float* out, int B, int T, int H, int mode, void* stream);
+/* attentive statistics pooling tail (speechbrain ASP as used at :87-106): given x f32 [B,T,H] and
+ * attention logits a f32 [B,T,H]: softmax over T per (b,c), weighted mean and
+ * std = sqrt(clamp(sum a (x-mean)^2, 1e-12)) -> out [B, 2H] = [mean || std]. */
+int w2v2_asp_pool(const float* x, const float* logits, float* out, int B, int T, int H, void* stream);
+/* ASP front: global mean/std over T (uniform weights, eps 1e-12) and the concatenated fp16
+ * operand [x, mean, std] -> cat16 [B*T, 3H]. */
+int w2v2_asp_concat(const float* x, void* cat16, int B, int T, int H, void* stream);
+/* ASP middle: y = tanh(BatchNorm(ReLU(z))) with given per-channel scale/shift (eval: from running
+ * stats); z f32 [rows, A] -> y16 f16 [rows, A]. */
+int w2v2_asp_relu_bn_tanh(const float* z, const float* scale, const float* shift, void* y16, int64_t rows, int A,
+                          void* stream);
+
+/* ---- heads / losses --------------------------------------------------------------------------- */
+/* Row-wise softmax + cross entropy + argmax over logits f32 [B, ldl] (first S valid):
+ * prob f32 [B,S] (may be NULL), loss_rows f32 [B] (-log p[label]), argmax i32 [B].
+ * (R:src/optim/loss/cross_entropy.py:19-33; mean over rows is done by w2v2_mean_rows.) */
+int w2v2_softmax_ce(const float* logits, int64_t ldl, const int64_t* labels, float* prob, float* loss_rows,
+                    int32_t* argmax, int B, int S, void* stream);
+/* AAM-softmax margin (R:src/optim/loss/aam_softmax.py:56-69) applied in place on cosine f32
+ * [B, ldl]: phi = cos*cos_m - sqrt(clamp(1-cos^2,0,1))*sin_m, phi = (cos-th>0) ? phi : cos-mm at
+ * the label column, then * scale everywhere; followed by softmax/CE/argmax as above. */
+int w2v2_aam_softmax_ce(float* cosine, int64_t ldl, const int64_t* labels, float margin, float scale,
+                        int easy_margin, float* prob, float* loss_rows, int32_t* argmax, int B, int S, void* stream);
+/* L2-normalise rows (F.normalize, eps 1e-12; :55) f32 [rows, E] -> f16 [rows, E]. */
+int w2v2_l2norm_rows_f16(const float* x, void* y16, int64_t rows, int E, void* stream);
+/* Error-compensated fp16 operands for the precision-critical classifier GEMMs: v = hi + lo with
+ * hi = half(v), lo = half(v - hi); rows are emitted 3E wide as [hi|lo|hi] (which = 0, activation
+ * side) or [hi|hi|lo] (which = 1, weight side) so that ONE w2v2_gemm_f16 call with cin = 3E computes
+ * x_hi w_hi + x_lo w_hi + x_hi w_lo in the fp32 TMEM accumulator (~2^-20 relative instead of 2^-11). */
+int w2v2_split3_rows(const float* x, void* y16, int64_t rows, int E, int which, void* stream);
+int w2v2_l2norm_rows_split3(const float* x, void* y16, int64_t rows, int E, int which, void* stream);
+/* mean of n floats -> out[0] (loss reduction 'mean'). */
+int w2v2_mean_rows(const float* x, float* out, int n, void* stream);
+
+/* ---- utility ---------------------------------------------------------------------------------- */
+/* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */
+int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream);
+/* Conv1d weight [Cout, Cin, K] f32 -> tap-major fp16 [Cout, K, Cin] (the W operand of w2v2_gemm_f16). */
+int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2V2_B200_H_ */

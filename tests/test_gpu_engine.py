@@ -1,0 +1,49 @@
+"""GPU parity of the full hot path (through the C ABI) against the CPU oracle and the fixtures
+generated from the reference (tests/golden).  Tolerance (BASELINE.json north_star): pooled
+embeddings within 1e-3 relative (norm-wise, per utterance) of the fp32 reference; argmax equal."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+EMB_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def engine(base_params):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from w2v2_speaker_b200.engine import BASE, EncoderEngine, PreparedWeights
+    p = {k: v.cuda() for k, v in base_params.items()}
+    return EncoderEngine(PreparedWeights(p, BASE))
+
+
+def rel_rows(a, b):
+    a = torch.as_tensor(a).double().cpu(); b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm(dim=-1) / b.norm(dim=-1)).max().item()
+
+
+@pytest.mark.parametrize("fname,B,N", [("ref_cfg0_b2_1s.npz", 2, 16000), ("ref_b3_ragged_0p7s.npz", 3, 11283)])
+def test_encoder_matches_reference_fixture(engine, fname, B, N):
+    from oracle.params import make_inputs
+    g = golden(fname)
+    wav, labels = make_inputs(B, N, 5994, seed=1234)
+    trace = {}
+    h = engine.forward(wav.cuda(), trace)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["last_hidden_state"])
+    assert h.shape == ref.shape
+    # stage-wise norms (diagnostic: tells which stage drifts first)
+    for i, c in enumerate(trace["conv"]):
+        n = c.float().norm().item()
+        assert abs(n - float(g[f"conv.{i}.norm"])) / float(g[f"conv.{i}.norm"]) < 1e-3, f"conv.{i}"
+    for i, hs in enumerate(trace["hidden_states"]):
+        n = hs.norm().item()
+        assert abs(n - float(g[f"hidden_states.{i}.norm"])) / float(g[f"hidden_states.{i}.norm"]) < 1e-3, f"hs.{i}"
+    r = ((h.cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+    assert r < 1.5e-3, r
+    emb = h.mean(1)
+    assert rel_rows(emb, g["mean.ce.embedding"]) < EMB_TOL

@@ -1,0 +1,88 @@
+"""ctypes binding of libw2v2_b200.so (the C ABI of include/w2v2_b200.h).
+
+The library is the product: if it is missing the import of any compute entry point fails
+loudly -- there is no PyTorch/CPU fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libw2v2_b200.so")
+
+# name -> (restype, argtypes); must list every symbol declared in include/w2v2_b200.h
+SIGNATURES = {
+    "w2v2_last_error": (c_char_p, []),
+    "w2v2_abi_version": (c_int, []),
+    "w2v2_sm_count": (c_int, []),
+    "w2v2_gemm_f16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_int64,
+                              c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "w2v2_conv0_stats_floats": (c_int64, [c_int, c_int]),
+    "w2v2_conv0_gn_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                   c_int, c_void_p]),
+    "w2v2_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                               c_int64, c_int, c_void_p]),
+    "w2v2_posconv_fold_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_posconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "w2v2_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "w2v2_stat_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "w2v2_asp_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_asp_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_asp_relu_bn_tanh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "w2v2_softmax_ce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "w2v2_aam_softmax_ce": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_int, c_void_p]),
+    "w2v2_l2norm_rows_f16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "w2v2_l2norm_rows_split3": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "w2v2_split3_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "w2v2_mean_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "w2v2_cast_f16": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "w2v2_conv_weight_tapmajor": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class W2V2Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise W2V2Error(
+                f"{LIB_PATH} is missing: build it with `python -m w2v2_speaker_b200.build` "
+                "(there is no fallback path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise W2V2Error with the library message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise W2V2Error(f"{name} failed ({rc}): {lib.w2v2_last_error().decode()}")
+    return rc

@@ -1,0 +1,690 @@
+// HBM-bound kernels of the hot path: conv layer 0 + GroupNorm + GELU, LayerNorm (+bias+residual),
+// pooling, ASP glue, softmax/CE/AAM heads, casts.  Warp-shuffle reductions, 16-byte vector
+// accesses, channels-last layouts.  See include/w2v2_b200.h for the contracts.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+namespace w2v2 {
+
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int device_sm_count();
+
+// =================================================================================================
+// casts / weight re-layout
+
+__global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t n, float scale) {
+  int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + i + 4));
+    uint4 q;
+    q.x = pack_half2(a.x * scale, a.y * scale);
+    q.y = pack_half2(a.z * scale, a.w * scale);
+    q.z = pack_half2(b.x * scale, b.y * scale);
+    q.w = pack_half2(b.z * scale, b.w * scale);
+    *reinterpret_cast<uint4*>(y + i) = q;
+  }
+  if (i < n) {  // tail (at most one thread lands here per tail element group)
+    for (int64_t j = i; j < n && j < i + 8; ++j) y[j] = __float2half_rn(x[j] * scale);
+  }
+}
+
+__global__ void conv_weight_tapmajor_kernel(const float* __restrict__ w, __half* __restrict__ o, int cout, int cin,
+                                            int k) {
+  // o[co][j][ci] = w[co][ci][j]
+  const int64_t n = int64_t(cout) * cin * k;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ci = i % cin;
+    const int j = (i / cin) % k;
+    const int co = i / (int64_t(cin) * k);
+    o[i] = __float2half_rn(w[(int64_t(co) * cin + ci) * k + j]);
+  }
+}
+
+// =================================================================================================
+// conv layer 0 + GroupNorm + GELU   (HF:302-323)
+//
+// GroupNorm with C groups over C channels = per-(b,c) standardisation over time.  Because the conv is
+// linear, its per-channel mean/variance over time follow EXACTLY from the first and second moments
+// of the ten stride-5 sample windows of the waveform:
+//     mean_c = sum_k w[c,k] m_k,     var_c = sum_{k,k'} w[c,k] w[c,k'] (S_kk'/L - m_k m_k')
+// so pass 1 only reads the waveform (65 fp64 moments per utterance) and the [B,C,L] pre-norm
+// activation is never materialised; pass 2 recomputes the conv, normalises, applies GELU and
+// writes fp16 channels-last with 16-byte stores.
+
+constexpr int C0_K = 10, C0_S = 5, C0_NMOM = 10 + 55;
+
+__global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L, double* __restrict__ mom) {
+  const int b = blockIdx.y;
+  const float* x = wav + int64_t(b) * N;
+  double acc[C0_NMOM];
+#pragma unroll
+  for (int i = 0; i < C0_NMOM; ++i) acc[i] = 0.0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L; t += gridDim.x * blockDim.x) {
+    float v[C0_K];
+#pragma unroll
+    for (int k = 0; k < C0_K; ++k) v[k] = __ldg(x + t * C0_S + k);
+    int idx = C0_K;
+#pragma unroll
+    for (int k = 0; k < C0_K; ++k) {
+      acc[k] += double(v[k]);
+#pragma unroll
+      for (int k2 = k; k2 < C0_K; ++k2) acc[idx++] += double(v[k]) * double(v[k2]);
+    }
+  }
+  __shared__ double red[8][C0_NMOM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < C0_NMOM; ++i) {
+    double a = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp][i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < C0_NMOM) {
+    double a = 0.0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) a += red[w][threadIdx.x];
+    atomicAdd(mom + int64_t(b) * C0_NMOM + threadIdx.x, a);
+  }
+}
+
+__global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w, int C, int L, float eps,
+                                   float* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* m = mom + int64_t(b) * C0_NMOM;
+  const double invL = 1.0 / double(L);
+  double wk[C0_K];
+#pragma unroll
+  for (int k = 0; k < C0_K; ++k) wk[k] = double(w[c * C0_K + k]);
+  double mean = 0.0;
+#pragma unroll
+  for (int k = 0; k < C0_K; ++k) mean += wk[k] * m[k] * invL;
+  double var = 0.0;
+  int idx = C0_K;
+#pragma unroll
+  for (int k = 0; k < C0_K; ++k) {
+#pragma unroll
+    for (int k2 = k; k2 < C0_K; ++k2) {
+      const double cov = m[idx++] * invL - (m[k] * invL) * (m[k2] * invL);
+      var += (k == k2 ? 1.0 : 2.0) * wk[k] * wk[k2] * cov;
+    }
+  }
+  if (var < 0.0) var = 0.0;
+  stats[(int64_t(b) * C + c) * 2 + 0] = float(mean);
+  stats[(int64_t(b) * C + c) * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+}
+
+constexpr int C0_TT = 64;       // time steps per block
+__global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav, int N, int L,
+                                                          const float* __restrict__ w, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ stats, __half* __restrict__ out,
+                                                          int C) {
+  __shared__ float xs[C0_TT * C0_S + C0_K];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * C0_TT;
+  const int nt = min(C0_TT, L - t0);
+  const float* x = wav + int64_t(b) * N + int64_t(t0) * C0_S;
+  const int nx = (nt - 1) * C0_S + C0_K;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = __ldg(x + i);
+  __syncthreads();
+  const int groups = C / 8;                      // 8 channels (16 B of fp16) per thread
+  for (int cg = threadIdx.x % groups, tsub = threadIdx.x / groups, tstep = blockDim.x / groups; cg < groups;
+       cg += groups) {
+    const int c0 = cg * 8;
+    float wr[8][C0_K], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int k = 0; k < C0_K; ++k) wr[j][k] = __ldg(w + (c0 + j) * C0_K + k);
+      const float mean = stats[(int64_t(b) * C + c0 + j) * 2], rstd = stats[(int64_t(b) * C + c0 + j) * 2 + 1];
+      sc[j] = rstd * __ldg(gamma + c0 + j);
+      sh[j] = __ldg(beta + c0 + j) - mean * sc[j];
+    }
+    for (int t = tsub; t < nt; t += tstep) {
+      float xv[C0_K];
+#pragma unroll
+      for (int k = 0; k < C0_K; ++k) xv[k] = xs[t * C0_S + k];
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < C0_K; ++k) a = fmaf(wr[j][k], xv[k], a);
+        y[j] = gelu_erf(fmaf(a, sc[j], sh[j]));
+      }
+      uint4 q;
+      q.x = pack_half2(y[0], y[1]);
+      q.y = pack_half2(y[2], y[3]);
+      q.z = pack_half2(y[4], y[5]);
+      q.w = pack_half2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(out + (int64_t(b) * L + t0 + t) * C + c0) = q;
+    }
+  }
+}
+
+// =================================================================================================
+// LayerNorm(x + bias + residual) -> f32 and/or f16   (one warp per row, values kept in registers)
+
+template <bool X_F32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, const float* __restrict__ bias,
+                                                        const float* __restrict__ residual,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, float* __restrict__ y32, __half* __restrict__ y16,
+                                                        int64_t rows, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  constexpr int MAXV = 8;                       // H <= 1024
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < H) {
+      float4 a;
+      if constexpr (X_F32) {
+        a = *reinterpret_cast<const float4*>(static_cast<const float*>(x_) + row * H + c);
+      } else {
+        const uint2 q = *reinterpret_cast<const uint2*>(static_cast<const __half*>(x_) + row * H + c);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        a = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+      if (bias != nullptr) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+        a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+      }
+      if (residual != nullptr) {
+        const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
+        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+      }
+      v[i] = a;
+      sum += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  const float mean = warp_sum(sum) / float(H);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < H) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / float(H) + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < H) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+      if (y32 != nullptr) *reinterpret_cast<float4*>(y32 + row * H + c) = o;
+      if (y16 != nullptr) {
+        uint2 q;
+        q.x = pack_half2(o.x, o.y);
+        q.y = pack_half2(o.z, o.w);
+        *reinterpret_cast<uint2*>(y16 + row * H + c) = q;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// pooling over time.  x [B,T,H]; one thread per (b, channel), T split over `TS` thread rows of the
+// block and combined through shared memory; reads are coalesced along channels.
+
+constexpr int POOL_TS = 8;     // time slices per block
+constexpr int POOL_CH = 32;    // channels per block
+
+__device__ __forceinline__ float block_slices_sum(float v, float (*sm)[POOL_CH], int ts, int ch) {
+  __syncthreads();
+  sm[ts][ch] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < POOL_TS; ++i) s += sm[i][ch];
+  return s;
+}
+__device__ __forceinline__ float block_slices_max(float v, float (*sm)[POOL_CH], int ts, int ch) {
+  __syncthreads();
+  sm[ts][ch] = v;
+  __syncthreads();
+  float s = sm[0][ch];
+#pragma unroll
+  for (int i = 1; i < POOL_TS; ++i) s = fmaxf(s, sm[i][ch]);
+  return s;
+}
+
+__global__ void __launch_bounds__(POOL_TS* POOL_CH) stat_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                      int T, int H, int mode) {
+  __shared__ float sm[POOL_TS][POOL_CH];
+  const int ch = threadIdx.x % POOL_CH, ts = threadIdx.x / POOL_CH;
+  const int c = blockIdx.x * POOL_CH + ch;
+  const int b = blockIdx.y;
+  const float* xb = x + int64_t(b) * T * H + c;
+  if (mode == 2) {
+    float m = -INFINITY;
+    for (int t = ts; t < T; t += POOL_TS) m = fmaxf(m, xb[int64_t(t) * H]);
+    m = block_slices_max(m, sm, ts, ch);
+    if (ts == 0) out[int64_t(b) * H + c] = m;
+    return;
+  }
+  float s = 0.f;
+  for (int t = ts; t < T; t += POOL_TS) s += xb[int64_t(t) * H];
+  const float mean = block_slices_sum(s, sm, ts, ch) / float(T);
+  if (mode == 0) {
+    if (ts == 0) out[int64_t(b) * H + c] = mean;
+    return;
+  }
+  float q = 0.f;
+  for (int t = ts; t < T; t += POOL_TS) {
+    const float d = xb[int64_t(t) * H] - mean;
+    q = fmaf(d, d, q);
+  }
+  q = block_slices_sum(q, sm, ts, ch);
+  if (ts == 0) {
+    out[int64_t(b) * 2 * H + c] = sqrtf(q / float(T - 1));        // [std (unbiased) || mean]
+    out[int64_t(b) * 2 * H + H + c] = mean;
+  }
+}
+
+// ASP front: uniform-weight mean/std (eps-clamped) + concatenated fp16 operand [x | mean | std]
+__global__ void __launch_bounds__(POOL_TS* POOL_CH) asp_concat_kernel(const float* __restrict__ x,
+                                                                       __half* __restrict__ cat, int T, int H) {
+  __shared__ float sm[POOL_TS][POOL_CH];
+  const int ch = threadIdx.x % POOL_CH, ts = threadIdx.x / POOL_CH;
+  const int c = blockIdx.x * POOL_CH + ch;
+  const int b = blockIdx.y;
+  const float* xb = x + int64_t(b) * T * H + c;
+  const float m = 1.0f / float(T);
+  float s = 0.f;
+  for (int t = ts; t < T; t += POOL_TS) s = fmaf(m, xb[int64_t(t) * H], s);
+  const float mean = block_slices_sum(s, sm, ts, ch);
+  float q = 0.f;
+  for (int t = ts; t < T; t += POOL_TS) {
+    const float d = xb[int64_t(t) * H] - mean;
+    q = fmaf(m * d, d, q);
+  }
+  const float stdv = sqrtf(fmaxf(block_slices_sum(q, sm, ts, ch), 1e-12f));
+  const __half hm = __float2half_rn(mean), hs = __float2half_rn(stdv);
+  __half* cb = cat + int64_t(b) * T * 3 * H;
+  for (int t = ts; t < T; t += POOL_TS) {
+    __half* row = cb + int64_t(t) * 3 * H;
+    row[c] = __float2half_rn(xb[int64_t(t) * H]);
+    row[H + c] = hm;
+    row[2 * H + c] = hs;
+  }
+}
+
+__global__ void asp_relu_bn_tanh_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, __half* __restrict__ y, int64_t n, int A) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int a = i % A;
+    const float r = fmaxf(z[i], 0.f);
+    y[i] = __float2half_rn(tanhf(fmaf(r, __ldg(scale + a), __ldg(shift + a))));
+  }
+}
+
+// ASP tail: softmax over T per (b,c) of the attention logits, weighted mean / std
+__global__ void __launch_bounds__(POOL_TS* POOL_CH) asp_pool_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ lg, float* __restrict__ out,
+                                                                     int T, int H) {
+  __shared__ float sm[POOL_TS][POOL_CH];
+  const int ch = threadIdx.x % POOL_CH, ts = threadIdx.x / POOL_CH;
+  const int c = blockIdx.x * POOL_CH + ch;
+  const int b = blockIdx.y;
+  const float* xb = x + int64_t(b) * T * H + c;
+  const float* lb = lg + int64_t(b) * T * H + c;
+  float mx = -INFINITY;
+  for (int t = ts; t < T; t += POOL_TS) mx = fmaxf(mx, lb[int64_t(t) * H]);
+  mx = block_slices_max(mx, sm, ts, ch);
+  float se = 0.f, sx = 0.f;
+  for (int t = ts; t < T; t += POOL_TS) {
+    const float e = expf(lb[int64_t(t) * H] - mx);
+    se += e;
+    sx = fmaf(e, xb[int64_t(t) * H], sx);
+  }
+  se = block_slices_sum(se, sm, ts, ch);
+  sx = block_slices_sum(sx, sm, ts, ch);
+  const float inv = 1.0f / se;
+  const float mean = sx * inv;
+  float q = 0.f;
+  for (int t = ts; t < T; t += POOL_TS) {
+    const float e = expf(lb[int64_t(t) * H] - mx) * inv;
+    const float d = xb[int64_t(t) * H] - mean;
+    q = fmaf(e * d, d, q);
+  }
+  q = block_slices_sum(q, sm, ts, ch);
+  if (ts == 0) {
+    out[int64_t(b) * 2 * H + c] = mean;                               // [mean || std]
+    out[int64_t(b) * 2 * H + H + c] = sqrtf(fmaxf(q, 1e-12f));
+  }
+}
+
+// =================================================================================================
+// heads: softmax + CE + argmax per row (one block per row); optional AAM margin applied in place
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* sm) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < int(blockDim.x >> 5); ++i) s += sm[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ logits, int64_t ldl,
+                                                         const int64_t* __restrict__ labels, int aam, float cos_m,
+                                                         float sin_m, float th, float mm, float scale, int easy,
+                                                         float* __restrict__ prob, float* __restrict__ loss_rows,
+                                                         int32_t* __restrict__ argmax, int S) {
+  __shared__ float smf[8];
+  __shared__ float smv[8];
+  __shared__ int smi[8];
+  const int b = blockIdx.x;
+  float* row = logits + int64_t(b) * ldl;
+  const int label = int(labels[b]);
+  if (aam) {
+    // R:src/optim/loss/aam_softmax.py:56-69
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      const float c = row[i];
+      float o = c;
+      if (i == label) {
+        const float sine = sqrtf(fminf(fmaxf(1.0f - c * c, 0.f), 1.f));
+        const float phi = c * cos_m - sine * sin_m;
+        o = easy ? (c > 0.f ? phi : c) : ((c - th) > 0.f ? phi : c - mm);
+      }
+      row[i] = o * scale;
+    }
+    __syncthreads();
+  }
+  // max + argmax (first occurrence)
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const float v = row[i];
+    if (v > mx) { mx = v; mi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { smv[threadIdx.x >> 5] = mx; smi[threadIdx.x >> 5] = mi; }
+  __syncthreads();
+  mx = smv[0]; mi = smi[0];
+  for (int i = 1; i < int(blockDim.x >> 5); ++i)
+    if (smv[i] > mx || (smv[i] == mx && smi[i] < mi)) { mx = smv[i]; mi = smi[i]; }
+  float se = 0.f;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) se += expf(row[i] - mx);
+  se = block_reduce_sum(se, smf);
+  const float inv = 1.0f / se;
+  if (prob != nullptr)
+    for (int i = threadIdx.x; i < S; i += blockDim.x) prob[int64_t(b) * S + i] = expf(row[i] - mx) * inv;
+  if (threadIdx.x == 0) {
+    loss_rows[b] = -(row[label] - mx - logf(se));
+    argmax[b] = mi;
+  }
+}
+
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restrict__ x, __half* __restrict__ y, int E,
+                                                          int split3, int which) {
+  // y = x / max(||x||, 1e-12).  split3: emit the error-compensated fp16 operand of width 3E:
+  //   which == 0 (activation side): [hi | lo | hi];  which == 1 (weight side): [hi | hi | lo]
+  __shared__ float smf[8];
+  const int64_t r = blockIdx.x;
+  const float* xr = x + r * E;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) s = fmaf(xr[i], xr[i], s);
+  s = block_reduce_sum(s, smf);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  if (!split3) {
+    for (int i = threadIdx.x; i < E; i += blockDim.x) y[r * E + i] = __float2half_rn(xr[i] * inv);
+  } else {
+    __half* yr = y + r * 3 * E;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+      const float v = xr[i] * inv;
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      yr[i] = hi;
+      yr[E + i] = which == 0 ? lo : hi;
+      yr[2 * E + i] = which == 0 ? hi : lo;
+    }
+  }
+}
+
+__global__ void split3_rows_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t rows, int E, int which) {
+  const int64_t n = rows * E;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / E;
+    const int c = i % E;
+    const float v = x[i];
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    __half* yr = y + r * 3 * E;
+    yr[c] = hi;
+    yr[E + c] = which == 0 ? lo : hi;
+    yr[2 * E + c] = which == 0 ? hi : lo;
+  }
+}
+
+__global__ void mean_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int n) {
+  __shared__ float smf[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_reduce_sum(s, smf);
+  if (threadIdx.x == 0) out[0] = s / float(n);
+}
+
+// weight-norm fold of the positional conv (HF:340-358): norm over (out, in) per tap
+__global__ void posconv_norm_kernel(const float* __restrict__ v, float* __restrict__ norm, int H, int I, int K) {
+  __shared__ float smf[8];
+  const int k = blockIdx.x;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < int64_t(H) * I; i += blockDim.x) {
+    const float a = v[i * K + k];
+    s = fmaf(a, a, s);
+  }
+  s = block_reduce_sum(s, smf);
+  if (threadIdx.x == 0) norm[k] = sqrtf(s);
+}
+__global__ void posconv_fold_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                    const float* __restrict__ norm, __half* __restrict__ w16, int H, int G, int K) {
+  // w16[grp][k][c][o][e] = g[k] * v[grp*O + o][c*8 + e][k] / norm[k]      (O = I = H/G, i = c*8 + e)
+  // = per (group, tap) an [O x I] K-major block already in UMMA no-swizzle core-matrix order
+  // (planes of O rows x 16 bytes), so posconv.cu can stream it with a flat bulk copy.
+  const int O = H / G, I = H / G;
+  const int64_t n = int64_t(H) * I * K;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int e = idx % 8;
+    const int o = (idx / 8) % O;
+    const int c = (idx / (8 * int64_t(O))) % (I / 8);
+    const int k = (idx / (int64_t(I) * O)) % K;
+    const int grp = idx / (int64_t(I) * O * K);
+    const float val = v[(int64_t(grp * O + o) * I + c * 8 + e) * K + k] * (g[k] / norm[k]);
+    w16[idx] = __float2half_rn(val);
+  }
+}
+
+static inline int grid_for(int64_t n, int per_block) {
+  int64_t g = (n + per_block - 1) / per_block;
+  const int64_t cap = int64_t(device_sm_count()) * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" {
+
+const char* w2v2_last_error(void) { return w2v2::g_err; }
+int w2v2_abi_version(void) { return 1; }
+int w2v2_sm_count(void) { return device_sm_count(); }
+
+int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream) {
+  W2V2_REQUIRE(n >= 0, "w2v2_cast_f16: negative n");
+  if (n == 0) return 0;
+  cast_f16_kernel<<<grid_for(n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, n, scale);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int k, void* stream) {
+  const int64_t n = int64_t(cout) * cin * k;
+  conv_weight_tapmajor_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)w16, cout, cin, k);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_conv0_workspace_bytes(int B, int C) { return int(sizeof(double)) * B * C0_NMOM; }
+
+int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
+                       float* stats, void* out_f16, int C, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  W2V2_REQUIRE(B > 0 && N >= C0_K, "w2v2_conv0_gn_gelu: need B>0 and N>=10 (got B=%d N=%d)", B, N);
+  W2V2_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "w2v2_conv0_gn_gelu: C=%d must divide 2048 and be a multiple of 8", C);
+  const int L = (N - C0_K) / C0_S + 1;
+  // fp64 window moments live at the tail of the stats workspace: stats must hold
+  // B*C*2 floats + B*65 doubles (see w2v2_conv0_stats_floats)
+  double* mom = reinterpret_cast<double*>(stats + ((int64_t(B) * C * 2 + 1) / 2) * 2);
+  W2V2_CHECK_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * B * C0_NMOM, stream));
+  dim3 g1((L + 256 * 8 - 1) / (256 * 8), B);
+  conv0_moments_kernel<<<g1, 256, 0, stream>>>(wav, N, L, mom);
+  dim3 g2((C + 127) / 128, B);
+  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, C, L, eps, stats);
+  dim3 g3((L + C0_TT - 1) / C0_TT, B);
+  conv0_apply_kernel<<<g3, 256, 0, stream>>>(wav, N, L, w, gamma, beta, stats, (__half*)out_f16, C);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t w2v2_conv0_stats_floats(int B, int C) {
+  return ((int64_t(B) * C * 2 + 1) / 2) * 2 + int64_t(B) * C0_NMOM * 2;
+}
+
+int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
+                   const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, void* stream) {
+  W2V2_REQUIRE(H % 4 == 0 && H <= 1024, "w2v2_layernorm: H=%d must be a multiple of 4 and <= 1024", H);
+  if (rows == 0) return 0;
+  const int grid = int((rows + 7) / 8);
+  if (x_dtype == 1)
+    layernorm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H);
+  else
+    layernorm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_stat_pool(const float* x, float* out, int B, int T, int H, int mode, void* stream) {
+  W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_stat_pool: H=%d must be a multiple of %d", H, POOL_CH);
+  W2V2_REQUIRE(mode >= 0 && mode <= 2, "w2v2_stat_pool: unknown mode %d", mode);
+  W2V2_REQUIRE(T >= 1 && (mode != 1 || T >= 2), "w2v2_stat_pool: T=%d too short", T);
+  dim3 g(H / POOL_CH, B);
+  stat_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, out, T, H, mode);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_asp_concat(const float* x, void* cat16, int B, int T, int H, void* stream) {
+  W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_asp_concat: H=%d must be a multiple of %d", H, POOL_CH);
+  dim3 g(H / POOL_CH, B);
+  asp_concat_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, (__half*)cat16, T, H);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_asp_relu_bn_tanh(const float* z, const float* scale, const float* shift, void* y16, int64_t rows, int A,
+                          void* stream) {
+  const int64_t n = rows * A;
+  asp_relu_bn_tanh_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, scale, shift, (__half*)y16, n, A);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_asp_pool(const float* x, const float* logits, float* out, int B, int T, int H, void* stream) {
+  W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_asp_pool: H=%d must be a multiple of %d", H, POOL_CH);
+  dim3 g(H / POOL_CH, B);
+  asp_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, logits, out, T, H);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_softmax_ce(const float* logits, int64_t ldl, const int64_t* labels, float* prob, float* loss_rows,
+                    int32_t* argmax, int B, int S, void* stream) {
+  softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(logits), ldl, labels, 0, 0.f, 0.f, 0.f, 0.f,
+                                                         1.f, 0, prob, loss_rows, argmax, S);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_aam_softmax_ce(float* cosine, int64_t ldl, const int64_t* labels, float margin, float scale, int easy_margin,
+                        float* prob, float* loss_rows, int32_t* argmax, int B, int S, void* stream) {
+  const double m = margin;
+  const double pi = 3.14159265358979323846;
+  softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cosine, ldl, labels, 1, float(cos(m)), float(sin(m)),
+                                                         float(cos(pi - m)), float(sin(pi - m) * m), scale, easy_margin,
+                                                         prob, loss_rows, argmax, S);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_l2norm_rows_f16(const float* x, void* y16, int64_t rows, int E, void* stream) {
+  l2norm_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, E, 0, 0);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_l2norm_rows_split3(const float* x, void* y16, int64_t rows, int E, int which, void* stream) {
+  l2norm_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, E, 1, which);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_split3_rows(const float* x, void* y16, int64_t rows, int E, int which, void* stream) {
+  split3_rows_kernel<<<grid_for(rows * E, 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, rows, E, which);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_mean_rows(const float* x, float* out, int n, void* stream) {
+  mean_rows_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // scratch for the K norms: reuse the head of w16?  No -- keep a tiny static device buffer per call site:
+  // the caller passes w16 sized H*(H/groups)*K halfs + K floats; norms live behind the weights.
+  float* norm = reinterpret_cast<float*>(static_cast<__half*>(w16) + int64_t(H) * (H / groups) * K);
+  posconv_norm_kernel<<<K, 256, 0, stream>>>(v, norm, H, H / groups, K);
+  const int64_t n = int64_t(H) * (H / groups) * K;
+  posconv_fold_kernel<<<grid_for(n, 256), 256, 0, stream>>>(v, g, norm, (__half*)w16, H, groups, K);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

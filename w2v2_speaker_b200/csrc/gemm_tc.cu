@@ -1,0 +1,350 @@
+// Tap-GEMM on tcgen05 tensor cores (sm_100a):
+//
+//     out[b, r, n] = act( sum_{tap, c} A[b, r*row_stride + tap*tap_stride + c] * W[n, tap*Cin + c] + bias[n] )
+//
+// One kernel serves every dense contraction of the hot path:
+//   * strided Conv1d layers 1..6 of the wav2vec2 feature extractor (HF:254-272) as an im2col-free
+//     implicit GEMM over a channels-last [B, L, C] activation: tap j of output row t reads input row
+//     (stride*t + j), which is just a TMA tensor map with row pitch stride*C and base offset j*C;
+//   * every Linear of the transformer (QKV, out_proj, FFN1, FFN2; HF:500-573), the feature
+//     projection (HF:429-434), the ASP 1x1 convs and the CE / AAM classifier GEMMs (ntaps = 1).
+//
+// Operands are fp16 (RNE-rounded by the producing kernel), accumulation is fp32 in TMEM.
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0    : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1    : MMA issuer    (one elected thread: tcgen05.mma 128xBNx16, commit -> mbarriers)
+//   warps 2-5 : epilogue      (tcgen05.ld 32 lanes x 32 cols -> bias/GELU -> fp16|fp32 ->
+//                              swizzled smem staging -> TMA store, which also clips M/N tails)
+// The TMEM accumulator is double-buffered (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+namespace w2v2 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // fp16 elements = 128 bytes = one swizzle row
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int CSTAGE_BYTES = BM * 128;   // one staging buffer: 128 rows x 128 bytes
+constexpr int NUM_THREADS = 192;
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB;
+  CUtensorMap tmOut;
+  const float* bias;
+  int ntaps, kblocks_per_tap;
+  int m_tiles, n_tiles, batch;
+  int N;
+  int act;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+template <int BN, bool OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* cstage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cstage + 2 * CSTAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles * p.batch;
+  const int k_iters = p.ntaps * p.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    for (int t = 0; t < p.ntaps; ++t) prefetch_tensormap(&p.tmA[t]);
+    prefetch_tensormap(&p.tmB);
+    prefetch_tensormap(&p.tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int mt = rest % p.m_tiles;
+        const int b = rest / p.m_tiles;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_3d(sa, &p.tmA[tap], &full_bar[stage], kb * BK, mt * BM, b);
+            tma_load_3d(sb, &p.tmB, &full_bar[stage], (tap * p.kblocks_per_tap + kb) * BK, nt * BN, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                     (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);       // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);           // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;        // row of the 128-row tile owned by this thread
+    const bool issuer = (threadIdx.x == 64);
+    constexpr int COLS_PER_GROUP = OUT_F32 ? 32 : 64;     // 128 bytes of output per row
+    constexpr int GROUPS = BN / COLS_PER_GROUP;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t gcount = 0;                        // running staging-group counter (buffer = gcount & 1)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int mt = rest % p.m_tiles;
+      const int b = rest / p.m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int g = 0; g < GROUPS; ++g, ++gcount) {
+        uint8_t* cbuf = cstage + (gcount & 1) * CSTAGE_BYTES;
+        // the TMA store that last read this buffer (two groups ago) must be done reading
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* crow = cbuf + row * 128;
+#pragma unroll
+        for (int h = 0; h < COLS_PER_GROUP / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + g * COLS_PER_GROUP + h * 32, r);
+          tmem_ld_wait();
+          const int n0 = nt * BN + g * COLS_PER_GROUP + h * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias != nullptr) x += (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            if (p.act == 1) x = gelu_erf(x);
+            v[j] = x;
+          }
+          if constexpr (OUT_F32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {          // 8 chunks of 16 B (4 floats)
+              const int pc = c ^ (row & 7);
+              *reinterpret_cast<float4*>(crow + pc * 16) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {          // 4 chunks of 16 B (8 halfs) per 32 columns
+              const int pc = (h * 4 + c) ^ (row & 7);
+              uint4 q;
+              q.x = pack_half2(v[8 * c], v[8 * c + 1]);
+              q.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
+              q.z = pack_half2(v[8 * c + 4], v[8 * c + 5]);
+              q.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
+              *reinterpret_cast<uint4*>(crow + pc * 16) = q;
+            }
+          }
+        }
+        if (g == GROUPS - 1) {
+          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (issuer) {
+          tma_store_3d(&p.tmOut, cbuf, nt * BN + g * COLS_PER_GROUP, mt * BM, b);
+          tma_store_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                 int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  W2V2_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
+  W2V2_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16B aligned", base);
+  W2V2_REQUIRE(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "TMA strides (%llu, %llu) not multiples of 16 B",
+               (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  W2V2_REQUIRE(r == CUDA_SUCCESS,
+               "cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u)", (int)r,
+               base, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+               (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, b0, b1, b2);
+  return 0;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+template <int BN, bool OUT_F32>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, OUT_F32>;
+  if (!configured) {
+    W2V2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.batch;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,
+                             int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N,
+                             const float* bias, int act, void* out, int out_dtype, int64_t ldo,
+                             int64_t out_batch_stride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  W2V2_REQUIRE(ntaps >= 1 && ntaps <= 3, "w2v2_gemm_f16: ntaps=%d not in [1,3]", ntaps);
+  W2V2_REQUIRE(cin % BK == 0, "w2v2_gemm_f16: cin=%d must be a multiple of %d", cin, BK);
+  W2V2_REQUIRE(out_dtype == 0 || out_dtype == 1, "w2v2_gemm_f16: out_dtype must be 0 (f16) or 1 (f32)");
+  W2V2_REQUIRE(a_rows > 0 && batch > 0 && N > 0, "w2v2_gemm_f16: empty problem");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int BN = (N <= 128) ? 128 : 256;
+  const int osz = out_dtype == 1 ? 4 : 2;
+  const uint64_t a_bstride = batch > 1 ? uint64_t(a_batch_stride) * 2 : uint64_t(a_rows) * uint64_t(a_row_stride) * 2;
+  for (int t = 0; t < ntaps; ++t) {
+    const __half* base = static_cast<const __half*>(A) + t * a_tap_stride;
+    int rc = make_tmap_3d(&p.tmA[t], base, 2, cin, a_rows, batch, uint64_t(a_row_stride) * 2, a_bstride, BK, BM, 1, 128);
+    if (rc) return rc;
+  }
+  int rc = make_tmap_3d(&p.tmB, W, 2, uint64_t(ntaps) * cin, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, BN, 1, 128);
+  if (rc) return rc;
+  const uint64_t o_bstride = batch > 1 ? uint64_t(out_batch_stride) * osz : uint64_t(a_rows) * uint64_t(ldo) * osz;
+  rc = make_tmap_3d(&p.tmOut, out, osz, N, a_rows, batch, uint64_t(ldo) * osz, o_bstride, out_dtype == 1 ? 32 : 64, BM, 1, 128);
+  if (rc) return rc;
+  p.bias = bias;
+  p.ntaps = ntaps;
+  p.kblocks_per_tap = cin / BK;
+  p.m_tiles = int((a_rows + BM - 1) / BM);
+  p.n_tiles = (N + BN - 1) / BN;
+  p.batch = batch;
+  p.N = N;
+  p.act = act;
+  if (BN == 256) return out_dtype == 1 ? launch_gemm<256, true>(p, stream) : launch_gemm<256, false>(p, stream);
+  return out_dtype == 1 ? launch_gemm<128, true>(p, stream) : launch_gemm<128, false>(p, stream);
+}

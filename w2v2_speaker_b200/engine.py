@@ -1,0 +1,180 @@
+"""Forward engine of the wav2vec2 encoder on the sm_100a kernels.
+
+This is the host-side schedule of the hot path (one launch sequence per batch):
+
+    wav f32 [B,N]
+      -> conv0+GroupNorm+GELU (fused, HBM-bound)                       -> f16 [B,L0,512] channels-last
+      -> conv1..6 as tap-GEMMs on tcgen05 (+GELU epilogue)             -> f16 ... f32 [B,T,512]
+      -> LayerNorm(512) -> proj GEMM(+bias) -> h0 f32 [B*T,H]
+      -> posconv (tcgen05, shifted-slab) ; LN(h0 + pos)                -> h f32 / f16
+      -> L x { QKV GEMM -> attention (tcgen05) -> out GEMM -> LN(+bias+res) -> FFN1 GEMM(+bias+GELU)
+               -> FFN2 GEMM -> LN(+bias+res) }
+      -> last_hidden_state f32 [B,T,H]
+
+GEMM operands are fp16 (rounded to nearest once, by the producing kernel), accumulation, residual
+stream, LayerNorm / GroupNorm / softmax statistics are fp32.  Follows HF:1327-1383 in eval mode
+(dropout, LayerDrop, SpecAugment are identity; R:src/models/wav2vec2.py:62-76).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+F16, F32 = torch.float16, torch.float32
+
+
+@dataclass(frozen=True)
+class ArchConfig:
+    """Architecture numbers (HF Wav2Vec2Config fields the kernels depend on)."""
+    name: str = "base"
+    hidden: int = 768
+    layers: int = 12
+    heads: int = 12
+    ffn: int = 3072
+    conv_dim: int = 512
+    conv_kernel: tuple = (10, 3, 3, 3, 3, 2, 2)
+    conv_stride: tuple = (5, 2, 2, 2, 2, 2, 2)
+    pos_kernel: int = 128
+    pos_groups: int = 16
+    eps: float = 1e-5
+
+    def conv_lengths(self, n: int) -> List[int]:
+        out = []
+        for k, s in zip(self.conv_kernel, self.conv_stride):
+            n = (n - k) // s + 1                 # HF:1012-1018
+            out.append(n)
+        return out
+
+
+BASE = ArchConfig()
+LARGE = ArchConfig(name="large", hidden=1024, layers=24, heads=16, ffn=4096)
+
+
+def arch_from_id(huggingface_id: str) -> ArchConfig:
+    """Size detection by substring of the HF id, as the reference does (R:src/models/wav2vec2.py:112-117)."""
+    if "base" in huggingface_id:
+        return BASE
+    if "large" in huggingface_id:
+        return LARGE
+    raise ValueError("cannot determine num features")
+
+
+class PreparedWeights:
+    """fp16 / re-laid-out copies of the encoder parameters in the form the kernels consume.
+
+    Built from a dict keyed by HF state_dict names (fp32, on the GPU).  Must be rebuilt after the
+    parameters change (optimizer step / load_state_dict)."""
+
+    def __init__(self, p: Dict[str, torch.Tensor], arch: ArchConfig):
+        self.arch = arch
+        H = arch.hidden
+        f = lambda k: p[k].detach().to(F32).contiguous()
+        self.conv0_w = f("feature_extractor.conv_layers.0.conv.weight").view(arch.conv_dim, arch.conv_kernel[0])
+        self.gn_g = f("feature_extractor.conv_layers.0.layer_norm.weight")
+        self.gn_b = f("feature_extractor.conv_layers.0.layer_norm.bias")
+        self.conv_w = [None] + [ops.conv_weight_tapmajor(f(f"feature_extractor.conv_layers.{i}.conv.weight"))
+                                for i in range(1, len(arch.conv_kernel))]
+        self.fp_ln_g = f("feature_projection.layer_norm.weight")
+        self.fp_ln_b = f("feature_projection.layer_norm.bias")
+        self.fp_w = ops.cast_f16(f("feature_projection.projection.weight"))
+        self.fp_b = f("feature_projection.projection.bias")
+        self.pos_w = ops.posconv_fold_weight(f("encoder.pos_conv_embed.conv.parametrizations.weight.original1"),
+                                             f("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1),
+                                             arch.pos_groups)
+        self.pos_b = f("encoder.pos_conv_embed.conv.bias")
+        self.enc_ln_g = f("encoder.layer_norm.weight")
+        self.enc_ln_b = f("encoder.layer_norm.bias")
+        d = H // arch.heads
+        scale = float(d) ** -0.5
+        self.layers = []
+        for l in range(arch.layers):
+            pre = f"encoder.layers.{l}."
+            wq, wk, wv = (f(pre + f"attention.{n}_proj.weight") for n in "qkv")
+            bq, bk, bv = (f(pre + f"attention.{n}_proj.bias") for n in "qkv")
+            # the softmax scale d^-0.5 is folded into the q projection (HF:528 scales q)
+            wqkv = ops.cast_f16(torch.cat([wq * scale, wk, wv], 0))
+            bqkv = torch.cat([bq * scale, bk, bv], 0).contiguous()
+            self.layers.append(dict(
+                wqkv=wqkv, bqkv=bqkv,
+                wo=ops.cast_f16(f(pre + "attention.out_proj.weight")), bo=f(pre + "attention.out_proj.bias"),
+                ln1_g=f(pre + "layer_norm.weight"), ln1_b=f(pre + "layer_norm.bias"),
+                w1=ops.cast_f16(f(pre + "feed_forward.intermediate_dense.weight")),
+                b1=f(pre + "feed_forward.intermediate_dense.bias"),
+                w2=ops.cast_f16(f(pre + "feed_forward.output_dense.weight")),
+                b2=f(pre + "feed_forward.output_dense.bias"),
+                ln2_g=f(pre + "final_layer_norm.weight"), ln2_b=f(pre + "final_layer_norm.bias")))
+
+
+class EncoderEngine:
+    """Runs the eval-mode forward of the encoder for one (weights, arch) pair."""
+
+    def __init__(self, weights: PreparedWeights):
+        self.w = weights
+        self.arch = weights.arch
+
+    # -- HF:409-419 ----------------------------------------------------------------------------
+    def feature_extractor(self, wav: torch.Tensor, stages: Optional[list] = None) -> torch.Tensor:
+        """wav f32 [B,N] -> channels-last f32 [B,T,C] (HF returns its transpose [B,C,T])."""
+        a, w = self.arch, self.w
+        if wav.dim() != 2:
+            raise ValueError(f"expected wav_input of shape [BATCH_SIZE, NUM_SAMPLES], got {tuple(wav.shape)}")
+        h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps)
+        if stages is not None:
+            stages.append(h)
+        n = len(a.conv_kernel)
+        for i in range(1, n):
+            h = ops.conv1d_cl_f16(h, w.conv_w[i], a.conv_kernel[i], a.conv_stride[i], act=1,
+                                  out_dtype=F32 if i == n - 1 else F16)
+            if stages is not None:
+                stages.append(h)
+        return h
+
+    # -- HF:429-434 ----------------------------------------------------------------------------
+    def feature_projection(self, feat_btc: torch.Tensor) -> torch.Tensor:
+        a, w = self.arch, self.w
+        B, T, C = feat_btc.shape
+        _, n16 = ops.layernorm(feat_btc.contiguous().view(B * T, C), w.fp_ln_g, w.fp_ln_b, a.eps, want32=False)
+        h0 = ops.gemm_f16(n16, w.fp_w, w.fp_b, 0, F32)
+        return h0.view(B, T, a.hidden)
+
+    # -- HF:668-727 ----------------------------------------------------------------------------
+    def encoder(self, h0: torch.Tensor, hidden_states: Optional[list] = None) -> torch.Tensor:
+        """h0 f32 [B,T',H] (any sequence, e.g. with a CLS frame prepended) -> last_hidden_state f32."""
+        a, w = self.arch, self.w
+        B, T, H = h0.shape
+        M = B * T
+        h0 = h0.contiguous()
+        x16 = ops.cast_f16(h0)
+        pos = ops.posconv(x16, w.pos_w, w.pos_b, a.pos_groups, a.pos_kernel)
+        h32, h16 = ops.layernorm(pos.view(M, H), w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0.view(M, H))
+        if hidden_states is not None:
+            hidden_states.append(h32.view(B, T, H))
+        for lw in w.layers:
+            qkv = ops.gemm_f16(h16, lw["wqkv"], lw["bqkv"], 0, F16)
+            att = ops.attention(qkv, B, T, H, a.heads)
+            o = ops.gemm_f16(att, lw["wo"], None, 0, F32)
+            h32, h16 = ops.layernorm(o, lw["ln1_g"], lw["ln1_b"], a.eps, bias=lw["bo"], residual=h32)
+            f1 = ops.gemm_f16(h16, lw["w1"], lw["b1"], 1, F16)
+            f2 = ops.gemm_f16(f1, lw["w2"], None, 0, F32)
+            h32, h16 = ops.layernorm(f2, lw["ln2_g"], lw["ln2_b"], a.eps, bias=lw["b2"], residual=h32)
+            if hidden_states is not None:
+                hidden_states.append(h32.view(B, T, H))
+        return h32.view(B, T, H)
+
+    # -- HF:1327-1383 --------------------------------------------------------------------------
+    def forward(self, wav: torch.Tensor, trace: Optional[dict] = None) -> torch.Tensor:
+        """wav f32 [B,N] -> last_hidden_state f32 [B,T,H]."""
+        stages = [] if trace is not None else None
+        feat = self.feature_extractor(wav, stages)
+        h0 = self.feature_projection(feat)
+        hs = [] if trace is not None else None
+        out = self.encoder(h0, hs)
+        if trace is not None:
+            trace["conv"] = stages
+            trace["proj"] = h0
+            trace["hidden_states"] = hs
+        return out

@@ -1,0 +1,167 @@
+"""Drop-in mirror of the reference's ``src/layers/pooling.py`` (same classes / signatures).
+
+mean, mean+std, max and attentive-statistics pooling run in the sm_100a kernels
+(w2v2_stat_pool / w2v2_asp_*); quantile / index / none are not on any measured configuration
+ and stay the reference's plain tensor ops.
+Inputs follow the reference: ``[B, T, C]`` with ``dim_to_reduce=1`` (as built at
+R:src/lightning_modules/speaker/wav2vec2_fc.py:238-272) or ``[B, C, T]`` with ``dim_to_reduce=2``.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def _as_btc(tensor: torch.Tensor, dim_to_reduce: int) -> torch.Tensor:
+    if tensor.dim() != 3:
+        raise ValueError("pooling expects a [BATCH, TIME, FEATURE] or [BATCH, FEATURE, TIME] tensor")
+    if dim_to_reduce == 1:
+        return tensor.float().contiguous()
+    if dim_to_reduce == 2:
+        return tensor.float().transpose(1, 2).contiguous()
+    raise ValueError("can only pool dimension 1 or 2")
+
+
+class MeanStatPool1D(nn.Module):
+    """R:src/layers/pooling.py:24-30."""
+
+    def __init__(self, dim_to_reduce: int = 2):
+        super().__init__()
+        self.dim_to_reduce = dim_to_reduce
+
+    def forward(self, tensor: torch.Tensor):
+        return ops.stat_pool(_as_btc(tensor, self.dim_to_reduce), 0)
+
+
+class MeanStdStatPool1D(nn.Module):
+    """R:src/layers/pooling.py:38-44: ``cat(std_mean(x))`` => [std (unbiased) || mean]."""
+
+    def __init__(self, dim_to_reduce: int = 2):
+        super().__init__()
+        self.dim_to_reduce = dim_to_reduce
+
+    def forward(self, tensor: torch.Tensor):
+        return ops.stat_pool(_as_btc(tensor, self.dim_to_reduce), 1)
+
+
+class MaxPool1D(nn.Module):
+    """R:src/layers/pooling.py:74-80."""
+
+    def __init__(self, dim_to_reduce: int = 2):
+        super().__init__()
+        self.dim_to_reduce = dim_to_reduce
+
+    def forward(self, tensor: torch.Tensor):
+        return ops.stat_pool(_as_btc(tensor, self.dim_to_reduce), 2)
+
+
+class QuantilePool1D(nn.Module):
+    """R:src/layers/pooling.py:51-67 (plain tensor op; not on a measured configuration)."""
+
+    def __init__(self, dim_to_reduce: int = 2):
+        super().__init__()
+        self.dim_to_reduce = dim_to_reduce
+        self.quantiles = torch.Tensor([0, 0.25, 0.5, 0.75, 1]).detach()
+
+    def forward(self, tensor: torch.Tensor):
+        q = torch.quantile(tensor, self.quantiles.to(tensor.device), dim=self.dim_to_reduce)
+        return torch.flatten(torch.transpose(q, 0, 1), start_dim=1, end_dim=2)
+
+
+class _AttentiveStatisticsPooling(nn.Module):
+    """Parameters of speechbrain's ``AttentiveStatisticsPooling(channels, attention_channels=128,
+    global_context=True)`` under speechbrain's state_dict names (tdnn.conv.conv / tdnn.norm.norm /
+    conv.conv); forward in the sm_100a kernels.  x: [N, C, L] -> [N, 2C, 1]."""
+
+    def __init__(self, channels: int, attention_channels: int = 128):
+        super().__init__()
+        self.channels, self.attention_channels = channels, attention_channels
+        self.eps = 1e-12
+
+        def holder(name, mod):
+            h = nn.Module()
+            h.add_module(name, mod)
+            return h
+        self.tdnn = nn.Module()
+        self.tdnn.add_module("conv", holder("conv", nn.Conv1d(channels * 3, attention_channels, 1)))
+        self.tdnn.add_module("norm", holder("norm", nn.BatchNorm1d(attention_channels)))
+        self.conv = holder("conv", nn.Conv1d(attention_channels, channels, 1))
+
+    def forward(self, x_ncl: torch.Tensor) -> torch.Tensor:
+        return self.forward_btc(x_ncl.transpose(1, 2).contiguous()).unsqueeze(2)
+
+    def forward_btc(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("attentive pooling with batch-statistics BatchNorm (train mode) is not "
+                                      "implemented in the sm_100a path yet; call .eval()")
+        B, T, C = x.shape
+        x = x.float().contiguous()
+        c1, bn, c2 = self.tdnn.conv.conv, self.tdnn.norm.norm, self.conv.conv
+        cat16 = ops.asp_concat(x)                                            # [B*T, 3C] fp16
+        z = ops.gemm_f16(cat16, ops.cast_f16(c1.weight.detach().view(self.attention_channels, 3 * C)),
+                         c1.bias.detach().float(), 0, torch.float32)           # Conv1d k=1
+        scale = (bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+        shift = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
+        y16 = ops.asp_relu_bn_tanh(z.contiguous(), scale, shift)             # tanh(BN(ReLU(.)))
+        logits = ops.gemm_f16(y16, ops.cast_f16(c2.weight.detach().view(C, self.attention_channels)),
+                              c2.bias.detach().float(), 0, torch.float32)
+        return ops.asp_pool(x, logits.contiguous().view(B, T, C))            # [B, 2C] = [mean || std]
+
+
+class AttentiveStatPool1D(nn.Module):
+    """R:src/layers/pooling.py:87-106."""
+
+    def __init__(self, embedding_size: int, dim_to_reduce: int = 2):
+        super().__init__()
+        self.pooling_layer = _AttentiveStatisticsPooling(embedding_size)
+        self.dim_to_reduce = dim_to_reduce
+
+    def forward(self, tensor: torch.Tensor):
+        if self.dim_to_reduce == 2:
+            pooled_embedding = self.pooling_layer.forward_btc(tensor.transpose(1, 2).contiguous())
+        elif self.dim_to_reduce == 1:
+            pooled_embedding = self.pooling_layer.forward_btc(tensor)
+        else:
+            raise ValueError("can only pool dimension 1 or 2")
+        pooled_embedding = pooled_embedding.squeeze()
+        if len(pooled_embedding.shape) == 1:
+            pooled_embedding = pooled_embedding[None, :]
+        return pooled_embedding
+
+
+class IndexPool1D(nn.Module):
+    """R:src/layers/pooling.py:112-154, including the upstream quirk that "middle" selects the
+    last frame."""
+
+    def __init__(self, selection_method: str, dim_to_reduce: int):
+        super().__init__()
+        self.selection_method = selection_method
+        self.dim_to_reduce = dim_to_reduce
+
+    def forward(self, tensor: torch.Tensor):
+        n = tensor.shape[self.dim_to_reduce]
+        if self.selection_method in ("first", "first+cls"):
+            idx = 0
+        elif self.selection_method in ("middle", "last"):
+            idx = n - 1
+        elif self.selection_method == "random":
+            idx = random.randint(0, int(n) - 1)
+        else:
+            raise ValueError(f"unknown index {self.selection_method}")
+        view = tensor[:, idx, :] if self.dim_to_reduce == 1 else tensor[:, :, idx]
+        return torch.clone(view)
+
+
+class NoPooling(nn.Module):
+    """R:src/layers/pooling.py:161-166."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, tensor: torch.Tensor):
+        return tensor

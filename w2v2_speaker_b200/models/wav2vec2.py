@@ -1,0 +1,280 @@
+"""Drop-in mirror of the reference's ``src/models/wav2vec2.py`` on the sm_100a kernels.
+
+Same class names, constructor arguments, attributes and tensor contracts as
+R:src/models/wav2vec2.py:83-169; the arithmetic of the wrapped HuggingFace ``Wav2Vec2Model``
+(R:src/models/wav2vec2.py:37-53, HF:1327-1383) is done by ``engine.EncoderEngine`` through the
+C ABI.  Parameters are ``nn.Parameter``s under HF's state_dict names, so ``parameters()``,
+``state_dict()``, ``load_state_dict(strict=False)`` and ``requires_grad_`` keep working
+(SURVEY 8b).
+
+This round ships the eval-mode forward; a grad-requiring training forward raises (there is no
+PyTorch fallback to fall into).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ..engine import ArchConfig, EncoderEngine, PreparedWeights, arch_from_id
+
+try:  # the reference derives from LightningModule; it is absent from this image
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # pragma: no cover - depends on the environment
+    class _Base(nn.Module):
+        """nn.Module with LightningModule's freeze / unfreeze semantics."""
+
+        def freeze(self) -> None:
+            for p in self.parameters():
+                p.requires_grad = False
+            self.eval()
+
+        def unfreeze(self) -> None:
+            for p in self.parameters():
+                p.requires_grad = True
+            self.train()
+
+
+@dataclass
+class Wav2Vec2RegularisationConfig:
+    """R:src/models/wav2vec2.py:83-94 (same fields and defaults)."""
+    gradient_checkpointing: bool = False
+    activation_dropout: float = 0.0
+    attention_dropout: float = 0.1
+    feat_proj_dropout: float = 0.1
+    hidden_dropout: float = 0.1
+    layerdrop: float = 0.05
+    mask_feature_length: int = 10
+    mask_feature_prob: float = 0.0
+    mask_time_length: int = 10
+    mask_time_prob: float = 0.05
+
+
+class _Holder(nn.Module):
+    """Anonymous container used to reproduce HF's module tree (and therefore its state_dict keys)."""
+
+
+def _set_param(root: nn.Module, dotted: str, value: torch.Tensor) -> None:
+    parts = dotted.split(".")
+    m = root
+    for name in parts[:-1]:
+        if not hasattr(m, name):
+            m.add_module(name, _Holder())
+        m = getattr(m, name)
+    m.register_parameter(parts[-1], nn.Parameter(value))
+
+
+@dataclass
+class Wav2Vec2BaseModelOutput:
+    last_hidden_state: torch.Tensor
+    extract_features: Optional[torch.Tensor] = None
+    hidden_states: Optional[tuple] = None
+
+
+class _EncoderOutput:
+    def __init__(self, last_hidden_state, hidden_states=None):
+        self.last_hidden_state = last_hidden_state
+        self.hidden_states = hidden_states
+
+
+class _FeatureExtractor(_Holder):
+    """``model.feature_extractor``: [B,N] -> [B,512,T] (HF:409-419)."""
+
+    def forward(self, input_values: torch.Tensor) -> torch.Tensor:
+        return self._owner()._engine().feature_extractor(input_values).transpose(1, 2)
+
+
+class _FeatureProjection(_Holder):
+    """``model.feature_projection``: [B,T,512] -> (hidden [B,T,H], normed input) (HF:429-434)."""
+
+    def forward(self, hidden_states: torch.Tensor):
+        h = self._owner()._engine().feature_projection(hidden_states.contiguous())
+        return h, None
+
+
+class _Encoder(_Holder):
+    """``model.encoder``: [B,T',H] -> object with ``last_hidden_state`` (HF:668-727)."""
+
+    def forward(self, hidden_states: torch.Tensor, output_hidden_states: bool = False, **_):
+        hs = [] if output_hidden_states else None
+        out = self._owner()._engine().encoder(hidden_states.float(), hs)
+        return _EncoderOutput(out, tuple(hs) if hs is not None else None)
+
+
+class Wav2Vec2ModelB200(nn.Module):
+    """Stand-in for ``transformers.Wav2Vec2Model`` (the object the reference keeps in ``.model``)."""
+
+    def __init__(self, arch: ArchConfig, reg_cfg: Optional[Wav2Vec2RegularisationConfig] = None):
+        super().__init__()
+        self.arch = arch
+        self.reg_cfg = reg_cfg or Wav2Vec2RegularisationConfig()
+        self.feature_extractor = _FeatureExtractor()
+        self.feature_projection = _FeatureProjection()
+        self.encoder = _Encoder()
+        for sub in (self.feature_extractor, self.feature_projection, self.encoder):
+            object.__setattr__(sub, "_owner", lambda self=self: self)
+        for name, value in init_hf_parameters(arch).items():
+            _set_param(self, name, value)
+        self._prepared = None
+        self._prepared_sig = None
+
+    # ---- weights in kernel form, rebuilt when any parameter changed -------------------------
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def refresh(self) -> None:
+        self._prepared = None
+
+    def _engine(self) -> EncoderEngine:
+        if any(not p.is_cuda for p in self.parameters()):
+            raise RuntimeError("Wav2Vec2ModelB200 runs on a CUDA device only: move the module with .cuda() "
+                               "(there is no CPU path)")
+        sig = self._signature()
+        if self._prepared is None or sig != self._prepared_sig:
+            self._prepared = EncoderEngine(PreparedWeights(dict(self.named_parameters()), self.arch))
+            self._prepared_sig = sig
+        return self._prepared
+
+    def _check_mode(self):
+        r = self.reg_cfg
+        stochastic = (r.activation_dropout + r.attention_dropout + r.feat_proj_dropout + r.hidden_dropout +
+                      r.layerdrop + r.mask_time_prob + r.mask_feature_prob) > 0
+        if self.training and stochastic:
+            raise NotImplementedError(
+                "training-mode regularisation (dropout / LayerDrop / SpecAugment) is not implemented in the "
+                "sm_100a path yet; call .eval() or zero the probabilities (SURVEY Appendix A Q10)")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the backward kernels are not part of this round: run under torch.no_grad()")
+
+    def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, **_):
+        """HF:1327-1383 (eval).  input_values f32 [B,N]."""
+        self._check_mode()
+        eng = self._engine()
+        trace = {} if output_hidden_states else None
+        out = eng.forward(input_values.float(), trace)
+        hs = tuple(trace["hidden_states"]) if trace is not None else None
+        return Wav2Vec2BaseModelOutput(last_hidden_state=out, hidden_states=hs)
+
+
+def init_hf_parameters(arch: ArchConfig) -> dict:
+    """Random initialisation following HF ``_init_weights`` (HF:968-1003) and the module defaults."""
+    C, H = arch.conv_dim, arch.hidden
+    p = {}
+    p["masked_spec_embed"] = torch.rand(H)
+    cin = 1
+    for i, k in enumerate(arch.conv_kernel):
+        w = torch.empty(C, cin, k)
+        nn.init.kaiming_normal_(w)
+        p[f"feature_extractor.conv_layers.{i}.conv.weight"] = w
+        if i == 0:
+            p["feature_extractor.conv_layers.0.layer_norm.weight"] = torch.ones(C)
+            p["feature_extractor.conv_layers.0.layer_norm.bias"] = torch.zeros(C)
+        cin = C
+    p["feature_projection.layer_norm.weight"] = torch.ones(C)
+    p["feature_projection.layer_norm.bias"] = torch.zeros(C)
+    kk = math.sqrt(1.0 / C)
+    p["feature_projection.projection.weight"] = torch.empty(H, C).uniform_(-kk, kk)
+    p["feature_projection.projection.bias"] = torch.empty(H).uniform_(-kk, kk)
+    gsz = H // arch.pos_groups
+    v = torch.randn(H, gsz, arch.pos_kernel) * (2.0 * math.sqrt(1.0 / (arch.pos_kernel * H)))
+    p["encoder.pos_conv_embed.conv.bias"] = torch.zeros(H)
+    p["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+    p["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = v
+    p["encoder.layer_norm.weight"] = torch.ones(H)
+    p["encoder.layer_norm.bias"] = torch.zeros(H)
+    for l in range(arch.layers):
+        pre = f"encoder.layers.{l}."
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            p[pre + f"attention.{nm}.weight"] = torch.randn(H, H) * 0.02
+            p[pre + f"attention.{nm}.bias"] = torch.zeros(H)
+        p[pre + "layer_norm.weight"] = torch.ones(H)
+        p[pre + "layer_norm.bias"] = torch.zeros(H)
+        p[pre + "feed_forward.intermediate_dense.weight"] = torch.randn(arch.ffn, H) * 0.02
+        p[pre + "feed_forward.intermediate_dense.bias"] = torch.zeros(arch.ffn)
+        p[pre + "feed_forward.output_dense.weight"] = torch.randn(H, arch.ffn) * 0.02
+        p[pre + "feed_forward.output_dense.bias"] = torch.zeros(H)
+        p[pre + "final_layer_norm.weight"] = torch.ones(H)
+        p[pre + "final_layer_norm.bias"] = torch.zeros(H)
+    return p
+
+
+def load_base_wav2vec2_model(huggingface_id: str, reg_cfg: Optional[Wav2Vec2RegularisationConfig] = None,
+                             device=torch.device("cpu")) -> Wav2Vec2ModelB200:
+    """R:src/models/wav2vec2.py:25-55.  No network / HF cache exists here, so the architecture named
+    by ``huggingface_id`` is random-initialised; load weights with ``load_state_dict`` (HF key names)."""
+    return Wav2Vec2ModelB200(arch_from_id(huggingface_id), reg_cfg).to(device)
+
+
+def wav2vec2_embed_raw_audio(input_tensor: torch.Tensor, model: Wav2Vec2ModelB200) -> torch.Tensor:
+    """R:src/models/wav2vec2.py:62-76: [B, num_samples] -> [B, H, num_frames]."""
+    output = model(input_tensor)
+    return output.last_hidden_state.transpose(1, 2)
+
+
+def reset_model(model: nn.Module) -> None:
+    """R:src/util.py:214-226 re-initialises every leaf with its PyTorch default ``reset_parameters``.
+    The parameter holders here have no torch leaf modules, so the equivalent is a fresh HF-style init."""
+    fresh = init_hf_parameters(model.arch)
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            prm.copy_(fresh[name].to(prm.device))
+
+
+class Wav2Vec2WrapperModule(_Base):
+    """R:src/models/wav2vec2.py:97-146."""
+
+    def __init__(self, wav2vec2_huggingface_id: str, reset_weights: bool,
+                 reg_cfg: Optional[Wav2Vec2RegularisationConfig] = None, insert_clc_token: bool = False,
+                 cls_token_constant: float = 1):
+        super().__init__()
+        self.model = load_base_wav2vec2_model(wav2vec2_huggingface_id, reg_cfg)
+        self.insert_cls_token = insert_clc_token
+        self.cls_token_constant = cls_token_constant
+        if "base" in wav2vec2_huggingface_id:
+            self.num_features = 768
+        elif "large" in wav2vec2_huggingface_id:
+            self.num_features = 1024
+        else:
+            raise ValueError("cannot determine num features")
+        if reset_weights:
+            reset_model(self.model)
+
+    @property
+    def num_embedding_features(self):
+        return self.num_features
+
+    def forward(self, wav_input: torch.Tensor):
+        # wav_input has shape [BATCH_SIZE, NUM_SAMPLES]
+        if self.insert_cls_token:
+            # R:src/models/wav2vec2.py:128-140 (the reference hard-codes the CLS width to 768)
+            features = self.model.feature_extractor(wav_input).transpose(1, 2)
+            features, _ = self.model.feature_projection(features)
+            cls_token = torch.ones((wav_input.shape[0], 1, 768), device=wav_input.device) * self.cls_token_constant
+            sequence = torch.cat([cls_token, features], dim=1)
+            embedding = self.model.encoder(sequence).last_hidden_state.transpose(1, 2)
+        else:
+            embedding = wav2vec2_embed_raw_audio(wav_input, self.model)
+        # [BATCH_SIZE, NUM_FEATURES, NUM_FRAMES]
+        return embedding
+
+
+class Wav2vecLiteWrapperModule(_Base):
+    """R:src/models/wav2vec2.py:149-169: CNN feature extractor only."""
+    num_features = 512
+
+    def __init__(self, wav2vec2_huggingface_id: str, reset_weights: bool):
+        super().__init__()
+        self.model = load_base_wav2vec2_model(wav2vec2_huggingface_id)
+        if reset_weights:
+            reset_model(self.model)
+
+    @property
+    def num_embedding_features(self):
+        return self.num_features
+
+    def forward(self, wav_input: torch.Tensor):
+        return self.model.feature_extractor(wav_input)

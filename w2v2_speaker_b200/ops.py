@@ -1,0 +1,200 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point of include/w2v2_b200.h).
+
+torch is used for device memory and streams only; every function launches hand-written CUDA on
+torch's current stream via libw2v2_b200.so and raises if the library is missing.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+F16 = torch.float16
+F32 = torch.float32
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.W2V2Error(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise _lib.W2V2Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
+             out_dtype=F16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias).  a, w fp16 row-major (row pitch = stride(0))."""
+    _chk(a, F16, "a"); _chk(w, F16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        ld = (N + 7) // 8 * 8                      # keep the row pitch a multiple of 16 bytes
+        buf = torch.empty(M, ld, dtype=out_dtype, device=a.device)
+        out = buf[:, :N]
+    call("w2v2_gemm_f16", ptr(a), M, a.stride(0), 0, 1, 1, 0, K, ptr(w), w.stride(0), N, ptr(bias), act,
+         ptr(out), 1 if out.dtype == F32 else 0, out.stride(0), 0, stream_ptr())
+    return out
+
+
+def conv1d_cl_f16(x: torch.Tensor, w_tap: torch.Tensor, ksize: int, stride: int, act: int = 1,
+                  out_dtype=F16) -> torch.Tensor:
+    """Strided Conv1d (no bias) + activation over a channels-last fp16 activation x[B,L,C] with the
+    tap-major weight w_tap[Cout, ksize*C] (HF:254-272)."""
+    _chk(x, F16, "x"); _chk(w_tap, F16, "w_tap")
+    B, L, C = x.shape
+    assert x.is_contiguous()
+    Lout = (L - ksize) // stride + 1
+    Cout = w_tap.shape[0]
+    out = torch.empty(B, Lout, Cout, dtype=out_dtype, device=x.device)
+    call("w2v2_gemm_f16", ptr(x), Lout, stride * C, L * C, B, ksize, C, C, ptr(w_tap), w_tap.stride(0), Cout,
+         None, act, ptr(out), 1 if out_dtype == F32 else 0, Cout, Lout * Cout, stream_ptr())
+    return out
+
+
+def conv_weight_tapmajor(w: torch.Tensor) -> torch.Tensor:
+    _chk(w, F32, "w")
+    cout, cin, k = w.shape
+    o = torch.empty(cout, k * cin, dtype=F16, device=w.device)
+    call("w2v2_conv_weight_tapmajor", ptr(w.contiguous()), ptr(o), cout, cin, k, stream_ptr())
+    return o
+
+
+def cast_f16(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    _chk(x, F32, "x")
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=F16, device=x.device)
+    call("w2v2_cast_f16", ptr(x), ptr(y), x.numel(), float(scale), stream_ptr())
+    return y
+
+
+def conv0_gn_gelu(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float = 1e-5) -> torch.Tensor:
+    """HF:302-323.  wav f32 [B,N] -> f16 channels-last [B, L0, C]."""
+    _chk(wav, F32, "wav")
+    B, N = wav.shape
+    C = w.shape[0]
+    L0 = (N - 10) // 5 + 1
+    lib = _lib.load()
+    stats = torch.empty(lib.w2v2_conv0_stats_floats(B, C), dtype=F32, device=wav.device)
+    out = torch.empty(B, L0, C, dtype=F16, device=wav.device)
+    call("w2v2_conv0_gn_gelu", ptr(wav.contiguous()), B, N, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps,
+         ptr(stats), ptr(out), C, stream_ptr())
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+              want32: bool = True, want16: bool = True):
+    """LayerNorm(x + bias + residual) over the last dim -> (y32 | None, y16 | None)."""
+    assert x.is_contiguous()
+    H = x.shape[-1]
+    rows = x.numel() // H
+    y32 = torch.empty(x.shape, dtype=F32, device=x.device) if want32 else None
+    y16 = torch.empty(x.shape, dtype=F16, device=x.device) if want16 else None
+    call("w2v2_layernorm", ptr(x), 1 if x.dtype == F32 else 0, ptr(bias), ptr(residual), ptr(gamma), ptr(beta),
+         eps, ptr(y32), ptr(y16), rows, H, stream_ptr())
+    return y32, y16
+
+
+def posconv_fold_weight(v: torch.Tensor, g: torch.Tensor, groups: int) -> torch.Tensor:
+    H, I, K = v.shape
+    buf = torch.empty(H * I * K + 2 * K, dtype=F16, device=v.device)
+    call("w2v2_posconv_fold_weight", ptr(v.contiguous()), ptr(g.contiguous()), ptr(buf), H, groups, K, stream_ptr())
+    return buf
+
+
+def posconv(x16: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, groups: int, K: int) -> torch.Tensor:
+    _chk(x16, F16, "x16")
+    B, T, H = x16.shape
+    out = torch.empty(B, T, H, dtype=F32, device=x16.device)
+    call("w2v2_posconv", ptr(x16), ptr(w16), ptr(bias), ptr(out), B, T, H, groups, K, stream_ptr())
+    return out
+
+
+def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int) -> torch.Tensor:
+    _chk(qkv16, F16, "qkv16")
+    out = torch.empty(B * T, H, dtype=F16, device=qkv16.device)
+    call("w2v2_attention", ptr(qkv16), ptr(out), B, T, H, heads, stream_ptr())
+    return out
+
+
+def stat_pool(x: torch.Tensor, mode: int) -> torch.Tensor:
+    _chk(x, F32, "x")
+    B, T, H = x.shape
+    out = torch.empty(B, H * (2 if mode == 1 else 1), dtype=F32, device=x.device)
+    call("w2v2_stat_pool", ptr(x.contiguous()), ptr(out), B, T, H, mode, stream_ptr())
+    return out
+
+
+def asp_concat(x: torch.Tensor) -> torch.Tensor:
+    B, T, H = x.shape
+    cat = torch.empty(B * T, 3 * H, dtype=F16, device=x.device)
+    call("w2v2_asp_concat", ptr(x), ptr(cat), B, T, H, stream_ptr())
+    return cat
+
+
+def asp_relu_bn_tanh(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    rows, A = z.shape
+    y = torch.empty(rows, A, dtype=F16, device=z.device)
+    call("w2v2_asp_relu_bn_tanh", ptr(z), ptr(scale), ptr(shift), ptr(y), rows, A, stream_ptr())
+    return y
+
+
+def asp_pool(x: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+    B, T, H = x.shape
+    out = torch.empty(B, 2 * H, dtype=F32, device=x.device)
+    call("w2v2_asp_pool", ptr(x), ptr(logits), ptr(out), B, T, H, stream_ptr())
+    return out
+
+
+def softmax_ce(logits: torch.Tensor, labels: torch.Tensor, want_prob: bool = True):
+    """-> (prob [B,S] | None, loss_rows [B], argmax [B] int32).  logits f32 [B,S] (any row pitch)."""
+    B, S = logits.shape
+    prob = torch.empty(B, S, dtype=F32, device=logits.device) if want_prob else None
+    loss = torch.empty(B, dtype=F32, device=logits.device)
+    am = torch.empty(B, dtype=torch.int32, device=logits.device)
+    call("w2v2_softmax_ce", ptr(logits), logits.stride(0), ptr(labels), ptr(prob), ptr(loss), ptr(am), B, S,
+         stream_ptr())
+    return prob, loss, am
+
+
+def aam_softmax_ce(cosine: torch.Tensor, labels: torch.Tensor, margin: float, scale: float,
+                   easy_margin: bool = False, want_prob: bool = True):
+    """In place on `cosine` (becomes the scaled margin logits).  -> (prob, loss_rows, argmax)."""
+    B, S = cosine.shape
+    prob = torch.empty(B, S, dtype=F32, device=cosine.device) if want_prob else None
+    loss = torch.empty(B, dtype=F32, device=cosine.device)
+    am = torch.empty(B, dtype=torch.int32, device=cosine.device)
+    call("w2v2_aam_softmax_ce", ptr(cosine), cosine.stride(0), ptr(labels), float(margin), float(scale),
+         int(easy_margin), ptr(prob), ptr(loss), ptr(am), B, S, stream_ptr())
+    return prob, loss, am
+
+
+def l2norm_rows_split3(x: torch.Tensor, which: int) -> torch.Tensor:
+    rows, E = x.shape
+    y = torch.empty(rows, 3 * E, dtype=F16, device=x.device)
+    call("w2v2_l2norm_rows_split3", ptr(x.contiguous()), ptr(y), rows, E, which, stream_ptr())
+    return y
+
+
+def l2norm_rows_f16(x: torch.Tensor) -> torch.Tensor:
+    rows, E = x.shape
+    y = torch.empty(rows, E, dtype=F16, device=x.device)
+    call("w2v2_l2norm_rows_f16", ptr(x.contiguous()), ptr(y), rows, E, stream_ptr())
+    return y
+
+
+def split3_rows(x: torch.Tensor, which: int) -> torch.Tensor:
+    rows, E = x.shape
+    y = torch.empty(rows, 3 * E, dtype=F16, device=x.device)
+    call("w2v2_split3_rows", ptr(x.contiguous()), ptr(y), rows, E, which, stream_ptr())
+    return y
+
+
+def mean_rows(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(1, dtype=F32, device=x.device)
+    call("w2v2_mean_rows", ptr(x), ptr(out), x.numel(), stream_ptr())
+    return out[0]
