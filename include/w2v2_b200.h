@@ -30,6 +30,7 @@ extern "C" {
 const char* w2v2_last_error(void);          /* thread-local, valid until the next failing call */
 int w2v2_abi_version(void);                 /* bump on any signature change */
 int w2v2_sm_count(void);                    /* SM count of the current device (grid sizing) */
+int64_t w2v2_launch_count(void);            /* kernels launched by this library since it was loaded */
 
 /* ---- dense contractions (tcgen05) ---------------------------------------------------------- */
 /* out[b,r,n] = act(sum_{tap,c} A[b][r*a_row_stride + tap*a_tap_stride + c] * W[n][tap*cin + c] + bias[n])

@@ -1,0 +1,106 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels are launched)."""
+import pytest
+import torch
+
+from w2v2_speaker_b200.engine import BASE, LARGE, arch_from_id
+from w2v2_speaker_b200.models.wav2vec2 import (Wav2Vec2RegularisationConfig, Wav2Vec2WrapperModule,
+                                               Wav2vecLiteWrapperModule)
+from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
+from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+
+
+def test_arch_detection_follows_reference_substring_rule():
+    assert arch_from_id("facebook/wav2vec2-base") is BASE
+    assert arch_from_id("facebook/wav2vec2-large-lv60") is LARGE
+    with pytest.raises(ValueError):
+        arch_from_id("facebook/hubert")
+    assert BASE.conv_lengths(48000) == [9599, 4799, 2399, 1199, 599, 299, 149]
+    assert BASE.conv_lengths(16000)[-1] == 49 and LARGE.conv_lengths(80000)[-1] == 249
+
+
+def test_regularisation_config_defaults_match_reference():
+    r = Wav2Vec2RegularisationConfig()
+    assert (r.activation_dropout, r.attention_dropout, r.feat_proj_dropout, r.hidden_dropout, r.layerdrop) == \
+        (0.0, 0.1, 0.1, 0.1, 0.05)
+    assert (r.mask_time_prob, r.mask_time_length, r.mask_feature_prob, r.mask_feature_length) == (0.05, 10, 0.0, 10)
+
+
+@pytest.fixture(scope="module")
+def wrapper():
+    return Wav2Vec2WrapperModule("facebook/wav2vec2-base", reset_weights=False)
+
+
+def test_wrapper_surface(wrapper):
+    assert wrapper.num_features == 768 and wrapper.num_embedding_features == 768
+    assert sum(p.numel() for p in wrapper.model.parameters()) == 94_371_712
+    for attr in ("feature_extractor", "feature_projection", "encoder"):
+        assert hasattr(wrapper.model, attr)
+    with pytest.raises(ValueError):
+        Wav2Vec2WrapperModule("facebook/other", reset_weights=False)
+    assert Wav2vecLiteWrapperModule.num_features == 512
+
+
+def test_state_dict_keys_match_huggingface(wrapper):
+    tr = pytest.importorskip("transformers")
+    hf = tr.Wav2Vec2Model(tr.Wav2Vec2Config())
+    ours = {k: tuple(v.shape) for k, v in wrapper.model.state_dict().items()}
+    theirs = {k: tuple(v.shape) for k, v in hf.state_dict().items()}
+    assert ours == theirs
+
+
+def test_freeze_unfreeze_semantics(wrapper):
+    wrapper.freeze()
+    assert not wrapper.training and all(not p.requires_grad for p in wrapper.parameters())
+    wrapper.unfreeze()
+    assert wrapper.training and all(p.requires_grad for p in wrapper.parameters())
+    wrapper.model.feature_extractor.requires_grad_(False)        # R:.../wav2vec2_fc.py:346-347
+    assert all(not p.requires_grad for p in wrapper.model.feature_extractor.parameters())
+    assert any(p.requires_grad for p in wrapper.model.encoder.parameters())
+    wrapper.eval()
+
+
+def test_no_cpu_fallback(wrapper):
+    wrapper.eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        with torch.no_grad():
+            wrapper(torch.zeros(1, 4000))
+
+
+def test_training_mode_fails_loudly(wrapper):
+    wrapper.train()
+    with pytest.raises(NotImplementedError):
+        wrapper(torch.zeros(1, 4000))
+    wrapper.eval()
+
+
+@pytest.mark.parametrize("pooling,dim", [("mean", 768), ("mean+std", 1536), ("attentive", 1536), ("max", 768),
+                                         ("quantile", 3840), ("first", 768), ("none", 768)])
+def test_fc_module_pooling_dispatch(pooling, dim):
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type=pooling, test_stat_pooling_type=pooling)
+    m = Wav2vec2FCModule(cfg, 100, CrossEntropyLoss)
+    assert m.stat_pool_dimension == dim
+    assert len(m.fc_list) == 1 and m.fc_list[0][0].out_features == 100
+    with pytest.raises(ValueError):
+        Wav2vec2FCModule(Wav2vec2FCModuleConfig(stat_pooling_type="bogus", test_stat_pooling_type="bogus"), 10,
+                         CrossEntropyLoss)
+
+
+def test_aam_head_surgery_and_constants():
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type="mean+std", test_stat_pooling_type="mean+std")
+    ctor = lambda: AngularAdditiveMarginSoftMaxLoss(input_features=1, output_features=1, margin=0.2, scale=30)
+    m = Wav2vec2FCModule(cfg, 5994, ctor)
+    assert len(m.fc_list) == 0                                     # R:.../wav2vec2_fc.py:212-214
+    assert tuple(m.loss_fn.fc_weights.shape) == (5994, 1536)
+    assert m.loss_fn.margin == 0.2 and m.loss_fn.scale == 30
+    assert abs(m.loss_fn.th - (-0.980067)) < 1e-5 and abs(m.loss_fn.mm - 0.0397339) < 1e-6
+    with pytest.raises(ValueError):
+        Wav2vec2FCModule(Wav2vec2FCModuleConfig(wav2vec_feature_encoder_only=True), 10, CrossEntropyLoss)
+
+
+def test_embedding_masker_is_identity_on_the_path():
+    from w2v2_speaker_b200.layers.embedding_masking import EmbeddingMasker
+    mk = EmbeddingMasker(0, 1, 0.5, 5, time_dim=2, embedding_dim=1).train()
+    x = torch.randn(3, 8, 1)
+    assert torch.equal(mk(x), x)
+    with pytest.raises(ValueError):
+        EmbeddingMasker(1.5, 1, 0, 1)

@@ -19,6 +19,7 @@ SIGNATURES = {
     "w2v2_last_error": (c_char_p, []),
     "w2v2_abi_version": (c_int, []),
     "w2v2_sm_count": (c_int, []),
+    "w2v2_launch_count": (c_int64, []),
     "w2v2_gemm_f16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_int64,
                               c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "w2v2_conv0_stats_floats": (c_int64, [c_int, c_int]),

@@ -208,6 +208,7 @@ extern "C" int w2v2_attention(const void* qkv16, void* out16, int B, int T, int 
   }
   dim3 grid((T + 127) / 128, heads, B);
   attention_kernel<<<grid, 128, smem, stream>>>(p);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

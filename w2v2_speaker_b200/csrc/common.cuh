@@ -12,6 +12,8 @@ namespace w2v2 {
 // --------------------------------------------------------------------------------------------
 // error plumbing (no exceptions cross the C ABI)
 void set_last_error(const char* fmt, ...);
+// number of kernels launched by this library since load (bench.py's `gpu_launches` evidence)
+void count_launches(int n);
 #define W2V2_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

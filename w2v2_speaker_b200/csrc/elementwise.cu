@@ -17,6 +17,8 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 int device_sm_count();
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 // =================================================================================================
 // casts / weight re-layout
@@ -543,11 +545,13 @@ extern "C" {
 const char* w2v2_last_error(void) { return w2v2::g_err; }
 int w2v2_abi_version(void) { return 1; }
 int w2v2_sm_count(void) { return device_sm_count(); }
+int64_t w2v2_launch_count(void) { return (int64_t)__atomic_load_n(&w2v2::g_launches, __ATOMIC_RELAXED); }
 
 int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream) {
   W2V2_REQUIRE(n >= 0, "w2v2_cast_f16: negative n");
   if (n == 0) return 0;
   cast_f16_kernel<<<grid_for(n, 256 * 8), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, n, scale);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -555,6 +559,7 @@ int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* strea
 int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int k, void* stream) {
   const int64_t n = int64_t(cout) * cin * k;
   conv_weight_tapmajor_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)w16, cout, cin, k);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -577,6 +582,7 @@ int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const flo
   conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, C, L, eps, stats);
   dim3 g3((L + C0_TT - 1) / C0_TT, B);
   conv0_apply_kernel<<<g3, 256, 0, stream>>>(wav, N, L, w, gamma, beta, stats, (__half*)out_f16, C);
+  count_launches(3);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -594,6 +600,7 @@ int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* r
     layernorm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H);
   else
     layernorm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -604,6 +611,7 @@ int w2v2_stat_pool(const float* x, float* out, int B, int T, int H, int mode, vo
   W2V2_REQUIRE(T >= 1 && (mode != 1 || T >= 2), "w2v2_stat_pool: T=%d too short", T);
   dim3 g(H / POOL_CH, B);
   stat_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, out, T, H, mode);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -612,6 +620,7 @@ int w2v2_asp_concat(const float* x, void* cat16, int B, int T, int H, void* stre
   W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_asp_concat: H=%d must be a multiple of %d", H, POOL_CH);
   dim3 g(H / POOL_CH, B);
   asp_concat_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, (__half*)cat16, T, H);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -620,6 +629,7 @@ int w2v2_asp_relu_bn_tanh(const float* z, const float* scale, const float* shift
                           void* stream) {
   const int64_t n = rows * A;
   asp_relu_bn_tanh_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, scale, shift, (__half*)y16, n, A);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -628,6 +638,7 @@ int w2v2_asp_pool(const float* x, const float* logits, float* out, int B, int T,
   W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_asp_pool: H=%d must be a multiple of %d", H, POOL_CH);
   dim3 g(H / POOL_CH, B);
   asp_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, logits, out, T, H);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -636,6 +647,7 @@ int w2v2_softmax_ce(const float* logits, int64_t ldl, const int64_t* labels, flo
                     int32_t* argmax, int B, int S, void* stream) {
   softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(logits), ldl, labels, 0, 0.f, 0.f, 0.f, 0.f,
                                                          1.f, 0, prob, loss_rows, argmax, S);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -647,30 +659,35 @@ int w2v2_aam_softmax_ce(float* cosine, int64_t ldl, const int64_t* labels, float
   softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cosine, ldl, labels, 1, float(cos(m)), float(sin(m)),
                                                          float(cos(pi - m)), float(sin(pi - m) * m), scale, easy_margin,
                                                          prob, loss_rows, argmax, S);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int w2v2_l2norm_rows_f16(const float* x, void* y16, int64_t rows, int E, void* stream) {
   l2norm_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, E, 0, 0);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int w2v2_l2norm_rows_split3(const float* x, void* y16, int64_t rows, int E, int which, void* stream) {
   l2norm_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, E, 1, which);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int w2v2_split3_rows(const float* x, void* y16, int64_t rows, int E, int which, void* stream) {
   split3_rows_kernel<<<grid_for(rows * E, 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, rows, E, which);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int w2v2_mean_rows(const float* x, float* out, int n, void* stream) {
   mean_rows_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -683,6 +700,7 @@ int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, i
   posconv_norm_kernel<<<K, 256, 0, stream>>>(v, norm, H, H / groups, K);
   const int64_t n = int64_t(H) * (H / groups) * K;
   posconv_fold_kernel<<<grid_for(n, 256), 256, 0, stream>>>(v, g, norm, (__half*)w16, H, groups, K);
+  count_launches(2);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -305,6 +305,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   const int tiles = p.m_tiles * p.n_tiles * p.batch;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -210,6 +210,7 @@ extern "C" int w2v2_posconv(const void* x16, const void* w16, const float* bias,
   }
   dim3 grid(groups, (B + NB - 1) / NB);
   posconv_kernel<<<grid, PC_THREADS, smem, stream>>>(p);
+  count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
