@@ -63,10 +63,13 @@ int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* r
                    const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, void* stream);
 
 /* ---- positional conv embedding --------------------------------------------------------------- */
+/* Number of taps U that share one tensor-core A tile for sequences of T frames (0 = T too long
+ * for the single-slab kernel).  The folded weight layout depends on it. */
+int w2v2_posconv_taps_per_mma(int T, int H, int groups);
 /* Fold weight_norm (HF:340-358): w[o,i,k] = g[k] * v[o,i,k] / ||v[:,:,k]||, and re-lay it out as
- * fp16 [G][K][I/8][O][8] (per (group, tap): an [O x I] K-major block in UMMA core-matrix order).  w16 must have room
- * for H*(H/groups)*K halfs followed by K floats of scratch (the per-tap norms). */
-int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, void* stream);
+ * fp16 [G][K/U][I/8][U][O][8] (per (group, tap group): a [U*O x I] K-major block in UMMA core-matrix
+ * order).  w16 must have room for H*(H/groups)*K halfs followed by K floats of scratch (per-tap norms). */
+int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, int U, void* stream);
 /* y[b,t,:] = GELU(conv1d(x, w, bias, pad=K/2, groups)[.., :T]) (HF:360-379); x f16 [B,T,H];
  * out f32 [B,T,H] (the encoder then does LN(h + y), fused in w2v2_layernorm via `residual`). */
 int w2v2_posconv(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H, int groups,

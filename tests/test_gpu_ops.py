@@ -217,7 +217,7 @@ def test_posconv(ops, B, T, H, G):
     v = _rand((H, H // G, K), 32, 2.0 * math.sqrt(1.0 / (K * H)))
     g = v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt() * (1 + 0.05 * _rand((1, 1, K), 33))
     bias = _rand((H,), 34, 0.02)
-    w16 = ops.posconv_fold_weight(v, g.view(-1), G)
+    w16 = ops.posconv_fold_weight(v, g.view(-1), G, ops.posconv_taps_per_mma(T, H, G))
     out = ops.posconv(x, w16, bias, G, K)
     torch.cuda.synchronize()
     w = (g * v / v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()).half().float()

@@ -61,7 +61,7 @@ total += timeit("proj GEMM 512->768", lambda: ops.gemm_f16(a16, wproj, bH, 0, to
 total += timeit("cast f16 [M,H]", lambda: ops.cast_f16(h32), bytes_=M * H * 6)
 v = torch.randn(H, H // 16, 128, device=dev) * 0.01
 gn = v.pow(2).sum(dim=(0, 1)).sqrt()
-pw = ops.posconv_fold_weight(v, gn, 16)
+pw = ops.posconv_fold_weight(v, gn, 16, ops.posconv_taps_per_mma(T, H, 16))
 x16 = h16.view(B, T, H)
 total += timeit("posconv", lambda: ops.posconv(x16, pw, bH, 16, 128), 2.0 * M * H * (H // 16) * 128)
 total += timeit("LN768 (+bias+res)", lambda: ops.layernorm(h32, gH, bH, bias=bH, residual=h32), bytes_=M * H * (4 + 4 + 4 + 2))

@@ -27,7 +27,8 @@ SIGNATURES = {
                                    c_int, c_void_p]),
     "w2v2_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                c_int64, c_int, c_void_p]),
-    "w2v2_posconv_fold_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_posconv_taps_per_mma": (c_int, [c_int, c_int, c_int]),
+    "w2v2_posconv_fold_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_posconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_stat_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

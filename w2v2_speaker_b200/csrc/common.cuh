@@ -201,20 +201,76 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
 }
 
 // ---- math ----------------------------------------------------------------------------------
-// exact-erf GELU (HF "gelu" == torch F.gelu default).  erf via Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, two SFU ops) -- well below the fp16 rounding applied to every consumer.
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2: two fp32 FMAs per issue slot) -----------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exact-erf GELU (HF "gelu" == torch F.gelu default):
+//     gelu(x) = x Phi(x) = max(x, 0) - |x| Phi(-|x|),      Phi(-a) = 2^Q(a)
+// Q = log2 of the normal tail, a degree-8 polynomial (weighted minimax fit on a in [0, 6.5], evaluated in
+// u = 2a/6.5 - 1; |x| is clamped to 6.5 where the tail term is < 5e-10).  Max abs error 2.7e-7 in fp32
+// (relative 4e-6 where |gelu| > 1e-2) -- three orders below the fp16 rounding every consumer applies.
+// One MUFU.EX2 and, in the packed form, 8 issue slots per element (vs ~35 for erff()).
+#define W2V2_GELU_C0 -10.75906753540039f
+#define W2V2_GELU_C1 -16.487607955932617f
+#define W2V2_GELU_C2 -7.1384711265563965f
+#define W2V2_GELU_C3 -0.22706320881843567f
+#define W2V2_GELU_C4 0.10637267678976059f
+#define W2V2_GELU_C5 -0.03946828097105026f
+#define W2V2_GELU_C6 0.02791619300842285f
+#define W2V2_GELU_C7 -0.013774366118013859f
+#define W2V2_GELU_C8 -0.004659503698348999f
+#define W2V2_GELU_A 6.5f
+
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);             // erf(|x|/sqrt2)
-  const float erf_s = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_s);
+  const float a = fabsf(x);
+  const float u = fmaf(fminf(a, W2V2_GELU_A), 2.0f / W2V2_GELU_A, -1.0f);
+  float q = fmaf(W2V2_GELU_C8, u, W2V2_GELU_C7);
+  q = fmaf(q, u, W2V2_GELU_C6);
+  q = fmaf(q, u, W2V2_GELU_C5);
+  q = fmaf(q, u, W2V2_GELU_C4);
+  q = fmaf(q, u, W2V2_GELU_C3);
+  q = fmaf(q, u, W2V2_GELU_C2);
+  q = fmaf(q, u, W2V2_GELU_C1);
+  q = fmaf(q, u, W2V2_GELU_C0);
+  return fmaf(-a, fast_ex2(q), fmaxf(x, 0.f));
+}
+
+// two elements at once on the packed fp32x2 pipe
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const f32x2 u = fma2(pack2(fminf(a0, W2V2_GELU_A), fminf(a1, W2V2_GELU_A)), splat2(2.0f / W2V2_GELU_A), splat2(-1.0f));
+  f32x2 q = fma2(splat2(W2V2_GELU_C8), u, splat2(W2V2_GELU_C7));
+  q = fma2(q, u, splat2(W2V2_GELU_C6));
+  q = fma2(q, u, splat2(W2V2_GELU_C5));
+  q = fma2(q, u, splat2(W2V2_GELU_C4));
+  q = fma2(q, u, splat2(W2V2_GELU_C3));
+  q = fma2(q, u, splat2(W2V2_GELU_C2));
+  q = fma2(q, u, splat2(W2V2_GELU_C1));
+  q = fma2(q, u, splat2(W2V2_GELU_C0));
+  float q0, q1;
+  unpack2(q, q0, q1);
+  const f32x2 r = fma2(pack2(-a0, -a1), pack2(fast_ex2(q0), fast_ex2(q1)), pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  unpack2(r, x0, x1);
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

@@ -144,37 +144,43 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
   for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = __ldg(x + i);
   __syncthreads();
   const int groups = C / 8;                      // 8 channels (16 B of fp16) per thread
-  for (int cg = threadIdx.x % groups, tsub = threadIdx.x / groups, tstep = blockDim.x / groups; cg < groups;
-       cg += groups) {
-    const int c0 = cg * 8;
-    float wr[8][C0_K], sc[8], sh[8];
+  const int cg = threadIdx.x % groups, tsub = threadIdx.x / groups, tstep = blockDim.x / groups;
+  const int c0 = cg * 8;
+  // packed fp32x2 math (FFMA2): channel pairs (c0+2j, c0+2j+1) share one instruction
+  f32x2 wr[4][C0_K], sc[4], sh[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
 #pragma unroll
-      for (int k = 0; k < C0_K; ++k) wr[j][k] = __ldg(w + (c0 + j) * C0_K + k);
-      const float mean = stats[(int64_t(b) * C + c0 + j) * 2], rstd = stats[(int64_t(b) * C + c0 + j) * 2 + 1];
-      sc[j] = rstd * __ldg(gamma + c0 + j);
-      sh[j] = __ldg(beta + c0 + j) - mean * sc[j];
+    for (int k = 0; k < C0_K; ++k)
+      wr[j][k] = pack2(__ldg(w + (c0 + 2 * j) * C0_K + k), __ldg(w + (c0 + 2 * j + 1) * C0_K + k));
+    float s2[2], h2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = c0 + 2 * j + e;
+      const float mean = stats[(int64_t(b) * C + c) * 2], rstd = stats[(int64_t(b) * C + c) * 2 + 1];
+      s2[e] = rstd * __ldg(gamma + c);
+      h2[e] = __ldg(beta + c) - mean * s2[e];
     }
-    for (int t = tsub; t < nt; t += tstep) {
-      float xv[C0_K];
+    sc[j] = pack2(s2[0], s2[1]);
+    sh[j] = pack2(h2[0], h2[1]);
+  }
+  for (int t = tsub; t < nt; t += tstep) {
+    f32x2 acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-      for (int k = 0; k < C0_K; ++k) xv[k] = xs[t * C0_S + k];
-      float y[8];
+    for (int k = 0; k < C0_K; ++k) {
+      const f32x2 xk = splat2(xs[t * C0_S + k]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < C0_K; ++k) a = fmaf(wr[j][k], xv[k], a);
-        y[j] = gelu_erf(fmaf(a, sc[j], sh[j]));
-      }
-      uint4 q;
-      q.x = pack_half2(y[0], y[1]);
-      q.y = pack_half2(y[2], y[3]);
-      q.z = pack_half2(y[4], y[5]);
-      q.w = pack_half2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(out + (int64_t(b) * L + t0 + t) * C + c0) = q;
+      for (int j = 0; j < 4; ++j) acc[j] = fma2(wr[j][k], xk, acc[j]);
     }
+    uint32_t q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y0, y1;
+      unpack2(fma2(acc[j], sc[j], sh[j]), y0, y1);
+      gelu_erf2(y0, y1);
+      q[j] = pack_half2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + (int64_t(b) * L + t0 + t) * C + c0) = make_uint4(q[0], q[1], q[2], q[3]);
   }
 }
 
@@ -513,18 +519,20 @@ __global__ void posconv_norm_kernel(const float* __restrict__ v, float* __restri
   if (threadIdx.x == 0) norm[k] = sqrtf(s);
 }
 __global__ void posconv_fold_kernel(const float* __restrict__ v, const float* __restrict__ g,
-                                    const float* __restrict__ norm, __half* __restrict__ w16, int H, int G, int K) {
-  // w16[grp][k][c][o][e] = g[k] * v[grp*O + o][c*8 + e][k] / norm[k]      (O = I = H/G, i = c*8 + e)
-  // = per (group, tap) an [O x I] K-major block already in UMMA no-swizzle core-matrix order
-  // (planes of O rows x 16 bytes), so posconv.cu can stream it with a flat bulk copy.
+                                    const float* __restrict__ norm, __half* __restrict__ w16, int H, int G, int K, int U) {
+  // w16[grp][j'][c][u][o][e] = g[k] * v[grp*O + o][c*8 + e][k] / norm[k],  k = U*j' + u   (O = I = H/G)
+  // = per (group, tap group j') a [U*O x I] K-major block already in UMMA no-swizzle core-matrix order
+  // (planes of U*O rows x 16 bytes), so posconv.cu can stream it with a flat bulk copy.
   const int O = H / G, I = H / G;
   const int64_t n = int64_t(H) * I * K;
   for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
     const int e = idx % 8;
     const int o = (idx / 8) % O;
-    const int c = (idx / (8 * int64_t(O))) % (I / 8);
-    const int k = (idx / (int64_t(I) * O)) % K;
+    const int u = (idx / (8 * int64_t(O))) % U;
+    const int c = (idx / (8 * int64_t(O) * U)) % (I / 8);
+    const int jp = (idx / (int64_t(I) * O * U)) % (K / U);
     const int grp = idx / (int64_t(I) * O * K);
+    const int k = U * jp + u;
     const float val = v[(int64_t(grp * O + o) * I + c * 8 + e) * K + k] * (g[k] / norm[k]);
     w16[idx] = __float2half_rn(val);
   }
@@ -692,14 +700,15 @@ int w2v2_mean_rows(const float* x, float* out, int n, void* stream) {
   return 0;
 }
 
-int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, void* stream_) {
+int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, int U, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   // scratch for the K norms: reuse the head of w16?  No -- keep a tiny static device buffer per call site:
   // the caller passes w16 sized H*(H/groups)*K halfs + K floats; norms live behind the weights.
   float* norm = reinterpret_cast<float*>(static_cast<__half*>(w16) + int64_t(H) * (H / groups) * K);
   posconv_norm_kernel<<<K, 256, 0, stream>>>(v, norm, H, H / groups, K);
   const int64_t n = int64_t(H) * (H / groups) * K;
-  posconv_fold_kernel<<<grid_for(n, 256), 256, 0, stream>>>(v, g, norm, (__half*)w16, H, groups, K);
+  W2V2_REQUIRE(U >= 1 && K % U == 0, "w2v2_posconv_fold_weight: taps per MMA U=%d must divide K=%d", U, K);
+  posconv_fold_kernel<<<grid_for(n, 256), 256, 0, stream>>>(v, g, norm, (__half*)w16, H, groups, K, U);
   count_launches(2);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -10,20 +10,21 @@
 //     projection (HF:429-434), the ASP 1x1 convs and the CE / AAM classifier GEMMs (ntaps = 1).
 //
 // Operands are fp16 (RNE-rounded by the producing kernel), accumulation is fp32 in TMEM.
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0    : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1    : MMA issuer    (one elected thread: tcgen05.mma 128xBNx16, commit -> mbarriers)
-//   warps 2-5 : epilogue      (tcgen05.ld 32 lanes x 32 cols -> bias/GELU -> fp16|fp32 ->
-//                              swizzled smem staging -> TMA store, which also clips M/N tails)
+//   warps 2-9 : epilogue      (two warps per TMEM lane quarter, each owning half of the tile's columns:
+//                              double-buffered tcgen05.ld 32x32b.x32 -> bias (from smem) / GELU ->
+//                              fp16|fp32 -> warp-private swizzled staging -> warp-issued TMA store,
+//                              which also clips the M / N tails; no CTA-wide barrier in steady state)
 // The TMEM accumulator is double-buffered (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
-#include <string>
-#include <unordered_map>
 
 #include "common.cuh"
 #include "w2v2_b200.h"
@@ -33,18 +34,19 @@ namespace w2v2 {
 constexpr int BM = 128;
 constexpr int BK = 64;            // fp16 elements = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int CSTAGE_BYTES = BM * 128;   // one staging buffer: 128 rows x 128 bytes
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int WSTAGE_BYTES = 32 * 128;   // per-warp staging: 32 rows x 128 bytes
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
-  CUtensorMap tmOut;
+  CUtensorMap tmOut;             // box {64 (f16) | 32 (f32) columns, 32 rows, 1}
   const float* bias;
   int ntaps, kblocks_per_tap;
   int m_tiles, n_tiles, batch;
   int N;
-  int act;
+  long long rows;                // valid rows per batch element
 };
 
 template <int BN>
@@ -53,17 +55,24 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE_BYTES + BIAS_BYTES + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
+  static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area too small");
 };
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int ACT, bool HAS_BIAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* cstage = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cstage + 2 * CSTAGE_BYTES);
+  // the 128B-swizzled tiles need a 1024-byte aligned base; the kernel has no static shared memory, so
+  // the dynamic window starts at the CTA's (1024-aligned) shared base -- verified, not assumed
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* wstage = smem + STAGES * Cfg::STAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(wstage + EPI_WARPS * WSTAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -153,80 +162,117 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;                    // 0..7
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;        // row of the 128-row tile owned by this thread
-    const bool issuer = (threadIdx.x == 64);
-    constexpr int COLS_PER_GROUP = OUT_F32 ? 32 : 64;     // 128 bytes of output per row
-    constexpr int GROUPS = BN / COLS_PER_GROUP;
+    const int half = ew >> 2;                   // which half of the tile's columns this warp owns
+    constexpr int HALF_COLS = BN / 2;
+    constexpr int NCHUNK = HALF_COLS / 32;      // 32-column chunks per warp per tile (4 or 2)
+    constexpr int CHUNKS_PER_STORE = OUT_F32 ? 1 : 2;      // 128 bytes of output per staged row
+    uint8_t* mystage = wstage + ew * WSTAGE_BYTES;
+    uint8_t* crow = mystage + lane * 128;
+    const int epi_tid = threadIdx.x - 64;       // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t gcount = 0;                        // running staging-group counter (buffer = gcount & 1)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    uint32_t tcount = 0;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
+      const float* bias_tile = sbias + (tcount & 1) * BN;
+      if constexpr (HAS_BIAS) {
+        // stage this tile's bias slice once (the previous user of this buffer was two tiles ago and
+        // every epilogue warp has passed the barrier of the tile in between)
+        if (epi_tid < BN) {
+          const int n = nt * BN + epi_tid;
+          sbias[(tcount & 1) * BN + epi_tid] = (n < p.N) ? __ldg(p.bias + n) : 0.f;
+        }
+        named_bar_sync(1, EPI_WARPS * 32);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
+      __syncwarp();
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int g = 0; g < GROUPS; ++g, ++gcount) {
-        uint8_t* cbuf = cstage + (gcount & 1) * CSTAGE_BYTES;
-        // the TMA store that last read this buffer (two groups ago) must be done reading
-        if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* crow = cbuf + row * 128;
+      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * HALF_COLS;
+      const int col0 = nt * BN + half * HALF_COLS;      // first output column of this warp
+      const int row0 = mt * BM + quarter * 32;          // first output row of this warp
+
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(t_addr, ra);
+
+      auto process = [&](uint32_t (&r)[32], int c) {
+        // c: chunk index within this warp's half; 32 consecutive columns of one row per thread
+        const float* bsrc = bias_tile + half * HALF_COLS + c * 32;
+        float v[32];
 #pragma unroll
-        for (int h = 0; h < COLS_PER_GROUP / 32; ++h) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + g * COLS_PER_GROUP + h * 32, r);
-          tmem_ld_wait();
-          const int n0 = nt * BN + g * COLS_PER_GROUP + h * 32;
-          float v[32];
+        for (int j = 0; j < 32; j += 4) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (HAS_BIAS) bb = *reinterpret_cast<const float4*>(bsrc + j);
+          v[j] = __uint_as_float(r[j]) + bb.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+        }
+        if constexpr (ACT == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.bias != nullptr) x += (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-            if (p.act == 1) x = gelu_erf(x);
-            v[j] = x;
+          for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
+        }
+        const int sub = c % CHUNKS_PER_STORE;            // position inside the staged 128-byte row
+        if (sub == 0) {
+          // staging buffer reuse: the previous TMA store of this warp must have finished reading it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {                  // 8 chunks of 16 B (4 floats)
+            const int pc = q ^ (lane & 7);
+            *reinterpret_cast<float4*>(crow + pc * 16) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
-          if constexpr (OUT_F32) {
+        } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {          // 8 chunks of 16 B (4 floats)
-              const int pc = c ^ (row & 7);
-              *reinterpret_cast<float4*>(crow + pc * 16) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {          // 4 chunks of 16 B (8 halfs) per 32 columns
-              const int pc = (h * 4 + c) ^ (row & 7);
-              uint4 q;
-              q.x = pack_half2(v[8 * c], v[8 * c + 1]);
-              q.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
-              q.z = pack_half2(v[8 * c + 4], v[8 * c + 5]);
-              q.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
-              *reinterpret_cast<uint4*>(crow + pc * 16) = q;
-            }
+          for (int q = 0; q < 4; ++q) {                  // 4 chunks of 16 B (8 halfs) per 32 columns
+            const int pc = (sub * 4 + q) ^ (lane & 7);
+            uint4 w;
+            w.x = pack_half2(v[8 * q], v[8 * q + 1]);
+            w.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+            w.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
+            w.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4*>(crow + pc * 16) = w;
           }
         }
-        if (g == GROUPS - 1) {
-          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+        if (sub == CHUNKS_PER_STORE - 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          const int scol = col0 + (c - sub) * 32;
+          if (lane == 0 && row0 < p.rows && scol < p.N) {   // skip boxes that lie entirely in the M / N tail
+            tma_store_3d(&p.tmOut, mystage, scol, row0, b);
+            tma_store_commit();
+          }
+        }
+      };
+
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);
+        process(ra, c);
+        tmem_ld_wait();
+        if (c + 2 < NCHUNK) {
+          tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
+        } else {
+          // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (issuer) {
-          tma_store_3d(&p.tmOut, cbuf, nt * BN + g * COLS_PER_GROUP, mt * BM, b);
-          tma_store_commit();
-        }
+        process(rb, c + 1);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (issuer) tma_store_wait<0>();
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -293,11 +339,11 @@ int device_sm_count() {
   return sms;
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int ACT, bool HAS_BIAS>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, OUT_F32>;
+  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, HAS_BIAS>;
   if (!configured) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -308,6 +354,13 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BN, bool OUT_F32>
+static int dispatch_epilogue(const GemmParams& p, int act, cudaStream_t stream) {
+  const bool hb = p.bias != nullptr;
+  if (act == 1) return hb ? launch_gemm<BN, OUT_F32, 1, true>(p, stream) : launch_gemm<BN, OUT_F32, 1, false>(p, stream);
+  return hb ? launch_gemm<BN, OUT_F32, 0, true>(p, stream) : launch_gemm<BN, OUT_F32, 0, false>(p, stream);
 }
 
 }  // namespace w2v2
@@ -322,6 +375,7 @@ extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride
   W2V2_REQUIRE(ntaps >= 1 && ntaps <= 3, "w2v2_gemm_f16: ntaps=%d not in [1,3]", ntaps);
   W2V2_REQUIRE(cin % BK == 0, "w2v2_gemm_f16: cin=%d must be a multiple of %d", cin, BK);
   W2V2_REQUIRE(out_dtype == 0 || out_dtype == 1, "w2v2_gemm_f16: out_dtype must be 0 (f16) or 1 (f32)");
+  W2V2_REQUIRE(act == 0 || act == 1, "w2v2_gemm_f16: act must be 0 (none) or 1 (gelu)");
   W2V2_REQUIRE(a_rows > 0 && batch > 0 && N > 0, "w2v2_gemm_f16: empty problem");
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -336,7 +390,7 @@ extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride
   int rc = make_tmap_3d(&p.tmB, W, 2, uint64_t(ntaps) * cin, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, BN, 1, 128);
   if (rc) return rc;
   const uint64_t o_bstride = batch > 1 ? uint64_t(out_batch_stride) * osz : uint64_t(a_rows) * uint64_t(ldo) * osz;
-  rc = make_tmap_3d(&p.tmOut, out, osz, N, a_rows, batch, uint64_t(ldo) * osz, o_bstride, out_dtype == 1 ? 32 : 64, BM, 1, 128);
+  rc = make_tmap_3d(&p.tmOut, out, osz, N, a_rows, batch, uint64_t(ldo) * osz, o_bstride, out_dtype == 1 ? 32 : 64, 32, 1, 128);
   if (rc) return rc;
   p.bias = bias;
   p.ntaps = ntaps;
@@ -345,7 +399,7 @@ extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride
   p.n_tiles = (N + BN - 1) / BN;
   p.batch = batch;
   p.N = N;
-  p.act = act;
-  if (BN == 256) return out_dtype == 1 ? launch_gemm<256, true>(p, stream) : launch_gemm<256, false>(p, stream);
-  return out_dtype == 1 ? launch_gemm<128, true>(p, stream) : launch_gemm<128, false>(p, stream);
+  p.rows = a_rows;
+  if (BN == 256) return out_dtype == 1 ? dispatch_epilogue<256, true>(p, act, stream) : dispatch_epilogue<256, false>(p, act, stream);
+  return out_dtype == 1 ? dispatch_epilogue<128, true>(p, act, stream) : dispatch_epilogue<128, false>(p, act, stream);
 }

@@ -82,11 +82,12 @@ class PreparedWeights:
         self.fp_ln_b = f("feature_projection.layer_norm.bias")
         self.fp_w = ops.cast_f16(f("feature_projection.projection.weight"))
         self.fp_b = f("feature_projection.projection.bias")
-        self.pos_w = ops.posconv_fold_weight(f("encoder.pos_conv_embed.conv.parametrizations.weight.original1"),
-                                             f("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1),
-                                             arch.pos_groups)
+        self._pos_v = f("encoder.pos_conv_embed.conv.parametrizations.weight.original1")
+        self._pos_g = f("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1)
+        self._pos_w = {}          # folded weight per "taps per MMA" layout (depends on the sequence length)
         self.pos_b = f("encoder.pos_conv_embed.conv.bias")
         self.enc_ln_g = f("encoder.layer_norm.weight")
+        self._groups = arch.pos_groups
         self.enc_ln_b = f("encoder.layer_norm.bias")
         d = H // arch.heads
         scale = float(d) ** -0.5
@@ -107,6 +108,16 @@ class PreparedWeights:
                 w2=ops.cast_f16(f(pre + "feed_forward.output_dense.weight")),
                 b2=f(pre + "feed_forward.output_dense.bias"),
                 ln2_g=f(pre + "final_layer_norm.weight"), ln2_b=f(pre + "final_layer_norm.bias")))
+
+
+def _pos_w(self, T: int) -> torch.Tensor:
+    u = ops.posconv_taps_per_mma(T, self.arch.hidden, self._groups)
+    if u not in self._pos_w:
+        self._pos_w[u] = ops.posconv_fold_weight(self._pos_v, self._pos_g, self._groups, u)
+    return self._pos_w[u]
+
+
+PreparedWeights.pos_w = _pos_w
 
 
 class EncoderEngine:
@@ -149,7 +160,7 @@ class EncoderEngine:
         M = B * T
         h0 = h0.contiguous()
         x16 = ops.cast_f16(h0)
-        pos = ops.posconv(x16, w.pos_w, w.pos_b, a.pos_groups, a.pos_kernel)
+        pos = ops.posconv(x16, w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel)
         h32, h16 = ops.layernorm(pos.view(M, H), w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0.view(M, H))
         if hidden_states is not None:
             hidden_states.append(h32.view(B, T, H))

@@ -99,10 +99,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return y32, y16
 
 
-def posconv_fold_weight(v: torch.Tensor, g: torch.Tensor, groups: int) -> torch.Tensor:
+def posconv_taps_per_mma(T: int, H: int, groups: int) -> int:
+    u = _lib.load().w2v2_posconv_taps_per_mma(T, H, groups)
+    if u < 1:
+        raise _lib.W2V2Error(f"w2v2_posconv: T={T} frames does not fit the single-slab kernel (needs time tiling)")
+    return u
+
+
+def posconv_fold_weight(v: torch.Tensor, g: torch.Tensor, groups: int, taps_per_mma: int) -> torch.Tensor:
     H, I, K = v.shape
     buf = torch.empty(H * I * K + 2 * K, dtype=F16, device=v.device)
-    call("w2v2_posconv_fold_weight", ptr(v.contiguous()), ptr(g.contiguous()), ptr(buf), H, groups, K, stream_ptr())
+    call("w2v2_posconv_fold_weight", ptr(v.contiguous()), ptr(g.contiguous()), ptr(buf), H, groups, K, taps_per_mma,
+         stream_ptr())
     return buf
 
 
