@@ -48,12 +48,14 @@ int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
 /* ---- feature extractor layer 0 -------------------------------------------------------------- */
 /* Conv1d(1->C,k=10,s=5,no bias) + GroupNorm(C groups == per-(b,c) instance norm over time, eps,
  * affine) + exact GELU  (HF:302-323).  wav f32 [B,N]; w f32 [C,10]; gamma/beta f32 [C];
- * stats f32 workspace of w2v2_conv0_stats_floats(B,C) floats ([B,C,2] mean/rstd + fp64 moments); out f16 channels-last [B,L0,C],
- * L0 = (N-10)/5+1.  Two fused passes (statistics, then normalise+GELU), the conv is recomputed
- * in both so the [B,C,L0] pre-norm tensor never touches HBM. */
-int64_t w2v2_conv0_stats_floats(int B, int C);   /* size of `stats` in floats (incl. fp64 moment scratch) */
+ * out f16 channels-last [B,L0,C], L0 = (N-10)/5+1.  `workspace`: w2v2_conv0_workspace_bytes(B,N,C)
+ * bytes, 256-byte aligned (GroupNorm scale/shift, fp64 window moments, im2col operand).
+ * The GroupNorm statistics come from the window moments of the waveform (the conv is linear), so the
+ * [B,C,L0] pre-norm tensor is never materialised; the conv itself runs on the tensor cores as a
+ * K=64 GEMM over error-compensated fp16 windows with the GroupNorm affine + GELU in the epilogue. */
+int64_t w2v2_conv0_workspace_bytes(int B, int N, int C);
 int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta,
-                       float eps, float* stats, void* out_f16, int C, void* stream);
+                       float eps, void* workspace, void* out_f16, int C, void* stream);
 
 /* ---- normalisation --------------------------------------------------------------------------- */
 /* y = LayerNorm(x (+ bias) (+ residual)) * gamma + beta over the last dim (HF:429-431, 690-693,

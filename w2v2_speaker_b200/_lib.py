@@ -22,7 +22,7 @@ SIGNATURES = {
     "w2v2_launch_count": (c_int64, []),
     "w2v2_gemm_f16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_int64,
                               c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
-    "w2v2_conv0_stats_floats": (c_int64, [c_int, c_int]),
+    "w2v2_conv0_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "w2v2_conv0_gn_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p]),
     "w2v2_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,

@@ -17,6 +17,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 int device_sm_count();
+int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch, int ntaps,
+                  int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N, const float* bias,
+                  const float* shift, int act, void* out, int out_dtype, int64_t ldo, int64_t out_batch_stride,
+                  cudaStream_t stream);
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
@@ -101,8 +105,10 @@ __global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L
   }
 }
 
-__global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w, int C, int L, float eps,
-                                   float* __restrict__ stats) {
+__global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int C, int L,
+                                   float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  // GroupNorm affine folded to y = conv * scale + shift  (scale = gamma * rstd, shift = beta - mean * scale)
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -125,62 +131,48 @@ __global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* 
     }
   }
   if (var < 0.0) var = 0.0;
-  stats[(int64_t(b) * C + c) * 2 + 0] = float(mean);
-  stats[(int64_t(b) * C + c) * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+  const double sc = double(gamma[c]) / sqrt(var + double(eps));
+  scale[int64_t(b) * C + c] = float(sc);
+  shift[int64_t(b) * C + c] = float(double(beta[c]) - mean * sc);
 }
 
-constexpr int C0_TT = 64;       // time steps per block
-__global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wav, int N, int L,
-                                                          const float* __restrict__ w, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta,
-                                                          const float* __restrict__ stats, __half* __restrict__ out,
-                                                          int C) {
-  __shared__ float xs[C0_TT * C0_S + C0_K];
+// Operands of the conv-as-GEMM: the 10-tap windows of the waveform and the filter bank, both as
+// error-compensated fp16 (v = hi + lo) over K = 64:  A' = [x_hi(10) | x_lo(10) | x_hi(10) | 0...],
+// W' = [w_hi | w_hi | w_lo | 0...]  ->  the fp32 TMEM accumulator holds x.w to ~2^-20 relative.
+constexpr int C0_KP = 64;
+__global__ void conv0_im2col_kernel(const float* __restrict__ wav, int N, int L, __half* __restrict__ a) {
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * C0_TT;
-  const int nt = min(C0_TT, L - t0);
-  const float* x = wav + int64_t(b) * N + int64_t(t0) * C0_S;
-  const int nx = (nt - 1) * C0_S + C0_K;
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = __ldg(x + i);
-  __syncthreads();
-  const int groups = C / 8;                      // 8 channels (16 B of fp16) per thread
-  const int cg = threadIdx.x % groups, tsub = threadIdx.x / groups, tstep = blockDim.x / groups;
-  const int c0 = cg * 8;
-  // packed fp32x2 math (FFMA2): channel pairs (c0+2j, c0+2j+1) share one instruction
-  f32x2 wr[4][C0_K], sc[4], sh[4];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const float* x = wav + int64_t(b) * N + int64_t(t) * C0_S;
+  __half hi[C0_K], lo[C0_K];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-#pragma unroll
-    for (int k = 0; k < C0_K; ++k)
-      wr[j][k] = pack2(__ldg(w + (c0 + 2 * j) * C0_K + k), __ldg(w + (c0 + 2 * j + 1) * C0_K + k));
-    float s2[2], h2[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int c = c0 + 2 * j + e;
-      const float mean = stats[(int64_t(b) * C + c) * 2], rstd = stats[(int64_t(b) * C + c) * 2 + 1];
-      s2[e] = rstd * __ldg(gamma + c);
-      h2[e] = __ldg(beta + c) - mean * s2[e];
-    }
-    sc[j] = pack2(s2[0], s2[1]);
-    sh[j] = pack2(h2[0], h2[1]);
+  for (int k = 0; k < C0_K; ++k) {
+    const float v = __ldg(x + k);
+    hi[k] = __float2half_rn(v);
+    lo[k] = __float2half_rn(v - __half2float(hi[k]));
   }
-  for (int t = tsub; t < nt; t += tstep) {
-    f32x2 acc[4] = {0ull, 0ull, 0ull, 0ull};
+  __half row[C0_KP];
 #pragma unroll
-    for (int k = 0; k < C0_K; ++k) {
-      const f32x2 xk = splat2(xs[t * C0_S + k]);
+  for (int k = 0; k < C0_KP; ++k) row[k] = __float2half_rn(0.f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fma2(wr[j][k], xk, acc[j]);
-    }
-    uint32_t q[4];
+  for (int k = 0; k < C0_K; ++k) { row[k] = hi[k]; row[C0_K + k] = lo[k]; row[2 * C0_K + k] = hi[k]; }
+  uint4* dst = reinterpret_cast<uint4*>(a + (int64_t(b) * L + t) * C0_KP);
+  const uint4* src = reinterpret_cast<const uint4*>(row);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float y0, y1;
-      unpack2(fma2(acc[j], sc[j], sh[j]), y0, y1);
-      gelu_erf2(y0, y1);
-      q[j] = pack_half2(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(out + (int64_t(b) * L + t0 + t) * C + c0) = make_uint4(q[0], q[1], q[2], q[3]);
+  for (int q = 0; q < C0_KP / 8; ++q) dst[q] = src[q];
+}
+__global__ void conv0_weight_split_kernel(const float* __restrict__ w, __half* __restrict__ o, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  __half* row = o + int64_t(c) * C0_KP;
+  for (int k = 0; k < C0_KP; ++k) row[k] = __float2half_rn(0.f);
+  for (int k = 0; k < C0_K; ++k) {
+    const float v = w[c * C0_K + k];
+    const __half hi = __float2half_rn(v);
+    row[k] = hi;
+    row[C0_K + k] = hi;
+    row[2 * C0_K + k] = __float2half_rn(v - __half2float(hi));
   }
 }
 
@@ -572,31 +564,49 @@ int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int 
   return 0;
 }
 
-int w2v2_conv0_workspace_bytes(int B, int C) { return int(sizeof(double)) * B * C0_NMOM; }
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+struct Conv0Ws { int64_t scale, shift, mom, w, a, total; };
+static Conv0Ws conv0_ws(int B, int N, int C) {
+  const int64_t L = (N - C0_K) / C0_S + 1;
+  Conv0Ws o;
+  o.scale = 0;
+  o.shift = align_up(o.scale + int64_t(B) * C * 4, 256);
+  o.mom = align_up(o.shift + int64_t(B) * C * 4, 256);
+  o.w = align_up(o.mom + int64_t(B) * C0_NMOM * 8, 256);
+  o.a = align_up(o.w + int64_t(C) * C0_KP * 2, 256);
+  o.total = align_up(o.a + int64_t(B) * L * C0_KP * 2, 256);
+  return o;
+}
+
+int64_t w2v2_conv0_workspace_bytes(int B, int N, int C) { return N >= C0_K ? conv0_ws(B, N, C).total : 0; }
 
 int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
-                       float* stats, void* out_f16, int C, void* stream_) {
+                       void* workspace, void* out_f16, int C, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   W2V2_REQUIRE(B > 0 && N >= C0_K, "w2v2_conv0_gn_gelu: need B>0 and N>=10 (got B=%d N=%d)", B, N);
-  W2V2_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "w2v2_conv0_gn_gelu: C=%d must divide 2048 and be a multiple of 8", C);
+  W2V2_REQUIRE(C > 128 && C % 8 == 0, "w2v2_conv0_gn_gelu: C=%d must be a multiple of 8 and > 128", C);
+  W2V2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "w2v2_conv0_gn_gelu: workspace must be 256-byte aligned");
   const int L = (N - C0_K) / C0_S + 1;
-  // fp64 window moments live at the tail of the stats workspace: stats must hold
-  // B*C*2 floats + B*65 doubles (see w2v2_conv0_stats_floats)
-  double* mom = reinterpret_cast<double*>(stats + ((int64_t(B) * C * 2 + 1) / 2) * 2);
+  const Conv0Ws ws = conv0_ws(B, N, C);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  float* scale = reinterpret_cast<float*>(base + ws.scale);
+  float* shift = reinterpret_cast<float*>(base + ws.shift);
+  double* mom = reinterpret_cast<double*>(base + ws.mom);
+  __half* w16 = reinterpret_cast<__half*>(base + ws.w);
+  __half* a16 = reinterpret_cast<__half*>(base + ws.a);
   W2V2_CHECK_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * B * C0_NMOM, stream));
   dim3 g1((L + 256 * 8 - 1) / (256 * 8), B);
   conv0_moments_kernel<<<g1, 256, 0, stream>>>(wav, N, L, mom);
   dim3 g2((C + 127) / 128, B);
-  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, C, L, eps, stats);
-  dim3 g3((L + C0_TT - 1) / C0_TT, B);
-  conv0_apply_kernel<<<g3, 256, 0, stream>>>(wav, N, L, w, gamma, beta, stats, (__half*)out_f16, C);
-  count_launches(3);
+  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, gamma, beta, C, L, eps, scale, shift);
+  conv0_weight_split_kernel<<<(C + 127) / 128, 128, 0, stream>>>(w, w16, C);
+  dim3 g3((L + 255) / 256, B);
+  conv0_im2col_kernel<<<g3, 256, 0, stream>>>(wav, N, L, a16);
+  count_launches(4);
   W2V2_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int64_t w2v2_conv0_stats_floats(int B, int C) {
-  return ((int64_t(B) * C * 2 + 1) / 2) * 2 + int64_t(B) * C0_NMOM * 2;
+  // y = GELU(conv * scale[b,c] + shift[b,c]) on the tensor cores, fp16 channels-last out
+  return gemm_f16_impl(a16, L, C0_KP, int64_t(L) * C0_KP, B, 1, 0, C0_KP, w16, C0_KP, C, scale, shift, 1, out_f16, 0, C,
+                       int64_t(L) * C, stream);
 }
 
 int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,

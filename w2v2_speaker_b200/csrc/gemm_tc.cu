@@ -42,7 +42,8 @@ struct alignas(64) GemmParams {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
   CUtensorMap tmOut;             // box {64 (f16) | 32 (f32) columns, 32 rows, 1}
-  const float* bias;
+  const float* bias;             // EPI 1: [N];  EPI 2: per-(batch, column) scale [batch, N]
+  const float* shift;            // EPI 2: per-(batch, column) shift [batch, N]
   int ntaps, kblocks_per_tap;
   int m_tiles, n_tiles, batch;
   int N;
@@ -61,7 +62,8 @@ struct GemmCfg {
   static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area too small");
 };
 
-template <int BN, bool OUT_F32, int ACT, bool HAS_BIAS>
+// EPI: 0 = none, 1 = + bias[n], 2 = * scale[b, n] + shift[b, n]  (GroupNorm affine of conv layer 0)
+template <int BN, bool OUT_F32, int ACT, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -82,6 +84,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles * p.batch;
   const int k_iters = p.ntaps * p.kblocks_per_tap;
+  // Tile schedule.  Default: grid-stride, n fastest (CTAs running concurrently share the A tile in L2).
+  // EPI 2 (per-(batch, column) affine): contiguous chunk per CTA, m fastest, so the (batch, n-tile)
+  // dependent scale/shift vectors change only once or twice per CTA.
+  constexpr bool CHUNKED = (EPI == 2);
+  const int tiles_per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = CHUNKED ? blockIdx.x * tiles_per_cta : blockIdx.x;
+  const int tile_end = CHUNKED ? min(num_tiles, tile_begin + tiles_per_cta) : num_tiles;
+  const int tile_step = CHUNKED ? 1 : gridDim.x;
+  auto decode = [&](int tile, int& nt, int& mt, int& b) {
+    if constexpr (CHUNKED) {
+      mt = tile % p.m_tiles;
+      const int rest = tile / p.m_tiles;
+      nt = rest % p.n_tiles;
+      b = rest / p.n_tiles;
+    } else {
+      nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      mt = rest % p.m_tiles;
+      b = rest / p.m_tiles;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     for (int t = 0; t < p.ntaps; ++t) prefetch_tensormap(&p.tmA[t]);
@@ -113,11 +136,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int rest = tile / p.n_tiles;
-        const int mt = rest % p.m_tiles;
-        const int b = rest / p.m_tiles;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        int nt, mt, b;
+        decode(tile, nt, mt, b);
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -176,13 +197,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     uint32_t acc_phase = 0;
     uint32_t tcount = 0;
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int nt = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int mt = rest % p.m_tiles;
-      const int b = rest / p.m_tiles;
-      const float* bias_tile = sbias + (tcount & 1) * BN;
-      if constexpr (HAS_BIAS) {
+    int prev_b = -1, prev_nt = -1;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
+      int nt, mt, b;
+      decode(tile, nt, mt, b);
+      const float* bias_tile = sbias + (EPI == 1 ? (tcount & 1) * BN : 0);
+      if constexpr (EPI == 1) {
         // stage this tile's bias slice once (the previous user of this buffer was two tiles ago and
         // every epilogue warp has passed the barrier of the tile in between)
         if (epi_tid < BN) {
@@ -190,6 +210,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           sbias[(tcount & 1) * BN + epi_tid] = (n < p.N) ? __ldg(p.bias + n) : 0.f;
         }
         named_bar_sync(1, EPI_WARPS * 32);
+      } else if constexpr (EPI == 2) {
+        // scale in sbias[0:BN], shift in sbias[BN:2BN]; single-buffered -> fence both sides.  With the
+        // chunked schedule (b, nt) changes at most a couple of times per CTA.
+        if (b != prev_b || nt != prev_nt) {
+          named_bar_sync(1, EPI_WARPS * 32);
+          if (epi_tid < BN) {
+            const int n = nt * BN + epi_tid;
+            sbias[epi_tid] = (n < p.N) ? __ldg(p.bias + (long long)b * p.N + n) : 0.f;
+            sbias[BN + epi_tid] = (n < p.N) ? __ldg(p.shift + (long long)b * p.N + n) : 0.f;
+          }
+          named_bar_sync(1, EPI_WARPS * 32);
+          prev_b = b; prev_nt = nt;
+        }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       __syncwarp();
@@ -207,12 +240,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (HAS_BIAS) bb = *reinterpret_cast<const float4*>(bsrc + j);
-          v[j] = __uint_as_float(r[j]) + bb.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+          if constexpr (EPI == 2) {
+            const float4 sc = *reinterpret_cast<const float4*>(bsrc + j);
+            const float4 sh = *reinterpret_cast<const float4*>(bsrc + BN + j);
+            v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
+            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+          } else {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EPI == 1) bb = *reinterpret_cast<const float4*>(bsrc + j);
+            v[j] = __uint_as_float(r[j]) + bb.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+          }
         }
         if constexpr (ACT == 1) {
 #pragma unroll
@@ -339,11 +381,11 @@ int device_sm_count() {
   return sms;
 }
 
-template <int BN, bool OUT_F32, int ACT, bool HAS_BIAS>
+template <int BN, bool OUT_F32, int ACT, int EPI>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, HAS_BIAS>;
+  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI>;
   if (!configured) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -358,20 +400,20 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 
 template <int BN, bool OUT_F32>
 static int dispatch_epilogue(const GemmParams& p, int act, cudaStream_t stream) {
-  const bool hb = p.bias != nullptr;
-  if (act == 1) return hb ? launch_gemm<BN, OUT_F32, 1, true>(p, stream) : launch_gemm<BN, OUT_F32, 1, false>(p, stream);
-  return hb ? launch_gemm<BN, OUT_F32, 0, true>(p, stream) : launch_gemm<BN, OUT_F32, 0, false>(p, stream);
+  const int epi = p.shift != nullptr ? 2 : (p.bias != nullptr ? 1 : 0);
+  if (epi == 2) {
+    if constexpr (!OUT_F32 && BN == 256) return launch_gemm<256, false, 1, 2>(p, stream);   // conv0: GN affine + GELU -> f16
+    set_last_error("w2v2 gemm: the per-batch affine epilogue is built for f16 output, N > 128");
+    return -1;
+  }
+  if (act == 1) return epi ? launch_gemm<BN, OUT_F32, 1, 1>(p, stream) : launch_gemm<BN, OUT_F32, 1, 0>(p, stream);
+  return epi ? launch_gemm<BN, OUT_F32, 0, 1>(p, stream) : launch_gemm<BN, OUT_F32, 0, 0>(p, stream);
 }
 
-}  // namespace w2v2
-
-using namespace w2v2;
-
-extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,
-                             int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N,
-                             const float* bias, int act, void* out, int out_dtype, int64_t ldo,
-                             int64_t out_batch_stride, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch, int ntaps,
+                  int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N, const float* bias,
+                  const float* shift, int act, void* out, int out_dtype, int64_t ldo, int64_t out_batch_stride,
+                  cudaStream_t stream) {
   W2V2_REQUIRE(ntaps >= 1 && ntaps <= 3, "w2v2_gemm_f16: ntaps=%d not in [1,3]", ntaps);
   W2V2_REQUIRE(cin % BK == 0, "w2v2_gemm_f16: cin=%d must be a multiple of %d", cin, BK);
   W2V2_REQUIRE(out_dtype == 0 || out_dtype == 1, "w2v2_gemm_f16: out_dtype must be 0 (f16) or 1 (f32)");
@@ -393,6 +435,7 @@ extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride
   rc = make_tmap_3d(&p.tmOut, out, osz, N, a_rows, batch, uint64_t(ldo) * osz, o_bstride, out_dtype == 1 ? 32 : 64, 32, 1, 128);
   if (rc) return rc;
   p.bias = bias;
+  p.shift = shift;
   p.ntaps = ntaps;
   p.kblocks_per_tap = cin / BK;
   p.m_tiles = int((a_rows + BM - 1) / BM);
@@ -402,4 +445,16 @@ extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride
   p.rows = a_rows;
   if (BN == 256) return out_dtype == 1 ? dispatch_epilogue<256, true>(p, act, stream) : dispatch_epilogue<256, false>(p, act, stream);
   return out_dtype == 1 ? dispatch_epilogue<128, true>(p, act, stream) : dispatch_epilogue<128, false>(p, act, stream);
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,
+                             int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N,
+                             const float* bias, int act, void* out, int out_dtype, int64_t ldo,
+                             int64_t out_batch_stride, void* stream_) {
+  return gemm_f16_impl(A, a_rows, a_row_stride, a_batch_stride, batch, ntaps, a_tap_stride, cin, W, ldw, N, bias, nullptr,
+                       act, out, out_dtype, ldo, out_batch_stride, static_cast<cudaStream_t>(stream_));
 }

@@ -16,6 +16,8 @@
 // folded, fp16, UMMA core-matrix order [I/8][U][O][8]) stream through a cp.async.bulk + mbarrier ring.
 //   warp 0: weight producer, warp 1: MMA issuer, warps 2-5: slab fill, then epilogue
 //   (TMEM -> smem (row shift) -> +bias -> GELU -> fp32 store).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "w2v2_b200.h"
 
@@ -44,7 +46,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
       : "memory");
 }
 
-__global__ void __launch_bounds__(PC_THREADS, 1) posconv_kernel(const PosconvParams p) {
+__global__ void __launch_bounds__(PC_THREADS, 2) posconv_kernel(const PosconvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int I = p.I, O = p.O, R = p.R, U = p.U;
   const int planes = I / 8;
@@ -193,7 +195,13 @@ __global__ void __launch_bounds__(PC_THREADS, 1) posconv_kernel(const PosconvPar
 
 static int posconv_plan(int T, int H, int groups, int* ntiles_out) {
   const int O = H / groups;
+  static int umax = -1;               // W2V2_POSCONV_U caps the taps per MMA (tuning knob)
+  if (umax < 0) {
+    const char* e = getenv("W2V2_POSCONV_U");
+    umax = (e != nullptr && atoi(e) >= 1) ? atoi(e) : 4;
+  }
   for (int U = 4; U >= 1; U >>= 1) {
+    if (U > umax) continue;
     const int nt = (T + U - 1 + 127) / 128;       // rows t + u (u < U) must all exist
     if (nt * U * O <= 512 && U * O <= 256) {
       if (ntiles_out) *ntiles_out = nt;

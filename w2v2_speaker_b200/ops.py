@@ -78,10 +78,10 @@ def conv0_gn_gelu(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta:
     C = w.shape[0]
     L0 = (N - 10) // 5 + 1
     lib = _lib.load()
-    stats = torch.empty(lib.w2v2_conv0_stats_floats(B, C), dtype=F32, device=wav.device)
+    ws = torch.empty(lib.w2v2_conv0_workspace_bytes(B, N, C), dtype=torch.uint8, device=wav.device)
     out = torch.empty(B, L0, C, dtype=F16, device=wav.device)
     call("w2v2_conv0_gn_gelu", ptr(wav.contiguous()), B, N, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps,
-         ptr(stats), ptr(out), C, stream_ptr())
+         ptr(ws), ptr(out), C, stream_ptr())
     return out
 
 
