@@ -79,8 +79,9 @@ int w2v2_posconv(const void* x16, const void* w16, const float* bias, float* out
 
 /* ---- self-attention core ---------------------------------------------------------------------- */
 /* o = softmax(q k^T) v per (batch, head), no mask (HF:438-463; the 1/sqrt(d) scale is folded
- * into the q projection).  qkv f16 [B*T, 3H] (q | k | v blocks); out f16 [B*T, H]. */
-int w2v2_attention(const void* qkv16, void* out16, int B, int T, int H, int heads, void* stream);
+ * into the q projection).  qkv f16 [B*T, 3H] (q | k | v blocks); out f16 [B*T, H];
+ * lse f32 [B, heads, T] = log-sum-exp of every score row (NULL in inference; saved for backward). */
+int w2v2_attention(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, void* stream);
 
 /* ---- pooling (R:src/layers/pooling.py) -------------------------------------------------------- */
 /* mode 0: mean -> [B,H] (:24-30); mode 1: [std_unbiased || mean] -> [B,2H] (:38-44);
@@ -119,6 +120,40 @@ int w2v2_split3_rows(const float* x, void* y16, int64_t rows, int E, int which, 
 int w2v2_l2norm_rows_split3(const float* x, void* y16, int64_t rows, int E, int which, void* stream);
 /* mean of n floats -> out[0] (loss reduction 'mean'). */
 int w2v2_mean_rows(const float* x, float* out, int n, void* stream);
+
+/* ---- backward pass (autograd of the path above: R:src/lightning_modules/speaker/speaker_recognition_module.py:148-220
+ *      calls loss.backward(); torch autograd then runs the backward of every op listed above) ---------------- */
+/* dW[n,k] += sum_m dY[m,n] * X[m,k]   (weight gradient of out = X W^T).  dY f16 [M, ldy], X f16 [M, ldx],
+ * dW f32 [N, ldw] (accumulated into: zero it first for a fresh gradient).  Both operands are consumed
+ * MN-major straight from their row-major layout; the M range is split over CTAs and reduced with TMA
+ * reduce-add stores. */
+int w2v2_gemm_wgrad_f16(const void* dY, int64_t ldy, const void* X, int64_t ldx, int64_t M, int N, int K, float* dW,
+                        int64_t ldw, void* stream);
+/* w f32 [R, C] -> wT f16 [C, ldt] (transpose + cast, columns >= R zero-filled, optional per-row scale):
+ * the B operand of the data-gradient GEMM dX = dY W, which is then a plain w2v2_gemm_f16 call. */
+int w2v2_cast_f16_transpose(const float* w, void* wt16, int R, int C, int ldt, const float* row_scale, void* stream);
+/* LayerNorm backward for y = LN(xa (+bias) (+residual)); dy = dy_a (+ dy_b).  x, mean, rstd are
+ * recomputed.  dx32 / dx16 may be NULL; dgamma / dbeta (f32 [H], may be NULL) are accumulated. */
+int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
+                       const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
+                       float* dbeta, int64_t rows, int H, void* stream);
+/* dz = dg * gelu'(z), all f16, n % 8 == 0. */
+int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void* stream);
+/* out[c] += scale * sum_r x[r, c]  (bias gradients); x f16 (x_dtype 0) or f32 (1), row pitch ld. */
+int w2v2_colsum(const void* x, int x_dtype, int64_t rows, int cols, int64_t ld, float scale, float* out, void* stream);
+/* dlogits = (prob - onehot(label)) * coef -> f16 [B, ldd] (columns >= S zero).  coef = loss_scale / B. */
+int w2v2_softmax_ce_bwd(const float* prob, const int64_t* labels, float coef, void* dlogits16, int B, int S, int ldd,
+                        void* stream);
+/* mean pooling backward: dh[b,t,:] = demb[b,:] / T. */
+int w2v2_mean_pool_bwd(const float* demb, float* dh, int B, int T, int H, void* stream);
+/* Attention backward (recomputes P from q, k and the saved log-sum-exp): qkv f16 [B*T, 3H], o f16 [B*T, H]
+ * (forward output), d_o f16 [B*T, H], lse f32 [B, heads, T]  ->  dqkv f16 [B*T, 3H].  T <= 192. */
+int w2v2_attention_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B, int T,
+                       int H, int heads, void* stream);
+/* torch.optim.Adam step (weight_decay 0) over flat fp32 buffers; `g` is multiplied by grad_scale first
+ * (undoes the loss scale and applies the 1/world_size of the data-parallel mean). */
+int w2v2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   int step, float grad_scale, void* stream);
 
 /* ---- utility ---------------------------------------------------------------------------------- */
 /* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */

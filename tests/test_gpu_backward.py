@@ -1,0 +1,155 @@
+"""GPU parity of the backward-pass entry points against torch autograd (fp32/fp64) on the same inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from w2v2_speaker_b200 import ops as _ops
+    return _ops
+
+
+def rel(a, b):
+    a = a.double(); b = b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(9536, 768, 768), (9536, 3072, 768), (9536, 768, 3072), (9536, 2304, 768),
+                                   (64, 5994, 768), (300, 512, 768), (149 * 3, 768, 512), (70, 128, 2304)])
+def test_gemm_wgrad(ops, M, N, K):
+    ldy = (N + 63) // 64 * 64                      # row pitch must be a multiple of 16 bytes (TMA)
+    dy = torch.zeros(M, ldy, dtype=torch.float16, device="cuda")[:, :N]
+    dy.copy_(_rand((M, N), 1, 0.5))
+    x = _rand((M, K), 2).half()
+    dw = torch.zeros(N, K, device="cuda")
+    ops.gemm_wgrad_f16(dy, x, dw)
+    torch.cuda.synchronize()
+    ref = dy.double().t() @ x.double()
+    assert torch.isfinite(dw).all()
+    assert rel(dw, ref) < 2e-5
+    ops.gemm_wgrad_f16(dy, x, dw)                 # accumulates like .grad
+    assert rel(dw, 2 * ref) < 2e-5
+
+
+def test_dgrad_via_transposed_weight(ops):
+    M, N, K = 1000, 768, 3072                      # y = x W^T, W [N, K];  dx = dy W
+    dy = _rand((M, N), 3).half()
+    W = _rand((N, K), 4, 0.02)
+    wt = ops.cast_f16_transpose(W)                  # [K, N]
+    assert wt.shape == (K, 768)
+    dx = ops.gemm_f16(dy, wt, None, 0, torch.float32)
+    ref = dy.double() @ W.half().double()
+    assert rel(dx, ref) < 2e-5
+    # padded / scaled variant (classifier: R=5994 -> 6016, rows scaled)
+    W2 = _rand((5994, 768), 5, 0.02)
+    sc = torch.rand(5994, generator=torch.Generator().manual_seed(6)).cuda() + 0.5
+    wt2 = ops.cast_f16_transpose(W2, 6016, sc)
+    assert wt2.shape == (768, 6016)
+    assert rel(wt2[:, :5994].float(), (W2 * sc[:, None]).t()) < 4e-4
+    assert (wt2[:, 5994:] == 0).all()
+
+
+@pytest.mark.parametrize("rows,H,use_b", [(9536, 768, True), (300, 512, False), (77, 1024, True)])
+def test_layernorm_bwd(ops, rows, H, use_b):
+    xa = _rand((rows, H), 7, 2.0)
+    bias = _rand((H,), 8)
+    res = _rand((rows, H), 9)
+    gamma = (1 + 0.1 * _rand((H,), 10)).requires_grad_(True)
+    beta = (0.1 * _rand((H,), 11)).requires_grad_(True)
+    dy_a = _rand((rows, H), 12)
+    dy_b = _rand((rows, H), 13) if use_b else None
+    x = (xa + bias + res).double().requires_grad_(True)
+    y = F.layer_norm(x, (H,), gamma.double(), beta.double(), 1e-5)
+    dy = (dy_a + (dy_b if use_b else 0)).double()
+    gx, gg, gb = torch.autograd.grad(y, [x, gamma, beta], dy)
+    dgamma = torch.zeros(H, device="cuda"); dbeta = torch.zeros(H, device="cuda")
+    dx32, dx16 = ops.layernorm_bwd(dy_a, xa, gamma.detach(), 1e-5, dy_b=dy_b, bias=bias, residual=res, dgamma=dgamma,
+                                   dbeta=dbeta)
+    torch.cuda.synchronize()
+    assert rel(dx32, gx) < 2e-5
+    assert rel(dx16.float(), gx) < 5e-4
+    assert rel(dgamma, gg) < 2e-5
+    assert rel(dbeta, gb) < 2e-5
+
+
+def test_gelu_bwd_colsum_ce_pool(ops):
+    z = _rand((9536, 3072), 14, 1.5).half()
+    dg = _rand((9536, 3072), 15).half()
+    dz = ops.gelu_bwd(dg, z)
+    zz = z.float().requires_grad_(True)
+    ref = torch.autograd.grad(F.gelu(zz), zz, dg.float())[0]
+    assert rel(dz.float(), ref) < 5e-4
+    out = torch.ones(3072, device="cuda")
+    ops.colsum(dz, out, 0.5)
+    assert rel(out, 1 + 0.5 * dz.double().sum(0)) < 1e-5
+    x32 = _rand((777, 768), 16)
+    out2 = torch.zeros(768, device="cuda")
+    ops.colsum(x32, out2)
+    assert rel(out2, x32.double().sum(0)) < 1e-5
+    # CE backward
+    B, S = 64, 5994
+    logits = _rand((B, S), 17, 2.0).requires_grad_(True)
+    labels = torch.randint(0, S, (B,), generator=torch.Generator().manual_seed(18)).cuda()
+    loss = F.cross_entropy(logits, labels)
+    g = torch.autograd.grad(loss, logits)[0]
+    prob = torch.softmax(logits.detach(), 1)
+    dl = ops.softmax_ce_bwd(prob, labels, 1024.0 / B, 6016)
+    assert dl.shape == (B, 6016) and (dl[:, S:] == 0).all()
+    assert rel(dl[:, :S].float() / 1024.0, g) < 6e-4
+    # mean pool backward
+    demb = _rand((5, 768), 19)
+    dh = ops.mean_pool_bwd(demb, 149)
+    assert rel(dh, (demb / 149)[:, None, :].expand(5, 149, 768)) < 1e-6
+
+
+@pytest.mark.parametrize("B,T,H,heads", [(2, 49, 768, 12), (3, 149, 768, 12), (2, 128, 768, 12), (1, 16, 768, 12),
+                                         (2, 192, 1024, 16), (1, 1, 768, 12)])
+def test_attention_bwd(ops, B, T, H, heads):
+    d = H // heads
+    qkv = _rand((B * T, 3 * H), 20).half()
+    qkv[:, :H] *= 0.35
+    d_o = _rand((B * T, H), 21, 0.7).half()
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True)
+    dqkv = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads)
+    torch.cuda.synchronize()
+    x = qkv.float().requires_grad_(True)
+    q, k, v = (x[:, i * H:(i + 1) * H].view(B, T, heads, d).transpose(1, 2) for i in range(3))
+    a = torch.softmax(q @ k.transpose(2, 3), -1)
+    o = (a @ v).transpose(1, 2).reshape(B * T, H)
+    ref = torch.autograd.grad(o, x, d_o.float())[0]
+    assert torch.isfinite(dqkv.float()).all()
+    ref_lse = torch.logsumexp(q.detach() @ k.detach().transpose(2, 3), -1)
+    assert rel(lse, ref_lse) < 1e-3
+    for i, name in enumerate("qkv"):
+        got, want = dqkv[:, i * H:(i + 1) * H].float(), ref[:, i * H:(i + 1) * H]
+        if want.abs().max().item() < 1e-6:          # T == 1: softmax over one key has zero q / k gradient
+            assert got.abs().max().item() < 1e-3, name
+        else:
+            assert rel(got, want) < 4e-3, name
+
+
+def test_adam_matches_torch(ops):
+    n = 100003
+    p0 = _rand((n,), 22)
+    g = _rand((n,), 23, 0.1)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(1, 4):
+        ref.grad = g * step
+        opt.step()
+        ops.adam_step(p, g * step * 128.0, m, v, 1e-3, 0.9, 0.999, 1e-8, step, grad_scale=1.0 / 128.0)
+    torch.cuda.synchronize()
+    assert rel(p, ref.detach()) < 1e-6

@@ -24,6 +24,7 @@ struct alignas(64) AttnParams {
   CUtensorMap tmQ;    // box {64, 128, 1}
   CUtensorMap tmKV;   // box {64, TK, 1}
   __half* out;
+  float* lse;         // [B, heads, T] or nullptr
   int T, TK, H, heads;
   int tmem_cols, o_col;
 };
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   tc_fence_after();
   const int t = mt * 128 + row;
   const float inv = 1.0f / sum;
+  if (p.lse != nullptr && t < p.T) p.lse[(int64_t(b) * p.heads + h) * p.T + t] = mx + __logf(sum);
   __half* dst = p.out + (int64_t(b) * p.T + (t < p.T ? t : 0)) * p.H + h * ATT_D;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
 
 using namespace w2v2;
 
-extern "C" int w2v2_attention(const void* qkv16, void* out16, int B, int T, int H, int heads, void* stream_) {
+extern "C" int w2v2_attention(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * ATT_D, "w2v2_attention: head dim must be 64 (H=%d heads=%d)", H, heads);
   W2V2_REQUIRE(T >= 1 && T <= 256,
@@ -196,6 +198,7 @@ extern "C" int w2v2_attention(const void* qkv16, void* out16, int B, int T, int 
   rc = make_tmap_3d(&p.tmKV, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, ATT_D, TK, 1, 128);
   if (rc) return rc;
   p.out = static_cast<__half*>(out16);
+  p.lse = lse;
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   if (TK <= 192) { p.tmem_cols = 256; p.o_col = 192; } else { p.tmem_cols = 512; p.o_col = 256; }
   if (TK <= 64) { p.tmem_cols = 128; p.o_col = 64; }

@@ -1,0 +1,325 @@
+// Self-attention backward on tcgen05 (backward of HF:438-463, softmax scale folded into q):
+//     P  = exp(S - lse),  S = Q K^T          (recomputed; lse saved by the forward)
+//     dP = dO V^T,  delta = rowsum(dO * O),  dS = P * (dP - delta)
+//     dV = P^T dO,  dQ = dS K,  dK = dS^T Q
+// One CTA per (batch, head) walks the (up to two) 128-query tiles; T <= 192 frames.  Every transpose in
+// the formulas is free: P / dS live in shared memory as [query rows x 64-key blocks] (128-byte swizzle)
+// and are consumed K-major (dQ = dS K) or MN-major (dV = P^T dO, dK = dS^T Q) through the UMMA
+// descriptor's major bit; Q, K, V, dO are the [t, d] tiles TMA delivers and serve as K-major or MN-major
+// operands as needed.  TMEM: S/dP [0,192) | dQ [192,256) | dV [256,384) | dK [384,512), fp32.
+// One thread per query row does the exp / dS arithmetic straight from tcgen05.ld, as in the forward.
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+namespace w2v2 {
+
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                 int swizzle_bytes);
+
+constexpr int AB_D = 64;
+constexpr int AB_PBLOCKS = 3;                 // 64-key blocks of P / dS (TK <= 192)
+constexpr int AB_COL_SP = 0, AB_COL_DQ = 192, AB_COL_DV = 256, AB_COL_DK = 384;
+
+struct alignas(64) AttnBwdParams {
+  CUtensorMap tmQ;     // qkv: box {64, 128, 1}
+  CUtensorMap tmKV;    // qkv: box {64, TK, 1}
+  CUtensorMap tmDO;    // dO : box {64, 128, 1}
+  const __half* o;     // [B*T, H]
+  const __half* d_o;   // [B*T, H]
+  const float* lse;    // [B, heads, T]
+  __half* dqkv;        // [B*T, 3H]
+  int T, TK, H, heads, qtiles;
+};
+
+__global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int TK = p.TK;
+  const int kv_bytes = ((TK * 128) + 1023) & ~1023;
+  uint8_t* sP = smem;                               // 3 x 16 KB   (phantom block 3 = sdS block 0)
+  uint8_t* sdS = sP + AB_PBLOCKS * 16384;           // 3 x 16 KB   (phantom block 3 = sQ tile 0)
+  uint8_t* sQ = sdS + AB_PBLOCKS * 16384;           // 2 x 16 KB
+  uint8_t* sdO = sQ + 2 * 16384;                    // 2 x 16 KB
+  uint8_t* sK = sdO + 2 * 16384;
+  uint8_t* sV = sK + kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kv_bytes);
+  uint64_t* bar_tma = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = warp * 32 + lane;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&p.tmQ);
+    prefetch_tensormap(&p.tmKV);
+    prefetch_tensormap(&p.tmDO);
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_tma, 4 * 16384 + 2 * TK * 128);
+    for (int i = 0; i < 2; ++i) {
+      tma_load_3d(sQ + i * 16384, &p.tmQ, bar_tma, h * AB_D, i * 128, b);
+      tma_load_3d(sdO + i * 16384, &p.tmDO, bar_tma, h * AB_D, i * 128, b);
+    }
+    tma_load_3d(sK, &p.tmKV, bar_tma, p.H + h * AB_D, 0, b);
+    tma_load_3d(sV, &p.tmKV, bar_tma, 2 * p.H + h * AB_D, 0, b);
+  }
+  mbar_wait(bar_tma, 0);
+  __syncwarp();
+  tc_fence_after();
+
+  const int nchunk = TK / 16;
+  const int ktiles = (TK + 127) / 128;
+  uint32_t mma_phase = 0;
+  const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS), aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK),
+                 aV = smem_u32(sV);
+
+  for (int qt = 0; qt < p.qtiles; ++qt) {
+    const int t = qt * 128 + row;
+    const bool valid = t < p.T;
+    // ---- (a) S = Q_qt K^T
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc_f16(128, TK);
+#pragma unroll
+      for (int k = 0; k < AB_D / 16; ++k)
+        umma_f16(tmem + AB_COL_SP, make_desc_k_sw128(aQ + qt * 16384 + k * 32), make_desc_k_sw128(aK + k * 32), idesc, k != 0);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    // per-row scalars while the MMA runs
+    float lse = 0.f, delta = 0.f;
+    if (valid) {
+      lse = p.lse[(int64_t(b) * p.heads + h) * p.T + t];
+      const uint4* po = reinterpret_cast<const uint4*>(p.o + (int64_t(b) * p.T + t) * p.H + h * AB_D);
+      const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (int64_t(b) * p.T + t) * p.H + h * AB_D);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 a = po[c], g = pd[c];
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* gh = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = __half22float2(ah[j]), y = __half22float2(gh[j]);
+          delta = fmaf(x.x, y.x, delta);
+          delta = fmaf(x.y, y.y, delta);
+        }
+      }
+    }
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    __syncwarp();
+    tc_fence_after();
+    // ---- (b) P = exp(S - lse) -> smem (fp16, K-major swizzled blocks); invalid rows / columns -> 0
+    uint8_t* prow = sP + row * 128;
+    const float lse2 = lse * 1.4426950408889634f;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + AB_COL_SP + c * 16, r);
+      tmem_ld_wait();
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float e0 = fast_ex2(fmaf(__uint_as_float(r[2 * j]), 1.4426950408889634f, -lse2));
+        float e1 = fast_ex2(fmaf(__uint_as_float(r[2 * j + 1]), 1.4426950408889634f, -lse2));
+        if (!valid || c * 16 + 2 * j >= p.T) e0 = 0.f;
+        if (!valid || c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
+        pk[j] = pack_half2(e0, e1);
+      }
+      const int col = c * 16;
+      uint8_t* blk = prow + (col >> 6) * 16384;
+      const int c16 = (col & 63) >> 3;
+      *reinterpret_cast<uint4*>(blk + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- (c) dP = dO_qt V^T (overwrites S) ;  dV += P^T dO_qt
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t idesc_dp = make_idesc_f16(128, TK);
+#pragma unroll
+      for (int k = 0; k < AB_D / 16; ++k)
+        umma_f16(tmem + AB_COL_SP, make_desc_k_sw128(adO + qt * 16384 + k * 32), make_desc_k_sw128(aV + k * 32), idesc_dp, k != 0);
+      const uint32_t idesc_t = make_idesc_f16(128, AB_D, 1, 1);            // A (P^T) and B (dO) MN-major
+      for (int kt = 0; kt < ktiles; ++kt) {
+        for (int ks = 0; ks < 8; ++ks) {                                  // 128 queries / 16
+          const uint64_t adesc = make_smem_desc(aP + kt * 2 * 16384 + ks * 2048, 16384, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(adO + qt * 16384 + ks * 2048, 16, 1024, 2);
+          umma_f16(tmem + AB_COL_DV + kt * AB_D, adesc, bdesc, idesc_t, (qt | ks) != 0);
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    __syncwarp();
+    tc_fence_after();
+    // ---- (d) dS = P * (dP - delta) -> smem
+    uint8_t* dsrow = sdS + row * 128;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + AB_COL_SP + c * 16, r);
+      tmem_ld_wait();
+      const int col = c * 16;
+      const int c16 = (col & 63) >> 3;
+      const uint4 p0 = *reinterpret_cast<const uint4*>(prow + (col >> 6) * 16384 + ((c16 ^ (row & 7)) << 4));
+      const uint4 p1 = *reinterpret_cast<const uint4*>(prow + (col >> 6) * 16384 + (((c16 + 1) ^ (row & 7)) << 4));
+      const __half2* ph0 = reinterpret_cast<const __half2*>(&p0);
+      const __half2* ph1 = reinterpret_cast<const __half2*>(&p1);
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 pp = __half22float2(j < 4 ? ph0[j] : ph1[j - 4]);
+        pk[j] = pack_half2(pp.x * (__uint_as_float(r[2 * j]) - delta), pp.y * (__uint_as_float(r[2 * j + 1]) - delta));
+      }
+      uint8_t* blk = dsrow + (col >> 6) * 16384;
+      *reinterpret_cast<uint4*>(blk + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- (e) dQ_qt = dS K ;  dK += dS^T Q_qt
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t idesc_dq = make_idesc_f16(128, AB_D, 0, 1);           // B (= K) MN-major
+      for (int kk = 0; kk < nchunk; ++kk) {
+        const uint64_t adesc = make_desc_k_sw128(adS + (kk >> 2) * 16384 + (kk & 3) * 32);
+        const uint64_t bdesc = make_smem_desc(aK + kk * 2048, 16, 1024, 2);
+        umma_f16(tmem + AB_COL_DQ, adesc, bdesc, idesc_dq, kk != 0);
+      }
+      const uint32_t idesc_t = make_idesc_f16(128, AB_D, 1, 1);
+      for (int kt = 0; kt < ktiles; ++kt) {
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t adesc = make_smem_desc(adS + kt * 2 * 16384 + ks * 2048, 16384, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(aQ + qt * 16384 + ks * 2048, 16, 1024, 2);
+          umma_f16(tmem + AB_COL_DK + kt * AB_D, adesc, bdesc, idesc_t, (qt | ks) != 0);
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    __syncwarp();
+    tc_fence_after();
+    // ---- (f) dQ rows -> global
+    {
+      __half* dst = p.dqkv + (int64_t(b) * p.T + (valid ? t : 0)) * 3 * p.H + h * AB_D;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + AB_COL_DQ + hh * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 q;
+            q.x = pack_half2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]));
+            q.y = pack_half2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+            q.z = pack_half2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+            q.w = pack_half2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+            *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = q;
+          }
+        }
+      }
+    }
+    // all threads must be done with S/dP and dQ columns before the next tile's MMAs overwrite them
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  // ---- dK, dV rows (keys) -> global
+  for (int kt = 0; kt < ktiles; ++kt) {
+    const int key = kt * 128 + row;
+    const bool kvalid = key < p.T;
+    __half* base = p.dqkv + (int64_t(b) * p.T + (kvalid ? key : 0)) * 3 * p.H + h * AB_D;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {               // 0: dK, 1: dV
+      const uint32_t col = (which == 0 ? AB_COL_DK : AB_COL_DV) + kt * AB_D;
+      __half* dst = base + (which == 0 ? p.H : 2 * p.H);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + col + hh * 32, r);
+        tmem_ld_wait();
+        if (kvalid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 q;
+            q.x = pack_half2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]));
+            q.y = pack_half2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+            q.z = pack_half2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+            q.w = pack_half2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+            *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = q;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" int w2v2_attention_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16,
+                                  int B, int T, int H, int heads, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  W2V2_REQUIRE(heads > 0 && H == heads * AB_D, "w2v2_attention_bwd: head dim must be 64 (H=%d heads=%d)", H, heads);
+  W2V2_REQUIRE(T >= 1 && T <= 192,
+               "w2v2_attention_bwd: T=%d frames not supported (the single-pass backward handles T <= 192)", T);
+  W2V2_REQUIRE(B >= 1 && B <= 65535, "w2v2_attention_bwd: bad batch %d", B);
+  AttnBwdParams p;
+  const int TK = (T + 15) / 16 * 16;
+  int rc = make_tmap_3d(&p.tmQ, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AB_D, 128, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmKV, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AB_D, TK, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmDO, do16, 2, H, T, B, uint64_t(H) * 2, uint64_t(T) * H * 2, AB_D, 128, 1, 128);
+  if (rc) return rc;
+  p.o = static_cast<const __half*>(o16);
+  p.d_o = static_cast<const __half*>(do16);
+  p.lse = lse;
+  p.dqkv = static_cast<__half*>(dqkv16);
+  p.T = T; p.TK = TK; p.H = H; p.heads = heads;
+  p.qtiles = (T + 127) / 128;
+  const int kvb = (TK * 128 + 1023) & ~1023;
+  const int smem = 2 * AB_PBLOCKS * 16384 + 4 * 16384 + 2 * kvb + 64;
+  W2V2_REQUIRE(smem <= 227 * 1024, "w2v2_attention_bwd: shared memory budget exceeded (%d bytes)", smem);
+  static int configured = 0;
+  if (smem > configured) {
+    W2V2_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid(heads, B);
+  attention_bwd_kernel<<<grid, 128, smem, stream>>>(p);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

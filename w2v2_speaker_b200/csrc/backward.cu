@@ -1,0 +1,347 @@
+// Backward-pass kernels that are not GEMMs: LayerNorm backward (+ parameter-gradient reductions),
+// GELU backward, column sums (bias gradients), softmax-CE backward, pooling backward, transposed
+// fp16 weight copies for the dgrad GEMMs, fused Adam.  All activation gradients are carried in a
+// loss-scaled fp16 copy (GEMM operand) next to the fp32 residual-stream gradient.
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+namespace w2v2 {
+
+int device_sm_count();
+
+static inline int grid_cap(int64_t blocks, int per_sm) {
+  const int64_t cap = int64_t(device_sm_count()) * per_sm;
+  return int(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// =================================================================================================
+// w [R, C] f32  ->  wT [C, ldt] f16 (transposed, columns >= R zero-filled up to ldt), optional row scale
+__global__ void cast_f16_transpose_kernel(const float* __restrict__ w, __half* __restrict__ wt, int R, int C, int ldt,
+                                          const float* __restrict__ row_scale) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) v = w[int64_t(r) * C + c] * (row_scale != nullptr ? row_scale[r] : 1.0f);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < ldt) wt[int64_t(c) * ldt + r] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// =================================================================================================
+// LayerNorm backward.  x = xa (+ bias) (+ residual) is recomputed (as are mean / rstd), so the forward
+// saves nothing extra.  dy = dy_a (+ dy_b).  Outputs dx (f32) and/or dx16 (f16);
+// dgamma / dbeta are accumulated with one atomicAdd per column per block.
+template <bool XA_F32>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy_a, const float* __restrict__ dy_b,
+                                                            const void* __restrict__ xa_, const float* __restrict__ bias,
+                                                            const float* __restrict__ residual,
+                                                            const float* __restrict__ gamma, float eps,
+                                                            float* __restrict__ dx32, __half* __restrict__ dx16,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int64_t rows, int H) {
+  constexpr int MAXV = 8;                       // H <= 1024
+  __shared__ float sred[8][1024];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 ag[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  const int64_t wstride = int64_t(gridDim.x) * 8;
+  for (int64_t row = int64_t(blockIdx.x) * 8 + warp; row < rows; row += wstride) {
+    float4 x[MAXV], d[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < H) {
+        float4 a;
+        if constexpr (XA_F32) {
+          a = *reinterpret_cast<const float4*>(static_cast<const float*>(xa_) + row * H + c);
+        } else {
+          const uint2 q = *reinterpret_cast<const uint2*>(static_cast<const __half*>(xa_) + row * H + c);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+          a = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        if (bias != nullptr) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+        }
+        if (residual != nullptr) {
+          const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
+          a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        }
+        x[i] = a;
+        sum += (a.x + a.y) + (a.z + a.w);
+        float4 g = *reinterpret_cast<const float4*>(dy_a + row * H + c);
+        if (dy_b != nullptr) {
+          const float4 g2 = *reinterpret_cast<const float4*>(dy_b + row * H + c);
+          g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+        }
+        d[i] = g;
+      }
+    }
+    const float mean = warp_sum(sum) / float(H);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < H) {
+        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+        sq += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / float(H) + eps);
+    // xhat = x * rstd ; g = dy * gamma ; dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < H) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        x[i].x *= rstd; x[i].y *= rstd; x[i].z *= rstd; x[i].w *= rstd;
+        ag[i].x += d[i].x * x[i].x; ag[i].y += d[i].y * x[i].y; ag[i].z += d[i].z * x[i].z; ag[i].w += d[i].w * x[i].w;
+        ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+        d[i].x *= gm.x; d[i].y *= gm.y; d[i].z *= gm.z; d[i].w *= gm.w;
+        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s2 += (d[i].x * x[i].x + d[i].y * x[i].y) + (d[i].z * x[i].z + d[i].w * x[i].w);
+      }
+    }
+    s1 = warp_sum(s1) / float(H);
+    s2 = warp_sum(s2) / float(H);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < H) {
+        float4 o;
+        o.x = rstd * (d[i].x - s1 - x[i].x * s2);
+        o.y = rstd * (d[i].y - s1 - x[i].y * s2);
+        o.z = rstd * (d[i].z - s1 - x[i].z * s2);
+        o.w = rstd * (d[i].w - s1 - x[i].w * s2);
+        if (dx32 != nullptr) *reinterpret_cast<float4*>(dx32 + row * H + c) = o;
+        if (dx16 != nullptr) {
+          uint2 q;
+          q.x = pack_half2(o.x, o.y);
+          q.y = pack_half2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx16 + row * H + c) = q;
+        }
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  // block reduction of the per-warp column sums, one atomic per column per block (gamma, then beta)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < H) *reinterpret_cast<float4*>(&sred[warp][c]) = pass == 0 ? ag[i] : ab[i];
+    }
+    __syncthreads();
+    if (dst != nullptr) {
+      for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sred[w][c];
+        atomicAdd(dst + c, t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =================================================================================================
+// dz = dg * gelu'(z)  (f16 in / f16 out), gelu'(z) = Phi(z) + z * phi(z)
+__device__ __forceinline__ float gelu_grad(float z) {
+  const float a = fabsf(z);
+  const float u = fmaf(fminf(a, W2V2_GELU_A), 2.0f / W2V2_GELU_A, -1.0f);
+  float q = fmaf(W2V2_GELU_C8, u, W2V2_GELU_C7);
+  q = fmaf(q, u, W2V2_GELU_C6);
+  q = fmaf(q, u, W2V2_GELU_C5);
+  q = fmaf(q, u, W2V2_GELU_C4);
+  q = fmaf(q, u, W2V2_GELU_C3);
+  q = fmaf(q, u, W2V2_GELU_C2);
+  q = fmaf(q, u, W2V2_GELU_C1);
+  q = fmaf(q, u, W2V2_GELU_C0);
+  const float tail = fast_ex2(q);                                   // Phi(-|z|)
+  const float cdf = z >= 0.f ? 1.0f - tail : tail;
+  const float pdf = 0.3989422804014327f * fast_ex2(z * z * -0.72134752044448170f);
+  return fmaf(z, pdf, cdf);
+}
+
+__global__ void gelu_bwd_kernel(const __half* __restrict__ dg, const __half* __restrict__ z, __half* __restrict__ dz,
+                                int64_t n) {
+  int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    const uint4 a = *reinterpret_cast<const uint4*>(dg + i);
+    const uint4 b = *reinterpret_cast<const uint4*>(z + i);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    uint4 o;
+    uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = __half22float2(ah[j]);
+      const float2 zz = __half22float2(bh[j]);
+      oo[j] = pack_half2(g.x * gelu_grad(zz.x), g.y * gelu_grad(zz.y));
+    }
+    *reinterpret_cast<uint4*>(dz + i) = o;
+  }
+}
+
+// =================================================================================================
+// out[c] += sum_r x[r, c] * scale   (bias gradients).  x f16 or f32 [rows, ld]; one atomic / column / block
+template <bool X_F32>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_, int64_t rows, int cols, int64_t ld,
+                                                     float scale, float* __restrict__ out) {
+  // block = 32 column-lanes x 8 row-lanes; blockIdx.x = column block (32 cols), blockIdx.y = row slab
+  __shared__ float sm[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < cols) {
+    for (int64_t r = int64_t(blockIdx.y) * 8 + rl; r < rows; r += int64_t(gridDim.y) * 8) {
+      if constexpr (X_F32) s += static_cast<const float*>(x_)[r * ld + c];
+      else s += __half2float(static_cast<const __half*>(x_)[r * ld + c]);
+    }
+  }
+  sm[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][cl];
+    atomicAdd(out + c, t * scale);
+  }
+}
+
+// =================================================================================================
+// softmax cross-entropy backward (mean reduction): dlogits = (prob - onehot) * (loss_scale / B)
+// written as the fp16 operand [B, ldd] (columns >= S zero-filled).
+__global__ void softmax_ce_bwd_kernel(const float* __restrict__ prob, const int64_t* __restrict__ labels, float coef,
+                                      __half* __restrict__ dl, int S, int ldd) {
+  const int b = blockIdx.x;
+  const int label = int(labels[b]);
+  for (int i = threadIdx.x; i < ldd; i += blockDim.x) {
+    float v = 0.f;
+    if (i < S) v = (prob[int64_t(b) * S + i] - (i == label ? 1.0f : 0.0f)) * coef;
+    dl[int64_t(b) * ldd + i] = __float2half_rn(v);
+  }
+}
+
+// mean pooling backward: dh[b, t, :] = demb[b, :] / T
+__global__ void mean_pool_bwd_kernel(const float* __restrict__ demb, float* __restrict__ dh, int T, int H) {
+  const int b = blockIdx.y;
+  const int64_t n = int64_t(T) * H;
+  const float inv = 1.0f / float(T);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    dh[int64_t(b) * n + i] = demb[int64_t(b) * H + (i % H)] * inv;
+}
+
+// =================================================================================================
+// Adam (torch.optim.Adam semantics, weight_decay = 0, amsgrad = False) over a flat fp32 parameter
+// buffer: p -= lr * m_hat / (sqrt(v_hat) + eps); the gradient carries the loss scale (grad_scale = 1/scale).
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                            float bc1, float bc2, float grad_scale) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * grad_scale;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] -= (lr / bc1) * mi / denom;
+  }
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" {
+
+int w2v2_cast_f16_transpose(const float* w, void* wt16, int R, int C, int ldt, const float* row_scale, void* stream) {
+  W2V2_REQUIRE(R > 0 && C > 0 && ldt >= R, "w2v2_cast_f16_transpose: bad shape R=%d C=%d ldt=%d", R, C, ldt);
+  dim3 grid((C + 31) / 32, (ldt + 31) / 32), block(32, 8);
+  cast_f16_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (__half*)wt16, R, C, ldt, row_scale);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
+                       const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
+                       float* dbeta, int64_t rows, int H, void* stream) {
+  W2V2_REQUIRE(H % 4 == 0 && H <= 1024, "w2v2_layernorm_bwd: H=%d must be a multiple of 4 and <= 1024", H);
+  if (rows == 0) return 0;
+  const int grid = grid_cap((rows + 7) / 8, 4);
+  if (xa_dtype == 1)
+    layernorm_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32,
+                                                                        (__half*)dx16, dgamma, dbeta, rows, H);
+  else
+    layernorm_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32,
+                                                                         (__half*)dx16, dgamma, dbeta, rows, H);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void* stream) {
+  W2V2_REQUIRE(n % 8 == 0, "w2v2_gelu_bwd: n=%lld must be a multiple of 8", (long long)n);
+  if (n == 0) return 0;
+  gelu_bwd_kernel<<<grid_cap((n / 8 + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>((const __half*)dg16, (const __half*)z16,
+                                                                                     (__half*)dz16, n);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_colsum(const void* x, int x_dtype, int64_t rows, int cols, int64_t ld, float scale, float* out, void* stream) {
+  if (rows == 0) return 0;
+  dim3 grid((cols + 31) / 32, (unsigned)grid_cap((rows + 63) / 64, 1));
+  if (grid.y > 64) grid.y = 64;
+  if (x_dtype == 1) colsum_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, scale, out);
+  else colsum_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, scale, out);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_softmax_ce_bwd(const float* prob, const int64_t* labels, float coef, void* dlogits16, int B, int S, int ldd,
+                        void* stream) {
+  W2V2_REQUIRE(ldd >= S, "w2v2_softmax_ce_bwd: ldd=%d < S=%d", ldd, S);
+  softmax_ce_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(prob, labels, coef, (__half*)dlogits16, S, ldd);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_mean_pool_bwd(const float* demb, float* dh, int B, int T, int H, void* stream) {
+  dim3 grid((unsigned)grid_cap((int64_t(T) * H + 255) / 256, 2), B);
+  mean_pool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(demb, dh, T, H);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   int step, float grad_scale, void* stream) {
+  W2V2_REQUIRE(step >= 1, "w2v2_adam_step: step counts from 1");
+  const float bc1 = 1.0f - powf(beta1, float(step));
+  const float bc2 = 1.0f - powf(beta2, float(step));
+  adam_kernel<<<grid_cap((n + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2,
+                                                                             grad_scale);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -122,11 +122,84 @@ def posconv(x16: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, groups: in
     return out
 
 
-def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int) -> torch.Tensor:
+def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, want_lse: bool = False):
+    """-> out f16 [B*T, H]  (and lse f32 [B, heads, T] when want_lse, for the backward pass)."""
     _chk(qkv16, F16, "qkv16")
     out = torch.empty(B * T, H, dtype=F16, device=qkv16.device)
-    call("w2v2_attention", ptr(qkv16), ptr(out), B, T, H, heads, stream_ptr())
+    lse = torch.empty(B, heads, T, dtype=F32, device=qkv16.device) if want_lse else None
+    call("w2v2_attention", ptr(qkv16), ptr(out), ptr(lse), B, T, H, heads, stream_ptr())
+    return (out, lse) if want_lse else out
+
+
+# ---- backward ------------------------------------------------------------------------------------
+
+
+def attention_bwd(qkv16, o16, do16, lse, B: int, T: int, H: int, heads: int) -> torch.Tensor:
+    dqkv = torch.empty(B * T, 3 * H, dtype=F16, device=qkv16.device)
+    call("w2v2_attention_bwd", ptr(qkv16), ptr(o16), ptr(do16), ptr(lse), ptr(dqkv), B, T, H, heads, stream_ptr())
+    return dqkv
+
+
+def gemm_wgrad_f16(dy16: torch.Tensor, x16: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+    """dw[N,K] (f32, accumulated) += dy16[M,N]^T @ x16[M,K]."""
+    _chk(dy16, F16, "dy16"); _chk(x16, F16, "x16"); _chk(dw, F32, "dw")
+    M, N = dy16.shape
+    K = x16.shape[1]
+    assert x16.shape[0] == M and tuple(dw.shape) == (N, K)
+    call("w2v2_gemm_wgrad_f16", ptr(dy16), dy16.stride(0), ptr(x16), x16.stride(0), M, N, K, ptr(dw), dw.stride(0),
+         stream_ptr())
+    return dw
+
+
+def cast_f16_transpose(w: torch.Tensor, ldt: Optional[int] = None, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """w f32 [R,C] -> f16 [C, ldt] (transposed; ldt >= R, zero padded; multiple of 8)."""
+    R, C = w.shape
+    ldt = ldt or (R + 63) // 64 * 64
+    out = torch.empty(C, ldt, dtype=F16, device=w.device)
+    call("w2v2_cast_f16_transpose", ptr(w.contiguous()), ptr(out), R, C, ldt, ptr(row_scale), stream_ptr())
     return out
+
+
+def layernorm_bwd(dy_a, xa, gamma, eps=1e-5, dy_b=None, bias=None, residual=None, dgamma=None, dbeta=None,
+                  want32=True, want16=True):
+    H = xa.shape[-1]
+    rows = xa.numel() // H
+    dx32 = torch.empty(rows, H, dtype=F32, device=xa.device) if want32 else None
+    dx16 = torch.empty(rows, H, dtype=F16, device=xa.device) if want16 else None
+    call("w2v2_layernorm_bwd", ptr(dy_a), ptr(dy_b), ptr(xa), 1 if xa.dtype == F32 else 0, ptr(bias), ptr(residual),
+         ptr(gamma), eps, ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, H, stream_ptr())
+    return dx32, dx16
+
+
+def gelu_bwd(dg16, z16):
+    dz = torch.empty_like(dg16)
+    call("w2v2_gelu_bwd", ptr(dg16), ptr(z16), ptr(dz), dg16.numel(), stream_ptr())
+    return dz
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    rows, cols = x.shape
+    call("w2v2_colsum", ptr(x), 1 if x.dtype == F32 else 0, rows, cols, x.stride(0), float(scale), ptr(out), stream_ptr())
+    return out
+
+
+def softmax_ce_bwd(prob, labels, coef: float, ldd: int):
+    B, S = prob.shape
+    dl = torch.empty(B, ldd, dtype=F16, device=prob.device)
+    call("w2v2_softmax_ce_bwd", ptr(prob), ptr(labels), float(coef), ptr(dl), B, S, ldd, stream_ptr())
+    return dl
+
+
+def mean_pool_bwd(demb, T: int):
+    B, H = demb.shape
+    dh = torch.empty(B, T, H, dtype=F32, device=demb.device)
+    call("w2v2_mean_pool_bwd", ptr(demb.contiguous()), ptr(dh), B, T, H, stream_ptr())
+    return dh
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step: int, grad_scale: float = 1.0):
+    call("w2v2_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         int(step), float(grad_scale), stream_ptr())
 
 
 def stat_pool(x: torch.Tensor, mode: int) -> torch.Tensor:
