@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the hot path (BASELINE.json metric: utterances/sec, 3 s @ 16 kHz, wav2vec2-base).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference path on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W [--mode train|forward]   # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...                # the reference path on the host CPU cores
 
-One "step" = one eval-mode pass of the hot path over one synthetic batch of 64 utterances per GPU:
-waveform -> wav2vec2-base encoder -> mean pool -> Linear(768->5994) -> softmax / CE / argmax
-(configs[1] of BASELINE.json), through the public module call
-``Wav2vec2FCModule.forward`` + ``loss_fn`` (w2v2_speaker_b200/speaker_module.py).
+Workload = configs[1] of BASELINE.json: wav2vec2-base + mean pool + Linear(768->5994) + CE on synthetic
+3 s utterances, 64 per GPU, driven through the public module API (w2v2_speaker_b200/speaker_module.py).
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` =
-the same call with pinned-host inputs (H2D inside the timed region) and the results (embedding, loss,
-argmax) read back to the host every step.  `roofline` aggregates every launch of the dominant kernel
-(the tcgen05 tap-GEMM) of one step; `roofline_hbm` does the same for the HBM-bound conv0+GroupNorm+GELU
-kernel; `cpu_baseline` times the CPU oracle (a torch-fp32 port of the reference path) on a bounded sample.
-Multi-GPU: one process per GPU (torchrun), utterances are independent so ranks shard the batch with no
-data-path collective (eval forward; weak scaling), timing is the max over ranks on the device.
+  --mode train   (default) one step = forward + backward + gradient all-reduce (N > 1) + Adam update
+                 (w2v2_speaker_b200/trainer.py); CNN feature extractor frozen as in the reference default
+                 (R:config/network/wav2vec2_fc.yaml:16), regularisation probabilities 0 (the stochastic
+                 dropout / LayerDrop / SpecAugment kernels are not written yet -- stated in `config`).
+  --mode forward one step = eval-mode embedding + logits + softmax/CE.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` = the
+same call with pinned-host inputs (H2D inside the timed region) and loss / arg-max (and the embedding in
+forward mode) read back to the host every step.  `roofline` aggregates every tensor-core GEMM launch
+(forward tap-GEMM + dgrad + wgrad) of one step: FLOPs from the launch arguments / CUDA-event time;
+`roofline_hbm` is the HBM-bound conv0+GroupNorm+GELU stage; `cpu_baseline` times the CPU oracle (a
+torch-fp32 port of the reference path, same mode) on a bounded sample.
+Multi-GPU: one process per GPU (torchrun), pure data parallel over utterances (weak scaling); train mode
+all-reduces the flat fp32 gradient over NCCL, forward mode has no collective.  Time = max over ranks.
 """
 from __future__ import annotations
 
@@ -36,10 +41,20 @@ METRIC = "utterances/sec (3 s@16 kHz, w2v2-base)"
 NUM_SPEAKERS = 5994
 SAMPLES = 48000
 BATCH = 64
+DEFAULT_MODE = "train"
 
 
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def workload_name(mode: str) -> str:
+    if mode == "train":
+        return ("cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, TRAIN step = forward + "
+                "backward + grad all-reduce + Adam; CNN frozen (reference default), dropout/LayerDrop/SpecAugment "
+                "probabilities 0")
+    return ("cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, eval forward "
+            "(embedding + logits + softmax/loss)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -81,6 +96,7 @@ class ClockSampler:
             if sm:
                 out["sm_mhz"] = sm[len(sm) // 2]
                 out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             seen = set()
             for r in rows:
@@ -98,12 +114,27 @@ class ClockSampler:
 # CPU baseline: the oracle (torch-fp32 port of the reference path) on the host cores
 
 
-def cpu_reference_step_fn(batch: int):
+def cpu_reference_step_fn(batch: int, mode: str):
     from oracle import w2v2_oracle as O
     from oracle.params import BASE, make_head_params, make_inputs, make_params
     p = make_params(BASE, seed=0)
     hp = make_head_params(768, NUM_SPEAKERS, seed=1)
     wav, labels = make_inputs(batch, SAMPLES, NUM_SPEAKERS, seed=1234)
+    if mode == "train":
+        train = [k for k in p if not k.startswith("feature_extractor") and k != "masked_spec_embed"]
+        for k in train:
+            p[k].requires_grad_(True)
+        fw, fb = hp["fc.weight"].requires_grad_(True), hp["fc.bias"].requires_grad_(True)
+        opt = torch.optim.Adam([p[k] for k in train] + [fw, fb], lr=1e-4)
+
+        def step():
+            opt.zero_grad()
+            emb = O.speaker_embedding(wav, p, "mean")
+            logits, loss, sm = O.cross_entropy_head(emb, fw, fb, labels)
+            loss.backward()
+            opt.step()
+            return float(loss)
+        return step
 
     def step():
         with torch.no_grad():
@@ -114,13 +145,13 @@ def cpu_reference_step_fn(batch: int):
 
 
 def pick_cpu_threads() -> int:
-    """torch CPU ops do not always scale to every hardware thread of a large host: probe a few
-    thread counts on a small batch and keep the fastest (the baseline gets its best configuration)."""
+    """torch CPU ops do not always scale to every hardware thread of a large host: probe a few thread
+    counts on a small batch and keep the fastest (the baseline gets its best configuration)."""
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (cores, cores // 2, 64, 32, 16) if 1 <= c <= cores}, reverse=True)
     if len(cands) == 1:
         return cands[0]
-    probe = cpu_reference_step_fn(2)
+    probe = cpu_reference_step_fn(2, "forward")
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
@@ -133,10 +164,10 @@ def pick_cpu_threads() -> int:
     return best
 
 
-def time_cpu(batch: int, steps: int, warmup: int):
+def time_cpu(batch: int, steps: int, warmup: int, mode: str):
     cores = pick_cpu_threads()
     torch.set_num_threads(cores)
-    step = cpu_reference_step_fn(batch)
+    step = cpu_reference_step_fn(batch, mode)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -150,18 +181,17 @@ def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    batch = 8
-    steps = max(1, args.steps)
-    uts, ms, cores = time_cpu(batch, steps, max(1, min(args.warmup, 2)))
+    batch = 8 if args.mode == "forward" else 4
+    steps = max(1, min(args.steps, 10))
+    uts, ms, cores = time_cpu(batch, steps, 1, args.mode)
     line = {
         "impl": "reference", "metric": METRIC, "value": uts, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, eval forward "
-                               "(embedding + logits + loss)", "batch_per_step": batch, "device": "host CPU"},
+        "config": {"workload": workload_name(args.mode), "batch_per_step": batch, "device": "host CPU", "mode": args.mode},
         "cpu_baseline": {"value": uts, "unit": "utt/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps x {batch} utterances of 3 s (oracle/w2v2_oracle.py, torch fp32, "
-                                   f"{cores} threads)"},
+                                   f"{cores} threads, mode {args.mode})"},
         "e2e": {"value": uts, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,55 +203,51 @@ def run_reference_arm(args):
 # our arm
 
 
-def build_module(device):
+def build_module(device, train: bool):
     from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
     from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
     torch.manual_seed(0)
+    kw = dict(activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
+              mask_time_prob=0.0, mask_feature_prob=0.0) if train else {}
     cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id="facebook/wav2vec2-base", stat_pooling_type="mean",
-                                 test_stat_pooling_type="mean")
-    m = Wav2vec2FCModule(cfg, NUM_SPEAKERS, CrossEntropyLoss).to(device).eval()
+                                 test_stat_pooling_type="mean", **kw)
+    m = Wav2vec2FCModule(cfg, NUM_SPEAKERS, CrossEntropyLoss).to(device)
+    if train:
+        m.train()
+        m.wav2vec.model.feature_extractor.requires_grad_(False)       # R:.../wav2vec2_fc.py:346-347
+    else:
+        m.eval()
     return m
 
 
-def gemm_flops_table(batch):
-    """Algorithmic FLOPs of every tap-GEMM launch of one cfg1 forward."""
-    Ls = [9599, 4799, 2399, 1199, 599, 299, 149]
-    ks = [3, 3, 3, 3, 2, 2]
-    M = batch * 149
-    fl = []
-    for i, k in enumerate(ks):
-        fl.append(2.0 * batch * Ls[i + 1] * 512 * 512 * k)
-    fl.append(2.0 * M * 768 * 512)
-    for _ in range(12):
-        fl += [2.0 * M * 2304 * 768, 2.0 * M * 768 * 768, 2.0 * M * 3072 * 768, 2.0 * M * 768 * 3072]
-    fl.append(2.0 * batch * NUM_SPEAKERS * 3 * 768)     # split-3 classifier GEMM (executed flops, 3x algorithmic)
-    return fl
-
-
-def instrumented_step(module, wav, labels):
-    """One extra (untimed) step with CUDA events around every tap-GEMM / conv0 launch."""
+def instrumented(step_fn):
+    """One extra (untimed) step with CUDA events around every tensor-core GEMM launch and the conv0 stage;
+    FLOPs come from the launch arguments."""
     from w2v2_speaker_b200 import ops
     rec = {"gemm": [], "conv0": []}
     orig_call = ops.call
 
     def traced(name, *a):
-        if name in ("w2v2_gemm_f16", "w2v2_conv0_gn_gelu"):
+        if name in ("w2v2_gemm_f16", "w2v2_gemm_wgrad_f16", "w2v2_conv0_gn_gelu"):
             s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
             s.record()
             r = orig_call(name, *a)
             e.record()
-            rec["gemm" if name == "w2v2_gemm_f16" else "conv0"].append((s, e))
+            if name == "w2v2_gemm_f16":          # (A, rows, row_stride, batch_stride, batch, ntaps, tap_stride, cin, W, ldw, N, ...)
+                rec["gemm"].append((s, e, 2.0 * a[1] * a[4] * a[5] * a[7] * a[10]))
+            elif name == "w2v2_gemm_wgrad_f16":  # (dY, ldy, X, ldx, M, N, K, ...)
+                rec["gemm"].append((s, e, 2.0 * a[4] * a[5] * a[6]))
+            else:
+                rec["conv0"].append((s, e, 0.0))
             return r
         return orig_call(name, *a)
     ops.call = traced
     try:
-        with torch.no_grad():
-            emb, pred = module(wav)
-            module.loss_fn(pred, labels)
+        step_fn()
         torch.cuda.synchronize()
     finally:
         ops.call = orig_call
-    return {k: [s.elapsed_time(e) for s, e in v] for k, v in rec.items()}
+    return {k: [(s.elapsed_time(e), f) for s, e, f in v] for k, v in rec.items()}
 
 
 def main():
@@ -230,6 +256,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=DEFAULT_MODE, choices=["train", "forward"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -252,18 +279,29 @@ def main():
     from oracle.params import make_inputs
     B = args.batch
     K, W = args.steps, max(3, args.warmup)
-    module = build_module(dev)
+    train = args.mode == "train"
+    module = build_module(dev, train)
+    trainer = None
+    if train:
+        from w2v2_speaker_b200.trainer import FlatAdamTrainer
+        trainer = FlatAdamTrainer(module, lr=1e-4)
     wav_cpu, labels_cpu = make_inputs(B, SAMPLES, NUM_SPEAKERS, seed=1234 + rank)
     wav_pin = wav_cpu[:, None, :].contiguous().pin_memory()          # [B,1,N] as the reference batches
     labels_pin = labels_cpu.pin_memory()
     wav_dev = wav_pin.to(dev)
     labels_dev = labels_pin.to(dev)
 
-    def step_device():
+    def run(w, l):
+        if train:
+            loss, prob = trainer.step(w, l)
+            return None, loss, prob
         with torch.no_grad():
-            emb, pred = module(wav_dev)
-            loss, prob = module.loss_fn(pred, labels_dev)
+            emb, pred = module(w)
+            loss, prob = module.loss_fn(pred, l)
         return emb, loss, prob
+
+    def step_device():
+        return run(wav_dev, labels_dev)
 
     emb_host = torch.empty(B, 768, dtype=torch.float32).pin_memory()
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -272,10 +310,9 @@ def main():
     def step_e2e():
         w = wav_pin.to(dev, non_blocking=True)
         l = labels_pin.to(dev, non_blocking=True)
-        with torch.no_grad():
-            emb, pred = module(w)
-            loss, prob = module.loss_fn(pred, l)
-        emb_host.copy_(emb, non_blocking=True)
+        emb, loss, prob = run(w, l)
+        if emb is not None:
+            emb_host.copy_(emb, non_blocking=True)
         loss_host.copy_(loss.view(1), non_blocking=True)
         arg_host.copy_(prob.argmax(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the user reads the step's result on the host
@@ -314,7 +351,6 @@ def main():
     value = world * B * K / (total_ms / 1e3)
     e2e_value = world * B * K / (e2e_ms / 1e3)
 
-    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -325,37 +361,41 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json: cuBLAS bf16 sustained; fp16 runs at the same tensor rate)" \
             if peaks else "fallback (B200_PROFILING.md)"
-        t = instrumented_step(module, wav_dev, labels_dev)
-        fl = gemm_flops_table(B)
+        t = instrumented(step_device)
         roof = None
-        if len(t["gemm"]) == len(fl):
-            g_ms = sum(t["gemm"])
-            ach = sum(fl) / (g_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 tap-GEMM), all launches of one step",
+        if t["gemm"]:
+            g_ms = sum(x[0] for x in t["gemm"])
+            fl = sum(x[1] for x in t["gemm"])
+            ach = fl / (g_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel + gemm_wgrad_kernel (tcgen05), all launches of one step",
                     "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak, "traffic": None,
-                    "peak_source": peak_src, "launches": len(fl), "ms_per_step": g_ms}
-        c0_bytes = B * (SAMPLES * 4 * 2 + 9599 * 512 * 2)
+                    "peak_source": peak_src, "launches": len(t["gemm"]), "ms_per_step": g_ms, "tflop_per_step": fl / 1e12}
         roof_hbm = None
         if t["conv0"]:
-            c_ms = sum(t["conv0"])
+            c0_bytes = B * (SAMPLES * 4 * 2 + 9599 * 512 * 2)
+            c_ms = sum(x[0] for x in t["conv0"])
             ach = c0_bytes / (c_ms * 1e-3) / 1e9
-            roof_hbm = {"bound": "hbm", "kernel": "conv0+GroupNorm+GELU (3 launches)", "achieved": ach,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "ms_per_step": c_ms}
+            roof_hbm = {"bound": "hbm", "kernel": "conv0+GroupNorm+GELU stage (moments, stats, im2col, tensor-core GEMM "
+                        "with GN+GELU epilogue)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": None, "ms_per_step": c_ms}
         cpu = None
         if not args.no_cpu_baseline:
-            uts, ms, cores = time_cpu(8, 4, 1)
+            cb = 4 if train else 8
+            uts, ms, cores = time_cpu(cb, 2 if train else 4, 1, args.mode)
             cpu = {"value": uts, "unit": "utt/s", "cores": cores, "kind": "port",
-                   "sample": f"4 steps x 8 utterances of 3 s (oracle/w2v2_oracle.py, torch fp32, {cores} threads)"}
+                   "sample": f"{2 if train else 4} steps x {cb} utterances of 3 s (oracle/w2v2_oracle.py, torch fp32 "
+                             f"{'+ autograd + torch Adam' if train else ''}, {cores} threads)"}
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands / f32 accumulate+statistics", "data": "synthetic",
-            "config": {"workload": "cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, "
-                                   "eval forward (embedding + logits + softmax/loss)",
-                       "global_batch": world * B, "parallelism": f"dp{world} (independent utterances, no collective)",
-                       "l2": "per-step working set (~1.6 GB activations + 0.19 GB fp16 weights) >> 126 MB L2"},
+            "dtype": "f16 operands / f32 accumulate+statistics+master weights", "data": "synthetic",
+            "config": {"workload": workload_name(args.mode), "mode": args.mode, "global_batch": world * B,
+                       "parallelism": f"dp{world}" + (" (NCCL all-reduce of the flat fp32 gradient)" if train else
+                                                       " (independent utterances, no collective)"),
+                       "l2": "per-step working set (> 1.5 GB activations + 0.19 GB fp16 weights) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": B * SAMPLES * 4 + B * 8, "d2h_bytes_per_step": B * 768 * 4 + 4 + B * 8},
+                    "h2d_bytes_per_step": B * SAMPLES * 4 + B * 8,
+                    "d2h_bytes_per_step": (0 if train else B * 768 * 4) + 4 + B * 8},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
             "cpu_baseline": cpu,
         }

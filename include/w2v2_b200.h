@@ -71,11 +71,17 @@ int w2v2_posconv_taps_per_mma(int T, int H, int groups);
 /* Fold weight_norm (HF:340-358): w[o,i,k] = g[k] * v[o,i,k] / ||v[:,:,k]||, and re-lay it out as
  * fp16 [G][K/U][I/8][U][O][8] (per (group, tap group): a [U*O x I] K-major block in UMMA core-matrix
  * order).  w16 must have room for H*(H/groups)*K halfs followed by K floats of scratch (per-tap norms). */
-int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, int U, void* stream);
+int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, int U, int mode,
+                             void* stream);   /* mode 0: forward weight; 1: data-gradient weight (in/out swapped, taps reversed) */
 /* y[b,t,:] = GELU(conv1d(x, w, bias, pad=K/2, groups)[.., :T]) (HF:360-379); x f16 [B,T,H];
  * out f32 [B,T,H] (the encoder then does LN(h + y), fused in w2v2_layernorm via `residual`). */
 int w2v2_posconv(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H, int groups,
                  int K, void* stream);
+/* General form: act = 0 leaves out the GELU (training keeps the pre-activation), bias may be NULL,
+ * in_shift = s reads input frame t + s (zero beyond T).  With the mode-1 folded weight, act = 0,
+ * bias = NULL, in_shift = 1 this is the data gradient of the positional conv. */
+int w2v2_posconv_ex(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H, int groups,
+                    int K, int act, int in_shift, void* stream);
 
 /* ---- self-attention core ---------------------------------------------------------------------- */
 /* o = softmax(q k^T) v per (batch, head), no mask (HF:438-463; the 1/sqrt(d) scale is folded
@@ -146,10 +152,29 @@ int w2v2_softmax_ce_bwd(const float* prob, const int64_t* labels, float coef, vo
                         void* stream);
 /* mean pooling backward: dh[b,t,:] = demb[b,:] / T. */
 int w2v2_mean_pool_bwd(const float* demb, float* dh, int B, int T, int H, void* stream);
+/* y = GELU(x) as a standalone pass (training: the GEMM / posconv ran without the fused activation);
+ * x, y f16 (dtype 0) or f32 (1); x16_copy (may be NULL) receives the rounded pre-activation. */
+int w2v2_gelu_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* x16_copy, int64_t n, void* stream);
+/* Positional-conv weight gradient: X_g[(b,t), j*I + i] = x[b, t+j-K/2, g*I+i] (f16 [B*T, K*I]) for one
+ * group; the gradient of the folded weight is then w2v2_gemm_wgrad_f16(dz[:, g*O:(g+1)*O], X_g). */
+int w2v2_posconv_im2col(const void* x16, void* xg16, int B, int T, int H, int groups, int K, int g, void* stream);
+/* weight_norm backward (HF:340-358): dw f32 [H][K][I] (gradient of the folded weight, rows as produced by
+ * the wgrad above) -> dv [H,I,K] += ..., dg [K] += ...; scratch: 2K floats; scale multiplies both. */
+int w2v2_weight_norm_bwd(const float* dw_hki, const float* v, const float* g, float* scratch_2k, float scale, float* dv,
+                         float* dg, int H, int I, int K, void* stream);
 /* Attention backward (recomputes P from q, k and the saved log-sum-exp): qkv f16 [B*T, 3H], o f16 [B*T, H]
  * (forward output), d_o f16 [B*T, H], lse f32 [B, heads, T]  ->  dqkv f16 [B*T, 3H].  T <= 192. */
 int w2v2_attention_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B, int T,
                        int H, int heads, void* stream);
+/* Gradient plumbing: out = a + b (b may be NULL) as f32 and/or f16 (n % 4 == 0); row-wise f32 -> f16 cast
+ * with zero padding to ldy and a scale; in-place scale; f32 CE gradient (prob - onehot) * coef * dloss[0]
+ * (dloss may be NULL = 1). */
+int w2v2_add2_cast(const float* a, const float* b, float* out32, void* out16, int64_t n, void* stream);
+int w2v2_cast_f16_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int64_t rows, int cols, float scale,
+                       void* stream);
+int w2v2_scale_f32(float* x, int64_t n, float s, void* stream);
+int w2v2_softmax_ce_bwd_f32(const float* prob, const int64_t* labels, const float* dloss, float coef, float* dlogits,
+                            int B, int S, void* stream);
 /* torch.optim.Adam step (weight_decay 0) over flat fp32 buffers; `g` is multiplied by grad_scale first
  * (undoes the loss scale and applies the 1/world_size of the data-parallel mean). */
 int w2v2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -1,0 +1,102 @@
+"""GPU parity of the training step (forward + hand-written backward through torch.autograd) against
+autograd of the CPU oracle: loss within 1e-3, every parameter gradient within 1e-2 norm-wise
+(gradients under reduced-precision operands), CNN feature extractor frozen as in the
+reference default, regularisation probabilities 0."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+S = 5994
+
+
+def _module(base_params, pooling="mean"):
+    from oracle.params import make_head_params
+    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type=pooling, test_stat_pooling_type=pooling, activation_dropout=0.0,
+                                 attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
+                                 mask_time_prob=0.0, mask_feature_prob=0.0)
+    m = Wav2vec2FCModule(cfg, S, CrossEntropyLoss)
+    m.wav2vec.model.load_state_dict(base_params, strict=False)
+    head = make_head_params(768, S, seed=1)
+    with torch.no_grad():
+        m.fc_list[-1][0].weight.copy_(head["fc.weight"]); m.fc_list[-1][0].bias.copy_(head["fc.bias"])
+    m = m.cuda().train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)          # R:.../wav2vec2_fc.py:346-347
+    return m, head
+
+
+@pytest.mark.parametrize("B,N", [(2, 16000), (3, 11283)])
+def test_training_step_gradients_match_oracle_autograd(base_params, B, N):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle import w2v2_oracle as O
+    from oracle.params import BASE, make_inputs
+    wav, labels = make_inputs(B, N, S, seed=1234)
+    m, head = _module(base_params)
+    emb, pred = m(wav[:, None, :].cuda())
+    loss, prob = m.loss_fn(pred, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    torch.set_num_threads(8)
+    p = {k: v.clone().requires_grad_(not k.startswith("feature_extractor")) for k, v in base_params.items()}
+    fw = head["fc.weight"].clone().requires_grad_(True)
+    fb = head["fc.bias"].clone().requires_grad_(True)
+    ref_emb = O.speaker_embedding(wav, p, "mean")
+    _, ref_loss, _ = O.cross_entropy_head(ref_emb, fw, fb, labels)
+    ref_loss.backward()
+
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-3
+    got = dict(m.wav2vec.model.named_parameters())
+    worst = (0.0, None)
+    for k, v in p.items():
+        if k.startswith("feature_extractor") or k == "masked_spec_embed":
+            assert got[k].grad is None
+            continue
+        assert got[k].grad is not None, k
+        g, r = got[k].grad.detach().cpu().double(), v.grad.double()
+        if k.endswith("k_proj.bias"):
+            # softmax is invariant to a per-row constant, so the key-bias gradient is exactly 0 in exact
+            # arithmetic: both sides are rounding noise -> compare against the scale of the q-bias gradient
+            scale = p[k.replace("k_proj", "q_proj")].grad.double().norm()
+            assert g.norm() < 1e-2 * scale and r.norm() < 1e-2 * scale, k
+            continue
+        rel = ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
+        worst = max(worst, (rel, k))
+        assert rel < 1e-2, (k, rel)
+    lin = m.fc_list[-1][0]
+    for g, r, k in ((lin.weight.grad, fw.grad, "fc.weight"), (lin.bias.grad, fb.grad, "fc.bias")):
+        rel = ((g.cpu().double() - r.double()).norm() / r.double().norm()).item()
+        assert rel < 1e-2, (k, rel)
+    print("worst parameter-gradient error", worst)
+
+
+def test_torch_adam_step_reduces_loss(base_params):
+    """The drop-in contract: loss.backward() + a stock torch optimizer train the module."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle.params import make_inputs
+    wav, labels = make_inputs(4, 16000, S, seed=7)
+    m, _ = _module(base_params)
+    opt = torch.optim.Adam([q for q in m.parameters() if q.requires_grad], lr=1e-4)
+    x, y = wav[:, None, :].cuda(), labels.cuda()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        emb, pred = m(x)
+        loss, _ = m.loss_fn(pred, y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0]
+
+
+def test_unfrozen_cnn_and_regularisation_fail_loudly(base_params):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    m, _ = _module(base_params)
+    m.wav2vec.model.feature_extractor.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 1, 8000, device="cuda"))

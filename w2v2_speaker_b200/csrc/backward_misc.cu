@@ -1,0 +1,101 @@
+// Small elementwise helpers of the backward pass (gradient plumbing between the tensor-core kernels).
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+namespace w2v2 {
+
+int device_sm_count();
+static inline int mgrid(int64_t n, int per_block, int per_sm) {
+  int64_t g = (n + per_block - 1) / per_block;
+  const int64_t cap = int64_t(device_sm_count()) * per_sm;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// out16 / out32 = a + b   (b may be NULL); n % 4 == 0
+__global__ void add2_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o32,
+                                 __half* __restrict__ o16, int64_t n) {
+  int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
+  for (; i < n; i += stride) {
+    float4 x = *reinterpret_cast<const float4*>(a + i);
+    if (b != nullptr) {
+      const float4 y = *reinterpret_cast<const float4*>(b + i);
+      x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    }
+    if (o32 != nullptr) *reinterpret_cast<float4*>(o32 + i) = x;
+    if (o16 != nullptr) {
+      uint2 q;
+      q.x = pack_half2(x.x, x.y);
+      q.y = pack_half2(x.z, x.w);
+      *reinterpret_cast<uint2*>(o16 + i) = q;
+    }
+  }
+}
+
+// y16[r, 0:ldy] = half(x[r, 0:cols] * scale), zero filled to ldy
+__global__ void cast_f16_rows_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
+                                     int64_t rows, int cols, float scale) {
+  const int64_t n = rows * ldy;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ldy;
+    const int c = int(i % ldy);
+    y[i] = __float2half_rn(c < cols ? x[r * ldx + c] * scale : 0.f);
+  }
+}
+
+__global__ void scale_f32_kernel(float* __restrict__ x, int64_t n, float s) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) x[i] *= s;
+}
+
+// dlogits (f32) = (prob - onehot) * coef
+__global__ void softmax_ce_bwd_f32_kernel(const float* __restrict__ prob, const int64_t* __restrict__ labels,
+                                          const float* __restrict__ coef_ptr, float coef, float* __restrict__ dl, int S) {
+  const int b = blockIdx.x;
+  const int label = int(labels[b]);
+  const float c = coef * (coef_ptr != nullptr ? coef_ptr[0] : 1.0f);
+  for (int i = threadIdx.x; i < S; i += blockDim.x)
+    dl[int64_t(b) * S + i] = (prob[int64_t(b) * S + i] - (i == label ? 1.0f : 0.0f)) * c;
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" {
+
+int w2v2_add2_cast(const float* a, const float* b, float* out32, void* out16, int64_t n, void* stream) {
+  W2V2_REQUIRE(n % 4 == 0, "w2v2_add2_cast: n=%lld must be a multiple of 4", (long long)n);
+  if (n == 0) return 0;
+  add2_cast_kernel<<<mgrid(n / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(a, b, out32, (__half*)out16, n);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_cast_f16_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int64_t rows, int cols, float scale,
+                       void* stream) {
+  W2V2_REQUIRE(ldy >= cols, "w2v2_cast_f16_rows: ldy < cols");
+  if (rows == 0) return 0;
+  cast_f16_rows_kernel<<<mgrid(rows * ldy, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, (__half*)y16, ldy, rows, cols, scale);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_scale_f32(float* x, int64_t n, float s, void* stream) {
+  if (n == 0) return 0;
+  scale_f32_kernel<<<mgrid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, n, s);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_softmax_ce_bwd_f32(const float* prob, const int64_t* labels, const float* dloss, float coef, float* dlogits,
+                            int B, int S, void* stream) {
+  softmax_ce_bwd_f32_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(prob, labels, dloss, coef, dlogits, S);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -511,7 +511,8 @@ __global__ void posconv_norm_kernel(const float* __restrict__ v, float* __restri
   if (threadIdx.x == 0) norm[k] = sqrtf(s);
 }
 __global__ void posconv_fold_kernel(const float* __restrict__ v, const float* __restrict__ g,
-                                    const float* __restrict__ norm, __half* __restrict__ w16, int H, int G, int K, int U) {
+                                    const float* __restrict__ norm, __half* __restrict__ w16, int H, int G, int K, int U,
+                                    int mode) {
   // w16[grp][j'][c][u][o][e] = g[k] * v[grp*O + o][c*8 + e][k] / norm[k],  k = U*j' + u   (O = I = H/G)
   // = per (group, tap group j') a [U*O x I] K-major block already in UMMA no-swizzle core-matrix order
   // (planes of U*O rows x 16 bytes), so posconv.cu can stream it with a flat bulk copy.
@@ -524,10 +525,18 @@ __global__ void posconv_fold_kernel(const float* __restrict__ v, const float* __
     const int c = (idx / (8 * int64_t(O) * U)) % (I / 8);
     const int jp = (idx / (int64_t(I) * O * U)) % (K / U);
     const int grp = idx / (int64_t(I) * O * K);
-    const int k = U * jp + u;
-    const float val = v[(int64_t(grp * O + o) * I + c * 8 + e) * K + k] * (g[k] / norm[k]);
+    // mode 0: forward weight.  mode 1: data-gradient weight = in/out channels swapped, taps reversed
+    //         (dx[s,i] = sum_{j',o} dz[s + j' + 1 - K/2, o] * w[o, i, K-1-j'];  the +1 is posconv's in_shift)
+    const int k = mode == 0 ? U * jp + u : K - 1 - (U * jp + u);
+    const int oo = mode == 0 ? o : c * 8 + e;
+    const int ii = mode == 0 ? c * 8 + e : o;
+    const float val = v[(int64_t(grp * O + oo) * I + ii) * K + k] * (g[k] / norm[k]);
     w16[idx] = __float2half_rn(val);
   }
+}
+
+void posconv_tap_norms(const float* v, float* norm, int H, int I, int K, cudaStream_t stream) {
+  posconv_norm_kernel<<<K, 256, 0, stream>>>(v, norm, H, I, K);
 }
 
 static inline int grid_for(int64_t n, int per_block) {
@@ -710,7 +719,8 @@ int w2v2_mean_rows(const float* x, float* out, int n, void* stream) {
   return 0;
 }
 
-int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, int U, void* stream_) {
+int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, int groups, int K, int U, int mode,
+                             void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   // scratch for the K norms: reuse the head of w16?  No -- keep a tiny static device buffer per call site:
   // the caller passes w16 sized H*(H/groups)*K halfs + K floats; norms live behind the weights.
@@ -718,7 +728,7 @@ int w2v2_posconv_fold_weight(const float* v, const float* g, void* w16, int H, i
   posconv_norm_kernel<<<K, 256, 0, stream>>>(v, norm, H, H / groups, K);
   const int64_t n = int64_t(H) * (H / groups) * K;
   W2V2_REQUIRE(U >= 1 && K % U == 0, "w2v2_posconv_fold_weight: taps per MMA U=%d must divide K=%d", U, K);
-  posconv_fold_kernel<<<grid_for(n, 256), 256, 0, stream>>>(v, g, norm, (__half*)w16, H, groups, K, U);
+  posconv_fold_kernel<<<grid_for(n, 256), 256, 0, stream>>>(v, g, norm, (__half*)w16, H, groups, K, U, mode);
   count_launches(2);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -36,6 +36,7 @@ struct PosconvParams {
   float* out;           // [B, T, H]
   int B, T, H, G, K, I, O, U;
   int ntiles, R;        // M tiles (128 rows), slab rows
+  int act, in_shift;    // apply GELU in the epilogue; slab row s holds input frame s - 64 + in_shift
   int tmem_cols;
 };
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(PC_THREADS, 2) posconv_kernel(const PosconvPar
     for (int idx = threadIdx.x; idx < total; idx += PC_THREADS) {
       const int s = idx % R, c = idx / R;
       uint4 v = make_uint4(0, 0, 0, 0);
-      const int t = s - PC_PAD;
+      const int t = s - PC_PAD + p.in_shift;
       if (t >= 0 && t < p.T)
         v = *reinterpret_cast<const uint4*>(p.x + (int64_t(b) * p.T + t) * p.H + g * I + c * 8);
       *reinterpret_cast<uint4*>(slab + c * plane_bytes + s * 16) = v;
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(PC_THREADS, 2) posconv_kernel(const PosconvPar
         float acc[PC_CHUNK];
 #pragma unroll
         for (int q = 0; q < PC_CHUNK; q += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + g * O + c0 + q));
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + g * O + c0 + q));
           acc[q] = bb.x; acc[q + 1] = bb.y; acc[q + 2] = bb.z; acc[q + 3] = bb.w;
         }
         for (int u = 0; u < U; ++u) {
@@ -176,7 +178,8 @@ __global__ void __launch_bounds__(PC_THREADS, 2) posconv_kernel(const PosconvPar
           }
         }
 #pragma unroll
-        for (int q = 0; q < PC_CHUNK; q += 2) gelu_erf2(acc[q], acc[q + 1]);
+        for (int q = 0; q < PC_CHUNK; q += 2)
+          if (p.act) gelu_erf2(acc[q], acc[q + 1]);
         float* dst = p.out + (int64_t(b) * p.T + t) * p.H + g * O + c0;
 #pragma unroll
         for (int q = 0; q < PC_CHUNK; q += 4)
@@ -221,8 +224,8 @@ extern "C" int w2v2_posconv_taps_per_mma(int T, int H, int groups) {
   return posconv_plan(T, H, groups, nullptr);
 }
 
-extern "C" int w2v2_posconv(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H,
-                            int groups, int K, void* stream_) {
+extern "C" int w2v2_posconv_ex(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H,
+                               int groups, int K, int act, int in_shift, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(groups > 0 && H % groups == 0, "w2v2_posconv: H=%d not divisible by groups=%d", H, groups);
   const int I = H / groups, O = H / groups;
@@ -237,6 +240,7 @@ extern "C" int w2v2_posconv(const void* x16, const void* w16, const float* bias,
   p.bias = bias;
   p.out = out;
   p.B = B; p.T = T; p.H = H; p.G = groups; p.K = K; p.I = I; p.O = O; p.U = U;
+  p.act = act; p.in_shift = in_shift;
   p.R = (p.ntiles * 128 + K + 7) / 8 * 8;
   const int ring = PC_STAGES * U * O * I * 2;
   const int cbuf = U * p.ntiles * 128 * PC_ROWF * 4;
@@ -255,4 +259,9 @@ extern "C" int w2v2_posconv(const void* x16, const void* w16, const float* bias,
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int w2v2_posconv(const void* x16, const void* w16, const float* bias, float* out, int B, int T, int H,
+                            int groups, int K, void* stream) {
+  return w2v2_posconv_ex(x16, w16, bias, out, B, T, H, groups, K, 1, 0, stream);
 }

@@ -23,6 +23,9 @@ class SpeakerLinear(nn.Linear):
         if self._w_split is None or sig != self._w_sig:
             self._w_split = ops.split3_rows(self.weight.detach().float(), 1)
             self._w_sig = sig
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            from ..training import SpeakerLinearFn
+            return SpeakerLinearFn.apply(x, self.weight, self.bias, self._w_split)
         xa = ops.split3_rows(x.detach().float().contiguous(), 0)
         b = self.bias.detach().float() if self.bias is not None else None
         return ops.gemm_f16(xa, self._w_split, b, 0, torch.float32)

@@ -35,7 +35,11 @@ class MeanStatPool1D(nn.Module):
         self.dim_to_reduce = dim_to_reduce
 
     def forward(self, tensor: torch.Tensor):
-        return ops.stat_pool(_as_btc(tensor, self.dim_to_reduce), 0)
+        x = _as_btc(tensor, self.dim_to_reduce)
+        if torch.is_grad_enabled() and x.requires_grad:
+            from ..training import MeanPoolFn
+            return MeanPoolFn.apply(x)
+        return ops.stat_pool(x, 0)
 
 
 class MeanStdStatPool1D(nn.Module):
@@ -46,7 +50,10 @@ class MeanStdStatPool1D(nn.Module):
         self.dim_to_reduce = dim_to_reduce
 
     def forward(self, tensor: torch.Tensor):
-        return ops.stat_pool(_as_btc(tensor, self.dim_to_reduce), 1)
+        x = _as_btc(tensor, self.dim_to_reduce)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the backward of mean+std pooling is not implemented yet (mean pooling is)")
+        return ops.stat_pool(x, 1)
 
 
 class MaxPool1D(nn.Module):
@@ -96,9 +103,9 @@ class _AttentiveStatisticsPooling(nn.Module):
         return self.forward_btc(x_ncl.transpose(1, 2).contiguous()).unsqueeze(2)
 
     def forward_btc(self, x: torch.Tensor) -> torch.Tensor:
-        if self.training:
-            raise NotImplementedError("attentive pooling with batch-statistics BatchNorm (train mode) is not "
-                                      "implemented in the sm_100a path yet; call .eval()")
+        if self.training or (torch.is_grad_enabled() and x.requires_grad):
+            raise NotImplementedError("attentive pooling in training (batch-statistics BatchNorm, backward) is not "
+                                      "implemented in the sm_100a path yet; call .eval() under torch.no_grad()")
         B, T, C = x.shape
         x = x.float().contiguous()
         c1, bn, c2 = self.tdnn.conv.conv, self.tdnn.norm.norm, self.conv.conv

@@ -139,6 +139,16 @@ class Wav2Vec2ModelB200(nn.Module):
             self._prepared_sig = sig
         return self._prepared
 
+    def _train_weights(self, eng: EncoderEngine):
+        """Transposed fp16 weight copies for the data-gradient GEMMs, cached per prepared weight set."""
+        from ..training import TrainWeights
+        if getattr(eng, "_train_weights", None) is None:
+            eng._train_weights = TrainWeights(eng.w, dict(self.named_parameters()))
+        return eng._train_weights
+
+    def _needs_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def _check_mode(self):
         r = self.reg_cfg
         stochastic = (r.activation_dropout + r.attention_dropout + r.feat_proj_dropout + r.hidden_dropout +
@@ -147,12 +157,23 @@ class Wav2Vec2ModelB200(nn.Module):
             raise NotImplementedError(
                 "training-mode regularisation (dropout / LayerDrop / SpecAugment) is not implemented in the "
                 "sm_100a path yet; call .eval() or zero the probabilities (SURVEY Appendix A Q10)")
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the backward kernels are not part of this round: run under torch.no_grad()")
+        if self._needs_grad() and any(p.requires_grad for p in self.feature_extractor.parameters()):
+            raise NotImplementedError(
+                "the backward of the CNN feature extractor is not implemented yet: freeze it with "
+                "model.feature_extractor.requires_grad_(False) (the reference default, "
+                "completely_freeze_feature_extractor: true)")
 
     def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, **_):
-        """HF:1327-1383 (eval).  input_values f32 [B,N]."""
+        """HF:1327-1383.  input_values f32 [B,N].  With gradients enabled the forward keeps what the
+        hand-written backward needs (training.EncoderFn) so that loss.backward() works."""
         self._check_mode()
+        if self._needs_grad():
+            if output_hidden_states:
+                raise NotImplementedError("output_hidden_states is only available without gradients")
+            from ..training import EncoderFn
+            names = [n for n, _ in self.named_parameters()]
+            out = EncoderFn.apply(input_values.float(), self, names, *[p for _, p in self.named_parameters()])
+            return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         eng = self._engine()
         trace = {} if output_hidden_states else None
         out = eng.forward(input_values.float(), trace)

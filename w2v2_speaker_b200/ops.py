@@ -106,11 +106,12 @@ def posconv_taps_per_mma(T: int, H: int, groups: int) -> int:
     return u
 
 
-def posconv_fold_weight(v: torch.Tensor, g: torch.Tensor, groups: int, taps_per_mma: int) -> torch.Tensor:
+def posconv_fold_weight(v: torch.Tensor, g: torch.Tensor, groups: int, taps_per_mma: int, mode: int = 0) -> torch.Tensor:
+    """mode 0: forward weight; mode 1: data-gradient weight (in/out channels swapped, taps reversed)."""
     H, I, K = v.shape
     buf = torch.empty(H * I * K + 2 * K, dtype=F16, device=v.device)
     call("w2v2_posconv_fold_weight", ptr(v.contiguous()), ptr(g.contiguous()), ptr(buf), H, groups, K, taps_per_mma,
-         stream_ptr())
+         mode, stream_ptr())
     return buf
 
 
@@ -120,6 +121,35 @@ def posconv(x16: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, groups: in
     out = torch.empty(B, T, H, dtype=F32, device=x16.device)
     call("w2v2_posconv", ptr(x16), ptr(w16), ptr(bias), ptr(out), B, T, H, groups, K, stream_ptr())
     return out
+
+
+def posconv_ex(x16, w16, bias, groups: int, K: int, act: int, in_shift: int) -> torch.Tensor:
+    B, T, H = x16.shape
+    out = torch.empty(B, T, H, dtype=F32, device=x16.device)
+    call("w2v2_posconv_ex", ptr(x16), ptr(w16), ptr(bias), ptr(out), B, T, H, groups, K, act, in_shift, stream_ptr())
+    return out
+
+
+def gelu_fwd(x: torch.Tensor, out_dtype, want_x16: bool = False):
+    """-> (gelu(x) in out_dtype, f16 copy of x | None)."""
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    x16 = torch.empty(x.shape, dtype=F16, device=x.device) if want_x16 else None
+    call("w2v2_gelu_fwd", ptr(x), 1 if x.dtype == F32 else 0, ptr(y), 1 if out_dtype == F32 else 0, ptr(x16), x.numel(),
+         stream_ptr())
+    return y, x16
+
+
+def posconv_im2col(x16: torch.Tensor, groups: int, K: int, g: int, out: torch.Tensor) -> torch.Tensor:
+    B, T, H = x16.shape
+    call("w2v2_posconv_im2col", ptr(x16), ptr(out), B, T, H, groups, K, g, stream_ptr())
+    return out
+
+
+def weight_norm_bwd(dw_hki, v, g, scale, dv, dg):
+    H, I, K = v.shape
+    scratch = torch.empty(2 * K, dtype=F32, device=v.device)
+    call("w2v2_weight_norm_bwd", ptr(dw_hki), ptr(v), ptr(g), ptr(scratch), float(scale), ptr(dv), ptr(dg), H, I, K,
+         stream_ptr())
 
 
 def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, want_lse: bool = False):
@@ -279,3 +309,29 @@ def mean_rows(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(1, dtype=F32, device=x.device)
     call("w2v2_mean_rows", ptr(x), ptr(out), x.numel(), stream_ptr())
     return out[0]
+
+
+def add2_cast(a, b=None, want32=True, want16=True):
+    o32 = torch.empty_like(a) if want32 else None
+    o16 = torch.empty(a.shape, dtype=F16, device=a.device) if want16 else None
+    call("w2v2_add2_cast", ptr(a), ptr(b), ptr(o32), ptr(o16), a.numel(), stream_ptr())
+    return o32, o16
+
+
+def cast_f16_rows(x: torch.Tensor, ldy: int, scale: float = 1.0) -> torch.Tensor:
+    rows, cols = x.shape
+    y = torch.empty(rows, ldy, dtype=F16, device=x.device)
+    call("w2v2_cast_f16_rows", ptr(x), x.stride(0), ptr(y), ldy, rows, cols, float(scale), stream_ptr())
+    return y
+
+
+def scale_f32_(x: torch.Tensor, s: float):
+    call("w2v2_scale_f32", ptr(x), x.numel(), float(s), stream_ptr())
+    return x
+
+
+def softmax_ce_bwd_f32(prob, labels, dloss, coef: float):
+    B, S = prob.shape
+    dl = torch.empty(B, S, dtype=F32, device=prob.device)
+    call("w2v2_softmax_ce_bwd_f32", ptr(prob), ptr(labels), ptr(dloss), float(coef), ptr(dl), B, S, stream_ptr())
+    return dl

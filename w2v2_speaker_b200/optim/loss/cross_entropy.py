@@ -18,6 +18,9 @@ class CrossEntropyLoss(nn.Module):
         # logits [BATCH_SIZE, NUM_SPEAKERS] (unnormalised), label indexes [BATCH_SIZE] int64
         if logits.dim() != 2 or label_indexes.shape[0] != logits.shape[0]:
             raise ValueError("expected logits [BATCH_SIZE, NUM_SPEAKERS] and labels [BATCH_SIZE]")
+        if torch.is_grad_enabled() and logits.requires_grad:
+            from ...training import CrossEntropyFn
+            return CrossEntropyFn.apply(logits, label_indexes.to(torch.int64))
         logits = logits.float()
         if logits.stride(1) != 1:
             logits = logits.contiguous()

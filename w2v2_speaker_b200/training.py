@@ -1,0 +1,290 @@
+"""Training path: forward that keeps what the backward needs, the hand-scheduled backward over the
+sm_100a kernels, and the torch.autograd.Function wrappers that make ``loss.backward()`` work on the
+reference-facing modules (the reference trains through Lightning's automatic optimisation,
+R:src/lightning_modules/speaker/speaker_recognition_module.py:148-220).
+
+Scope of this round: wav2vec2-base/large encoder with the CNN feature extractor frozen (the reference
+default ``completely_freeze_feature_extractor: true``, R:config/network/wav2vec2_fc.yaml:16), all
+stochastic regularisation at probability 0 (dropout / LayerDrop / SpecAugment), mean pooling + CE head.
+
+Gradient convention between the Functions of this module: activation gradients carry ``LOSS_SCALE``
+(their fp16 copies feed the tensor cores), parameter gradients are unscaled before they are returned
+to autograd.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import ArchConfig, EncoderEngine, PreparedWeights
+
+F16, F32 = torch.float16, torch.float32
+
+LOSS_SCALE = 4096.0          # static scale of the activation gradients (fp16 operands of dgrad / wgrad)
+
+
+class TrainWeights:
+    """Transposed fp16 weight copies for the data-gradient GEMMs (dX = dY W == gemm(dY, W^T))."""
+
+    def __init__(self, w: PreparedWeights, p: Dict[str, torch.Tensor]):
+        a = w.arch
+        f = lambda k: p[k].detach().to(F32).contiguous()
+        self.fp_wT = ops.cast_f16_transpose(f("feature_projection.projection.weight"))          # [512, H]
+        d = a.hidden // a.heads
+        scale = float(d) ** -0.5
+        self.layers = []
+        for l in range(a.layers):
+            pre = f"encoder.layers.{l}."
+            wq, wk, wv = (f(pre + f"attention.{n}_proj.weight") for n in "qkv")
+            wqkv = torch.cat([wq * scale, wk, wv], 0)                                        # folded, [3H, H]
+            self.layers.append(dict(
+                wqkvT=ops.cast_f16_transpose(wqkv),                                           # [H, 3H]
+                woT=ops.cast_f16_transpose(f(pre + "attention.out_proj.weight")),             # [H, H]
+                w1T=ops.cast_f16_transpose(f(pre + "feed_forward.intermediate_dense.weight")),   # [H, FF]
+                w2T=ops.cast_f16_transpose(f(pre + "feed_forward.output_dense.weight"))))     # [FF, H]
+        u = None
+        self._pos_dgrad = {}
+        self._w = w
+
+    def pos_dgrad_w(self, T: int) -> torch.Tensor:
+        w = self._w
+        u = ops.posconv_taps_per_mma(T, w.arch.hidden, w._groups)
+        if u not in self._pos_dgrad:
+            self._pos_dgrad[u] = ops.posconv_fold_weight(w._pos_v, w._pos_g, w._groups, u, mode=1)
+        return self._pos_dgrad[u]
+
+
+# ---------------------------------------------------------------------------------------------------
+# encoder forward (training) / backward
+
+
+def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor):
+    """Same arithmetic as EncoderEngine.forward (the GELUs run as separate passes so the pre-activations
+    can be kept); returns (last_hidden_state f32 [B,T,H], saved)."""
+    a, w = eng.arch, eng.w
+    S = {}
+    feat = eng.feature_extractor(wav)                         # frozen CNN: nothing saved from inside
+    B, T, C = feat.shape
+    H, M = a.hidden, B * T
+    feat2 = feat.contiguous().view(M, C)
+    _, n16 = ops.layernorm(feat2, w.fp_ln_g, w.fp_ln_b, a.eps, want32=False)
+    h0 = ops.gemm_f16(n16, w.fp_w, w.fp_b, 0, F32)            # [M,H]
+    x16 = ops.cast_f16(h0)
+    zpos = ops.posconv_ex(x16.view(B, T, H), w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel, 0, 0)
+    pos, zpos16 = ops.gelu_fwd(zpos.view(M, H), F32, want_x16=True)
+    h32, h16 = ops.layernorm(pos, w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0)
+    S.update(B=B, T=T, feat=feat2, n16=n16, h0=h0, x16=x16, pos=pos, zpos16=zpos16, layers=[])
+    for lw in w.layers:
+        L = dict(h_in32=h32, h_in16=h16)
+        L["qkv"] = ops.gemm_f16(h16, lw["wqkv"], lw["bqkv"], 0, F16)
+        L["att"], L["lse"] = ops.attention(L["qkv"], B, T, H, a.heads, want_lse=True)
+        L["o"] = ops.gemm_f16(L["att"], lw["wo"], None, 0, F32)
+        h32, h16 = ops.layernorm(L["o"], lw["ln1_g"], lw["ln1_b"], a.eps, bias=lw["bo"], residual=L["h_in32"])
+        L["h1_32"], L["h1_16"] = h32, h16
+        L["z"] = ops.gemm_f16(h16, lw["w1"], lw["b1"], 0, F16)
+        L["g"], _ = ops.gelu_fwd(L["z"], F16)
+        L["f2"] = ops.gemm_f16(L["g"], lw["w2"], None, 0, F32)
+        h32, h16 = ops.layernorm(L["f2"], lw["ln2_g"], lw["ln2_b"], a.eps, bias=lw["b2"], residual=L["h1_32"])
+        S["layers"].append(L)
+    return h32.view(B, T, H), S
+
+
+class GradBook:
+    """Flat fp32 gradient buffer with named views (q/k/v of a layer are adjacent so the fused QKV
+    weight gradient lands in place)."""
+
+    def __init__(self, shapes: Dict[str, torch.Size], order: List[str], device):
+        self.offsets = {}
+        n = 0
+        for k in order:
+            self.offsets[k] = n
+            n += int(torch.Size(shapes[k]).numel())
+        self.flat = torch.zeros(n, dtype=F32, device=device)
+        self.shapes = shapes
+
+    def view(self, k: str) -> torch.Tensor:
+        o = self.offsets[k]
+        return self.flat[o:o + int(torch.Size(self.shapes[k]).numel())].view(self.shapes[k])
+
+    def span(self, first: str, rows: int, cols: int) -> torch.Tensor:
+        o = self.offsets[first]
+        return self.flat[o:o + rows * cols].view(rows, cols)
+
+
+def encoder_grad_order(arch: ArchConfig) -> List[str]:
+    order = ["feature_projection.layer_norm.weight", "feature_projection.layer_norm.bias",
+             "feature_projection.projection.weight", "feature_projection.projection.bias",
+             "encoder.pos_conv_embed.conv.bias", "encoder.pos_conv_embed.conv.parametrizations.weight.original0",
+             "encoder.pos_conv_embed.conv.parametrizations.weight.original1",
+             "encoder.layer_norm.weight", "encoder.layer_norm.bias"]
+    for l in range(arch.layers):
+        pre = f"encoder.layers.{l}."
+        order += [pre + "attention.q_proj.weight", pre + "attention.k_proj.weight", pre + "attention.v_proj.weight",
+                  pre + "attention.q_proj.bias", pre + "attention.k_proj.bias", pre + "attention.v_proj.bias",
+                  pre + "attention.out_proj.weight", pre + "attention.out_proj.bias",
+                  pre + "layer_norm.weight", pre + "layer_norm.bias",
+                  pre + "feed_forward.intermediate_dense.weight", pre + "feed_forward.intermediate_dense.bias",
+                  pre + "feed_forward.output_dense.weight", pre + "feed_forward.output_dense.bias",
+                  pre + "final_layer_norm.weight", pre + "final_layer_norm.bias"]
+    return order
+
+
+def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, torch.Tensor], S: dict,
+                     dh: torch.Tensor) -> GradBook:
+    """dh: f32 [B,T,H] gradient of last_hidden_state, carrying LOSS_SCALE.  Returns the (still scaled)
+    parameter gradients of everything behind the frozen CNN."""
+    a, w = eng.arch, eng.w
+    B, T = S["B"], S["T"]
+    H, M, FF = a.hidden, B * T, a.ffn
+    dev = dh.device
+    order = encoder_grad_order(a)
+    G = GradBook({k: params[k].shape for k in order}, order, dev)
+    d = H // a.heads
+    qscale = float(d) ** -0.5
+    dy_a, dy_b = dh.contiguous().view(M, H), None
+    for l in reversed(range(a.layers)):
+        pre = f"encoder.layers.{l}."
+        lw, tl, L = w.layers[l], tw.layers[l], S["layers"][l]
+        # LN2:  h2 = LN(f2 + b2 + h1)
+        dx2_32, dx2_16 = ops.layernorm_bwd(dy_a, L["f2"], lw["ln2_g"], a.eps, dy_b=dy_b, bias=lw["b2"], residual=L["h1_32"],
+                                           dgamma=G.view(pre + "final_layer_norm.weight"),
+                                           dbeta=G.view(pre + "final_layer_norm.bias"))
+        ops.colsum(dx2_16, G.view(pre + "feed_forward.output_dense.bias"))
+        ops.gemm_wgrad_f16(dx2_16, L["g"], G.view(pre + "feed_forward.output_dense.weight"))
+        dg16 = ops.gemm_f16(dx2_16, tl["w2T"], None, 0, F16)                     # [M, FF]
+        dz16 = ops.gelu_bwd(dg16, L["z"])
+        ops.colsum(dz16, G.view(pre + "feed_forward.intermediate_dense.bias"))
+        ops.gemm_wgrad_f16(dz16, L["h1_16"], G.view(pre + "feed_forward.intermediate_dense.weight"))
+        dh1_a = ops.gemm_f16(dz16, tl["w1T"], None, 0, F32)                      # [M, H]
+        # LN1:  h1 = LN(o + bo + h_in)
+        dx1_32, dx1_16 = ops.layernorm_bwd(dh1_a, L["o"], lw["ln1_g"], a.eps, dy_b=dx2_32, bias=lw["bo"],
+                                           residual=L["h_in32"], dgamma=G.view(pre + "layer_norm.weight"),
+                                           dbeta=G.view(pre + "layer_norm.bias"))
+        ops.colsum(dx1_16, G.view(pre + "attention.out_proj.bias"))
+        ops.gemm_wgrad_f16(dx1_16, L["att"], G.view(pre + "attention.out_proj.weight"))
+        datt16 = ops.gemm_f16(dx1_16, tl["woT"], None, 0, F16)
+        dqkv16 = ops.attention_bwd(L["qkv"], L["att"], datt16, L["lse"], B, T, H, a.heads)
+        ops.colsum(dqkv16, G.span(pre + "attention.q_proj.bias", 1, 3 * H).view(3 * H))
+        ops.gemm_wgrad_f16(dqkv16, L["h_in16"], G.span(pre + "attention.q_proj.weight", 3 * H, H))
+        # the q projection was used pre-scaled by d^-0.5: chain rule for the unscaled parameters
+        ops.scale_f32_(G.view(pre + "attention.q_proj.weight"), qscale)
+        ops.scale_f32_(G.view(pre + "attention.q_proj.bias"), qscale)
+        dy_a = ops.gemm_f16(dqkv16, tl["wqkvT"], None, 0, F32)                   # d h_in via qkv
+        dy_b = dx1_32                                                            # + residual path
+    # encoder top:  h_e = LN(pos + h0),  pos = GELU(zpos),  zpos = posconv(h0) + b
+    dxe32, dxe16 = ops.layernorm_bwd(dy_a, S["pos"], w.enc_ln_g, a.eps, dy_b=dy_b, residual=S["h0"],
+                                     dgamma=G.view("encoder.layer_norm.weight"), dbeta=G.view("encoder.layer_norm.bias"))
+    dz16 = ops.gelu_bwd(dxe16, S["zpos16"])
+    ops.colsum(dz16, G.view("encoder.pos_conv_embed.conv.bias"))
+    dx_pos = ops.posconv_ex(dz16.view(B, T, H), tw.pos_dgrad_w(T), None, a.pos_groups, a.pos_kernel, 0, 1)
+    # positional-conv weight gradient: one im2col + wgrad per group, then weight-norm backward
+    I = H // a.pos_groups
+    K = a.pos_kernel
+    dw_hki = torch.zeros(H, K * I, dtype=F32, device=dev)
+    xg = torch.empty(M, K * I, dtype=F16, device=dev)
+    for g in range(a.pos_groups):
+        ops.posconv_im2col(S["x16"].view(B, T, H), a.pos_groups, K, g, xg)
+        ops.gemm_wgrad_f16(dz16[:, g * I:(g + 1) * I], xg, dw_hki[g * I:(g + 1) * I])
+    ops.weight_norm_bwd(dw_hki, w._pos_v, w._pos_g, 1.0,
+                        G.view("encoder.pos_conv_embed.conv.parametrizations.weight.original1"),
+                        G.view("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1))
+    # feature projection:  h0 = LN512(feat) Wp^T + bp
+    _, dh0_16 = ops.add2_cast(dxe32, dx_pos.view(M, H), want32=False)
+    ops.colsum(dh0_16, G.view("feature_projection.projection.bias"))
+    ops.gemm_wgrad_f16(dh0_16, S["n16"], G.view("feature_projection.projection.weight"))
+    dn32 = ops.gemm_f16(dh0_16, tw.fp_wT, None, 0, F32)                           # [M, 512]
+    ops.layernorm_bwd(dn32, S["feat"], w.fp_ln_g, a.eps, dgamma=G.view("feature_projection.layer_norm.weight"),
+                      dbeta=G.view("feature_projection.layer_norm.bias"), want32=False, want16=False)
+    return G
+
+
+# ---------------------------------------------------------------------------------------------------
+# autograd glue
+
+
+class EncoderFn(torch.autograd.Function):
+    """last_hidden_state = encoder(wav; parameters)."""
+
+    @staticmethod
+    def forward(ctx, wav, model, names, *params):
+        eng = model._engine()
+        out, saved = encoder_forward_train(eng, wav)
+        ctx.model, ctx.names, ctx.saved, ctx.eng = model, names, saved, eng
+        return out
+
+    @staticmethod
+    def backward(ctx, dh):
+        model, names, eng = ctx.model, ctx.names, ctx.eng
+        pd = dict(model.named_parameters())
+        tw = model._train_weights(eng)
+        G = encoder_backward(eng, tw, pd, ctx.saved, dh.float())
+        ops.scale_f32_(G.flat, 1.0 / LOSS_SCALE)
+        grads = []
+        for n in names:
+            grads.append(G.view(n) if (n in G.offsets and pd[n].requires_grad) else None)
+        ctx.saved = None
+        return (None, None, None, *grads)
+
+
+class MeanPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.T = x.shape[1]
+        return ops.stat_pool(x.contiguous(), 0)
+
+    @staticmethod
+    def backward(ctx, demb):
+        return ops.mean_pool_bwd(demb.float().contiguous(), ctx.T)
+
+
+class SpeakerLinearFn(torch.autograd.Function):
+    """logits = x W^T + b with error-compensated fp16 operands (forward) and plain fp16 gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_split):
+        xa = ops.split3_rows(x.detach().float().contiguous(), 0)
+        out = ops.gemm_f16(xa, w_split, bias.detach().float() if bias is not None else None, 0, F32)
+        ctx.save_for_backward(x.detach(), weight.detach())
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, W = ctx.saved_tensors
+        Bn, S = dlogits.shape
+        E = W.shape[1]
+        ld = (S + 63) // 64 * 64
+        dl16 = ops.cast_f16_rows(dlogits.float(), ld)                          # already carries LOSS_SCALE
+        x16 = ops.cast_f16(x.float().contiguous())
+        dW = torch.zeros(S, E, dtype=F32, device=W.device)
+        ops.gemm_wgrad_f16(dl16[:, :S], x16, dW)
+        ops.scale_f32_(dW, 1.0 / LOSS_SCALE)
+        db = None
+        if ctx.has_bias:
+            db = torch.zeros(S, dtype=F32, device=W.device)
+            ops.colsum(dl16[:, :S], db, 1.0 / LOSS_SCALE)
+        wT = ops.cast_f16_transpose(W.float(), ld)                              # [E, ld]
+        dx = ops.gemm_f16(dl16, wT, None, 0, F32)                               # scaled, flows on
+        return dx, dW, db, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """(loss, softmax) = CE(logits, labels); the gradient that leaves this node carries LOSS_SCALE."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits = logits.float()
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
+        prob, loss_rows, _ = ops.softmax_ce(logits, labels)
+        ctx.save_for_backward(prob, labels)
+        ctx.mark_non_differentiable(prob)
+        return ops.mean_rows(loss_rows), prob
+
+    @staticmethod
+    def backward(ctx, dloss, _dprob):
+        prob, labels = ctx.saved_tensors
+        dl = ops.softmax_ce_bwd_f32(prob, labels, dloss.float().contiguous().view(1), LOSS_SCALE / prob.shape[0])
+        return dl, None
