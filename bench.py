@@ -350,6 +350,8 @@ def main():
 
     value = world * B * K / (total_ms / 1e3)
     e2e_value = world * B * K / (e2e_ms / 1e3)
+    # the instrumented step contains the gradient all-reduce in train mode: every rank must take part
+    t = instrumented(step_device)
 
     if rank == 0:
         peaks = {}
@@ -361,7 +363,6 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json: cuBLAS bf16 sustained; fp16 runs at the same tensor rate)" \
             if peaks else "fallback (B200_PROFILING.md)"
-        t = instrumented(step_device)
         roof = None
         if t["gemm"]:
             g_ms = sum(x[0] for x in t["gemm"])

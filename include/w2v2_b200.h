@@ -166,6 +166,36 @@ int w2v2_weight_norm_bwd(const float* dw_hki, const float* v, const float* g, fl
  * (forward output), d_o f16 [B*T, H], lse f32 [B, heads, T]  ->  dqkv f16 [B*T, 3H].  T <= 192. */
 int w2v2_attention_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B, int T,
                        int H, int heads, void* stream);
+/* mean+std pooling backward: dx from dout = [dstd || dmean] (recomputes mean / std). */
+int w2v2_meanstd_pool_bwd(const float* x, const float* dout, float* dx, int B, int T, int H, void* stream);
+/* AAM-softmax forward that also saves the pre-margin cosine of the label column (cos_label f32 [B]). */
+int w2v2_aam_softmax_ce_ex(float* cosine, int64_t ldl, const int64_t* labels, float margin, float scale,
+                           int easy_margin, float* prob, float* loss_rows, int32_t* argmax, float* cos_label, int B,
+                           int S, void* stream);
+/* dcos = scale * (prob - onehot) * coef * dloss[0] * (label column ? phi'(cos) : 1) -> f16 [B, ldd]. */
+int w2v2_aam_bwd_dcos(const float* prob, const float* cos_label, const int64_t* labels, const float* dloss, float coef,
+                      float margin, float scale, int easy_margin, void* dcos16, int B, int S, int ldd, void* stream);
+/* inv[r] = 1 / max(||x_r||, 1e-12);  and the backward of row L2 normalisation:
+ * dx (+)= scale * (dxh - xh (xh . dxh)) / ||x||   (dxh row pitch ldd). */
+int w2v2_row_inv_norm(const float* x, float* inv, int64_t rows, int E, void* stream);
+int w2v2_l2norm_rows_bwd(const float* x, const float* dxh, int64_t ldd, float* dx, int64_t rows, int E, float scale,
+                         int accumulate, void* stream);
+/* ---- train-mode regularisation (HF:433, 456, 546-600, 693, 1280-1324) -------------------------------
+ * Dropout masks are a pure function of (seed, element index) -- regenerated in the backward, never stored:
+ * keep <=> 16 random bits >= round(p * 65536), bits = splitmix64(seed + (index/2) * 0x9E3779B97F4A7C15) >> 16,
+ * low / high half for the even / odd element.
+ * w2v2_dropout: y = keep ? (x + bias[col]) / (1-p) : 0 over n elements (x, y f32 (dtype 1) or f16 (0),
+ * y may alias x; optional extra f16 copy y16).  The attention kernels take the probability-dropout the
+ * same way (index = ((b*heads + h)*T + q) * TK + k).  Time mask: rows with mask != 0 are overwritten by
+ * the learned embedding; backward zeroes those gradient rows and accumulates them into d_embed. */
+int w2v2_dropout(const void* x, int dtype, const float* bias, int H, void* y, void* y16, int64_t n, float p,
+                 uint64_t seed, void* stream);
+int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, float drop_p,
+                      uint64_t drop_seed, void* stream);
+int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
+                          int T, int H, int heads, float drop_p, uint64_t drop_seed, void* stream);
+int w2v2_time_mask_apply(float* h, const uint8_t* mask, const float* embed, int64_t rows, int H, void* stream);
+int w2v2_time_mask_bwd(float* dh, const uint8_t* mask, float* dembed, int64_t rows, int H, float scale, void* stream);
 /* Gradient plumbing: out = a + b (b may be NULL) as f32 and/or f16 (n % 4 == 0); row-wise f32 -> f16 cast
  * with zero padding to ldy and a scale; in-place scale; f32 CE gradient (prob - onehot) * coef * dloss[0]
  * (dloss may be NULL = 1). */

@@ -1,0 +1,144 @@
+"""Train-mode regularisation kernels (dropout masks as a pure function of (seed, index), attention
+dropout inside the tcgen05 attention forward/backward, SpecAugment time mask) against torch, using a
+numpy replica of the counter-based mask; plus an end-to-end step with the reference's default
+regularisation (R:src/models/wav2vec2.py:83-94)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+S = 5994
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from w2v2_speaker_b200 import ops as _ops
+    return _ops
+
+
+def keep_mask(seed: int, n: int, p: float) -> np.ndarray:
+    """numpy replica of csrc/common.cuh::dropout_hash + the 16-bit threshold test (n even)."""
+    thr = int(p * 65536.0 + 0.5)
+    with np.errstate(over="ignore"):
+        idx = np.arange(n // 2, dtype=np.uint64)
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    bits = (z >> np.uint64(16)) & np.uint64(0xFFFFFFFF)
+    lo, hi = bits & np.uint64(0xFFFF), bits >> np.uint64(16)
+    keep = np.empty(n, dtype=bool)
+    keep[0::2] = lo >= thr
+    keep[1::2] = hi >= thr
+    return keep, 1.0 / (1.0 - thr / 65536.0)
+
+
+def rel(a, b):
+    a = a.double(); b = b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_dropout_kernel_matches_replica(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 768, generator=g).cuda()
+    bias = torch.randn(768, generator=g).cuda()
+    seed, p = 123456789012345, 0.1
+    keep, inv = keep_mask(seed, x.numel(), p)
+    keep_t = torch.from_numpy(keep).view(300, 768).cuda()
+    ref = torch.where(keep_t, (x + bias) * inv, torch.zeros_like(x))
+    y, y16 = ops.dropout_(x.clone(), p, seed, bias=bias, want16=True)
+    assert rel(y, ref) < 1e-6
+    assert rel(y16.float(), ref) < 5e-4
+    assert abs(keep.mean() - 0.9) < 5e-3
+    xh = x.half()
+    yh, _ = ops.dropout_(xh.clone(), 0.25, 7)
+    k2, inv2 = keep_mask(7, x.numel(), 0.25)
+    ref2 = torch.where(torch.from_numpy(k2).view(300, 768).cuda(), xh.float() * inv2, torch.zeros_like(x))
+    assert rel(yh.float(), ref2) < 5e-4
+    # p = 0 is the identity
+    y0, _ = ops.dropout_(x.clone(), 0.0, 99)
+    assert torch.equal(y0, x)
+
+
+@pytest.mark.parametrize("B,T,H,heads", [(2, 49, 768, 12), (2, 149, 768, 12)])
+def test_attention_dropout_forward_backward(ops, B, T, H, heads):
+    d = H // heads
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(B * T, 3 * H, generator=g).cuda().half()
+    qkv[:, :H] *= 0.35
+    d_o = (torch.randn(B * T, H, generator=g) * 0.7).cuda().half()
+    p, seed = 0.1, 424242
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True, drop_p=p, drop_seed=seed)
+    dqkv = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads, drop_p=p, drop_seed=seed)
+    torch.cuda.synchronize()
+    TK = (T + 15) // 16 * 16
+    keep, inv = keep_mask(seed, B * heads * T * TK, p)
+    m = torch.from_numpy(keep).view(B, heads, T, TK)[..., :T].cuda()
+    x = qkv.float().requires_grad_(True)
+    q, k, v = (x[:, i * H:(i + 1) * H].view(B, T, heads, d).transpose(1, 2) for i in range(3))
+    a = torch.softmax(q @ k.transpose(2, 3), -1)
+    a = torch.where(m, a * inv, torch.zeros_like(a))
+    o = (a @ v).transpose(1, 2).reshape(B * T, H)
+    ref = torch.autograd.grad(o, x, d_o.float())[0]
+    assert rel(out.float(), o.detach()) < 2e-3
+    for i in range(3):
+        assert rel(dqkv[:, i * H:(i + 1) * H].float(), ref[:, i * H:(i + 1) * H]) < 5e-3, "qkv"[i]
+
+
+def test_time_mask_apply_and_backward(ops):
+    from w2v2_speaker_b200.training import compute_time_mask
+    B, T, H = 4, 149, 768
+    rng = np.random.default_rng(3)
+    mask = torch.from_numpy(compute_time_mask(B, T, 0.05, 10, 2, rng)).cuda()
+    g = torch.Generator().manual_seed(2)
+    h = torch.randn(B * T, H, generator=g).cuda()
+    emb = torch.rand(H, generator=g).cuda()
+    out = ops.time_mask_apply_(h.clone(), mask, emb)
+    ref = torch.where(mask.bool()[:, None], emb[None, :].expand(B * T, H), h)
+    assert torch.equal(out, ref)
+    dh = torch.randn(B * T, H, generator=g).cuda()
+    dembed = torch.zeros(H, device="cuda")
+    d2 = ops.time_mask_bwd_(dh.clone(), mask, dembed, 0.5)
+    assert torch.equal(d2, torch.where(mask.bool()[:, None], torch.zeros_like(dh), dh))
+    assert rel(dembed, 0.5 * dh[mask.bool()].sum(0)) < 1e-5
+
+
+def test_training_step_with_reference_default_regularisation(base_params):
+    """dropout 0.1 x3, LayerDrop 0.05, SpecAugment 0.05 (the reference defaults): the step runs, every
+    gradient is finite, LayerDrop-skipped layers get exactly zero gradient, masked_spec_embed trains."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle.params import make_head_params, make_inputs
+    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    torch.manual_seed(0)
+    cfg = Wav2vec2FCModuleConfig(layerdrop=0.3)                   # other probabilities: reference defaults
+    m = Wav2vec2FCModule(cfg, S, CrossEntropyLoss)
+    m.wav2vec.model.load_state_dict(base_params, strict=False)
+    m = m.cuda().train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    wav, labels = make_inputs(4, 48000, S, seed=11)
+    emb, pred = m(wav[:, None, :].cuda())
+    loss, prob = m.loss_fn(pred, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss)
+    model = m.wav2vec.model
+    skipped = 0
+    for l in range(12):
+        g = dict(model.named_parameters())[f"encoder.layers.{l}.feed_forward.output_dense.weight"].grad
+        assert torch.isfinite(g).all()
+        skipped += int(g.abs().max().item() == 0.0)
+    assert 1 <= skipped <= 9                                       # p = 0.3 over 12 layers
+    assert model.masked_spec_embed.grad.abs().max().item() > 0     # SpecAugment rows feed the embedding
+    for n, q in model.named_parameters():
+        if q.grad is not None:
+            assert torch.isfinite(q.grad).all(), n
+    # eval mode is deterministic and unaffected
+    m.eval()
+    with torch.no_grad():
+        e1, _ = m(wav[:, None, :].cuda())
+        e2, _ = m(wav[:, None, :].cuda())
+    assert torch.equal(e1, e2)

@@ -51,8 +51,11 @@ def test_training_step_gradients_match_oracle_autograd(base_params, B, N):
     got = dict(m.wav2vec.model.named_parameters())
     worst = (0.0, None)
     for k, v in p.items():
-        if k.startswith("feature_extractor") or k == "masked_spec_embed":
+        if k.startswith("feature_extractor"):
             assert got[k].grad is None
+            continue
+        if k == "masked_spec_embed":                  # unused without SpecAugment: no or zero gradient
+            assert got[k].grad is None or got[k].grad.abs().max().item() == 0.0
             continue
         assert got[k].grad is not None, k
         g, r = got[k].grad.detach().cpu().double(), v.grad.double()
@@ -100,3 +103,45 @@ def test_unfrozen_cnn_and_regularisation_fail_loudly(base_params):
     m.wav2vec.model.feature_extractor.requires_grad_(True)
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 1, 8000, device="cuda"))
+
+
+def test_training_step_meanstd_aam_matches_oracle_autograd(base_params):
+    """configs[3] shape of the path: mean+std pooling + AAM-softmax (margin 0.2, scale 30)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_head_params, make_inputs
+    from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    B, N = 3, 16000
+    wav, labels = make_inputs(B, N, S, seed=99)
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type="mean+std", test_stat_pooling_type="mean+std", activation_dropout=0.0,
+                                 attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
+                                 mask_time_prob=0.0)
+    m = Wav2vec2FCModule(cfg, S, lambda: AngularAdditiveMarginSoftMaxLoss(1, 1, margin=0.2, scale=30))
+    m.wav2vec.model.load_state_dict(base_params, strict=False)
+    head = make_head_params(1536, S, seed=1)
+    with torch.no_grad():
+        m.loss_fn.fc_weights.copy_(head["aam.fc_weights"])
+    m = m.cuda().train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    emb, pred = m(wav[:, None, :].cuda())
+    loss, prob = m.loss_fn(pred, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    torch.set_num_threads(8)
+    p = {k: v.clone().requires_grad_(not k.startswith("feature_extractor")) for k, v in base_params.items()}
+    fw = head["aam.fc_weights"].clone().requires_grad_(True)
+    ref_emb = O.speaker_embedding(wav, p, "mean+std")
+    _, ref_loss, _ = O.aam_softmax(ref_emb, fw, labels, 0.2, 30.0)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-3
+    got = dict(m.wav2vec.model.named_parameters())
+    for k in ("encoder.layers.11.feed_forward.output_dense.weight", "encoder.layers.0.attention.q_proj.weight",
+              "encoder.layers.5.layer_norm.weight", "feature_projection.projection.weight",
+              "encoder.pos_conv_embed.conv.parametrizations.weight.original1"):
+        g, r = got[k].grad.cpu().double(), p[k].grad.double()
+        assert ((g - r).norm() / r.norm()).item() < 1e-2, k
+    g, r = m.loss_fn.fc_weights.grad.cpu().double(), fw.grad.double()
+    assert ((g - r).norm() / r.norm()).item() < 1e-2

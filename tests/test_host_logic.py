@@ -66,11 +66,21 @@ def test_no_cpu_fallback(wrapper):
             wrapper(torch.zeros(1, 4000))
 
 
-def test_training_mode_fails_loudly(wrapper):
+def test_training_mode_without_cuda_fails_loudly(wrapper):
     wrapper.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises((NotImplementedError, RuntimeError)):
         wrapper(torch.zeros(1, 4000))
     wrapper.eval()
+
+
+def test_time_mask_follows_hf_span_rules():
+    import numpy as np
+    from w2v2_speaker_b200.training import compute_time_mask
+    rng = np.random.default_rng(0)
+    m = compute_time_mask(64, 149, 0.05, 10, 2, rng).reshape(64, 149)
+    per_utt = m.sum(1)
+    assert per_utt.max() <= 20 and per_utt.min() >= 10       # two spans of 10 frames, possibly overlapping
+    assert compute_time_mask(2, 5, 0.05, 10, 2, rng).sum() == 0   # utterance shorter than one span
 
 
 @pytest.mark.parametrize("pooling,dim", [("mean", 768), ("mean+std", 1536), ("attentive", 1536), ("max", 768),

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -46,6 +46,19 @@ SIGNATURES = {
     "w2v2_colsum": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_float, c_void_p, c_void_p]),
     "w2v2_softmax_ce_bwd": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_mean_pool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_meanstd_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_aam_softmax_ce_ex": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "w2v2_aam_bwd_dcos": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_int, c_void_p,
+                                  c_int, c_int, c_int, c_void_p]),
+    "w2v2_row_inv_norm": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "w2v2_l2norm_rows_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "w2v2_dropout": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_float, c_uint64, c_void_p]),
+    "w2v2_attention_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_uint64, c_void_p]),
+    "w2v2_attention_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_float, c_uint64, c_void_p]),
+    "w2v2_time_mask_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "w2v2_time_mask_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "w2v2_add2_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "w2v2_cast_f16_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]),
     "w2v2_scale_f32": (c_int, [c_void_p, c_int64, c_float, c_void_p]),

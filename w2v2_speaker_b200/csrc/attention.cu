@@ -27,6 +27,9 @@ struct alignas(64) AttnParams {
   float* lse;         // [B, heads, T] or nullptr
   int T, TK, H, heads;
   int tmem_cols, o_col;
+  uint32_t drop_thr;  // attention dropout (HF:456): keep <=> 16 random bits >= thr; 0 = off
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
 constexpr int ATT_D = 64;
@@ -119,10 +122,17 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
     uint32_t pk[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const __half2 hh = __floats2half2_rn(e[2 * j], e[2 * j + 1]);
-      pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      __half2 hh = __floats2half2_rn(e[2 * j], e[2 * j + 1]);
       const float2 f = __half22float2(hh);
-      sum += f.x + f.y;
+      sum += f.x + f.y;                           // the normaliser is that of the un-dropped softmax
+      if (p.drop_thr != 0) {
+        const int t_q = mt * 128 + row;
+        const uint64_t pair = ((uint64_t(b) * p.heads + h) * p.T + t_q) * uint64_t(TK / 2) + (c * 8 + j);
+        const uint32_t hb = dropout_hash(p.drop_seed, pair);
+        hh = __floats2half2_rn((hb & 0xffffu) >= p.drop_thr ? f.x * p.drop_inv_keep : 0.f,
+                               (hb >> 16) >= p.drop_thr ? f.y * p.drop_inv_keep : 0.f);
+      }
+      pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
     }
     const int col = c * 16;                     // 16 halfs = two 16-byte chunks
     uint8_t* blk = prow + (col >> 6) * 16384;
@@ -184,7 +194,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
 
 using namespace w2v2;
 
-extern "C" int w2v2_attention(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, void* stream_) {
+extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, float drop_p,
+                                 uint64_t drop_seed, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * ATT_D, "w2v2_attention: head dim must be 64 (H=%d heads=%d)", H, heads);
   W2V2_REQUIRE(T >= 1 && T <= 256,
@@ -199,6 +210,10 @@ extern "C" int w2v2_attention(const void* qkv16, void* out16, float* lse, int B,
   if (rc) return rc;
   p.out = static_cast<__half*>(out16);
   p.lse = lse;
+  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention: dropout p=%f out of [0,1)", drop_p);
+  p.drop_thr = uint32_t(drop_p * 65536.0f + 0.5f);
+  p.drop_inv_keep = 1.0f / (1.0f - float(p.drop_thr) / 65536.0f);
+  p.drop_seed = drop_seed;
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   if (TK <= 192) { p.tmem_cols = 256; p.o_col = 192; } else { p.tmem_cols = 512; p.o_col = 256; }
   if (TK <= 64) { p.tmem_cols = 128; p.o_col = 64; }
@@ -214,4 +229,8 @@ extern "C" int w2v2_attention(const void* qkv16, void* out16, float* lse, int B,
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int w2v2_attention(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, void* stream) {
+  return w2v2_attention_ex(qkv16, out16, lse, B, T, H, heads, 0.f, 0, stream);
 }

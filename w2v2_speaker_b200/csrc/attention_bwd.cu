@@ -30,6 +30,9 @@ struct alignas(64) AttnBwdParams {
   const float* lse;    // [B, heads, T]
   __half* dqkv;        // [B*T, 3H]
   int T, TK, H, heads, qtiles;
+  uint32_t drop_thr;
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
 __global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_cons
       uint32_t r[16];
       tmem_ld_32x32b_x16(t_row + AB_COL_SP + c * 16, r);
       tmem_ld_wait();
-      uint32_t pk[8];
+      uint32_t pk[8], pd[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float e0 = fast_ex2(fmaf(__uint_as_float(r[2 * j]), 1.4426950408889634f, -lse2));
@@ -140,12 +143,24 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_cons
         if (!valid || c * 16 + 2 * j >= p.T) e0 = 0.f;
         if (!valid || c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
         pk[j] = pack_half2(e0, e1);
+        if (p.drop_thr != 0) {
+          const uint64_t pair = ((uint64_t(b) * p.heads + h) * p.T + (valid ? t : 0)) * uint64_t(TK / 2) + (c * 8 + j);
+          const uint32_t hb = dropout_hash(p.drop_seed, pair);
+          pd[j] = pack_half2((hb & 0xffffu) >= p.drop_thr ? e0 * p.drop_inv_keep : 0.f,
+                             (hb >> 16) >= p.drop_thr ? e1 * p.drop_inv_keep : 0.f);
+        }
       }
       const int col = c * 16;
       uint8_t* blk = prow + (col >> 6) * 16384;
       const int c16 = (col & 63) >> 3;
       *reinterpret_cast<uint4*>(blk + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if (p.drop_thr != 0) {
+        // the dropped probabilities (operand of dV = Pd^T dO) borrow the dS buffer until step (d) fills it
+        uint8_t* blk2 = sdS + row * 128 + (col >> 6) * 16384;
+        *reinterpret_cast<uint4*>(blk2 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pd[0], pd[1], pd[2], pd[3]);
+        *reinterpret_cast<uint4*>(blk2 + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pd[4], pd[5], pd[6], pd[7]);
+      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_cons
       const uint32_t idesc_t = make_idesc_f16(128, AB_D, 1, 1);            // A (P^T) and B (dO) MN-major
       for (int kt = 0; kt < ktiles; ++kt) {
         for (int ks = 0; ks < 8; ++ks) {                                  // 128 queries / 16
-          const uint64_t adesc = make_smem_desc(aP + kt * 2 * 16384 + ks * 2048, 16384, 1024, 2);
+          const uint64_t adesc = make_smem_desc((p.drop_thr != 0 ? adS : aP) + kt * 2 * 16384 + ks * 2048, 16384, 1024, 2);
           const uint64_t bdesc = make_smem_desc(adO + qt * 16384 + ks * 2048, 16, 1024, 2);
           umma_f16(tmem + AB_COL_DV + kt * AB_D, adesc, bdesc, idesc_t, (qt | ks) != 0);
         }
@@ -188,7 +203,14 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 pp = __half22float2(j < 4 ? ph0[j] : ph1[j - 4]);
-        pk[j] = pack_half2(pp.x * (__uint_as_float(r[2 * j]) - delta), pp.y * (__uint_as_float(r[2 * j + 1]) - delta));
+        float d0 = __uint_as_float(r[2 * j]), d1 = __uint_as_float(r[2 * j + 1]);
+        if (p.drop_thr != 0) {                     // dP arrives for the dropped probabilities: mask / keep
+          const uint64_t pair = ((uint64_t(b) * p.heads + h) * p.T + (valid ? t : 0)) * uint64_t(TK / 2) + (c * 8 + j);
+          const uint32_t hb = dropout_hash(p.drop_seed, pair);
+          d0 = (hb & 0xffffu) >= p.drop_thr ? d0 * p.drop_inv_keep : 0.f;
+          d1 = (hb >> 16) >= p.drop_thr ? d1 * p.drop_inv_keep : 0.f;
+        }
+        pk[j] = pack_half2(pp.x * (d0 - delta), pp.y * (d1 - delta));
       }
       uint8_t* blk = dsrow + (col >> 6) * 16384;
       *reinterpret_cast<uint4*>(blk + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -288,8 +310,8 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_kernel(const __grid_cons
 
 using namespace w2v2;
 
-extern "C" int w2v2_attention_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16,
-                                  int B, int T, int H, int heads, void* stream_) {
+extern "C" int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16,
+                                     int B, int T, int H, int heads, float drop_p, uint64_t drop_seed, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * AB_D, "w2v2_attention_bwd: head dim must be 64 (H=%d heads=%d)", H, heads);
   W2V2_REQUIRE(T >= 1 && T <= 192,
@@ -309,6 +331,10 @@ extern "C" int w2v2_attention_bwd(const void* qkv16, const void* o16, const void
   p.dqkv = static_cast<__half*>(dqkv16);
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   p.qtiles = (T + 127) / 128;
+  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention_bwd: dropout p=%f out of [0,1)", drop_p);
+  p.drop_thr = uint32_t(drop_p * 65536.0f + 0.5f);
+  p.drop_inv_keep = 1.0f / (1.0f - float(p.drop_thr) / 65536.0f);
+  p.drop_seed = drop_seed;
   const int kvb = (TK * 128 + 1023) & ~1023;
   const int smem = 2 * AB_PBLOCKS * 16384 + 4 * 16384 + 2 * kvb + 64;
   W2V2_REQUIRE(smem <= 227 * 1024, "w2v2_attention_bwd: shared memory budget exceeded (%d bytes)", smem);
@@ -322,4 +348,9 @@ extern "C" int w2v2_attention_bwd(const void* qkv16, const void* o16, const void
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int w2v2_attention_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16,
+                                  int B, int T, int H, int heads, void* stream) {
+  return w2v2_attention_bwd_ex(qkv16, o16, do16, lse, dqkv16, B, T, H, heads, 0.f, 0, stream);
 }

@@ -222,6 +222,37 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_
   }
 }
 
+// fp16 fast path: 16-byte loads, a warp covers 256 consecutive columns of one row, 8 rows per block pass
+__global__ void __launch_bounds__(256) colsum_f16_vec_kernel(const __half* __restrict__ x, int64_t rows, int cols,
+                                                             int64_t ld, float scale, float* __restrict__ out) {
+  __shared__ float sm[8][256 + 8];
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < cols) {
+    for (int64_t r = int64_t(blockIdx.y) * 8 + rl; r < rows; r += int64_t(gridDim.y) * 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(x + r * ld + c);
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x;
+        s[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[rl][lane * 8 + j] = s[j];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(out + cc, t * scale);
+  }
+}
+
 // =================================================================================================
 // softmax cross-entropy backward (mean reduction): dlogits = (prob - onehot) * (loss_scale / B)
 // written as the fp16 operand [B, ldd] (columns >= S zero-filled).
@@ -306,6 +337,15 @@ int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void
 
 int w2v2_colsum(const void* x, int x_dtype, int64_t rows, int cols, int64_t ld, float scale, float* out, void* stream) {
   if (rows == 0) return 0;
+  if (x_dtype == 0 && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    dim3 vgrid((cols + 255) / 256, (unsigned)grid_cap((rows + 63) / 64, 1));
+    const unsigned want = (unsigned)(2 * device_sm_count() / vgrid.x + 1);
+    if (vgrid.y > want) vgrid.y = want;
+    colsum_f16_vec_kernel<<<vgrid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, rows, cols, ld, scale, out);
+    count_launches(1);
+    W2V2_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((cols + 31) / 32, (unsigned)grid_cap((rows + 63) / 64, 1));
   if (grid.y > 64) grid.y = 64;
   if (x_dtype == 1) colsum_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, scale, out);

@@ -273,6 +273,16 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   unpack2(r, x0, x1);
 }
 
+// counter-based random bits for dropout: splitmix64 finaliser of (seed + pair_index * golden ratio);
+// low / high 16 bits decide the two elements of the pair
+__device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t pair_idx) {
+  uint64_t z = seed + pair_idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return uint32_t(z >> 16);
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

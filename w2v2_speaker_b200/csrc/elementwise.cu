@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ log
                                                          const int64_t* __restrict__ labels, int aam, float cos_m,
                                                          float sin_m, float th, float mm, float scale, int easy,
                                                          float* __restrict__ prob, float* __restrict__ loss_rows,
-                                                         int32_t* __restrict__ argmax, int S) {
+                                                         int32_t* __restrict__ argmax, float* __restrict__ cos_label,
+                                                         int S) {
   __shared__ float smf[8];
   __shared__ float smv[8];
   __shared__ int smi[8];
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ log
       const float c = row[i];
       float o = c;
       if (i == label) {
+        if (cos_label != nullptr) cos_label[b] = c;          // pre-margin cosine, needed by the backward
         const float sine = sqrtf(fminf(fmaxf(1.0f - c * c, 0.f), 1.f));
         const float phi = c * cos_m - sine * sin_m;
         o = easy ? (c > 0.f ? phi : c) : ((c - th) > 0.f ? phi : c - mm);
@@ -673,7 +675,19 @@ int w2v2_asp_pool(const float* x, const float* logits, float* out, int B, int T,
 int w2v2_softmax_ce(const float* logits, int64_t ldl, const int64_t* labels, float* prob, float* loss_rows,
                     int32_t* argmax, int B, int S, void* stream) {
   softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(logits), ldl, labels, 0, 0.f, 0.f, 0.f, 0.f,
-                                                         1.f, 0, prob, loss_rows, argmax, S);
+                                                         1.f, 0, prob, loss_rows, argmax, nullptr, S);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_aam_softmax_ce_ex(float* cosine, int64_t ldl, const int64_t* labels, float margin, float scale, int easy_margin,
+                           float* prob, float* loss_rows, int32_t* argmax, float* cos_label, int B, int S, void* stream) {
+  const double m = margin;
+  const double pi = 3.14159265358979323846;
+  softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cosine, ldl, labels, 1, float(cos(m)), float(sin(m)),
+                                                         float(cos(pi - m)), float(sin(pi - m) * m), scale, easy_margin,
+                                                         prob, loss_rows, argmax, cos_label, S);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -681,14 +695,8 @@ int w2v2_softmax_ce(const float* logits, int64_t ldl, const int64_t* labels, flo
 
 int w2v2_aam_softmax_ce(float* cosine, int64_t ldl, const int64_t* labels, float margin, float scale, int easy_margin,
                         float* prob, float* loss_rows, int32_t* argmax, int B, int S, void* stream) {
-  const double m = margin;
-  const double pi = 3.14159265358979323846;
-  softmax_ce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cosine, ldl, labels, 1, float(cos(m)), float(sin(m)),
-                                                         float(cos(pi - m)), float(sin(pi - m) * m), scale, easy_margin,
-                                                         prob, loss_rows, argmax, S);
-  count_launches(1);
-  W2V2_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return w2v2_aam_softmax_ce_ex(cosine, ldl, labels, margin, scale, easy_margin, prob, loss_rows, argmax, nullptr, B, S,
+                                stream);
 }
 
 int w2v2_l2norm_rows_f16(const float* x, void* y16, int64_t rows, int E, void* stream) {

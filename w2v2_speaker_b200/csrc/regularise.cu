@@ -1,0 +1,108 @@
+// Train-mode regularisation of the wav2vec2 encoder (HF:433, 693, 546-600, 1280-1324):
+// counter-based dropout masks (regenerated in the backward from (seed, element index), never stored)
+// and the SpecAugment time mask.  mask(seed, idx): one 64-bit mix per element PAIR, 16 random bits per
+// element, keep <=> bits >= round(p * 65536).  tests/test_gpu_regularise.py holds the numpy replica.
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+namespace w2v2 {
+
+int device_sm_count();
+static inline int rgrid(int64_t n, int per_block, int per_sm) {
+  int64_t g = (n + per_block - 1) / per_block;
+  const int64_t cap = int64_t(device_sm_count()) * per_sm;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// y = keep ? (x + bias[col]) / (1 - p) : 0     (x, y f32 or f16; optional second f16 output)
+template <bool F32>
+__global__ void dropout_kernel(const void* __restrict__ x_, const float* __restrict__ bias, int H, void* __restrict__ y_,
+                               __half* __restrict__ y16, int64_t n, uint32_t thr, float inv_keep, uint64_t seed) {
+  // two elements (one hash) per thread iteration; n % 2 == 0
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < n;
+       i += int64_t(gridDim.x) * blockDim.x * 2) {
+    const uint32_t h = dropout_hash(seed, uint64_t(i >> 1));
+    float a, b;
+    if constexpr (F32) {
+      const float2 v = *reinterpret_cast<const float2*>(static_cast<const float*>(x_) + i);
+      a = v.x; b = v.y;
+    } else {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(static_cast<const __half*>(x_) + i));
+      a = v.x; b = v.y;
+    }
+    if (bias != nullptr) {
+      const int c = int(i % H);
+      a += bias[c];
+      b += bias[c + 1];
+    }
+    a = (h & 0xffffu) >= thr ? a * inv_keep : 0.f;
+    b = (h >> 16) >= thr ? b * inv_keep : 0.f;
+    if constexpr (F32) *reinterpret_cast<float2*>(static_cast<float*>(y_) + i) = make_float2(a, b);
+    else *reinterpret_cast<uint32_t*>(static_cast<__half*>(y_) + i) = pack_half2(a, b);
+    if (y16 != nullptr) *reinterpret_cast<uint32_t*>(y16 + i) = pack_half2(a, b);
+  }
+}
+
+// SpecAugment: rows with mask != 0 are overwritten by the learned embedding (HF:1301-1310)
+__global__ void time_mask_apply_kernel(float* __restrict__ h, const uint8_t* __restrict__ mask,
+                                       const float* __restrict__ embed, int64_t rows, int H) {
+  const int64_t n = rows * H;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / H;
+    if (mask[r]) h[i] = embed[i % H];
+  }
+}
+// backward: d_embed += sum of masked rows of dh ; dh[masked rows] = 0
+__global__ void time_mask_bwd_kernel(float* __restrict__ dh, const uint8_t* __restrict__ mask, float* __restrict__ dembed,
+                                     int64_t rows, int H, float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float s = 0.f;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    if (mask[r]) {
+      s += dh[r * H + c];
+      dh[r * H + c] = 0.f;
+    }
+  }
+  if (s != 0.f) atomicAdd(dembed + c, s * scale);
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" {
+
+int w2v2_dropout(const void* x, int dtype, const float* bias, int H, void* y, void* y16, int64_t n, float p,
+                 uint64_t seed, void* stream) {
+  W2V2_REQUIRE(n % 2 == 0 && (bias == nullptr || H % 2 == 0), "w2v2_dropout: n (and H) must be even");
+  W2V2_REQUIRE(p >= 0.f && p < 1.f, "w2v2_dropout: p=%f out of [0,1)", p);
+  if (n == 0) return 0;
+  const uint32_t thr = uint32_t(p * 65536.0f + 0.5f);
+  const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
+  const int grid = rgrid(n / 2, 256, 8);
+  if (dtype == 1) dropout_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
+  else dropout_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_time_mask_apply(float* h, const uint8_t* mask, const float* embed, int64_t rows, int H, void* stream) {
+  if (rows == 0) return 0;
+  time_mask_apply_kernel<<<rgrid(rows * H, 256, 8), 256, 0, (cudaStream_t)stream>>>(h, mask, embed, rows, H);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_time_mask_bwd(float* dh, const uint8_t* mask, float* dembed, int64_t rows, int H, float scale, void* stream) {
+  if (rows == 0) return 0;
+  dim3 grid((H + 127) / 128, 64);
+  time_mask_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dh, mask, dembed, rows, H, scale);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

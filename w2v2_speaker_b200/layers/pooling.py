@@ -52,7 +52,8 @@ class MeanStdStatPool1D(nn.Module):
     def forward(self, tensor: torch.Tensor):
         x = _as_btc(tensor, self.dim_to_reduce)
         if torch.is_grad_enabled() and x.requires_grad:
-            raise NotImplementedError("the backward of mean+std pooling is not implemented yet (mean pooling is)")
+            from ..training import MeanStdPoolFn
+            return MeanStdPoolFn.apply(x)
         return ops.stat_pool(x, 1)
 
 

@@ -149,14 +149,30 @@ class Wav2Vec2ModelB200(nn.Module):
     def _needs_grad(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def _check_mode(self):
+    def _stochastic(self) -> bool:
         r = self.reg_cfg
-        stochastic = (r.activation_dropout + r.attention_dropout + r.feat_proj_dropout + r.hidden_dropout +
-                      r.layerdrop + r.mask_time_prob + r.mask_feature_prob) > 0
-        if self.training and stochastic:
+        return (r.activation_dropout + r.attention_dropout + r.feat_proj_dropout + r.hidden_dropout +
+                r.layerdrop + r.mask_time_prob + r.mask_feature_prob) > 0
+
+    def _draw_reg_plan(self, wav: torch.Tensor, eng: EncoderEngine):
+        """Host-side draw of this step's regularisation (None in eval mode or when every probability is 0)."""
+        if not self.training or not self._stochastic():
+            return None
+        import numpy as np
+        from ..training import RegPlan
+        if getattr(self, "_rng", None) is None:
+            self._rng = np.random.default_rng(torch.initial_seed() % (1 << 63))
+        T = self.arch.conv_lengths(wav.shape[1])[-1]
+        return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device)
+
+    def _check_mode(self):
+        if self.reg_cfg.mask_feature_prob > 0 and self.training:
+            raise NotImplementedError("feature-axis SpecAugment (mask_feature_prob > 0) is not implemented "
+                                      "(the reference configurations keep it at 0)")
+        if self.training and self._stochastic() and not self._needs_grad():
             raise NotImplementedError(
-                "training-mode regularisation (dropout / LayerDrop / SpecAugment) is not implemented in the "
-                "sm_100a path yet; call .eval() or zero the probabilities (SURVEY Appendix A Q10)")
+                "train-mode regularisation is implemented on the training path only: enable gradients, or call "
+                ".eval() for inference")
         if self._needs_grad() and any(p.requires_grad for p in self.feature_extractor.parameters()):
             raise NotImplementedError(
                 "the backward of the CNN feature extractor is not implemented yet: freeze it with "

@@ -152,21 +152,25 @@ def weight_norm_bwd(dw_hki, v, g, scale, dv, dg):
          stream_ptr())
 
 
-def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, want_lse: bool = False):
+def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, want_lse: bool = False, drop_p: float = 0.0,
+              drop_seed: int = 0):
     """-> out f16 [B*T, H]  (and lse f32 [B, heads, T] when want_lse, for the backward pass)."""
     _chk(qkv16, F16, "qkv16")
     out = torch.empty(B * T, H, dtype=F16, device=qkv16.device)
     lse = torch.empty(B, heads, T, dtype=F32, device=qkv16.device) if want_lse else None
-    call("w2v2_attention", ptr(qkv16), ptr(out), ptr(lse), B, T, H, heads, stream_ptr())
+    call("w2v2_attention_ex", ptr(qkv16), ptr(out), ptr(lse), B, T, H, heads, float(drop_p), int(drop_seed),
+         stream_ptr())
     return (out, lse) if want_lse else out
 
 
 # ---- backward ------------------------------------------------------------------------------------
 
 
-def attention_bwd(qkv16, o16, do16, lse, B: int, T: int, H: int, heads: int) -> torch.Tensor:
+def attention_bwd(qkv16, o16, do16, lse, B: int, T: int, H: int, heads: int, drop_p: float = 0.0,
+                  drop_seed: int = 0) -> torch.Tensor:
     dqkv = torch.empty(B * T, 3 * H, dtype=F16, device=qkv16.device)
-    call("w2v2_attention_bwd", ptr(qkv16), ptr(o16), ptr(do16), ptr(lse), ptr(dqkv), B, T, H, heads, stream_ptr())
+    call("w2v2_attention_bwd_ex", ptr(qkv16), ptr(o16), ptr(do16), ptr(lse), ptr(dqkv), B, T, H, heads, float(drop_p),
+         int(drop_seed), stream_ptr())
     return dqkv
 
 
@@ -335,3 +339,66 @@ def softmax_ce_bwd_f32(prob, labels, dloss, coef: float):
     dl = torch.empty(B, S, dtype=F32, device=prob.device)
     call("w2v2_softmax_ce_bwd_f32", ptr(prob), ptr(labels), ptr(dloss), float(coef), ptr(dl), B, S, stream_ptr())
     return dl
+
+
+def dropout_(x: torch.Tensor, p: float, seed: int, bias: Optional[torch.Tensor] = None, want16: bool = False):
+    """In place: x = keep ? (x + bias) / (1-p) : 0.  Returns (x, f16 copy | None)."""
+    H = x.shape[-1]
+    y16 = torch.empty(x.shape, dtype=F16, device=x.device) if want16 else None
+    call("w2v2_dropout", ptr(x), 1 if x.dtype == F32 else 0, ptr(bias), H, ptr(x), ptr(y16), x.numel(), float(p), int(seed),
+         stream_ptr())
+    return x, y16
+
+
+def time_mask_apply_(h: torch.Tensor, mask_u8: torch.Tensor, embed: torch.Tensor):
+    rows, H = h.shape
+    call("w2v2_time_mask_apply", ptr(h), ptr(mask_u8), ptr(embed), rows, H, stream_ptr())
+    return h
+
+
+def time_mask_bwd_(dh: torch.Tensor, mask_u8: torch.Tensor, dembed: torch.Tensor, scale: float = 1.0):
+    rows, H = dh.shape
+    call("w2v2_time_mask_bwd", ptr(dh), ptr(mask_u8), ptr(dembed), rows, H, float(scale), stream_ptr())
+    return dh
+
+
+def meanstd_pool_bwd(x: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+    B, T, H = x.shape
+    dx = torch.empty_like(x)
+    call("w2v2_meanstd_pool_bwd", ptr(x), ptr(dout.contiguous()), ptr(dx), B, T, H, stream_ptr())
+    return dx
+
+
+def aam_softmax_ce_train(cosine, labels, margin, scale, easy_margin=False):
+    """Like aam_softmax_ce, additionally returning the pre-margin label cosines (saved for backward)."""
+    B, S = cosine.shape
+    prob = torch.empty(B, S, dtype=F32, device=cosine.device)
+    loss = torch.empty(B, dtype=F32, device=cosine.device)
+    am = torch.empty(B, dtype=torch.int32, device=cosine.device)
+    cl = torch.empty(B, dtype=F32, device=cosine.device)
+    call("w2v2_aam_softmax_ce_ex", ptr(cosine), cosine.stride(0), ptr(labels), float(margin), float(scale),
+         int(easy_margin), ptr(prob), ptr(loss), ptr(am), ptr(cl), B, S, stream_ptr())
+    return prob, loss, am, cl
+
+
+def aam_bwd_dcos(prob, cos_label, labels, dloss, coef, margin, scale, easy_margin, ldd):
+    B, S = prob.shape
+    dc = torch.empty(B, ldd, dtype=F16, device=prob.device)
+    call("w2v2_aam_bwd_dcos", ptr(prob), ptr(cos_label), ptr(labels), ptr(dloss), float(coef), float(margin), float(scale),
+         int(easy_margin), ptr(dc), B, S, ldd, stream_ptr())
+    return dc
+
+
+def row_inv_norm(x: torch.Tensor) -> torch.Tensor:
+    rows, E = x.shape
+    inv = torch.empty(rows, dtype=F32, device=x.device)
+    call("w2v2_row_inv_norm", ptr(x.contiguous()), ptr(inv), rows, E, stream_ptr())
+    return inv
+
+
+def l2norm_rows_bwd(x: torch.Tensor, dxh: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    rows, E = x.shape
+    dx = torch.empty(rows, E, dtype=F32, device=x.device)
+    call("w2v2_l2norm_rows_bwd", ptr(x.contiguous()), ptr(dxh), dxh.stride(0), ptr(dx), rows, E, float(scale), 0,
+         stream_ptr())
+    return dx

@@ -41,8 +41,9 @@ class AngularAdditiveMarginSoftMaxLoss(nn.Module):
         assert x.size()[0] == label.size()[0]
         assert x.size()[1] == self.input_features
         if torch.is_grad_enabled() and (x.requires_grad or self.fc_weights.requires_grad):
-            raise NotImplementedError("the backward of the AAM-softmax head is not implemented yet "
-                                      "(run under torch.no_grad(), or train with the CE head)")
+            from ...training import AamSoftmaxFn
+            return AamSoftmaxFn.apply(x, self.fc_weights, label.to(torch.int64), self.margin, self.scale,
+                                      self.easy_margin, self._weights())
         xa = ops.l2norm_rows_split3(x.detach().float(), 0)
         cosine = ops.gemm_f16(xa, self._weights(), None, 0, torch.float32)       # [B, S] (padded pitch)
         prob, loss_rows, _ = ops.aam_softmax_ce(cosine, label.to(torch.int64), self.margin, self.scale,

@@ -5,18 +5,23 @@
     -> fused Adam over the flat fp32 parameter buffer (w2v2_adam_step).
 
 Parameters and gradients of the trainable tensors are views into two flat fp32 buffers (so the
-all-reduce is one message -- bucketed below -- and Adam is one launch), which is also what the
-reference's Lightning DDP + ``torch.optim.Adam`` (R:config/optim/algo/adam.yaml, R:config/trainer/trainer.yaml:6-9)
-amount to.  LayerDrop-skipped or unused parameters simply keep a zero gradient.
+all-reduce is one message -- bucketed below -- and Adam is one launch per segment), which is also what
+the reference's Lightning DDP + ``torch.optim.Adam`` (R:config/optim/algo/adam.yaml,
+R:config/trainer/trainer.yaml:6-9) amount to.  The encoder's backward writes its weight gradients
+straight into the flat buffer (``model._grad_sink``), so no per-parameter accumulation pass exists;
+they stay loss-scaled and Adam undoes the scale.  Unused / LayerDrop-skipped parameters keep a zero
+gradient.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist
 
 from . import ops
+from .models.wav2vec2 import Wav2Vec2ModelB200
+from .training import LOSS_SCALE, GradBook, encoder_grad_order
 
 
 class FlatAdamTrainer:
@@ -24,22 +29,38 @@ class FlatAdamTrainer:
                  bucket_bytes: int = 64 << 20):
         self.module = module
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
+        self.model = next((m for m in module.modules() if isinstance(m, Wav2Vec2ModelB200)), None)
+        named = dict(module.named_parameters())
+        enc_named = dict(self.model.named_parameters()) if self.model is not None else {}
+        # segment 0: encoder parameters in the order the backward wants (q|k|v adjacent), loss-scaled grads
+        enc_order = [k for k in (encoder_grad_order(self.model.arch) if self.model is not None else [])
+                     if enc_named[k].requires_grad]
+        if self.model is not None and len(enc_order) != len(encoder_grad_order(self.model.arch)):
+            enc_order = []          # partially frozen encoder: fall back to autograd accumulation
+        enc_ids = {id(enc_named[k]) for k in enc_order}
+        seg0 = [enc_named[k] for k in enc_order]
+        seg1 = [p for p in named.values() if p.requires_grad and id(p) not in enc_ids]
+        self.params: List[torch.nn.Parameter] = seg0 + seg1
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
+        self.n0 = sum(p.numel() for p in seg0)
         n = sum(p.numel() for p in self.params)
         self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         o = 0
-        for p in self.params:
+        for i, p in enumerate(self.params):
             k = p.numel()
             self.flat_p[o:o + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + k].view_as(p)
-            p.grad = self.flat_g[o:o + k].view_as(p)
+            if i >= len(seg0):
+                p.grad = self.flat_g[o:o + k].view_as(p)      # autograd accumulates the (unscaled) head grads here
             o += k
+        if seg0:
+            self.model._grad_sink = GradBook({k: enc_named[k].shape for k in enc_order}, enc_order, dev,
+                                             flat=self.flat_g[:self.n0])
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_elems = max(1, bucket_bytes // 4)
@@ -74,7 +95,13 @@ class FlatAdamTrainer:
         loss.backward()
         self.allreduce_grads()
         self.step_count += 1
-        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                      self.step_count, grad_scale=1.0 / self.world)
+        b1, b2 = self.betas
+        n0, n = self.n0, self.flat_p.numel()
+        if n0:
+            ops.adam_step(self.flat_p[:n0], self.flat_g[:n0], self.m[:n0], self.v[:n0], self.lr, b1, b2, self.eps,
+                          self.step_count, grad_scale=1.0 / (LOSS_SCALE * self.world))
+        if n > n0:
+            ops.adam_step(self.flat_p[n0:], self.flat_g[n0:], self.m[n0:], self.v[n0:], self.lr, b1, b2, self.eps,
+                          self.step_count, grad_scale=1.0 / self.world)
         self._refresh_module_weights()
         return loss.detach(), prob
