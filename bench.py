@@ -8,9 +8,10 @@ Workload = configs[1] of BASELINE.json: wav2vec2-base + mean pool + Linear(768->
 3 s utterances, 64 per GPU, driven through the public module API (w2v2_speaker_b200/speaker_module.py).
 
   --mode train   (default) one step = forward + backward + gradient all-reduce (N > 1) + Adam update
-                 (w2v2_speaker_b200/trainer.py); CNN feature extractor frozen as in the reference default
-                 (R:config/network/wav2vec2_fc.yaml:16), regularisation probabilities 0 (the stochastic
-                 dropout / LayerDrop / SpecAugment kernels are not written yet -- stated in `config`).
+                 (w2v2_speaker_b200/trainer.py); CNN feature extractor frozen and dropout 0.1 (feature
+                 projection / hidden / attention), LayerDrop 0.05, SpecAugment 0.05 switched ON -- the reference's
+                 default training configuration (R:config/network/wav2vec2_fc.yaml, R:src/models/wav2vec2.py:83-94);
+                 --no-reg sets every regularisation probability to 0.
   --mode forward one step = eval-mode embedding + logits + softmax/CE.
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` = the
@@ -48,11 +49,12 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def workload_name(mode: str) -> str:
+def workload_name(mode: str, reg: bool = True) -> str:
     if mode == "train":
         return ("cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, TRAIN step = forward + "
-                "backward + grad all-reduce + Adam; CNN frozen (reference default), dropout/LayerDrop/SpecAugment "
-                "probabilities 0")
+                "backward + grad all-reduce + Adam; CNN frozen, " +
+                ("dropout 0.1 / LayerDrop 0.05 / SpecAugment 0.05 on (reference defaults)" if reg else
+                 "regularisation probabilities 0"))
     return ("cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, eval forward "
             "(embedding + logits + softmax/loss)")
 
@@ -121,6 +123,7 @@ def cpu_reference_step_fn(batch: int, mode: str):
     hp = make_head_params(768, NUM_SPEAKERS, seed=1)
     wav, labels = make_inputs(batch, SAMPLES, NUM_SPEAKERS, seed=1234)
     if mode == "train":
+        O.TRAIN_REG = {"feat": 0.1, "hidden": 0.1, "attn": 0.1, "layerdrop": 0.05}     # reference defaults
         train = [k for k in p if not k.startswith("feature_extractor") and k != "masked_spec_embed"]
         for k in train:
             p[k].requires_grad_(True)
@@ -135,6 +138,8 @@ def cpu_reference_step_fn(batch: int, mode: str):
             opt.step()
             return float(loss)
         return step
+
+    O.TRAIN_REG = None
 
     def step():
         with torch.no_grad():
@@ -203,12 +208,12 @@ def run_reference_arm(args):
 # our arm
 
 
-def build_module(device, train: bool):
+def build_module(device, train: bool, reg: bool = True):
     from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
     from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
     torch.manual_seed(0)
     kw = dict(activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
-              mask_time_prob=0.0, mask_feature_prob=0.0) if train else {}
+              mask_time_prob=0.0, mask_feature_prob=0.0) if (train and not reg) else {}
     cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id="facebook/wav2vec2-base", stat_pooling_type="mean",
                                  test_stat_pooling_type="mean", **kw)
     m = Wav2vec2FCModule(cfg, NUM_SPEAKERS, CrossEntropyLoss).to(device)
@@ -259,6 +264,7 @@ def main():
     ap.add_argument("--mode", default=DEFAULT_MODE, choices=["train", "forward"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reg", action="store_true", help="train mode without dropout / LayerDrop / SpecAugment")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -280,7 +286,7 @@ def main():
     B = args.batch
     K, W = args.steps, max(3, args.warmup)
     train = args.mode == "train"
-    module = build_module(dev, train)
+    module = build_module(dev, train, not args.no_reg)
     trainer = None
     if train:
         from w2v2_speaker_b200.trainer import FlatAdamTrainer
@@ -390,7 +396,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate+statistics+master weights", "data": "synthetic",
-            "config": {"workload": workload_name(args.mode), "mode": args.mode, "global_batch": world * B,
+            "config": {"workload": workload_name(args.mode, not args.no_reg), "mode": args.mode, "global_batch": world * B,
                        "parallelism": f"dp{world}" + (" (NCCL all-reduce of the flat fp32 gradient)" if train else
                                                        " (independent utterances, no collective)"),
                        "l2": "per-step working set (> 1.5 GB activations + 0.19 GB fp16 weights) >> 126 MB L2"},

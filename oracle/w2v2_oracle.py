@@ -23,6 +23,16 @@ from .params import ArchConfig, BASE
 
 P = Dict[str, torch.Tensor]
 
+# Train-mode regularisation of the reference defaults (R:src/models/wav2vec2.py:83-94), used by bench.py's CPU
+# train-step baseline only (parity runs keep it None = eval semantics): {"feat":, "hidden":, "attn":, "layerdrop":}
+TRAIN_REG: Optional[dict] = None
+
+
+def _drop(x: torch.Tensor, key: str) -> torch.Tensor:
+    if TRAIN_REG is None or TRAIN_REG.get(key, 0.0) <= 0.0:
+        return x
+    return F.dropout(x, TRAIN_REG[key], training=True)
+
 
 # --------------------------------------------------------------------------------------
 # feature extractor: HF:409-419 (Wav2Vec2FeatureEncoder.forward)
@@ -64,7 +74,7 @@ def feature_projection(feat_btc: torch.Tensor, p: P, arch: ArchConfig = BASE) ->
     """LayerNorm(C) -> Linear(C->H) (-> dropout, identity in eval).  [B,T,C] -> [B,T,H]."""
     n = F.layer_norm(feat_btc, (arch.conv_dim,), p["feature_projection.layer_norm.weight"],
                      p["feature_projection.layer_norm.bias"], arch.eps)
-    return F.linear(n, p["feature_projection.projection.weight"], p["feature_projection.projection.bias"])
+    return _drop(F.linear(n, p["feature_projection.projection.weight"], p["feature_projection.projection.bias"]), "feat")
 
 
 # --------------------------------------------------------------------------------------
@@ -102,7 +112,7 @@ def attention(h: torch.Tensor, l: int, p: P, arch: ArchConfig = BASE) -> torch.T
     k = F.linear(h, p[pre + "k_proj.weight"], p[pre + "k_proj.bias"]).view(B, T, nh, d).transpose(1, 2)
     v = F.linear(h, p[pre + "v_proj.weight"], p[pre + "v_proj.bias"]).view(B, T, nh, d).transpose(1, 2)
     s = torch.matmul(q, k.transpose(2, 3)) * (d ** -0.5)
-    a = torch.softmax(s, dim=-1)
+    a = _drop(torch.softmax(s, dim=-1), "attn")
     o = torch.matmul(a, v).transpose(1, 2).reshape(B, T, H)
     return F.linear(o, p[pre + "out_proj.weight"], p[pre + "out_proj.bias"])
 
@@ -110,12 +120,12 @@ def attention(h: torch.Tensor, l: int, p: P, arch: ArchConfig = BASE) -> torch.T
 def encoder_layer(h: torch.Tensor, l: int, p: P, arch: ArchConfig = BASE) -> torch.Tensor:
     """Post-LN block (HF:592-609): h = LN1(h + attn(h)); h = LN2(h + FFN(h))."""
     pre = f"encoder.layers.{l}."
-    h = h + attention(h, l, p, arch)
+    h = h + _drop(attention(h, l, p, arch), "hidden")
     h = F.layer_norm(h, (arch.hidden,), p[pre + "layer_norm.weight"], p[pre + "layer_norm.bias"], arch.eps)
     f = F.gelu(F.linear(h, p[pre + "feed_forward.intermediate_dense.weight"],
                         p[pre + "feed_forward.intermediate_dense.bias"]))
     f = F.linear(f, p[pre + "feed_forward.output_dense.weight"], p[pre + "feed_forward.output_dense.bias"])
-    h = F.layer_norm(h + f, (arch.hidden,), p[pre + "final_layer_norm.weight"],
+    h = F.layer_norm(h + _drop(f, "hidden"), (arch.hidden,), p[pre + "final_layer_norm.weight"],
                      p[pre + "final_layer_norm.bias"], arch.eps)
     return h
 
@@ -123,10 +133,13 @@ def encoder_layer(h: torch.Tensor, l: int, p: P, arch: ArchConfig = BASE) -> tor
 def encoder(h: torch.Tensor, p: P, arch: ArchConfig = BASE, hidden_states: Optional[list] = None) -> torch.Tensor:
     """Wav2Vec2Encoder.forward (HF:668-727), eval mode: h = LN(h + pos_conv(h)); 12 x layer."""
     h = h + pos_conv_embed(h, p, arch)
-    h = F.layer_norm(h, (arch.hidden,), p["encoder.layer_norm.weight"], p["encoder.layer_norm.bias"], arch.eps)
+    h = _drop(F.layer_norm(h, (arch.hidden,), p["encoder.layer_norm.weight"], p["encoder.layer_norm.bias"], arch.eps),
+              "hidden")
     if hidden_states is not None:
         hidden_states.append(h)
     for l in range(arch.layers):
+        if TRAIN_REG is not None and torch.rand([]).item() < TRAIN_REG.get("layerdrop", 0.0):
+            continue                                        # LayerDrop (HF:701-713)
         h = encoder_layer(h, l, p, arch)
         if hidden_states is not None:
             hidden_states.append(h)
