@@ -63,6 +63,11 @@ int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const flo
  * or NULL; outputs: y32 (f32, may be NULL) and y16 (f16, may be NULL). */
 int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
                    const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, void* stream);
+/* Train mode: y = LayerNorm(dropout(x + bias) + residual), the hidden dropout of HF:546-549 / 572-574
+ * fused in (mask = w2v2_dropout's counter-based mask over the flat [rows, H] index; drop_p = 0: none). */
+int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
+                      const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, float drop_p,
+                      uint64_t drop_seed, void* stream);
 
 /* ---- positional conv embedding --------------------------------------------------------------- */
 /* Number of taps U that share one tensor-core A tile for sequences of T frames (0 = T too long
@@ -143,6 +148,11 @@ int w2v2_cast_f16_transpose(const float* w, void* wt16, int R, int C, int ldt, c
 int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
                        const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
                        float* dbeta, int64_t rows, int H, void* stream);
+/* Backward of w2v2_layernorm_ex: the mask is regenerated from (drop_p, drop_seed); dx32 is the gradient
+ * of the residual input, dx16 the gradient of the dropped branch input (dx * mask / (1 - p)). */
+int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
+                          const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
+                          float* dbeta, int64_t rows, int H, float drop_p, uint64_t drop_seed, void* stream);
 /* dz = dg * gelu'(z), all f16, n % 8 == 0. */
 int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void* stream);
 /* out[c] += scale * sum_r x[r, c]  (bias gradients); x f16 (x_dtype 0) or f32 (1), row pitch ld. */
@@ -155,6 +165,12 @@ int w2v2_mean_pool_bwd(const float* demb, float* dh, int B, int T, int H, void* 
 /* y = GELU(x) as a standalone pass (training: the GEMM / posconv ran without the fused activation);
  * x, y f16 (dtype 0) or f32 (1); x16_copy (may be NULL) receives the rounded pre-activation. */
 int w2v2_gelu_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* x16_copy, int64_t n, void* stream);
+/* Weight gradient of the positional conv without an im2col:
+ *   dW[g*I + o][k][i] += sum_{b,t} dz[b,t,g*I+o] * x[b, t + k - K/2, g*I + i]      (I = H / groups, 48 or 64)
+ * dz16, x16: f16 [B,T,H]; dw_hki f32 [H][K][I] is accumulated into (zero it for a fresh gradient), the
+ * layout w2v2_weight_norm_bwd consumes.  Any T.  (autograd of HF:360-368 / cuDNN grouped backward-filter) */
+int w2v2_posconv_wgrad(const void* dz16, const void* x16, float* dw_hki, int B, int T, int H, int groups, int K,
+                       void* stream);
 /* Positional-conv weight gradient: X_g[(b,t), j*I + i] = x[b, t+j-K/2, g*I+i] (f16 [B*T, K*I]) for one
  * group; the gradient of the folded weight is then w2v2_gemm_wgrad_f16(dz[:, g*O:(g+1)*O], X_g). */
 int w2v2_posconv_im2col(const void* x16, void* xg16, int B, int T, int H, int groups, int K, int g, void* stream);

@@ -153,3 +153,23 @@ def test_adam_matches_torch(ops):
         ops.adam_step(p, g * step * 128.0, m, v, 1e-3, 0.9, 0.999, 1e-8, step, grad_scale=1.0 / 128.0)
     torch.cuda.synchronize()
     assert rel(p, ref.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("B,T,H,G", [(3, 149, 768, 16), (2, 49, 768, 16), (2, 249, 1024, 16), (1, 1, 768, 16),
+                                     (150, 149, 768, 16)])
+def test_posconv_wgrad_matches_conv1d_autograd(ops, B, T, H, G):
+    """dW of the grouped k=128 conv (HF:360-368): shifted-slab tensor-core kernel vs torch's conv1d backward."""
+    K, I = 128, H // G
+    x16 = _rand((B, T, H), 11).half()
+    dz16 = _rand((B, T, H), 12, 0.25).half()
+    dw = torch.zeros(H, K * I, device="cuda")
+    ops.posconv_wgrad(dz16, x16, G, K, dw)
+    torch.cuda.synchronize()
+    w = torch.zeros(H, I, K, dtype=torch.float64, requires_grad=True)
+    y = F.conv1d(x16.double().cpu().transpose(1, 2), w, None, padding=K // 2, groups=G)[:, :, :T]
+    y.backward(dz16.double().cpu().transpose(1, 2))
+    ref = w.grad.permute(0, 2, 1).reshape(H, K * I).cuda()          # [o][k][i]
+    assert torch.isfinite(dw).all()
+    assert rel(dw, ref) < 2e-5
+    ops.posconv_wgrad(dz16, x16, G, K, dw)                          # accumulates like .grad
+    assert rel(dw, 2 * ref) < 2e-5

@@ -47,3 +47,37 @@ def test_encoder_matches_reference_fixture(engine, fname, B, N):
     assert r < 1.5e-3, r
     emb = h.mean(1)
     assert rel_rows(emb, g["mean.ce.embedding"]) < EMB_TOL
+
+
+def test_large_architecture_forward_matches_oracle():
+    """configs[4] architecture (wav2vec2-large: 24 layers, H=1024, 16 heads, FFN 4096) on a short input."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle import w2v2_oracle as O
+    from oracle.params import LARGE as O_LARGE, make_inputs, make_params
+    from w2v2_speaker_b200.engine import LARGE, EncoderEngine, PreparedWeights
+    torch.set_num_threads(8)
+    p = make_params(O_LARGE, seed=3)
+    eng = EncoderEngine(PreparedWeights({k: v.cuda() for k, v in p.items()}, LARGE))
+    wav, _ = make_inputs(2, 12000, seed=5)
+    h = eng.forward(wav.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.wav2vec2_forward(wav, p, O_LARGE)
+    assert h.shape == ref.shape == (2, 37, 1024)
+    assert rel_rows(h.mean(1), ref.mean(1)) < 1.5e-3          # 24 layers: twice the depth of the base bound
+    r = ((h.cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+    assert r < 3e-3, r
+
+
+def test_five_second_utterances_use_the_wide_tiles(engine, base_params):
+    """5 s -> 249 frames: attention TK = 256 (512 TMEM columns), two positional-conv row tiles."""
+    from oracle import w2v2_oracle as O
+    from oracle.params import BASE, make_inputs
+    torch.set_num_threads(8)
+    wav, _ = make_inputs(1, 80000, seed=6)
+    h = engine.forward(wav.cuda())
+    with torch.no_grad():
+        ref = O.wav2vec2_forward(wav, base_params, BASE)
+    assert h.shape == ref.shape == (1, 249, 768)
+    assert rel_rows(h.mean(1), ref.mean(1)) < 1e-3

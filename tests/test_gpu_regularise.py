@@ -142,3 +142,33 @@ def test_training_step_with_reference_default_regularisation(base_params):
         e1, _ = m(wav[:, None, :].cuda())
         e2, _ = m(wav[:, None, :].cuda())
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize("rows,H", [(1000, 768), (37, 1024), (300, 512)])
+def test_layernorm_with_fused_dropout_equals_two_pass(rows, H):
+    """LayerNorm(dropout(x + bias) + residual) with the mask generated inside the kernel == the standalone
+    dropout pass followed by the plain LayerNorm (bit-identical: same hash, same arithmetic), forward and backward."""
+    from w2v2_speaker_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(rows, H, generator=g).cuda()
+    res = torch.randn(rows, H, generator=g).cuda()
+    bias = torch.randn(H, generator=g).cuda()
+    gamma = (torch.rand(H, generator=g) + 0.5).cuda()
+    beta = torch.randn(H, generator=g).cuda()
+    dy = torch.randn(rows, H, generator=g).cuda()
+    p, seed = 0.1, 0x1234567890AB
+    y32, y16 = ops.layernorm(x, gamma, beta, 1e-5, bias=bias, residual=res, drop_p=p, drop_seed=seed)
+    xd = x.clone()
+    ops.dropout_(xd, p, seed, bias=bias)
+    r32, r16 = ops.layernorm(xd, gamma, beta, 1e-5, residual=res)
+    assert torch.equal(y32, r32) and torch.equal(y16, r16)
+    dg, db = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    dx32, dx16 = ops.layernorm_bwd(dy, x, gamma, 1e-5, bias=bias, residual=res, dgamma=dg, dbeta=db, drop_p=p, drop_seed=seed)
+    dg2, db2 = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    e32, e16 = ops.layernorm_bwd(dy, xd, gamma, 1e-5, residual=res, dgamma=dg2, dbeta=db2)
+    assert torch.equal(dx32, e32)                       # residual gradient: unmasked
+    ops.dropout_(e16, p, seed)                          # branch gradient: masked and rescaled
+    assert (dx16.float() - e16.float()).abs().max().item() <= 2e-3 * e16.float().abs().max().item()
+    kept = (e16 != 0)
+    assert torch.equal(dx16 != 0, kept) or ((dx16 != 0) ^ kept).float().mean().item() < 1e-3
+    assert torch.allclose(dg, dg2, rtol=1e-4, atol=1e-4) and torch.allclose(db, db2, rtol=1e-4, atol=1e-4)

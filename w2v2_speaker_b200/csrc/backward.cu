@@ -34,19 +34,21 @@ __global__ void cast_f16_transpose_kernel(const float* __restrict__ w, __half* _
 }
 
 // =================================================================================================
-// LayerNorm backward.  x = xa (+ bias) (+ residual) is recomputed (as are mean / rstd), so the forward
-// saves nothing extra.  dy = dy_a (+ dy_b).  Outputs dx (f32) and/or dx16 (f16);
+// LayerNorm backward.  x = drop(xa (+ bias)) (+ residual) is recomputed (as are mean / rstd and the dropout
+// mask), so the forward saves nothing extra.  dy = dy_a (+ dy_b).  Outputs dx (f32, the gradient of the
+// residual input) and/or dx16 (f16, the gradient of the branch input: dx times the dropout mask);
 // dgamma / dbeta are accumulated with one atomicAdd per column per block.
-template <bool XA_F32>
+template <bool XA_F32, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy_a, const float* __restrict__ dy_b,
                                                             const void* __restrict__ xa_, const float* __restrict__ bias,
                                                             const float* __restrict__ residual,
                                                             const float* __restrict__ gamma, float eps,
                                                             float* __restrict__ dx32, __half* __restrict__ dx16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            int64_t rows, int H) {
-  constexpr int MAXV = 8;                       // H <= 1024
-  __shared__ float sred[8][1024];
+                                                            int64_t rows, int H, uint32_t thr, float inv_keep,
+                                                            uint64_t seed) {
+  // MAXV = ceil(H / 128) float4 slots per lane (4: H <= 512, 6: H <= 768, 8: H <= 1024)
+  __shared__ float sred[8][MAXV * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 ag[MAXV], ab[MAXV];
 #pragma unroll
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
           const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
           a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
         }
+        if (thr != 0) dropout4(a, seed, row * H + c, thr, inv_keep);
         if (residual != nullptr) {
           const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
           a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.w = rstd * (d[i].w - s1 - x[i].w * s2);
         if (dx32 != nullptr) *reinterpret_cast<float4*>(dx32 + row * H + c) = o;
         if (dx16 != nullptr) {
+          if (thr != 0) dropout4(o, seed, row * H + c, thr, inv_keep);
           uint2 q;
           q.x = pack_half2(o.x, o.y);
           q.y = pack_half2(o.z, o.w);
@@ -311,15 +315,28 @@ int w2v2_cast_f16_transpose(const float* w, void* wt16, int R, int C, int ldt, c
 int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
                        const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
                        float* dbeta, int64_t rows, int H, void* stream) {
+  return w2v2_layernorm_bwd_ex(dy_a, dy_b, xa, xa_dtype, bias, residual, gamma, eps, dx32, dx16, dgamma, dbeta, rows, H,
+                               0.f, 0, stream);
+}
+
+int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
+                          const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
+                          float* dbeta, int64_t rows, int H, float drop_p, uint64_t drop_seed, void* stream) {
   W2V2_REQUIRE(H % 4 == 0 && H <= 1024, "w2v2_layernorm_bwd: H=%d must be a multiple of 4 and <= 1024", H);
+  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_layernorm_bwd: drop_p=%f out of [0,1)", drop_p);
   if (rows == 0) return 0;
+  const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
+  const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
   const int grid = grid_cap((rows + 7) / 8, 4);
-  if (xa_dtype == 1)
-    layernorm_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32,
-                                                                        (__half*)dx16, dgamma, dbeta, rows, H);
-  else
-    layernorm_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32,
-                                                                         (__half*)dx16, dgamma, dbeta, rows, H);
+  cudaStream_t st = (cudaStream_t)stream;
+#define W2V2_LNB(F32, NV) \
+  layernorm_bwd_kernel<F32, NV><<<grid, 256, 0, st>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32, (__half*)dx16, dgamma, dbeta, rows, H, thr, inv_keep, drop_seed)
+  if (xa_dtype == 1) {
+    if (H <= 512) W2V2_LNB(true, 4); else if (H <= 768) W2V2_LNB(true, 6); else W2V2_LNB(true, 8);
+  } else {
+    if (H <= 512) W2V2_LNB(false, 4); else if (H <= 768) W2V2_LNB(false, 6); else W2V2_LNB(false, 8);
+  }
+#undef W2V2_LNB
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -283,6 +283,16 @@ __device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t pair_id
   return uint32_t(z >> 16);
 }
 
+// inverted dropout of four consecutive elements starting at the (even) flat element index `idx`
+__device__ __forceinline__ void dropout4(float4& a, uint64_t seed, int64_t idx, uint32_t thr, float inv_keep) {
+  const uint32_t h0 = dropout_hash(seed, uint64_t(idx >> 1));
+  const uint32_t h1 = dropout_hash(seed, uint64_t(idx >> 1) + 1);
+  a.x = (h0 & 0xffffu) >= thr ? a.x * inv_keep : 0.f;
+  a.y = (h0 >> 16) >= thr ? a.y * inv_keep : 0.f;
+  a.z = (h1 & 0xffffu) >= thr ? a.z * inv_keep : 0.f;
+  a.w = (h1 >> 16) >= thr ? a.w * inv_keep : 0.f;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -177,19 +177,19 @@ __global__ void conv0_weight_split_kernel(const float* __restrict__ w, __half* _
 }
 
 // =================================================================================================
-// LayerNorm(x + bias + residual) -> f32 and/or f16   (one warp per row, values kept in registers)
+// LayerNorm(drop(x + bias) + residual) -> f32 and/or f16   (one warp per row, values kept in registers;
+// thr > 0: counter-based inverted dropout of the branch, regenerated in the backward from the same seed)
 
-template <bool X_F32>
+template <bool X_F32, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, const float* __restrict__ bias,
                                                         const float* __restrict__ residual,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float* __restrict__ y32, __half* __restrict__ y16,
-                                                        int64_t rows, int H) {
+                                                        int64_t rows, int H, uint32_t thr, float inv_keep, uint64_t seed) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
-  constexpr int MAXV = 8;                       // H <= 1024
-  float4 v[MAXV];
+  float4 v[MAXV];                               // MAXV = ceil(H / 128) float4 slots per lane
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
         const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
         a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
       }
+      if (thr != 0) dropout4(a, seed, row * H + c, thr, inv_keep);
       if (residual != nullptr) {
         const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
         a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
@@ -622,13 +623,26 @@ int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const flo
 
 int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
                    const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, void* stream) {
+  return w2v2_layernorm_ex(x, x_dtype, bias, residual, gamma, beta, eps, y32, y16, rows, H, 0.f, 0, stream);
+}
+
+int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
+                      const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, float drop_p,
+                      uint64_t drop_seed, void* stream) {
   W2V2_REQUIRE(H % 4 == 0 && H <= 1024, "w2v2_layernorm: H=%d must be a multiple of 4 and <= 1024", H);
+  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_layernorm: drop_p=%f out of [0,1)", drop_p);
   if (rows == 0) return 0;
+  const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
+  const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
   const int grid = int((rows + 7) / 8);
-  if (x_dtype == 1)
-    layernorm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H);
-  else
-    layernorm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H);
+  cudaStream_t st = (cudaStream_t)stream;
+#define W2V2_LN(F32, NV) layernorm_kernel<F32, NV><<<grid, 256, 0, st>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed)
+  if (x_dtype == 1) {
+    if (H <= 512) W2V2_LN(true, 4); else if (H <= 768) W2V2_LN(true, 6); else W2V2_LN(true, 8);
+  } else {
+    if (H <= 512) W2V2_LN(false, 4); else if (H <= 768) W2V2_LN(false, 6); else W2V2_LN(false, 8);
+  }
+#undef W2V2_LN
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

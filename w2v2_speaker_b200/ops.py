@@ -87,15 +87,15 @@ def conv0_gn_gelu(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta:
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
               bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-              want32: bool = True, want16: bool = True):
-    """LayerNorm(x + bias + residual) over the last dim -> (y32 | None, y16 | None)."""
+              want32: bool = True, want16: bool = True, drop_p: float = 0.0, drop_seed: int = 0):
+    """LayerNorm(dropout(x + bias) + residual) over the last dim -> (y32 | None, y16 | None)."""
     assert x.is_contiguous()
     H = x.shape[-1]
     rows = x.numel() // H
     y32 = torch.empty(x.shape, dtype=F32, device=x.device) if want32 else None
     y16 = torch.empty(x.shape, dtype=F16, device=x.device) if want16 else None
-    call("w2v2_layernorm", ptr(x), 1 if x.dtype == F32 else 0, ptr(bias), ptr(residual), ptr(gamma), ptr(beta),
-         eps, ptr(y32), ptr(y16), rows, H, stream_ptr())
+    call("w2v2_layernorm_ex", ptr(x), 1 if x.dtype == F32 else 0, ptr(bias), ptr(residual), ptr(gamma), ptr(beta),
+         eps, ptr(y32), ptr(y16), rows, H, float(drop_p), int(drop_seed), stream_ptr())
     return y32, y16
 
 
@@ -143,6 +143,17 @@ def posconv_im2col(x16: torch.Tensor, groups: int, K: int, g: int, out: torch.Te
     B, T, H = x16.shape
     call("w2v2_posconv_im2col", ptr(x16), ptr(out), B, T, H, groups, K, g, stream_ptr())
     return out
+
+
+def posconv_wgrad(dz16: torch.Tensor, x16: torch.Tensor, groups: int, K: int, dw_hki: torch.Tensor) -> torch.Tensor:
+    """dw_hki[o, k*I + i] += sum_{b,t} dz[b,t,o] x[b,t+k-K/2, g(o)*I+i]   (f32 [H, K*I], accumulated)."""
+    _chk(dz16, F16, "dz16")
+    _chk(x16, F16, "x16")
+    B, T, H = x16.shape
+    assert dz16.shape == x16.shape and dw_hki.dtype == F32 and dw_hki.is_contiguous()
+    assert dw_hki.shape == (H, K * (H // groups))
+    call("w2v2_posconv_wgrad", ptr(dz16), ptr(x16), ptr(dw_hki), B, T, H, groups, K, stream_ptr())
+    return dw_hki
 
 
 def weight_norm_bwd(dw_hki, v, g, scale, dv, dg):
@@ -195,13 +206,15 @@ def cast_f16_transpose(w: torch.Tensor, ldt: Optional[int] = None, row_scale: Op
 
 
 def layernorm_bwd(dy_a, xa, gamma, eps=1e-5, dy_b=None, bias=None, residual=None, dgamma=None, dbeta=None,
-                  want32=True, want16=True):
+                  want32=True, want16=True, drop_p: float = 0.0, drop_seed: int = 0):
+    """-> (dx32: gradient of the residual input, dx16: gradient of the (dropped) branch input xa)."""
     H = xa.shape[-1]
     rows = xa.numel() // H
     dx32 = torch.empty(rows, H, dtype=F32, device=xa.device) if want32 else None
     dx16 = torch.empty(rows, H, dtype=F16, device=xa.device) if want16 else None
-    call("w2v2_layernorm_bwd", ptr(dy_a), ptr(dy_b), ptr(xa), 1 if xa.dtype == F32 else 0, ptr(bias), ptr(residual),
-         ptr(gamma), eps, ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, H, stream_ptr())
+    call("w2v2_layernorm_bwd_ex", ptr(dy_a), ptr(dy_b), ptr(xa), 1 if xa.dtype == F32 else 0, ptr(bias), ptr(residual),
+         ptr(gamma), eps, ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, H, float(drop_p), int(drop_seed),
+         stream_ptr())
     return dx32, dx16
 
 

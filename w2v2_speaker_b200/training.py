@@ -135,20 +135,17 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
         L["att"], L["lse"] = ops.attention(L["qkv"], B, T, H, a.heads, want_lse=True,
                                            drop_p=plan.p_attn if plan is not None else 0.0, drop_seed=seed + 100 + l)
         L["o"] = ops.gemm_f16(L["att"], lw["wo"], None, 0, F32).contiguous()
-        if ph > 0:
-            ops.dropout_(L["o"], ph, seed + 200 + l, bias=lw["bo"])      # x1 = h_in + drop(o + bo)  (HF:546-549)
-        h32, h16 = ops.layernorm(L["o"], lw["ln1_g"], lw["ln1_b"], a.eps, bias=None if ph > 0 else lw["bo"],
-                                 residual=L["h_in32"])
+        # x1 = h_in + drop(o + bo) (HF:546-549), the dropout is generated inside the LayerNorm kernel
+        h32, h16 = ops.layernorm(L["o"], lw["ln1_g"], lw["ln1_b"], a.eps, bias=lw["bo"], residual=L["h_in32"],
+                                 drop_p=ph, drop_seed=seed + 200 + l)
         L["h1_32"], L["h1_16"] = h32, h16
         L["z"] = ops.gemm_f16(h16, lw["w1"], lw["b1"], 0, F16).contiguous()
         L["g"], _ = ops.gelu_fwd(L["z"], F16)
         if plan is not None and plan.p_act > 0:
             ops.dropout_(L["g"], plan.p_act, seed + 400 + l)             # HF:568
         L["f2"] = ops.gemm_f16(L["g"], lw["w2"], None, 0, F32).contiguous()
-        if ph > 0:
-            ops.dropout_(L["f2"], ph, seed + 300 + l, bias=lw["b2"])     # HF:572
-        h32, h16 = ops.layernorm(L["f2"], lw["ln2_g"], lw["ln2_b"], a.eps, bias=None if ph > 0 else lw["b2"],
-                                 residual=L["h1_32"])
+        h32, h16 = ops.layernorm(L["f2"], lw["ln2_g"], lw["ln2_b"], a.eps, bias=lw["b2"], residual=L["h1_32"],
+                                 drop_p=ph, drop_seed=seed + 300 + l)                      # HF:572-574
         S["layers"].append(L)
     return h32.view(B, T, H), S
 
@@ -219,12 +216,10 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
             continue
         pre = f"encoder.layers.{l}."
         lw, tl = w.layers[l], tw.layers[l]
-        # LN2:  h2 = LN(drop(f2 + b2) + h1)   (L["f2"] already holds drop(f2 + b2) when dropout is on)
-        dx2_32, dx2_16 = ops.layernorm_bwd(dy_a, L["f2"], lw["ln2_g"], a.eps, dy_b=dy_b, bias=None if ph > 0 else lw["b2"],
+        # LN2:  h2 = LN(drop(f2 + b2) + h1); dx2_16 is the gradient of the dropped branch, the residual keeps dx2_32
+        dx2_32, dx2_16 = ops.layernorm_bwd(dy_a, L["f2"], lw["ln2_g"], a.eps, dy_b=dy_b, bias=lw["b2"],
                                            residual=L["h1_32"], dgamma=G.view(pre + "final_layer_norm.weight"),
-                                           dbeta=G.view(pre + "final_layer_norm.bias"))
-        if ph > 0:
-            ops.dropout_(dx2_16, ph, seed + 300 + l)    # gradient of the dropped branch; the residual keeps dx2_32
+                                           dbeta=G.view(pre + "final_layer_norm.bias"), drop_p=ph, drop_seed=seed + 300 + l)
         ops.colsum(dx2_16, G.view(pre + "feed_forward.output_dense.bias"))
         ops.gemm_wgrad_f16(dx2_16, L["g"], G.view(pre + "feed_forward.output_dense.weight"))
         dg16 = ops.gemm_f16(dx2_16, tl["w2T"], None, 0, F16).contiguous()       # [M, FF]
@@ -235,11 +230,9 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
         ops.gemm_wgrad_f16(dz16, L["h1_16"], G.view(pre + "feed_forward.intermediate_dense.weight"))
         dh1_a = ops.gemm_f16(dz16, tl["w1T"], None, 0, F32)                      # [M, H]
         # LN1:  h1 = LN(drop(o + bo) + h_in)
-        dx1_32, dx1_16 = ops.layernorm_bwd(dh1_a, L["o"], lw["ln1_g"], a.eps, dy_b=dx2_32, bias=None if ph > 0 else lw["bo"],
+        dx1_32, dx1_16 = ops.layernorm_bwd(dh1_a, L["o"], lw["ln1_g"], a.eps, dy_b=dx2_32, bias=lw["bo"],
                                            residual=L["h_in32"], dgamma=G.view(pre + "layer_norm.weight"),
-                                           dbeta=G.view(pre + "layer_norm.bias"))
-        if ph > 0:
-            ops.dropout_(dx1_16, ph, seed + 200 + l)
+                                           dbeta=G.view(pre + "layer_norm.bias"), drop_p=ph, drop_seed=seed + 200 + l)
         ops.colsum(dx1_16, G.view(pre + "attention.out_proj.bias"))
         ops.gemm_wgrad_f16(dx1_16, L["att"], G.view(pre + "attention.out_proj.weight"))
         datt16 = ops.gemm_f16(dx1_16, tl["woT"], None, 0, F16)
@@ -262,14 +255,11 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
     dz16 = ops.gelu_bwd(dxe16, S["zpos16"])
     ops.colsum(dz16, G.view("encoder.pos_conv_embed.conv.bias"))
     dx_pos = ops.posconv_ex(dz16.view(B, T, H), tw.pos_dgrad_w(T), None, a.pos_groups, a.pos_kernel, 0, 1)
-    # positional-conv weight gradient: one im2col + wgrad per group, then weight-norm backward
+    # positional-conv weight gradient (shifted-slab tensor-core kernel, no im2col), then weight-norm backward
     I = H // a.pos_groups
     K = a.pos_kernel
     dw_hki = torch.zeros(H, K * I, dtype=F32, device=dev)
-    xg = torch.empty(M, K * I, dtype=F16, device=dev)
-    for g in range(a.pos_groups):
-        ops.posconv_im2col(S["x16"].view(B, T, H), a.pos_groups, K, g, xg)
-        ops.gemm_wgrad_f16(dz16[:, g * I:(g + 1) * I], xg, dw_hki[g * I:(g + 1) * I])
+    ops.posconv_wgrad(dz16.view(B, T, H), S["x16"].view(B, T, H), a.pos_groups, K, dw_hki)
     ops.weight_norm_bwd(dw_hki, w._pos_v, w._pos_g, 1.0,
                         G.view("encoder.pos_conv_embed.conv.parametrizations.weight.original1"),
                         G.view("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1))
