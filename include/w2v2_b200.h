@@ -149,12 +149,17 @@ int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int
                        const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
                        float* dbeta, int64_t rows, int H, void* stream);
 /* Backward of w2v2_layernorm_ex: the mask is regenerated from (drop_p, drop_seed); dx32 is the gradient
- * of the residual input, dx16 the gradient of the dropped branch input (dx * mask / (1 - p)). */
+ * of the residual input, dx16 the gradient of the dropped branch input (dx * mask / (1 - p)); dbias (f32 [H]
+ * or NULL) accumulates the column sums of that branch gradient = the gradient of `bias`. */
 int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
                           const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
-                          float* dbeta, int64_t rows, int H, float drop_p, uint64_t drop_seed, void* stream);
+                          float* dbeta, float* dbias, int64_t rows, int H, float drop_p, uint64_t drop_seed,
+                          void* stream);
 /* dz = dg * gelu'(z), all f16, n % 8 == 0. */
 int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void* stream);
+/* Same over [rows, cols], plus dbias[c] += sum_r dz[r, c] (gradient of the bias that was added to form z). */
+int w2v2_gelu_bwd_colsum(const void* dg16, const void* z16, void* dz16, int64_t rows, int cols, float* dbias,
+                         void* stream);
 /* out[c] += scale * sum_r x[r, c]  (bias gradients); x f16 (x_dtype 0) or f32 (1), row pitch ld. */
 int w2v2_colsum(const void* x, int x_dtype, int64_t rows, int cols, int64_t ld, float scale, float* out, void* stream);
 /* dlogits = (prob - onehot(label)) * coef -> f16 [B, ldd] (columns >= S zero).  coef = loss_scale / B. */
@@ -198,8 +203,9 @@ int w2v2_l2norm_rows_bwd(const float* x, const float* dxh, int64_t ldd, float* d
                          int accumulate, void* stream);
 /* ---- train-mode regularisation (HF:433, 456, 546-600, 693, 1280-1324) -------------------------------
  * Dropout masks are a pure function of (seed, element index) -- regenerated in the backward, never stored:
- * keep <=> 16 random bits >= round(p * 65536), bits = splitmix64(seed + (index/2) * 0x9E3779B97F4A7C15) >> 16,
- * low / high half for the even / odd element.
+ * keep <=> 16 random bits >= round(p * 65536); bits = a 32-bit multiply / xor-shift mix of (index/2) and the
+ * two seed halves (csrc/common.cuh::dropout_hash; numpy replica in tests/test_gpu_regularise.py), low / high
+ * half for the even / odd element.
  * w2v2_dropout: y = keep ? (x + bias[col]) / (1-p) : 0 over n elements (x, y f32 (dtype 1) or f16 (0),
  * y may alias x; optional extra f16 copy y16).  The attention kernels take the probability-dropout the
  * same way (index = ((b*heads + h)*T + q) * TK + k).  Time mask: rows with mask != 0 are overwritten by
@@ -229,6 +235,23 @@ int w2v2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
 /* ---- utility ---------------------------------------------------------------------------------- */
 /* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */
 int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream);
+/* Batched weight preparation after an optimizer step (one launch for all trainable matrices):
+ * per job, v = src[r, c] * scale is written to any of  dst16[r*ld + c] (f16),  dst32[r*ld + c] (f32),
+ * dstT16[c*ldt + r] (f16, transposed; point it at a column offset to assemble fused W^T operands).
+ * The table lives in device memory; tile_begin is the exclusive prefix sum of ceil(R/32)*ceil(C/32).
+ * (replaces the per-step .half() / .t() / torch.cat the reference's AMP autocast does implicitly) */
+typedef struct {
+  const void* src;      /* f32 [R, C] row-major */
+  void* dst16;          /* or NULL */
+  void* dstT16;         /* or NULL */
+  void* dst32;          /* or NULL */
+  int32_t R, C;
+  int32_t ld, ldt;      /* row pitch (elements) of dst16 / dst32, and of dstT16 */
+  float scale;
+  int32_t pad_;
+  int64_t tile_begin;
+} w2v2_prep_job;
+int w2v2_prepare_weights(const w2v2_prep_job* jobs_dev, int njobs, int64_t total_tiles, void* stream);
 /* Conv1d weight [Cout, Cin, K] f32 -> tap-major fp16 [Cout, K, Cin] (the W operand of w2v2_gemm_f16). */
 int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int k, void* stream);
 

@@ -173,3 +173,29 @@ def test_posconv_wgrad_matches_conv1d_autograd(ops, B, T, H, G):
     assert rel(dw, ref) < 2e-5
     ops.posconv_wgrad(dz16, x16, G, K, dw)                          # accumulates like .grad
     assert rel(dw, 2 * ref) < 2e-5
+
+
+def test_fused_bias_gradients(ops):
+    """Column sums fused into their producers: gelu_bwd(dbias=...) and layernorm_bwd(dbias=...) must equal the
+    standalone passes."""
+    M, FF, H = 1003, 3072, 768
+    dg = _rand((M, FF), 21, 0.3).half()
+    z = _rand((M, FF), 22, 1.5).half()
+    db = torch.zeros(FF, device="cuda")
+    dz = ops.gelu_bwd(dg, z, dbias=db)
+    dz_ref = ops.gelu_bwd(dg, z)
+    assert torch.equal(dz, dz_ref)
+    assert rel(db, dz_ref.double().sum(0)) < 1e-5
+    dz = ops.gelu_bwd(dg, z, dbias=db)                      # accumulates
+    assert rel(db, 2 * dz_ref.double().sum(0)) < 1e-5
+    x = _rand((M, H), 23)
+    res = _rand((M, H), 24)
+    dy = _rand((M, H), 25)
+    gamma = _rand((H,), 26).abs() + 0.5
+    bias = _rand((H,), 27)
+    dbias = torch.zeros(H, device="cuda")
+    dx32, dx16 = ops.layernorm_bwd(dy, x, gamma, 1e-5, bias=bias, residual=res, dbias=dbias)
+    assert rel(dbias, dx32.double().sum(0)) < 1e-5
+    dbias.zero_()
+    dx32, dx16 = ops.layernorm_bwd(dy, x, gamma, 1e-5, bias=bias, residual=res, dbias=dbias, drop_p=0.1, drop_seed=77)
+    assert rel(dbias, dx16.double().sum(0)) < 2e-3         # dx16 is the fp16-rounded branch gradient

@@ -21,13 +21,27 @@ def ops():
 def keep_mask(seed: int, n: int, p: float) -> np.ndarray:
     """numpy replica of csrc/common.cuh::dropout_hash + the 16-bit threshold test (n even)."""
     thr = int(p * 65536.0 + 0.5)
-    with np.errstate(over="ignore"):
-        idx = np.arange(n // 2, dtype=np.uint64)
-        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    bits = (z >> np.uint64(16)) & np.uint64(0xFFFFFFFF)
+    M32 = 0xFFFFFFFF
+
+    def fmix32(x):          # python ints
+        x ^= x >> 16
+        x = (x * 0x85EBCA6B) & M32
+        x ^= x >> 13
+        x = (x * 0xC2B2AE35) & M32
+        return x ^ (x >> 16)
+
+    k0 = fmix32(((seed & M32) + 0x9E3779B9) & M32)
+    k1 = fmix32(((seed >> 32) & M32) ^ k0 ^ 0x7F4A7C15)
+    m32 = np.uint64(M32)
+    idx = np.arange(n // 2, dtype=np.uint64)
+    x = (((idx & m32) ^ np.uint64(k0)) * np.uint64(0x9E3779B1)) & m32
+    x ^= x >> np.uint64(15)
+    x = (x + np.uint64(k1) + (idx >> np.uint64(32)) * np.uint64(0x7FEB352D)) & m32
+    x = (x * np.uint64(0x85EBCA6B)) & m32
+    x ^= x >> np.uint64(13)
+    x = (x * np.uint64(0xC2B2AE35)) & m32
+    x ^= x >> np.uint64(16)
+    bits = x
     lo, hi = bits & np.uint64(0xFFFF), bits >> np.uint64(16)
     keep = np.empty(n, dtype=bool)
     keep[0::2] = lo >= thr

@@ -145,3 +145,42 @@ def test_training_step_meanstd_aam_matches_oracle_autograd(base_params):
         assert ((g - r).norm() / r.norm()).item() < 1e-2, k
     g, r = m.loss_fn.fc_weights.grad.cpu().double(), fw.grad.double()
     assert ((g - r).norm() / r.norm()).item() < 1e-2
+
+
+def test_inplace_weight_refresh_equals_rebuild(base_params):
+    """After a fused optimizer step the fp16 / transposed / folded operand copies are re-derived by ONE batched
+    launch (w2v2_prepare_weights); they must equal what a from-scratch preparation of the new parameters gives."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from w2v2_speaker_b200.engine import PreparedWeights
+    from w2v2_speaker_b200.training import TrainWeights
+    m, _ = _module(base_params)
+    model = m.wav2vec.model
+    eng = model._engine()
+    tw = model._train_weights(eng)
+    ptrs = (eng.w.layers[3]["wqkv"].data_ptr(), tw.layers[3]["w1T"].data_ptr())
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in model.parameters():                       # raw in-place update, invisible to autograd versions
+            torch.add(p.data, torch.randn(p.shape, generator=g).to(p.device) * 0.01, out=p.data)
+    model.refresh()
+    assert model._engine() is eng                          # updated in place, not rebuilt
+    assert ptrs == (eng.w.layers[3]["wqkv"].data_ptr(), tw.layers[3]["w1T"].data_ptr())
+    named = dict(model.named_parameters())
+    fresh = PreparedWeights(named, model.arch)
+    fresh_t = TrainWeights(fresh, named)
+    H = model.arch.hidden
+    scale = float(H // model.arch.heads) ** -0.5
+    for l in (0, 5, 11):
+        for k in ("wqkv", "bqkv", "wo", "w1", "w2"):
+            assert torch.equal(eng.w.layers[l][k], fresh.layers[l][k]), (l, k)
+        for k in ("wqkvT", "woT", "w1T", "w2T"):
+            assert torch.equal(tw.layers[l][k], fresh_t.layers[l][k]), (l, k)
+        pre = f"encoder.layers.{l}."
+        ref = torch.cat([named[pre + "attention.q_proj.weight"] * scale, named[pre + "attention.k_proj.weight"],
+                         named[pre + "attention.v_proj.weight"]], 0).half()
+        assert torch.equal(eng.w.layers[l]["wqkv"], ref)
+        assert torch.equal(tw.layers[l]["wqkvT"], ref.t())
+        assert torch.equal(tw.layers[l]["w2T"], named[pre + "feed_forward.output_dense.weight"].half().t())
+    assert torch.equal(eng.w.fp_w, named["feature_projection.projection.weight"].half())
+    assert torch.equal(tw.fp_wT, eng.w.fp_w.t())

@@ -30,12 +30,13 @@ SIGNATURES = {
     "w2v2_layernorm_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                   c_int64, c_int, c_float, c_uint64, c_void_p]),
     "w2v2_layernorm_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_uint64, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_uint64, c_void_p]),
     "w2v2_posconv_taps_per_mma": (c_int, [c_int, c_int, c_int]),
     "w2v2_posconv_fold_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_posconv_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p]),
     "w2v2_gelu_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "w2v2_prepare_weights": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     "w2v2_posconv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_posconv_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_weight_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int,
@@ -48,6 +49,7 @@ SIGNATURES = {
     "w2v2_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "w2v2_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "w2v2_gelu_bwd_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "w2v2_colsum": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_float, c_void_p, c_void_p]),
     "w2v2_softmax_ce_bwd": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_mean_pool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -38,29 +38,42 @@ __global__ void cast_f16_transpose_kernel(const float* __restrict__ w, __half* _
 // mask), so the forward saves nothing extra.  dy = dy_a (+ dy_b).  Outputs dx (f32, the gradient of the
 // residual input) and/or dx16 (f16, the gradient of the branch input: dx times the dropout mask);
 // dgamma / dbeta are accumulated with one atomicAdd per column per block.
-template <bool XA_F32, int MAXV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy_a, const float* __restrict__ dy_b,
+// EXACT: H == 128 * MAXV, the per-slot bounds checks (and the branches that would serialise the loads) vanish.
+// The per-warp dgamma / dbeta partial sums live in shared memory (registers are what limits the number of
+// rows in flight per SM), one private strip per warp, reduced over the block's warps at the end.
+constexpr int LNB_WARPS = 4;
+template <bool XA_F32, int MAXV, bool EXACT>
+__global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_bwd_kernel(const float* __restrict__ dy_a, const float* __restrict__ dy_b,
                                                             const void* __restrict__ xa_, const float* __restrict__ bias,
                                                             const float* __restrict__ residual,
                                                             const float* __restrict__ gamma, float eps,
                                                             float* __restrict__ dx32, __half* __restrict__ dx16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dbias,
                                                             int64_t rows, int H, uint32_t thr, float inv_keep,
                                                             uint64_t seed) {
   // MAXV = ceil(H / 128) float4 slots per lane (4: H <= 512, 6: H <= 768, 8: H <= 1024)
-  __shared__ float sred[8][MAXV * 128];
+  // strips: 0 = dgamma, 1 = dbeta, 2 = dbias (column sums of the branch gradient, i.e. the bias gradient of
+  // the Linear that produced xa)
+  __shared__ float4 sacc[LNB_WARPS][3][MAXV * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 ag[MAXV], ab[MAXV];
+  float4* sg = sacc[warp][0];
+  float4* sb = sacc[warp][1];
+  float4* sd = sacc[warp][2];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
-  const int64_t wstride = int64_t(gridDim.x) * 8;
-  for (int64_t row = int64_t(blockIdx.x) * 8 + warp; row < rows; row += wstride) {
+  for (int i = 0; i < MAXV; ++i) {
+    sg[i * 32 + lane] = make_float4(0, 0, 0, 0);
+    sb[i * 32 + lane] = make_float4(0, 0, 0, 0);
+    sd[i * 32 + lane] = make_float4(0, 0, 0, 0);
+  }
+  const int64_t wstride = int64_t(gridDim.x) * LNB_WARPS;
+  for (int64_t row = int64_t(blockIdx.x) * LNB_WARPS + warp; row < rows; row += wstride) {
     float4 x[MAXV], d[MAXV];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < H) {
+      if (EXACT || c < H) {
         float4 a;
         if constexpr (XA_F32) {
           a = *reinterpret_cast<const float4*>(static_cast<const float*>(xa_) + row * H + c);
@@ -70,6 +83,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
           const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
           a = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
+        float4 g = *reinterpret_cast<const float4*>(dy_a + row * H + c);
+        if (dy_b != nullptr) {
+          const float4 g2 = *reinterpret_cast<const float4*>(dy_b + row * H + c);
+          g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+        }
+        d[i] = g;
         if (bias != nullptr) {
           const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
           a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
@@ -81,12 +100,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         }
         x[i] = a;
         sum += (a.x + a.y) + (a.z + a.w);
-        float4 g = *reinterpret_cast<const float4*>(dy_a + row * H + c);
-        if (dy_b != nullptr) {
-          const float4 g2 = *reinterpret_cast<const float4*>(dy_b + row * H + c);
-          g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
-        }
-        d[i] = g;
       }
     }
     const float mean = warp_sum(sum) / float(H);
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < H) {
+      if (EXACT || c < H) {
         x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
         sq += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
       }
@@ -105,11 +118,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < H) {
+      if (EXACT || c < H) {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
         x[i].x *= rstd; x[i].y *= rstd; x[i].z *= rstd; x[i].w *= rstd;
-        ag[i].x += d[i].x * x[i].x; ag[i].y += d[i].y * x[i].y; ag[i].z += d[i].z * x[i].z; ag[i].w += d[i].w * x[i].w;
-        ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+        float4 ag = sg[i * 32 + lane], ab = sb[i * 32 + lane];
+        ag.x += d[i].x * x[i].x; ag.y += d[i].y * x[i].y; ag.z += d[i].z * x[i].z; ag.w += d[i].w * x[i].w;
+        ab.x += d[i].x; ab.y += d[i].y; ab.z += d[i].z; ab.w += d[i].w;
+        sg[i * 32 + lane] = ag;
+        sb[i * 32 + lane] = ab;
         d[i].x *= gm.x; d[i].y *= gm.y; d[i].z *= gm.z; d[i].w *= gm.w;
         s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
         s2 += (d[i].x * x[i].x + d[i].y * x[i].y) + (d[i].z * x[i].z + d[i].w * x[i].w);
@@ -120,43 +136,48 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < H) {
+      if (EXACT || c < H) {
         float4 o;
         o.x = rstd * (d[i].x - s1 - x[i].x * s2);
         o.y = rstd * (d[i].y - s1 - x[i].y * s2);
         o.z = rstd * (d[i].z - s1 - x[i].z * s2);
         o.w = rstd * (d[i].w - s1 - x[i].w * s2);
         if (dx32 != nullptr) *reinterpret_cast<float4*>(dx32 + row * H + c) = o;
-        if (dx16 != nullptr) {
+        if (dx16 != nullptr || dbias != nullptr) {
           if (thr != 0) dropout4(o, seed, row * H + c, thr, inv_keep);
-          uint2 q;
-          q.x = pack_half2(o.x, o.y);
-          q.y = pack_half2(o.z, o.w);
-          *reinterpret_cast<uint2*>(dx16 + row * H + c) = q;
+          if (dx16 != nullptr) {
+            uint2 q;
+            q.x = pack_half2(o.x, o.y);
+            q.y = pack_half2(o.z, o.w);
+            *reinterpret_cast<uint2*>(dx16 + row * H + c) = q;
+          }
+          if (dbias != nullptr) {
+            float4 a = sd[i * 32 + lane];
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            sd[i * 32 + lane] = a;
+          }
         }
       }
     }
   }
-  if (dgamma == nullptr && dbeta == nullptr) return;
-  // block reduction of the per-warp column sums, one atomic per column per block (gamma, then beta)
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    float* dst = pass == 0 ? dgamma : dbeta;
+  if (dgamma == nullptr && dbeta == nullptr && dbias == nullptr) return;
+  // block reduction of the per-warp column sums, one (vector) atomic per 4 columns per block
+  __syncthreads();
+  for (int v = threadIdx.x; v < H / 4; v += LNB_WARPS * 32) {
+    float4 tg = sacc[0][0][v], tb = sacc[0][1][v], td = sacc[0][2][v];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < H) *reinterpret_cast<float4*>(&sred[warp][c]) = pass == 0 ? ag[i] : ab[i];
+    for (int w = 1; w < LNB_WARPS; ++w) {
+      const float4 a = sacc[w][0][v], b = sacc[w][1][v], d = sacc[w][2][v];
+      tg.x += a.x; tg.y += a.y; tg.z += a.z; tg.w += a.w;
+      tb.x += b.x; tb.y += b.y; tb.z += b.z; tb.w += b.w;
+      td.x += d.x; td.y += d.y; td.z += d.z; td.w += d.w;
     }
-    __syncthreads();
-    if (dst != nullptr) {
-      for (int c = threadIdx.x; c < H; c += blockDim.x) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += sred[w][c];
-        atomicAdd(dst + c, t);
-      }
-    }
-    __syncthreads();
+    if (dbias != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias + 4 * v), "f"(td.x), "f"(td.y), "f"(td.z), "f"(td.w) : "memory");
+    if (dgamma != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + 4 * v), "f"(tg.x), "f"(tg.y), "f"(tg.z), "f"(tg.w) : "memory");
+    if (dbeta != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + 4 * v), "f"(tb.x), "f"(tb.y), "f"(tb.z), "f"(tb.w) : "memory");
   }
 }
 
@@ -197,6 +218,50 @@ __global__ void gelu_bwd_kernel(const __half* __restrict__ dg, const __half* __r
       oo[j] = pack_half2(g.x * gelu_grad(zz.x), g.y * gelu_grad(zz.y));
     }
     *reinterpret_cast<uint4*>(dz + i) = o;
+  }
+}
+
+// dz = dg * gelu'(z) over [rows, cols] f16, plus dbias[c] += sum_r dz[r, c] (the bias gradient of the Linear
+// that produced z) in the same pass: block = 32 column lanes (8 columns each) x 8 row lanes.
+__global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const __half* __restrict__ dg, const __half* __restrict__ z,
+                                                              __half* __restrict__ dz, int64_t rows, int cols,
+                                                              float* __restrict__ dbias) {
+  __shared__ float sm[8][256 + 8];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cl * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < cols) {
+    for (int64_t r = int64_t(blockIdx.y) * 8 + rl; r < rows; r += int64_t(gridDim.y) * 8) {
+      const uint4 a = *reinterpret_cast<const uint4*>(dg + r * cols + c);
+      const uint4 b = *reinterpret_cast<const uint4*>(z + r * cols + c);
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b);
+      uint4 o;
+      uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g = __half22float2(ah[j]);
+        const float2 zz = __half22float2(bh[j]);
+        const __half2 h = __floats2half2_rn(g.x * gelu_grad(zz.x), g.y * gelu_grad(zz.y));
+        oo[j] = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 f = __half22float2(h);              // sum what the weight-gradient GEMM will see
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+      *reinterpret_cast<uint4*>(dz + r * cols + c) = o;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[rl][cl * 8 + j] = acc[j];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+    atomicAdd(dbias + cc, t);
   }
 }
 
@@ -315,26 +380,32 @@ int w2v2_cast_f16_transpose(const float* w, void* wt16, int R, int C, int ldt, c
 int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
                        const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
                        float* dbeta, int64_t rows, int H, void* stream) {
-  return w2v2_layernorm_bwd_ex(dy_a, dy_b, xa, xa_dtype, bias, residual, gamma, eps, dx32, dx16, dgamma, dbeta, rows, H,
-                               0.f, 0, stream);
+  return w2v2_layernorm_bwd_ex(dy_a, dy_b, xa, xa_dtype, bias, residual, gamma, eps, dx32, dx16, dgamma, dbeta, nullptr,
+                               rows, H, 0.f, 0, stream);
 }
 
 int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,
                           const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
-                          float* dbeta, int64_t rows, int H, float drop_p, uint64_t drop_seed, void* stream) {
+                          float* dbeta, float* dbias, int64_t rows, int H, float drop_p, uint64_t drop_seed,
+                          void* stream) {
   W2V2_REQUIRE(H % 4 == 0 && H <= 1024, "w2v2_layernorm_bwd: H=%d must be a multiple of 4 and <= 1024", H);
   W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_layernorm_bwd: drop_p=%f out of [0,1)", drop_p);
   if (rows == 0) return 0;
   const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
   const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
-  const int grid = grid_cap((rows + 7) / 8, 4);
+  // one wave of resident blocks, every warp the same number of rows (+-1)
+  const int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS, slots = int64_t(device_sm_count()) * (H <= 768 ? 4 : 3);
+  const int64_t per_warp = (want + slots - 1) / slots;
+  const int grid = int((want + per_warp - 1) / per_warp);
   cudaStream_t st = (cudaStream_t)stream;
-#define W2V2_LNB(F32, NV) \
-  layernorm_bwd_kernel<F32, NV><<<grid, 256, 0, st>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32, (__half*)dx16, dgamma, dbeta, rows, H, thr, inv_keep, drop_seed)
+#define W2V2_LNB(F32, NV, EX) \
+  layernorm_bwd_kernel<F32, NV, EX><<<grid, LNB_WARPS * 32, 0, st>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32, (__half*)dx16, dgamma, dbeta, dbias, rows, H, thr, inv_keep, drop_seed)
   if (xa_dtype == 1) {
-    if (H <= 512) W2V2_LNB(true, 4); else if (H <= 768) W2V2_LNB(true, 6); else W2V2_LNB(true, 8);
+    if (H == 512) W2V2_LNB(true, 4, true); else if (H == 768) W2V2_LNB(true, 6, true);
+    else if (H == 1024) W2V2_LNB(true, 8, true); else W2V2_LNB(true, 8, false);
   } else {
-    if (H <= 512) W2V2_LNB(false, 4); else if (H <= 768) W2V2_LNB(false, 6); else W2V2_LNB(false, 8);
+    if (H == 512) W2V2_LNB(false, 4, true); else if (H == 768) W2V2_LNB(false, 6, true);
+    else if (H == 1024) W2V2_LNB(false, 8, true); else W2V2_LNB(false, 8, false);
   }
 #undef W2V2_LNB
   count_launches(1);
@@ -347,6 +418,20 @@ int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void
   if (n == 0) return 0;
   gelu_bwd_kernel<<<grid_cap((n / 8 + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>((const __half*)dg16, (const __half*)z16,
                                                                                      (__half*)dz16, n);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_gelu_bwd_colsum(const void* dg16, const void* z16, void* dz16, int64_t rows, int cols, float* dbias, void* stream) {
+  W2V2_REQUIRE(cols % 8 == 0, "w2v2_gelu_bwd_colsum: cols=%d must be a multiple of 8", cols);
+  W2V2_REQUIRE(dbias != nullptr, "w2v2_gelu_bwd_colsum: dbias is required (use w2v2_gelu_bwd without it)");
+  if (rows == 0) return 0;
+  dim3 grid((cols + 255) / 256, 1);
+  int64_t want = (int64_t(device_sm_count()) * 6 + grid.x - 1) / grid.x, cap = (rows + 7) / 8;
+  grid.y = unsigned(want < cap ? want : cap);
+  gelu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)dg16, (const __half*)z16, (__half*)dz16, rows,
+                                                                cols, dbias);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -273,14 +273,31 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   unpack2(r, x0, x1);
 }
 
-// counter-based random bits for dropout: splitmix64 finaliser of (seed + pair_index * golden ratio);
-// low / high 16 bits decide the two elements of the pair
-__device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t pair_idx) {
-  uint64_t z = seed + pair_idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return uint32_t(z >> 16);
+// counter-based random bits for dropout: a 32-bit multiply / xor-shift mix (murmur3 finaliser) of the pair
+// index with both seed halves folded in; low / high 16 bits decide the two elements of the pair.
+// (32-bit on purpose: a 64-bit mix costs ~3x the instructions, and the attention kernels run it on a
+// one-thread-per-row critical path.)
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t pair_idx) {
+  // two keys derived from the seed (loop invariant: hoisted by the compiler), so that nearby seeds --
+  // the per-layer / per-site offsets of one step -- give unrelated masks
+  const uint32_t k0 = fmix32(uint32_t(seed) + 0x9E3779B9u);
+  const uint32_t k1 = fmix32(uint32_t(seed >> 32) ^ k0 ^ 0x7F4A7C15u);
+  uint32_t x = (uint32_t(pair_idx) ^ k0) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x += k1 + uint32_t(pair_idx >> 32) * 0x7FEB352Du;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
 }
 
 // inverted dropout of four consecutive elements starting at the (even) flat element index `idx`

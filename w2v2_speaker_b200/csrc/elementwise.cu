@@ -180,7 +180,8 @@ __global__ void conv0_weight_split_kernel(const float* __restrict__ w, __half* _
 // LayerNorm(drop(x + bias) + residual) -> f32 and/or f16   (one warp per row, values kept in registers;
 // thr > 0: counter-based inverted dropout of the branch, regenerated in the backward from the same seed)
 
-template <bool X_F32, int MAXV>
+// EXACT: H == 128 * MAXV (no per-slot bounds checks, so all loads of a row issue back to back)
+template <bool X_F32, int MAXV, bool EXACT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x_, const float* __restrict__ bias,
                                                         const float* __restrict__ residual,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 32 + lane) * 4;
-    if (c < H) {
+    if (EXACT || c < H) {
       float4 a;
       if constexpr (X_F32) {
         a = *reinterpret_cast<const float4*>(static_cast<const float*>(x_) + row * H + c);
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 32 + lane) * 4;
-    if (c < H) {
+    if (EXACT || c < H) {
       const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
       sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 32 + lane) * 4;
-    if (c < H) {
+    if (EXACT || c < H) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
       float4 o;
@@ -636,11 +637,13 @@ int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float
   const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
   const int grid = int((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define W2V2_LN(F32, NV) layernorm_kernel<F32, NV><<<grid, 256, 0, st>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed)
+#define W2V2_LN(F32, NV, EX) layernorm_kernel<F32, NV, EX><<<grid, 256, 0, st>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed)
   if (x_dtype == 1) {
-    if (H <= 512) W2V2_LN(true, 4); else if (H <= 768) W2V2_LN(true, 6); else W2V2_LN(true, 8);
+    if (H == 512) W2V2_LN(true, 4, true); else if (H == 768) W2V2_LN(true, 6, true);
+    else if (H == 1024) W2V2_LN(true, 8, true); else W2V2_LN(true, 8, false);
   } else {
-    if (H <= 512) W2V2_LN(false, 4); else if (H <= 768) W2V2_LN(false, 6); else W2V2_LN(false, 8);
+    if (H == 512) W2V2_LN(false, 4, true); else if (H == 768) W2V2_LN(false, 6, true);
+    else if (H == 1024) W2V2_LN(false, 8, true); else W2V2_LN(false, 8, false);
   }
 #undef W2V2_LN
   count_launches(1);

@@ -20,11 +20,60 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
 
 F16, F32 = torch.float16, torch.float32
+
+
+class WeightPrep:
+    """Job table of ``w2v2_prepare_weights``: every trainable matrix -> fp16 copy (+ transposed fp16 copy,
+    + folded scalar), every fused bias -> assembled fp32 vector, all in ONE launch per optimizer step."""
+
+    DT = np.dtype([("src", "<u8"), ("dst16", "<u8"), ("dstT16", "<u8"), ("dst32", "<u8"), ("R", "<i4"), ("C", "<i4"),
+                   ("ld", "<i4"), ("ldt", "<i4"), ("scale", "<f4"), ("pad", "<i4"), ("tile_begin", "<i8")])
+
+    def __init__(self):
+        self.jobs: Dict[str, dict] = {}
+        self._table = None
+        self._tiles = 0
+        self._keep = []
+
+    def add(self, key: str, src: torch.Tensor, dst16=None, dst32=None, scale: float = 1.0):
+        src2 = src if src.dim() == 2 else src.view(1, -1)
+        assert src2.dtype == F32 and src2.is_contiguous()
+        d = dst16 if dst16 is not None else dst32
+        d2 = d if d.dim() == 2 else d.view(1, -1)
+        assert d2.shape == src2.shape and d2.stride(-1) == 1
+        self.jobs[key] = dict(src=src2, dst16=d2 if dst16 is not None else None, dst32=d2 if dst32 is not None else None,
+                              dstT=None, scale=float(scale))
+        self._table = None
+
+    def add_transposed(self, key: str, dstT: torch.Tensor):
+        """dstT: f16 view [C, R] (row pitch = ldt) receiving the transpose of job `key`."""
+        j = self.jobs[key]
+        assert dstT.shape == (j["src"].shape[1], j["src"].shape[0]) and dstT.stride(1) == 1
+        j["dstT"] = dstT
+        self._table = None
+
+    def run(self):
+        if self._table is None:
+            rec = np.zeros(len(self.jobs), dtype=self.DT)
+            t = 0
+            for i, j in enumerate(self.jobs.values()):
+                R, C = j["src"].shape
+                rec[i] = (j["src"].data_ptr(), j["dst16"].data_ptr() if j["dst16"] is not None else 0,
+                          j["dstT"].data_ptr() if j["dstT"] is not None else 0,
+                          j["dst32"].data_ptr() if j["dst32"] is not None else 0, R, C,
+                          (j["dst16"] if j["dst16"] is not None else j["dst32"]).stride(0) if R > 1 else C,
+                          j["dstT"].stride(0) if j["dstT"] is not None else 0, j["scale"], 0, t)
+                t += ((R + 31) // 32) * ((C + 31) // 32)
+            dev = next(iter(self.jobs.values()))["src"].device
+            self._table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
+            self._tiles = t
+        ops.prepare_weights(self._table, len(self.jobs), self._tiles)
 
 
 @dataclass(frozen=True)
@@ -80,7 +129,6 @@ class PreparedWeights:
                                 for i in range(1, len(arch.conv_kernel))]
         self.fp_ln_g = f("feature_projection.layer_norm.weight")
         self.fp_ln_b = f("feature_projection.layer_norm.bias")
-        self.fp_w = ops.cast_f16(f("feature_projection.projection.weight"))
         self.fp_b = f("feature_projection.projection.bias")
         self._pos_v = f("encoder.pos_conv_embed.conv.parametrizations.weight.original1")
         self._pos_g = f("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1)
@@ -91,23 +139,49 @@ class PreparedWeights:
         self.enc_ln_b = f("encoder.layer_norm.bias")
         d = H // arch.heads
         scale = float(d) ** -0.5
+        dev = self.enc_ln_g.device
+        # fp16 operand copies, filled (and re-filled after every optimizer step) by one batched launch
+        self.prep = WeightPrep()
+        self._aliased = True          # do the job sources alias the live parameters (fp32, contiguous)?
+
+        def src(k):
+            t = f(k)
+            self._aliased = self._aliased and t.data_ptr() == p[k].data_ptr()
+            return t
+
+        self.fp_w = torch.empty(H, arch.conv_dim, dtype=F16, device=dev)
+        self.prep.add("feature_projection.projection.weight", src("feature_projection.projection.weight"), dst16=self.fp_w)
         self.layers = []
         for l in range(arch.layers):
             pre = f"encoder.layers.{l}."
-            wq, wk, wv = (f(pre + f"attention.{n}_proj.weight") for n in "qkv")
-            bq, bk, bv = (f(pre + f"attention.{n}_proj.bias") for n in "qkv")
             # the softmax scale d^-0.5 is folded into the q projection (HF:528 scales q)
-            wqkv = ops.cast_f16(torch.cat([wq * scale, wk, wv], 0))
-            bqkv = torch.cat([bq * scale, bk, bv], 0).contiguous()
-            self.layers.append(dict(
-                wqkv=wqkv, bqkv=bqkv,
-                wo=ops.cast_f16(f(pre + "attention.out_proj.weight")), bo=f(pre + "attention.out_proj.bias"),
-                ln1_g=f(pre + "layer_norm.weight"), ln1_b=f(pre + "layer_norm.bias"),
-                w1=ops.cast_f16(f(pre + "feed_forward.intermediate_dense.weight")),
-                b1=f(pre + "feed_forward.intermediate_dense.bias"),
-                w2=ops.cast_f16(f(pre + "feed_forward.output_dense.weight")),
-                b2=f(pre + "feed_forward.output_dense.bias"),
-                ln2_g=f(pre + "final_layer_norm.weight"), ln2_b=f(pre + "final_layer_norm.bias")))
+            wqkv = torch.empty(3 * H, H, dtype=F16, device=dev)
+            bqkv = torch.empty(3 * H, dtype=F32, device=dev)
+            for i, n in enumerate("qkv"):
+                self.prep.add(pre + f"attention.{n}_proj.weight", src(pre + f"attention.{n}_proj.weight"),
+                              dst16=wqkv[i * H:(i + 1) * H], scale=scale if n == "q" else 1.0)
+                self.prep.add(pre + f"attention.{n}_proj.bias", src(pre + f"attention.{n}_proj.bias"),
+                              dst32=bqkv[i * H:(i + 1) * H], scale=scale if n == "q" else 1.0)
+            L = dict(wqkv=wqkv, bqkv=bqkv, bo=f(pre + "attention.out_proj.bias"),
+                     ln1_g=f(pre + "layer_norm.weight"), ln1_b=f(pre + "layer_norm.bias"),
+                     b1=f(pre + "feed_forward.intermediate_dense.bias"), b2=f(pre + "feed_forward.output_dense.bias"),
+                     ln2_g=f(pre + "final_layer_norm.weight"), ln2_b=f(pre + "final_layer_norm.bias"))
+            for name, key in (("wo", "attention.out_proj.weight"), ("w1", "feed_forward.intermediate_dense.weight"),
+                              ("w2", "feed_forward.output_dense.weight")):
+                w = src(pre + key)
+                L[name] = torch.empty(w.shape, dtype=F16, device=dev)
+                self.prep.add(pre + key, w, dst16=L[name])
+            self.layers.append(L)
+        self.prep.run()
+
+    def update(self) -> bool:
+        """Re-derive the kernel-form copies of the (non-CNN) parameters after an in-place parameter update.
+        False if the sources do not alias the parameters (then the caller rebuilds from scratch)."""
+        if not self._aliased:
+            return False
+        self.prep.run()
+        self._pos_w.clear()
+        return True
 
 
 def _pos_w(self, T: int) -> torch.Tensor:

@@ -127,6 +127,14 @@ class Wav2Vec2ModelB200(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def refresh(self) -> None:
+        """Call after the parameters were updated in place behind autograd's back (fused optimizer):
+        re-derives the fp16 / transposed operand copies with one batched launch."""
+        eng = self._prepared
+        if eng is not None and self._prepared_sig == self._signature() and eng.w.update():
+            tw = getattr(eng, "_train_weights", None)
+            if tw is not None:
+                tw._pos_dgrad.clear()
+            return
         self._prepared = None
 
     def _engine(self) -> EncoderEngine:

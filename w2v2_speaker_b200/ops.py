@@ -196,6 +196,12 @@ def gemm_wgrad_f16(dy16: torch.Tensor, x16: torch.Tensor, dw: torch.Tensor) -> t
     return dw
 
 
+def prepare_weights(table_u8: torch.Tensor, njobs: int, tiles: int):
+    """table_u8: device copy of an array of w2v2_prep_job records (see engine.WeightPrep)."""
+    assert table_u8.dtype == torch.uint8 and table_u8.numel() == 64 * njobs
+    call("w2v2_prepare_weights", ptr(table_u8), njobs, tiles, stream_ptr())
+
+
 def cast_f16_transpose(w: torch.Tensor, ldt: Optional[int] = None, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """w f32 [R,C] -> f16 [C, ldt] (transposed; ldt >= R, zero padded; multiple of 8)."""
     R, C = w.shape
@@ -206,21 +212,28 @@ def cast_f16_transpose(w: torch.Tensor, ldt: Optional[int] = None, row_scale: Op
 
 
 def layernorm_bwd(dy_a, xa, gamma, eps=1e-5, dy_b=None, bias=None, residual=None, dgamma=None, dbeta=None,
-                  want32=True, want16=True, drop_p: float = 0.0, drop_seed: int = 0):
-    """-> (dx32: gradient of the residual input, dx16: gradient of the (dropped) branch input xa)."""
+                  want32=True, want16=True, drop_p: float = 0.0, drop_seed: int = 0, dbias=None):
+    """-> (dx32: gradient of the residual input, dx16: gradient of the (dropped) branch input xa);
+    dbias (f32 [H]) accumulates the column sums of the branch gradient (= gradient of `bias`)."""
     H = xa.shape[-1]
     rows = xa.numel() // H
     dx32 = torch.empty(rows, H, dtype=F32, device=xa.device) if want32 else None
     dx16 = torch.empty(rows, H, dtype=F16, device=xa.device) if want16 else None
     call("w2v2_layernorm_bwd_ex", ptr(dy_a), ptr(dy_b), ptr(xa), 1 if xa.dtype == F32 else 0, ptr(bias), ptr(residual),
-         ptr(gamma), eps, ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, H, float(drop_p), int(drop_seed),
-         stream_ptr())
+         ptr(gamma), eps, ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), ptr(dbias), rows, H, float(drop_p),
+         int(drop_seed), stream_ptr())
     return dx32, dx16
 
 
-def gelu_bwd(dg16, z16):
+def gelu_bwd(dg16, z16, dbias=None):
+    """dz = dg * gelu'(z); with dbias (f32 [cols]): also dbias += column sums of dz, in the same pass."""
     dz = torch.empty_like(dg16)
-    call("w2v2_gelu_bwd", ptr(dg16), ptr(z16), ptr(dz), dg16.numel(), stream_ptr())
+    if dbias is None:
+        call("w2v2_gelu_bwd", ptr(dg16), ptr(z16), ptr(dz), dg16.numel(), stream_ptr())
+    else:
+        assert dg16.is_contiguous() and z16.is_contiguous()
+        cols = dg16.shape[-1]
+        call("w2v2_gelu_bwd_colsum", ptr(dg16), ptr(z16), ptr(dz), dg16.numel() // cols, cols, ptr(dbias), stream_ptr())
     return dz
 
 

@@ -30,21 +30,25 @@ class TrainWeights:
 
     def __init__(self, w: PreparedWeights, p: Dict[str, torch.Tensor]):
         a = w.arch
-        f = lambda k: p[k].detach().to(F32).contiguous()
-        self.fp_wT = ops.cast_f16_transpose(f("feature_projection.projection.weight"))          # [512, H]
-        d = a.hidden // a.heads
-        scale = float(d) ** -0.5
+        H, FF, dev = a.hidden, a.ffn, w.fp_w.device
+        prep = w.prep                      # the transposes ride on the batched weight-preparation launch
+
+        def tbuf(cols, rows):              # [cols(in), rows(out)] = W^T
+            return torch.empty(cols, rows, dtype=F16, device=dev)
+
+        self.fp_wT = tbuf(a.conv_dim, H)                                                          # [512, H]
+        prep.add_transposed("feature_projection.projection.weight", self.fp_wT)
         self.layers = []
         for l in range(a.layers):
             pre = f"encoder.layers.{l}."
-            wq, wk, wv = (f(pre + f"attention.{n}_proj.weight") for n in "qkv")
-            wqkv = torch.cat([wq * scale, wk, wv], 0)                                        # folded, [3H, H]
-            self.layers.append(dict(
-                wqkvT=ops.cast_f16_transpose(wqkv),                                           # [H, 3H]
-                woT=ops.cast_f16_transpose(f(pre + "attention.out_proj.weight")),             # [H, H]
-                w1T=ops.cast_f16_transpose(f(pre + "feed_forward.intermediate_dense.weight")),   # [H, FF]
-                w2T=ops.cast_f16_transpose(f(pre + "feed_forward.output_dense.weight"))))     # [FF, H]
-        u = None
+            L = dict(wqkvT=tbuf(H, 3 * H), woT=tbuf(H, H), w1T=tbuf(H, FF), w2T=tbuf(FF, H))
+            for i, n in enumerate("qkv"):                                                      # folded, [H, 3H]
+                prep.add_transposed(pre + f"attention.{n}_proj.weight", L["wqkvT"][:, i * H:(i + 1) * H])
+            prep.add_transposed(pre + "attention.out_proj.weight", L["woT"])
+            prep.add_transposed(pre + "feed_forward.intermediate_dense.weight", L["w1T"])
+            prep.add_transposed(pre + "feed_forward.output_dense.weight", L["w2T"])
+            self.layers.append(L)
+        prep.run()
         self._pos_dgrad = {}
         self._w = w
 
@@ -219,21 +223,20 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
         # LN2:  h2 = LN(drop(f2 + b2) + h1); dx2_16 is the gradient of the dropped branch, the residual keeps dx2_32
         dx2_32, dx2_16 = ops.layernorm_bwd(dy_a, L["f2"], lw["ln2_g"], a.eps, dy_b=dy_b, bias=lw["b2"],
                                            residual=L["h1_32"], dgamma=G.view(pre + "final_layer_norm.weight"),
-                                           dbeta=G.view(pre + "final_layer_norm.bias"), drop_p=ph, drop_seed=seed + 300 + l)
-        ops.colsum(dx2_16, G.view(pre + "feed_forward.output_dense.bias"))
+                                           dbeta=G.view(pre + "final_layer_norm.bias"), drop_p=ph, drop_seed=seed + 300 + l,
+                                           dbias=G.view(pre + "feed_forward.output_dense.bias"))
         ops.gemm_wgrad_f16(dx2_16, L["g"], G.view(pre + "feed_forward.output_dense.weight"))
         dg16 = ops.gemm_f16(dx2_16, tl["w2T"], None, 0, F16).contiguous()       # [M, FF]
         if plan is not None and plan.p_act > 0:
             ops.dropout_(dg16, plan.p_act, seed + 400 + l)
-        dz16 = ops.gelu_bwd(dg16, L["z"])
-        ops.colsum(dz16, G.view(pre + "feed_forward.intermediate_dense.bias"))
+        dz16 = ops.gelu_bwd(dg16, L["z"], dbias=G.view(pre + "feed_forward.intermediate_dense.bias"))
         ops.gemm_wgrad_f16(dz16, L["h1_16"], G.view(pre + "feed_forward.intermediate_dense.weight"))
         dh1_a = ops.gemm_f16(dz16, tl["w1T"], None, 0, F32)                      # [M, H]
         # LN1:  h1 = LN(drop(o + bo) + h_in)
         dx1_32, dx1_16 = ops.layernorm_bwd(dh1_a, L["o"], lw["ln1_g"], a.eps, dy_b=dx2_32, bias=lw["bo"],
                                            residual=L["h_in32"], dgamma=G.view(pre + "layer_norm.weight"),
-                                           dbeta=G.view(pre + "layer_norm.bias"), drop_p=ph, drop_seed=seed + 200 + l)
-        ops.colsum(dx1_16, G.view(pre + "attention.out_proj.bias"))
+                                           dbeta=G.view(pre + "layer_norm.bias"), drop_p=ph, drop_seed=seed + 200 + l,
+                                           dbias=G.view(pre + "attention.out_proj.bias"))
         ops.gemm_wgrad_f16(dx1_16, L["att"], G.view(pre + "attention.out_proj.weight"))
         datt16 = ops.gemm_f16(dx1_16, tl["woT"], None, 0, F16)
         dqkv16 = ops.attention_bwd(L["qkv"], L["att"], datt16, L["lse"], B, T, H, a.heads,
@@ -252,8 +255,7 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
         ops.dropout_(dy_a, ph, seed + 2)
     dxe32, dxe16 = ops.layernorm_bwd(dy_a, S["pos"], w.enc_ln_g, a.eps, dy_b=dy_b, residual=S["h0"],
                                      dgamma=G.view("encoder.layer_norm.weight"), dbeta=G.view("encoder.layer_norm.bias"))
-    dz16 = ops.gelu_bwd(dxe16, S["zpos16"])
-    ops.colsum(dz16, G.view("encoder.pos_conv_embed.conv.bias"))
+    dz16 = ops.gelu_bwd(dxe16, S["zpos16"], dbias=G.view("encoder.pos_conv_embed.conv.bias"))
     dx_pos = ops.posconv_ex(dz16.view(B, T, H), tw.pos_dgrad_w(T), None, a.pos_groups, a.pos_kernel, 0, 1)
     # positional-conv weight gradient (shifted-slab tensor-core kernel, no im2col), then weight-norm backward
     I = H // a.pos_groups
