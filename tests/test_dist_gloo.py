@@ -20,6 +20,21 @@ def _worker(rank, world, port, q):
     # ... and the reported time is the max over ranks
     t = du.max_over_ranks(10.0 + rank)
     du.barrier()
+    # the trainer's gradient exchange: per-layer spans sent deepest layer first, then the complement --
+    # together exactly one sum over the whole flat buffer
+    n = 1000
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    sent = []
+    for lo, hi in [(700, 1000), (400, 700), (100, 400)]:
+        torch.distributed.all_reduce(flat[lo:hi])
+        sent.append((lo, hi))
+    rest = du.remaining_spans(sent, n)
+    assert rest == [(0, 100)]
+    for lo, hi in rest:
+        torch.distributed.all_reduce(flat[lo:hi])
+    assert torch.equal(flat, torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world)))
+    assert du.remaining_spans([], 5) == [(0, 5)] and du.remaining_spans([(0, 5)], 5) == []
+    assert du.remaining_spans([(3, 4), (1, 2)], 6) == [(0, 1), (2, 3), (4, 6)]
     q.put((rank, gathered, t, du.global_batch(64)))
     torch.distributed.destroy_process_group()
 

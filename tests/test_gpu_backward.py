@@ -115,7 +115,8 @@ def test_gelu_bwd_colsum_ce_pool(ops):
 
 
 @pytest.mark.parametrize("B,T,H,heads", [(2, 49, 768, 12), (3, 149, 768, 12), (2, 128, 768, 12), (1, 16, 768, 12),
-                                         (2, 192, 1024, 16), (1, 1, 768, 12)])
+                                         (2, 192, 1024, 16), (1, 1, 768, 12), (2, 249, 1024, 16), (1, 256, 768, 12),
+                                         (1, 200, 768, 12), (2, 64, 768, 12), (1, 130, 768, 12)])
 def test_attention_bwd(ops, B, T, H, heads):
     d = H // heads
     qkv = _rand((B * T, 3 * H), 20).half()

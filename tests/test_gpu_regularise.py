@@ -76,7 +76,7 @@ def test_dropout_kernel_matches_replica(ops):
     assert torch.equal(y0, x)
 
 
-@pytest.mark.parametrize("B,T,H,heads", [(2, 49, 768, 12), (2, 149, 768, 12)])
+@pytest.mark.parametrize("B,T,H,heads", [(2, 49, 768, 12), (2, 149, 768, 12), (1, 249, 1024, 16)])
 def test_attention_dropout_forward_backward(ops, B, T, H, heads):
     d = H // heads
     g = torch.Generator().manual_seed(1)

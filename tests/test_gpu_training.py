@@ -26,7 +26,7 @@ def _module(base_params, pooling="mean"):
     return m, head
 
 
-@pytest.mark.parametrize("B,N", [(2, 16000), (3, 11283)])
+@pytest.mark.parametrize("B,N", [(2, 16000), (3, 11283), (2, 80000)])      # 80000 samples = 5 s -> 249 frames
 def test_training_step_gradients_match_oracle_autograd(base_params, B, N):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")

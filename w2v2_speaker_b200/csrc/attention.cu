@@ -6,8 +6,9 @@
 //   TMA   : Q tile [128 x 64], K [TK x 64], V [TK x 64] straight out of the fused qkv activation
 //           (3-D tensor map (column, t, b): rows t >= T are zero-filled, TK = round_up(T, 16))
 //   MMA 1 : S = Q K^T   (M=128, N=TK, K=64; both operands K-major, 128B swizzle) -> TMEM fp32
-//   softmax: one thread per query row reads its row from TMEM (tcgen05.ld 32x32b), max / exp / sum in
-//           registers -- no shuffles; P (fp16, unnormalised) goes to smem in the K-major swizzled layout
+//   softmax: two threads per query row (one per column half) read the row from TMEM (tcgen05.ld 32x32b),
+//           max / exp / sum in registers, halves combined through smem; P (fp16, unnormalised) goes to
+//           smem in the K-major swizzled layout
 //   MMA 2 : O = P V     (M=128, N=64, K=TK; V is consumed as an MN-major B operand, i.e. exactly the
 //           [t, d] tile TMA delivered -- no transpose)
 //   epilogue: O / rowsum -> fp16 -> out[b*T + t, h*64 : h*64+64]
@@ -33,8 +34,12 @@ struct alignas(64) AttnParams {
 };
 
 constexpr int ATT_D = 64;
+constexpr int ATT_THREADS = 256;      // 8 warps: warp & 3 = TMEM lane quarter (32 query rows), warp >> 2 = column half
 
-__global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ AttnParams p) {
+// Two threads per query row (one per column half): the per-row max / sum meet through shared memory.
+// Warps whose 32 query rows all lie beyond T (most of the second tile of a 149-frame utterance) skip the
+// arithmetic; their P rows stay unwritten and only feed output rows that are never stored.
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int TK = p.TK;
@@ -44,7 +49,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   uint8_t* sK = sQ + 16384;
   uint8_t* sV = sK + ((kv_bytes + 1023) & ~1023);
   uint8_t* sP = sV + ((kv_bytes + 1023) & ~1023);   // pblocks x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + pblocks * 16384);
+  float* red_max = reinterpret_cast<float*>(sP + pblocks * 16384);   // [2][128]
+  float* red_sum = red_max + 256;                                    // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_sum + 256);
   uint64_t* bar_tma = bars;
   uint64_t* bar_s = bars + 1;
   uint64_t* bar_o = bars + 2;
@@ -54,6 +61,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, cg = warp >> 2;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&p.tmQ);
@@ -89,57 +97,70 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   }
   __syncwarp();
 
-  // ---- softmax: thread <-> query row
-  const int row = warp * 32 + lane;
-  const uint32_t t_row = tmem + (uint32_t(warp * 32) << 16);
+  // ---- softmax: two threads <-> one query row, each owning half of the 16-column chunks
+  const int row = quarter * 32 + lane;
+  const int t_q = mt * 128 + row;
+  const bool warp_valid = mt * 128 + quarter * 32 < p.T;         // warp-uniform
+  const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
+  const int nchunk = TK / 16;
+  const int c_begin = (nchunk * cg) >> 1, c_end = (nchunk * (cg + 1)) >> 1;
+  const DropKeys dkeys = drop_keys(p.drop_seed);
+  const uint32_t drop_thr = p.drop_thr;
+  const float inv_keep = p.drop_inv_keep;
+  // flat pair index of this row's first pair in the [B, heads, T, TK] mask (fits 32 bits: checked on the host)
+  const uint32_t pair_row = ((uint32_t(b) * p.heads + h) * p.T + (t_q < p.T ? t_q : 0)) * uint32_t(TK / 2);
+
   mbar_wait(bar_s, 0);
   __syncwarp();
   tc_fence_after();
-  const int nchunk = TK / 16;
   float mx = -INFINITY;
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t r[16];
-    tmem_ld_32x32b_x16(t_row + c * 16, r);
-    tmem_ld_wait();
+  if (warp_valid) {
+    for (int c = c_begin; c < c_end; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + c * 16, r);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c * 16 + j < p.T) mx = fmaxf(mx, __uint_as_float(r[j]));
+      for (int j = 0; j < 16; ++j)
+        if (c * 16 + j < p.T) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
   }
+  red_max[cg * 128 + row] = mx;
+  __syncthreads();
+  mx = fmaxf(red_max[row], red_max[128 + row]);
   const float mxl = mx * 1.4426950408889634f;
   float sum = 0.f;
-  uint8_t* prow = sP + row * 128;
-  for (int c = 0; c < nchunk; ++c) {
-    uint32_t r[16];
-    tmem_ld_32x32b_x16(t_row + c * 16, r);
-    tmem_ld_wait();
-    float e[16];
+  if (warp_valid) {
+    uint8_t* prow = sP + row * 128;
+    for (int c = c_begin; c < c_end; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(t_row + c * 16, r);
+      tmem_ld_wait();
+      uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float v = exp2f(fmaf(__uint_as_float(r[j]), 1.4426950408889634f, -mxl));
-      e[j] = (c * 16 + j < p.T) ? v : 0.f;
-    }
-    // the value the tensor core will see is the fp16-rounded one: sum those for a consistent normaliser
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __half2 hh = __floats2half2_rn(e[2 * j], e[2 * j + 1]);
-      const float2 f = __half22float2(hh);
-      sum += f.x + f.y;                           // the normaliser is that of the un-dropped softmax
-      if (p.drop_thr != 0) {
-        const int t_q = mt * 128 + row;
-        const uint64_t pair = ((uint64_t(b) * p.heads + h) * p.T + t_q) * uint64_t(TK / 2) + (c * 8 + j);
-        const uint32_t hb = dropout_hash(p.drop_seed, pair);
-        hh = __floats2half2_rn((hb & 0xffffu) >= p.drop_thr ? f.x * p.drop_inv_keep : 0.f,
-                               (hb >> 16) >= p.drop_thr ? f.y * p.drop_inv_keep : 0.f);
+      for (int j = 0; j < 8; ++j) {
+        float e0 = fast_ex2(fmaf(__uint_as_float(r[2 * j]), 1.4426950408889634f, -mxl));
+        float e1 = fast_ex2(fmaf(__uint_as_float(r[2 * j + 1]), 1.4426950408889634f, -mxl));
+        if (c * 16 + 2 * j >= p.T) e0 = 0.f;
+        if (c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
+        // the value the tensor core will see is the fp16-rounded one: sum those for a consistent normaliser
+        __half2 hh = __floats2half2_rn(e0, e1);
+        const float2 f = __half22float2(hh);
+        sum += f.x + f.y;                           // the normaliser is that of the un-dropped softmax
+        if (drop_thr != 0) {
+          const uint32_t hb = dropout_hash32(dkeys, pair_row + uint32_t(c * 8 + j));
+          hh = __floats2half2_rn((hb & 0xffffu) >= drop_thr ? f.x * inv_keep : 0.f,
+                                 (hb >> 16) >= drop_thr ? f.y * inv_keep : 0.f);
+        }
+        pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
       }
-      pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      const int col = c * 16;                     // 16 halfs = two 16-byte chunks
+      uint8_t* blk = prow + (col >> 6) * 16384;
+      const int c16 = (col & 63) >> 3;
+      *reinterpret_cast<uint4*>(blk + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-    const int col = c * 16;                     // 16 halfs = two 16-byte chunks
-    uint8_t* blk = prow + (col >> 6) * 16384;
-    const int c16 = (col & 63) >> 3;
-    *reinterpret_cast<uint4*>(blk + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
+  red_sum[cg * 128 + row] = sum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -157,20 +178,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
     umma_commit(bar_o);
   }
   __syncwarp();
+  sum = red_sum[row] + red_sum[128 + row];
 
   mbar_wait(bar_o, 0);
   __syncwarp();
   tc_fence_after();
-  const int t = mt * 128 + row;
-  const float inv = 1.0f / sum;
-  if (p.lse != nullptr && t < p.T) p.lse[(int64_t(b) * p.heads + h) * p.T + t] = mx + __logf(sum);
-  __half* dst = p.out + (int64_t(b) * p.T + (t < p.T ? t : 0)) * p.H + h * ATT_D;
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
+  if (warp_valid) {
+    const float inv = 1.0f / sum;
+    if (cg == 0 && p.lse != nullptr && t_q < p.T) p.lse[(int64_t(b) * p.heads + h) * p.T + t_q] = mx + __logf(sum);
+    __half* dst = p.out + (int64_t(b) * p.T + (t_q < p.T ? t_q : 0)) * p.H + h * ATT_D + cg * 32;
     uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + p.o_col + hh * 32, r);
+    tmem_ld_32x32b_x32(t_row + p.o_col + cg * 32, r);
     tmem_ld_wait();
-    if (t < p.T) {
+    if (t_q < p.T) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 q;
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
         q.y = pack_half2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
         q.z = pack_half2(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
         q.w = pack_half2(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = q;
+        *reinterpret_cast<uint4*>(dst + 8 * c) = q;
       }
     }
   }
@@ -218,14 +238,15 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
   if (TK <= 192) { p.tmem_cols = 256; p.o_col = 192; } else { p.tmem_cols = 512; p.o_col = 256; }
   if (TK <= 64) { p.tmem_cols = 128; p.o_col = 64; }
   const int kvb = (TK * 128 + 1023) & ~1023;
-  const int smem = 16384 + 2 * kvb + ((TK + 63) / 64) * 16384 + 64 + 1024;
+  const int smem = 16384 + 2 * kvb + ((TK + 63) / 64) * 16384 + 2048 /*row max / sum exchange*/ + 64 + 1024;
+  W2V2_REQUIRE(uint64_t(B) * heads * T * (TK / 2) < (1ull << 32), "w2v2_attention: dropout mask index exceeds 32 bits");
   static int configured_smem = 0;
   if (smem > configured_smem) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   dim3 grid((T + 127) / 128, heads, B);
-  attention_kernel<<<grid, 128, smem, stream>>>(p);
+  attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(p);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
     sd[i * 32 + lane] = make_float4(0, 0, 0, 0);
   }
   const int64_t wstride = int64_t(gridDim.x) * LNB_WARPS;
+  const DropKeys dkeys = drop_keys(seed);
   for (int64_t row = int64_t(blockIdx.x) * LNB_WARPS + warp; row < rows; row += wstride) {
     float4 x[MAXV], d[MAXV];
     float sum = 0.f;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
           const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
           a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
         }
-        if (thr != 0) dropout4(a, seed, row * H + c, thr, inv_keep);
+        if (thr != 0) dropout4(a, dkeys, row * H + c, thr, inv_keep);
         if (residual != nullptr) {
           const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
           a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
         o.w = rstd * (d[i].w - s1 - x[i].w * s2);
         if (dx32 != nullptr) *reinterpret_cast<float4*>(dx32 + row * H + c) = o;
         if (dx16 != nullptr || dbias != nullptr) {
-          if (thr != 0) dropout4(o, seed, row * H + c, thr, inv_keep);
+          if (thr != 0) dropout4(o, dkeys, row * H + c, thr, inv_keep);
           if (dx16 != nullptr) {
             uint2 q;
             q.x = pack_half2(o.x, o.y);

@@ -285,29 +285,54 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
-__host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t pair_idx) {
-  // two keys derived from the seed (loop invariant: hoisted by the compiler), so that nearby seeds --
-  // the per-layer / per-site offsets of one step -- give unrelated masks
-  const uint32_t k0 = fmix32(uint32_t(seed) + 0x9E3779B9u);
-  const uint32_t k1 = fmix32(uint32_t(seed >> 32) ^ k0 ^ 0x7F4A7C15u);
-  uint32_t x = (uint32_t(pair_idx) ^ k0) * 0x9E3779B1u;
+// The two 32-bit keys derived from the 64-bit seed.  Kernels derive them ONCE per thread (drop_keys at
+// kernel entry): left inside the per-element call the compiler re-derives them for every pair.
+struct DropKeys {
+  uint32_t k0, k1;
+};
+__host__ __device__ __forceinline__ DropKeys drop_keys(uint64_t seed) {
+  // nearby seeds -- the per-layer / per-site offsets of one step -- give unrelated masks
+  DropKeys k;
+  k.k0 = fmix32(uint32_t(seed) + 0x9E3779B9u);
+  k.k1 = fmix32(uint32_t(seed >> 32) ^ k.k0 ^ 0x7F4A7C15u);
+  return k;
+}
+// pair indices below 2^32 (the attention kernels check this on the host): 3 multiplies, 3 xor-shifts, 1 add
+__host__ __device__ __forceinline__ uint32_t dropout_hash32(DropKeys k, uint32_t pair_idx) {
+  uint32_t x = (pair_idx ^ k.k0) * 0x9E3779B1u;
   x ^= x >> 15;
-  x += k1 + uint32_t(pair_idx >> 32) * 0x7FEB352Du;
+  x += k.k1;
   x *= 0x85EBCA6Bu;
   x ^= x >> 13;
   x *= 0xC2B2AE35u;
   x ^= x >> 16;
   return x;
 }
+__host__ __device__ __forceinline__ uint32_t dropout_hash_k(DropKeys k, uint64_t pair_idx) {
+  uint32_t x = (uint32_t(pair_idx) ^ k.k0) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x += k.k1 + uint32_t(pair_idx >> 32) * 0x7FEB352Du;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint64_t pair_idx) {
+  return dropout_hash_k(drop_keys(seed), pair_idx);
+}
 
 // inverted dropout of four consecutive elements starting at the (even) flat element index `idx`
-__device__ __forceinline__ void dropout4(float4& a, uint64_t seed, int64_t idx, uint32_t thr, float inv_keep) {
-  const uint32_t h0 = dropout_hash(seed, uint64_t(idx >> 1));
-  const uint32_t h1 = dropout_hash(seed, uint64_t(idx >> 1) + 1);
+__device__ __forceinline__ void dropout4(float4& a, DropKeys k, int64_t idx, uint32_t thr, float inv_keep) {
+  const uint32_t h0 = dropout_hash_k(k, uint64_t(idx >> 1));
+  const uint32_t h1 = dropout_hash_k(k, uint64_t(idx >> 1) + 1);
   a.x = (h0 & 0xffffu) >= thr ? a.x * inv_keep : 0.f;
   a.y = (h0 >> 16) >= thr ? a.y * inv_keep : 0.f;
   a.z = (h1 & 0xffffu) >= thr ? a.z * inv_keep : 0.f;
   a.w = (h1 >> 16) >= thr ? a.w * inv_keep : 0.f;
+}
+__device__ __forceinline__ void dropout4(float4& a, uint64_t seed, int64_t idx, uint32_t thr, float inv_keep) {
+  dropout4(a, drop_keys(seed), idx, thr, inv_keep);
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
+  const DropKeys dkeys = drop_keys(seed);
   float4 v[MAXV];                               // MAXV = ceil(H / 128) float4 slots per lane
   float sum = 0.f;
 #pragma unroll
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
         const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
         a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
       }
-      if (thr != 0) dropout4(a, seed, row * H + c, thr, inv_keep);
+      if (thr != 0) dropout4(a, dkeys, row * H + c, thr, inv_keep);
       if (residual != nullptr) {
         const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
         a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;

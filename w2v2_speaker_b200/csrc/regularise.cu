@@ -19,9 +19,10 @@ template <bool F32>
 __global__ void dropout_kernel(const void* __restrict__ x_, const float* __restrict__ bias, int H, void* __restrict__ y_,
                                __half* __restrict__ y16, int64_t n, uint32_t thr, float inv_keep, uint64_t seed) {
   // two elements (one hash) per thread iteration; n % 2 == 0
+  const DropKeys dkeys = drop_keys(seed);
   for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < n;
        i += int64_t(gridDim.x) * blockDim.x * 2) {
-    const uint32_t h = dropout_hash(seed, uint64_t(i >> 1));
+    const uint32_t h = dropout_hash_k(dkeys, uint64_t(i >> 1));
     float a, b;
     if constexpr (F32) {
       const float2 v = *reinterpret_cast<const float2*>(static_cast<const float*>(x_) + i);

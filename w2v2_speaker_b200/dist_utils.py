@@ -50,3 +50,16 @@ def max_over_ranks(value: float, device="cpu") -> float:
 def barrier():
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+def remaining_spans(done, n: int):
+    """Complement of the (possibly unordered) half-open spans `done` inside [0, n): what the trainer still has
+    to all-reduce after the backward sent the per-layer spans (trainer.FlatAdamTrainer.allreduce_grads)."""
+    pos, rest = 0, []
+    for lo, hi in sorted(done):
+        if lo > pos:
+            rest.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < n:
+        rest.append((pos, n))
+    return rest

@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from .dist_utils import remaining_spans
 from .models.wav2vec2 import Wav2Vec2ModelB200
 from .training import LOSS_SCALE, GradBook, encoder_grad_order
 
@@ -65,6 +66,9 @@ class FlatAdamTrainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._overlapped = []
+        if seg0 and self.world > 1:
+            self.model._grad_ready_hook = self._reduce_span      # spans of flat_g[:n0] == GradBook offsets
 
     def _refresh_module_weights(self):
         for m in self.module.modules():
@@ -74,18 +78,29 @@ class FlatAdamTrainer:
                 if hasattr(m, attr):
                     setattr(m, attr, None)
 
+    def _reduce_span(self, lo: int, hi: int):
+        """Enqueue the sum-all-reduce of flat_g[lo:hi] on the communication stream, ordered after everything
+        the compute stream has enqueued so far (called while the backward is still being scheduled: NCCL
+        then runs concurrently with the remaining layers)."""
+        if hi <= lo:
+            return
+        self._overlapped.append((lo, hi))
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            for s in range(lo, hi, self.bucket_elems):
+                dist.all_reduce(self.flat_g[s:min(hi, s + self.bucket_elems)], op=dist.ReduceOp.SUM)
+
     def allreduce_grads(self):
-        """Sum-all-reduce of the flat gradient in buckets on a side stream (the mean's 1/world is folded
-        into the Adam gradient scale)."""
+        """Sum-all-reduce of whatever part of the flat gradient the backward has not already sent (the
+        per-layer spans go out from inside the backward, deepest layer first), then join the streams.
+        The mean's 1/world is folded into the Adam gradient scale.  Every rank issues the same spans in
+        the same order."""
         if self.world == 1:
             return
-        cur = torch.cuda.current_stream()
-        self.comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comm_stream):
-            n = self.flat_g.numel()
-            for s in range(0, n, self.bucket_elems):
-                dist.all_reduce(self.flat_g[s:min(n, s + self.bucket_elems)], op=dist.ReduceOp.SUM)
-        cur.wait_stream(self.comm_stream)
+        for lo, hi in remaining_spans(self._overlapped, self.flat_g.numel()):
+            self._reduce_span(lo, hi)
+        self._overlapped = []
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def step(self, wav: torch.Tensor, labels: torch.Tensor):
         """One optimisation step; returns (loss, softmax) like the reference's training_step uses them."""

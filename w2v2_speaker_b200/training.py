@@ -199,9 +199,11 @@ def encoder_grad_order(arch: ArchConfig) -> List[str]:
 
 
 def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, torch.Tensor], S: dict,
-                     dh: torch.Tensor, sink: Optional[GradBook] = None) -> GradBook:
+                     dh: torch.Tensor, sink: Optional[GradBook] = None, on_layer_done=None) -> GradBook:
     """dh: f32 [B,T,H] gradient of last_hidden_state, carrying LOSS_SCALE.  Returns the (still scaled)
-    parameter gradients of everything behind the frozen CNN."""
+    parameter gradients of everything behind the frozen CNN.  `on_layer_done(lo, hi)` is called (in
+    reverse layer order, also for LayerDrop-skipped layers) once flat[lo:hi] -- all gradients of one
+    transformer layer -- has been enqueued: the trainer overlaps that span's all-reduce with the rest."""
     a, w = eng.arch, eng.w
     B, T = S["B"], S["T"]
     H, M, FF = a.hidden, B * T, a.ffn
@@ -214,9 +216,17 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
     d = H // a.heads
     qscale = float(d) ** -0.5
     dy_a, dy_b = dh.contiguous().view(M, H), None
+
+    def layer_done(l):
+        if on_layer_done is not None:
+            lo = G.offsets[f"encoder.layers.{l}.attention.q_proj.weight"]
+            hi = G.offsets[f"encoder.layers.{l + 1}.attention.q_proj.weight"] if l + 1 < a.layers else G.numel
+            on_layer_done(lo, hi)
+
     for l in reversed(range(a.layers)):
         L = S["layers"][l]
         if L is None:                                   # LayerDrop: identity in forward, identity in backward
+            layer_done(l)
             continue
         pre = f"encoder.layers.{l}."
         lw, tl = w.layers[l], tw.layers[l]
@@ -248,6 +258,7 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
         ops.scale_f32_(G.view(pre + "attention.q_proj.bias"), qscale)
         dy_a = ops.gemm_f16(dqkv16, tl["wqkvT"], None, 0, F32)                   # d h_in via qkv
         dy_b = dx1_32                                                            # + residual path
+        layer_done(l)
     # encoder top:  h_e = drop(LN(pos + h0)),  pos = GELU(zpos),  zpos = posconv(h0) + b
     if ph > 0:
         dy_a, _ = ops.add2_cast(dy_a, dy_b, want16=False)
@@ -302,7 +313,8 @@ class EncoderFn(torch.autograd.Function):
         pd = dict(model.named_parameters())
         tw = model._train_weights(eng)
         sink = getattr(model, "_grad_sink", None)
-        G = encoder_backward(eng, tw, pd, ctx.saved, dh.float(), sink)
+        G = encoder_backward(eng, tw, pd, ctx.saved, dh.float(), sink,
+                             getattr(model, "_grad_ready_hook", None) if sink is not None else None)
         ctx.saved = None
         if sink is not None:
             # the trainer owns the (loss-scaled) flat gradient: nothing goes back through autograd
