@@ -6,7 +6,7 @@
 //   TMA   : Q tile [128 x 64], K [TK x 64], V [TK x 64] straight out of the fused qkv activation
 //           (3-D tensor map (column, t, b): rows t >= T are zero-filled, TK = round_up(T, 16))
 //   MMA 1 : S = Q K^T   (M=128, N=TK, K=64; both operands K-major, 128B swizzle) -> TMEM fp32
-//   softmax: two threads per query row (one per column half) read the row from TMEM (tcgen05.ld 32x32b),
+//   softmax: four threads per query row (one per column group) read the row from TMEM (tcgen05.ld 32x32b),
 //           max / exp / sum in registers, halves combined through smem; P (fp16, unnormalised) goes to
 //           smem in the K-major swizzled layout
 //   MMA 2 : O = P V     (M=128, N=64, K=TK; V is consumed as an MN-major B operand, i.e. exactly the
@@ -34,9 +34,10 @@ struct alignas(64) AttnParams {
 };
 
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 256;      // 8 warps: warp & 3 = TMEM lane quarter (32 query rows), warp >> 2 = column half
+constexpr int ATT_THREADS = 512;      // 16 warps: warp & 3 = TMEM lane quarter (32 query rows), warp >> 2 = column group
+constexpr int ATT_NCG = ATT_THREADS / 128;
 
-// Two threads per query row (one per column half): the per-row max / sum meet through shared memory.
+// Four threads per query row (one per column group): the per-row max / sum meet through shared memory.
 // Warps whose 32 query rows all lie beyond T (most of the second tile of a 149-frame utterance) skip the
 // arithmetic; their P rows stay unwritten and only feed output rows that are never stored.
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -49,9 +50,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   uint8_t* sK = sQ + 16384;
   uint8_t* sV = sK + ((kv_bytes + 1023) & ~1023);
   uint8_t* sP = sV + ((kv_bytes + 1023) & ~1023);   // pblocks x 16 KB
-  float* red_max = reinterpret_cast<float*>(sP + pblocks * 16384);   // [2][128]
-  float* red_sum = red_max + 256;                                    // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red_sum + 256);
+  float* red_max = reinterpret_cast<float*>(sP + pblocks * 16384);   // [ATT_NCG][128]
+  float* red_sum = red_max + ATT_NCG * 128;                          // [ATT_NCG][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_sum + ATT_NCG * 128);
   uint64_t* bar_tma = bars;
   uint64_t* bar_s = bars + 1;
   uint64_t* bar_o = bars + 2;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   const bool warp_valid = mt * 128 + quarter * 32 < p.T;         // warp-uniform
   const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
   const int nchunk = TK / 16;
-  const int c_begin = (nchunk * cg) >> 1, c_end = (nchunk * (cg + 1)) >> 1;
+  const int c_begin = (nchunk * cg) / ATT_NCG, c_end = (nchunk * (cg + 1)) / ATT_NCG;
   const DropKeys dkeys = drop_keys(p.drop_seed);
   const uint32_t drop_thr = p.drop_thr;
   const float inv_keep = p.drop_inv_keep;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   }
   red_max[cg * 128 + row] = mx;
   __syncthreads();
-  mx = fmaxf(red_max[row], red_max[128 + row]);
+  mx = fmaxf(fmaxf(red_max[row], red_max[128 + row]), fmaxf(red_max[256 + row], red_max[384 + row]));
   const float mxl = mx * 1.4426950408889634f;
   float sum = 0.f;
   if (warp_valid) {
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
     umma_commit(bar_o);
   }
   __syncwarp();
-  sum = red_sum[row] + red_sum[128 + row];
+  sum = (red_sum[row] + red_sum[128 + row]) + (red_sum[256 + row] + red_sum[384 + row]);
 
   mbar_wait(bar_o, 0);
   __syncwarp();
@@ -186,13 +187,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   if (warp_valid) {
     const float inv = 1.0f / sum;
     if (cg == 0 && p.lse != nullptr && t_q < p.T) p.lse[(int64_t(b) * p.heads + h) * p.T + t_q] = mx + __logf(sum);
-    __half* dst = p.out + (int64_t(b) * p.T + (t_q < p.T ? t_q : 0)) * p.H + h * ATT_D + cg * 32;
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + p.o_col + cg * 32, r);
+    __half* dst = p.out + (int64_t(b) * p.T + (t_q < p.T ? t_q : 0)) * p.H + h * ATT_D + cg * 16;
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(t_row + p.o_col + cg * 16, r);
     tmem_ld_wait();
     if (t_q < p.T) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint4 q;
         q.x = pack_half2(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
         q.y = pack_half2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
@@ -238,7 +239,7 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
   if (TK <= 192) { p.tmem_cols = 256; p.o_col = 192; } else { p.tmem_cols = 512; p.o_col = 256; }
   if (TK <= 64) { p.tmem_cols = 128; p.o_col = 64; }
   const int kvb = (TK * 128 + 1023) & ~1023;
-  const int smem = 16384 + 2 * kvb + ((TK + 63) / 64) * 16384 + 2048 /*row max / sum exchange*/ + 64 + 1024;
+  const int smem = 16384 + 2 * kvb + ((TK + 63) / 64) * 16384 + 4096 /*row max / sum exchange*/ + 64 + 1024;
   W2V2_REQUIRE(uint64_t(B) * heads * T * (TK / 2) < (1ull << 32), "w2v2_attention: dropout mask index exceeds 32 bits");
   static int configured_smem = 0;
   if (smem > configured_smem) {

@@ -12,7 +12,8 @@
 //     that contract over queries (dV, dK) run ONCE at the end over all rows: their 256 accumulator
 //     columns reuse the S / dP regions, which is what makes room for separate S and dP in the first place;
 //   * dQ of tile 0 is computed in the same MMA group as S / dP of tile 1 and drained while the tile-1
-//     arithmetic runs; lse / delta of both tiles are fetched before the TMA wait.
+//     arithmetic runs; the O tiles ride in the same TMA transaction as Q / K / V / dO (they land in the
+//     dS buffer, which is not written before delta = rowsum(dO * O) has been formed from shared memory).
 // Three MMA round trips and two arithmetic passes per (batch, head) instead of six and four.
 // 16 warps: warp & 3 = TMEM lane quarter (32 query rows), warp >> 2 = one of four column groups.
 // TMEM (fp32 columns): S [0,160) | dP [160,320) | dQ tile 0 [320,384) | dQ tile 1 [384,448); at the end
@@ -57,8 +58,8 @@ struct alignas(64) AttnBwdFusedParams {
   CUtensorMap tmKV;    // qkv: box {64, TK, 1}
   CUtensorMap tmDO0;   // dO : box {64, 128, 1}
   CUtensorMap tmDO1;   // dO : box {64, 32, 1}
-  const __half* o;     // [B*T, H]
-  const __half* d_o;   // [B*T, H]
+  CUtensorMap tmO0;    // O  : box {64, 128, 1}
+  CUtensorMap tmO1;    // O  : box {64, 32, 1}
   const float* lse;    // [B, heads, T]
   __half* dqkv;        // [B*T, 3H]
   int T, TK, H, heads, qtiles;
@@ -100,9 +101,11 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
     prefetch_tensormap(&p.tmQ0);
     prefetch_tensormap(&p.tmKV);
     prefetch_tensormap(&p.tmDO0);
+    prefetch_tensormap(&p.tmO0);
     if (p.qtiles > 1) {
       prefetch_tensormap(&p.tmQ1);
       prefetch_tensormap(&p.tmDO1);
+      prefetch_tensormap(&p.tmO1);
     }
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
@@ -120,50 +123,27 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
   const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_tma, 2 * 16384 + (p.qtiles > 1 ? 2 * 4096 : 0) + 2 * TK * 128);
+    mbar_arrive_expect_tx(bar_tma, 3 * 16384 + (p.qtiles > 1 ? 3 * 4096 : 0) + 2 * TK * 128);
     tma_load_3d(smem + AF_Q0, &p.tmQ0, bar_tma, h * AF_D, 0, b);
     tma_load_3d(smem + AF_DO0, &p.tmDO0, bar_tma, h * AF_D, 0, b);
     tma_load_3d(smem + AF_K, &p.tmKV, bar_tma, p.H + h * AF_D, 0, b);
     tma_load_3d(smem + AF_V, &p.tmKV, bar_tma, 2 * p.H + h * AF_D, 0, b);
+    tma_load_3d(smem + AF_DS0, &p.tmO0, bar_tma, h * AF_D, 0, b);                  // O tile 0 (borrowed buffer)
     if (p.qtiles > 1) {
       tma_load_3d(smem + AF_Q1, &p.tmQ1, bar_tma, h * AF_D, 128, b);
       tma_load_3d(smem + AF_DO1, &p.tmDO1, bar_tma, h * AF_D, 128, b);
+      tma_load_3d(smem + AF_DS0 + 16384, &p.tmO1, bar_tma, h * AF_D, 128, b);     // O tile 1
     }
   }
-
-  // ---- per-row scalars of both tiles while the TMA is in flight: lse, and this thread's quarter (16 of the
-  //      64 head dims) of delta = rowsum(dO * O), combined through shared memory
+  // lse of both tiles: fetched now, first used in the arithmetic passes
   float lse_t[2] = {0.f, 0.f};
 #pragma unroll
   for (int qt = 0; qt < 2; ++qt) {
     const int t = qt * 128 + row;
-    float part = 0.f;
-    if (qt < p.qtiles && t < p.T) {
-      lse_t[qt] = p.lse[(int64_t(b) * p.heads + h) * p.T + t];
-      const uint4* po = reinterpret_cast<const uint4*>(p.o + (int64_t(b) * p.T + t) * p.H + h * AF_D + cg * 16);
-      const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (int64_t(b) * p.T + t) * p.H + h * AF_D + cg * 16);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 a = po[c], g = pd[c];
-        const __half2* ah = reinterpret_cast<const __half2*>(&a);
-        const __half2* gh = reinterpret_cast<const __half2*>(&g);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 x = __half22float2(ah[j]), y = __half22float2(gh[j]);
-          part = fmaf(x.x, y.x, part);
-          part = fmaf(x.y, y.y, part);
-        }
-      }
-    }
-    red[(qt * 4 + cg) * 128 + row] = part;
+    if (qt < p.qtiles && t < p.T) lse_t[qt] = __ldg(p.lse + (int64_t(b) * p.heads + h) * p.T + t);
   }
-  __syncthreads();
-  float delta_t[2];
-#pragma unroll
-  for (int qt = 0; qt < 2; ++qt)
-    delta_t[qt] = (red[(qt * 4 + 0) * 128 + row] + red[(qt * 4 + 1) * 128 + row]) +
-                  (red[(qt * 4 + 2) * 128 + row] + red[(qt * 4 + 3) * 128 + row]);
 
+  float delta_t[2] = {0.f, 0.f};
   mbar_wait(bar_tma, 0);
   __syncwarp();
   tc_fence_after();
@@ -290,9 +270,46 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
     tc_fence_after();
   };
 
-  // ---- round 1: S0, dP0
-  if (threadIdx.x == 0) issue_s_dp(0);
-  commit_and_wait();
+  // ---- round 1: S0, dP0 -- issued first, delta is formed while they run
+  if (threadIdx.x == 0) {
+    issue_s_dp(0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  // ---- delta = rowsum(dO * O) of both tiles from shared memory: this thread's quarter (16 of the 64 head
+  //      dims = two 16-byte chunks of the swizzled row), combined across the four column groups
+#pragma unroll
+  for (int qt = 0; qt < 2; ++qt) {
+    float part = 0.f;
+    if (qt < p.qtiles && (qt == 0 || quarter == 0)) {      // tile 1 holds 32 rows: lane quarter 0
+      const uint8_t* orow = smem + AF_DS0 + qt * 16384 + row * 128;
+      const uint8_t* grow = smem + (qt == 0 ? AF_DO0 : AF_DO1) + row * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int off = ((2 * cg + c) ^ (row & 7)) << 4;
+        const uint4 a = *reinterpret_cast<const uint4*>(orow + off), g = *reinterpret_cast<const uint4*>(grow + off);
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* gh = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = __half22float2(ah[j]), y = __half22float2(gh[j]);
+          part = fmaf(x.x, y.x, part);
+          part = fmaf(x.y, y.y, part);
+        }
+      }
+    }
+    red[(qt * 4 + cg) * 128 + row] = part;
+  }
+  __syncthreads();           // also: every read of the borrowed O tiles precedes the first dS write
+#pragma unroll
+  for (int qt = 0; qt < 2; ++qt)
+    delta_t[qt] = (red[(qt * 4 + 0) * 128 + row] + red[(qt * 4 + 1) * 128 + row]) +
+                  (red[(qt * 4 + 2) * 128 + row] + red[(qt * 4 + 3) * 128 + row]);
+
+  mbar_wait(bar_mma, mma_phase);
+  mma_phase ^= 1;
+  __syncwarp();
+  tc_fence_after();
   if (quarter * 32 < p.T) pass(0);                      // warp-uniform
   publish_smem();
   if (p.qtiles > 1) {
@@ -368,8 +385,10 @@ int attention_bwd_fused_launch(const void* qkv16, const void* o16, const void* d
   if (rc) return rc;
   rc = make_tmap_3d(&p.tmDO1, do16, 2, H, T, B, uint64_t(H) * 2, uint64_t(T) * H * 2, AF_D, 32, 1, 128);
   if (rc) return rc;
-  p.o = static_cast<const __half*>(o16);
-  p.d_o = static_cast<const __half*>(do16);
+  rc = make_tmap_3d(&p.tmO0, o16, 2, H, T, B, uint64_t(H) * 2, uint64_t(T) * H * 2, AF_D, 128, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmO1, o16, 2, H, T, B, uint64_t(H) * 2, uint64_t(T) * H * 2, AF_D, 32, 1, 128);
+  if (rc) return rc;
   p.lse = lse;
   p.dqkv = static_cast<__half*>(dqkv16);
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;

@@ -48,13 +48,57 @@ struct alignas(64) GemmParams {
   int m_tiles, n_tiles, batch;
   int N;
   long long rows;                // valid rows per batch element
+  unsigned int* sk_flags;        // stream-K: per-tile hand-shake counters (nullptr = whole tiles per CTA)
 };
 
-template <int BN>
+// Stream-K (fp32 output, no activation): the (tile, k-block) iteration space is cut into gridDim.x equal
+// contiguous ranges, so a problem of 1.5 waves of tiles costs 1.5 instead of 2 tile times.  A tile cut
+// by a range boundary is produced by two CTAs: the one holding its leading k-blocks stores bias + partial
+// sums plainly, the other one adds its partial sums with TMA reduce-add stores once the first is done.
+// Every CTA walks its range from the top, so the plain store is the first thing the lower-numbered CTA
+// does and the reduce-add the last thing the higher-numbered one does: the wait is (almost) never
+// taken, and it only ever points at a CTA that was scheduled earlier.
+constexpr int SK_RING = 8, SK_MAX_TILES = 4096;
+__device__ unsigned int g_sk_flags[SK_RING * SK_MAX_TILES];
+
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// The per-CTA work list, identical for the three warp roles: (tile, first k-iteration, end k-iteration).
+struct WorkIter {
+  int tile, tile_end, tile_step;       // whole-tile schedules
+  long long cur, lo;                   // stream-K: remaining range [lo, cur) of global k-iterations
+  int k_iters;
+  bool sk;
+  __device__ __forceinline__ bool next(int& t, int& kb, int& ke) {
+    if (!sk) {
+      if (tile >= tile_end) return false;
+      t = tile; kb = 0; ke = k_iters;
+      tile += tile_step;
+      return true;
+    }
+    if (cur <= lo) return false;
+    t = int((cur - 1) / k_iters);
+    const long long t0 = (long long)t * k_iters;
+    const long long seg_lo = t0 > lo ? t0 : lo;
+    kb = int(seg_lo - t0);
+    ke = int(cur - t0);
+    cur = seg_lo;
+    return true;
+  }
+};
+
+// CL = CTAs per MMA: 1 (tcgen05.mma.cta_group::1, tile 128 x BN) or 2 (a CTA pair, cta_group::2, tile 256 x BN:
+// each CTA stages its 128 rows of A and BN/2 columns of B)
+template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && CL == 1) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias tile
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE_BYTES + BIAS_BYTES + 256 /*barriers*/;
@@ -63,9 +107,9 @@ struct GemmCfg {
 };
 
 // EPI: 0 = none, 1 = + bias[n], 2 = * scale[b, n] + shift[b, n]  (GroupNorm affine of conv layer 0)
-template <int BN, bool OUT_F32, int ACT, int EPI>
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   // the 128B-swizzled tiles need a 1024-byte aligned base; the kernel has no static shared memory, so
   // the dynamic window starts at the CTA's (1024-aligned) shared base -- verified, not assumed
@@ -88,10 +132,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   // EPI 2 (per-(batch, column) affine): contiguous chunk per CTA, m fastest, so the (batch, n-tile)
   // dependent scale/shift vectors change only once or twice per CTA.
   constexpr bool CHUNKED = (EPI == 2);
-  const int tiles_per_cta = (num_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile_begin = CHUNKED ? blockIdx.x * tiles_per_cta : blockIdx.x;
+  constexpr bool SK_OK = OUT_F32 && ACT == 0 && EPI != 2;       // stream-K is only ever requested for these
+  // the scheduling unit is the CTA (CL = 1) or the CTA pair (CL = 2): both CTAs of a pair walk the same list
+  const int cta_rank = CL == 2 ? int(cluster_ctarank()) : 0;
+  const int sched_id = blockIdx.x / CL, num_sched = gridDim.x / CL;
+  const int tiles_per_cta = (num_tiles + num_sched - 1) / num_sched;
+  const int tile_begin = CHUNKED ? sched_id * tiles_per_cta : sched_id;
   const int tile_end = CHUNKED ? min(num_tiles, tile_begin + tiles_per_cta) : num_tiles;
-  const int tile_step = CHUNKED ? 1 : gridDim.x;
+  const int tile_step = CHUNKED ? 1 : num_sched;
+  WorkIter work0;
+  work0.tile = tile_begin; work0.tile_end = tile_end; work0.tile_step = tile_step;
+  work0.k_iters = k_iters;
+  work0.sk = SK_OK && p.sk_flags != nullptr;
+  work0.cur = work0.lo = 0;
+  if (work0.sk) {
+    const long long total = (long long)num_tiles * k_iters;
+    const long long per = total / num_sched, rem = total % num_sched;
+    work0.lo = per * sched_id + (sched_id < rem ? sched_id : rem);
+    work0.cur = work0.lo + per + (sched_id < rem ? 1 : 0);
+  }
   auto decode = [&](int tile, int& nt, int& mt, int& b) {
     if constexpr (CHUNKED) {
       mt = tile % p.m_tiles;
@@ -118,16 +177,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_WARPS);
+      mbar_init(&tmem_empty[a], EPI_WARPS * CL);     // pair: the peer's epilogue warps arrive remotely
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CL == 2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();         // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -136,48 +201,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      WorkIter work = work0;
+      int tile, k_begin, k_end;
+      while (work.next(tile, k_begin, k_end)) {
         int nt, mt, b;
         decode(tile, nt, mt, b);
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + A_BYTES;
+        int tap = k_begin / p.kblocks_per_tap, kb = k_begin % p.kblocks_per_tap;
+        for (int it = k_begin; it < k_end; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if constexpr (CL == 2) {
+            // both CTAs load their halves; the bytes of both are counted on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_3d_2sm(sa, &p.tmA[tap], lead_bar, kb * BK, (mt * 2 + cta_rank) * BM, b);
+            tma_load_3d_2sm(sb, &p.tmB, lead_bar, (tap * p.kblocks_per_tap + kb) * BK, nt * BN + cta_rank * (BN / 2), 0);
+          } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_3d(sa, &p.tmA[tap], &full_bar[stage], kb * BK, mt * BM, b);
             tma_load_3d(sb, &p.tmB, &full_bar[stage], (tap * p.kblocks_per_tap + kb) * BK, nt * BN, 0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {               // pair: the leader CTA issues for both
+      constexpr uint32_t idesc = make_idesc_f16(BM * CL, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      WorkIter work = work0;
+      int tile, k_begin, k_end;
+      while (work.next(tile, k_begin, k_end)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = 0; it < k_end - k_begin; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_f16(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
-                     (it | k) != 0);
+            if constexpr (CL == 2)
+              umma_f16_2sm(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                           (it | k) != 0);
+            else
+              umma_f16(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                       (it | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);       // smem slot free once these MMAs retire
+          // smem slot free once these MMAs retire (pair: in both CTAs)
+          if constexpr (CL == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);           // accumulator complete
+        // accumulator complete
+        if constexpr (CL == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -198,9 +281,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     uint32_t tcount = 0;
 
     int prev_b = -1, prev_nt = -1;
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
+    WorkIter work = work0;
+    int tile, k_begin, k_end;
+    for (; work.next(tile, k_begin, k_end); ++tcount) {
       int nt, mt, b;
       decode(tile, nt, mt, b);
+      // stream-K roles of this segment: `lead` holds the tile's first k-blocks (plain store, adds the bias,
+      // then signals), `trail` the rest (waits for the signal, reduce-adds, no bias)
+      const bool sk_lead = SK_OK && k_begin == 0 && k_end < k_iters;
+      const bool sk_trail = SK_OK && k_begin != 0;
       const float* bias_tile = sbias + (EPI == 1 ? (tcount & 1) * BN : 0);
       if constexpr (EPI == 1) {
         // stage this tile's bias slice once (the previous user of this buffer was two tiles ago and
@@ -229,8 +318,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * HALF_COLS;
       const int col0 = nt * BN + half * HALF_COLS;      // first output column of this warp
-      const int row0 = mt * BM + quarter * 32;          // first output row of this warp
+      const int row0 = (mt * CL + cta_rank) * BM + quarter * 32;      // first output row of this warp
 
+      if (SK_OK && sk_trail) {
+        // the lead CTA's plain stores of this tile must have landed before anything is added to them
+        if (lane == 0) {
+          volatile unsigned int* f = p.sk_flags + tile;
+          unsigned int spins = 0;
+          while (*f < EPI_WARPS * CL) {
+            if (++spins > (1u << 28)) __trap();       // a lost hand-shake must fail loudly, not hang
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
       uint32_t ra[32], rb[32];
       tmem_ld_32x32b_x32(t_addr, ra);
 
@@ -249,7 +350,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
           } else {
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (EPI == 1) bb = *reinterpret_cast<const float4*>(bsrc + j);
+            if constexpr (EPI == 1) {
+              if (!sk_trail) bb = *reinterpret_cast<const float4*>(bsrc + j);
+            }
             v[j] = __uint_as_float(r[j]) + bb.x;
             v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
             v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
@@ -289,7 +392,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           __syncwarp();
           const int scol = col0 + (c - sub) * 32;
           if (lane == 0 && row0 < p.rows && scol < p.N) {   // skip boxes that lie entirely in the M / N tail
-            tma_store_3d(&p.tmOut, mystage, scol, row0, b);
+            if (SK_OK && sk_trail) tma_reduce_add_3d(&p.tmOut, mystage, scol, row0, b);
+            else tma_store_3d(&p.tmOut, mystage, scol, row0, b);
             tma_store_commit();
           }
         }
@@ -307,9 +411,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         process(rb, c + 1);
+      }
+      if (SK_OK && (sk_lead || sk_trail) && lane == 0) {
+        if (sk_lead) {
+          tma_store_wait<0>();                        // the stores have been performed, not merely read out
+          __threadfence();
+          atomicAdd(p.sk_flags + tile, 1u);
+        } else if (atomicAdd(p.sk_flags + tile, 1u) == 2 * EPI_WARPS * CL - 1) {
+          atomicExch(p.sk_flags + tile, 0u);          // last trailing warp: re-arm the counter for the next launch
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -318,10 +434,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();         // nothing of the peer may still point at this CTA
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -381,33 +499,82 @@ int device_sm_count() {
   return sms;
 }
 
-template <int BN, bool OUT_F32, int ACT, int EPI>
+// W2V2_STREAMK=0 disables the stream-K schedule (A/B measurements, tools/time_ops.py)
+static bool sk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("W2V2_STREAMK");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// W2V2_GEMM_PAIR=0 keeps every GEMM on the single-CTA MMA (A/B measurements)
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("W2V2_GEMM_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI>;
+  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI, CL>;
   if (!configured) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles * p.batch;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  const int tiles = p.m_tiles * p.n_tiles * p.batch;          // scheduling units: CTAs (CL = 1) or CTA pairs
+  const int units = device_sm_count() / CL;
+  const int grid = tiles < units ? tiles : units;
+  GemmParams q = p;
+  if constexpr (OUT_F32 && ACT == 0 && EPI != 2) {
+    // stream-K when whole tiles would leave a large part of the last wave idle (e.g. 225 tiles on 148 SMs)
+    const int waves = (tiles + grid - 1) / grid;
+    if (tiles > grid && tiles <= SK_MAX_TILES && double(tiles) / (double(waves) * grid) < 0.9 && sk_enabled()) {
+      static unsigned int* flags = nullptr;
+      static unsigned int slot = 0;
+      if (flags == nullptr) W2V2_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&flags), g_sk_flags));
+      q.sk_flags = flags + (slot++ % SK_RING) * SK_MAX_TILES;
+    }
+  }
+  if constexpr (CL == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid * 2);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    W2V2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
+  } else {
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(q);
+  }
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int CL>
 static int dispatch_epilogue(const GemmParams& p, int act, cudaStream_t stream) {
   const int epi = p.shift != nullptr ? 2 : (p.bias != nullptr ? 1 : 0);
   if (epi == 2) {
-    if constexpr (!OUT_F32 && BN == 256) return launch_gemm<256, false, 1, 2>(p, stream);   // conv0: GN affine + GELU -> f16
+    if constexpr (!OUT_F32 && BN == 256) return launch_gemm<256, false, 1, 2, CL>(p, stream);   // conv0: GN affine + GELU -> f16
     set_last_error("w2v2 gemm: the per-batch affine epilogue is built for f16 output, N > 128");
     return -1;
   }
-  if (act == 1) return epi ? launch_gemm<BN, OUT_F32, 1, 1>(p, stream) : launch_gemm<BN, OUT_F32, 1, 0>(p, stream);
-  return epi ? launch_gemm<BN, OUT_F32, 0, 1>(p, stream) : launch_gemm<BN, OUT_F32, 0, 0>(p, stream);
+  if (act == 1) return epi ? launch_gemm<BN, OUT_F32, 1, 1, CL>(p, stream) : launch_gemm<BN, OUT_F32, 1, 0, CL>(p, stream);
+  return epi ? launch_gemm<BN, OUT_F32, 0, 1, CL>(p, stream) : launch_gemm<BN, OUT_F32, 0, 0, CL>(p, stream);
 }
 
 int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch, int ntaps,
@@ -422,6 +589,7 @@ int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int BN = (N <= 128) ? 128 : 256;
+  const int CL = (BN == 256 && pair_enabled()) ? 2 : 1;         // CTA pairs for every wide GEMM
   const int osz = out_dtype == 1 ? 4 : 2;
   const uint64_t a_bstride = batch > 1 ? uint64_t(a_batch_stride) * 2 : uint64_t(a_rows) * uint64_t(a_row_stride) * 2;
   for (int t = 0; t < ntaps; ++t) {
@@ -429,7 +597,7 @@ int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
     int rc = make_tmap_3d(&p.tmA[t], base, 2, cin, a_rows, batch, uint64_t(a_row_stride) * 2, a_bstride, BK, BM, 1, 128);
     if (rc) return rc;
   }
-  int rc = make_tmap_3d(&p.tmB, W, 2, uint64_t(ntaps) * cin, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, BN, 1, 128);
+  int rc = make_tmap_3d(&p.tmB, W, 2, uint64_t(ntaps) * cin, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, BN / CL, 1, 128);
   if (rc) return rc;
   const uint64_t o_bstride = batch > 1 ? uint64_t(out_batch_stride) * osz : uint64_t(a_rows) * uint64_t(ldo) * osz;
   rc = make_tmap_3d(&p.tmOut, out, osz, N, a_rows, batch, uint64_t(ldo) * osz, o_bstride, out_dtype == 1 ? 32 : 64, 32, 1, 128);
@@ -438,13 +606,14 @@ int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
   p.shift = shift;
   p.ntaps = ntaps;
   p.kblocks_per_tap = cin / BK;
-  p.m_tiles = int((a_rows + BM - 1) / BM);
+  p.m_tiles = int((a_rows + BM * CL - 1) / (BM * CL));
   p.n_tiles = (N + BN - 1) / BN;
   p.batch = batch;
   p.N = N;
   p.rows = a_rows;
-  if (BN == 256) return out_dtype == 1 ? dispatch_epilogue<256, true>(p, act, stream) : dispatch_epilogue<256, false>(p, act, stream);
-  return out_dtype == 1 ? dispatch_epilogue<128, true>(p, act, stream) : dispatch_epilogue<128, false>(p, act, stream);
+  if (CL == 2) return out_dtype == 1 ? dispatch_epilogue<256, true, 2>(p, act, stream) : dispatch_epilogue<256, false, 2>(p, act, stream);
+  if (BN == 256) return out_dtype == 1 ? dispatch_epilogue<256, true, 1>(p, act, stream) : dispatch_epilogue<256, false, 1>(p, act, stream);
+  return out_dtype == 1 ? dispatch_epilogue<128, true, 1>(p, act, stream) : dispatch_epilogue<128, false, 1>(p, act, stream);
 }
 
 }  // namespace w2v2
