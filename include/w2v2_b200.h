@@ -232,6 +232,133 @@ int w2v2_softmax_ce_bwd_f32(const float* prob, const int64_t* labels, const floa
 int w2v2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    int step, float grad_scale, void* stream);
 
+/* ---- attentive-statistics pooling in training (R:src/layers/pooling.py:87-106; speechbrain
+ * AttentiveStatisticsPooling, restated in oracle/w2v2_oracle.py::attentive_stat_pool) -------------------
+ * w2v2_asp_bn_batch_stats: BatchNorm1d(A) in training mode over the rows of relu(z) [rows, A]: writes the
+ *   affine the forward kernel w2v2_asp_relu_bn_tanh applies (scale = gamma * rstd, shift = beta - mean *
+ *   scale), the batch mean / rstd (kept for the backward) and updates running_mean / running_var (NULL =
+ *   skip) with torch semantics (momentum, unbiased variance).  sums_ws: 2*A doubles of workspace.
+ * w2v2_asp_pool_bwd: from d out [B, 2C] = (d mean || d std): d logits (f16 [B*T, C]) of the softmax over
+ *   time and the direct part of d x (f32 [B,T,C], overwritten).  `out` is the saved forward output.
+ * w2v2_asp_act_bwd: d h [rows, A] -> d z (f16) through tanh, BatchNorm (batch_stats = 1: training-mode
+ *   statistics; 0: running statistics) and ReLU; d gamma / d beta (x grad_scale; NULL = skip).
+ * w2v2_asp_front_bwd: d x += d cat[:, :C] + the gradient through the uniform mean / std broadcast in
+ *   cat[:, C:3C] (d cat f32, row pitch ldc). */
+/* cat = [x | mean | std] (uniform statistics) as error-compensated fp16 operand [hi | lo | hi], f16 [B*T, 9H]:
+ * z = cat W1^T is then one GEMM against w2v2_split3_rows(W1, 1) = [hi | hi | lo]; cat16x3[:, :3H] is the plain
+ * fp16 cat. */
+int w2v2_asp_concat_split3(const float* x, void* cat16x3, int B, int T, int H, void* stream);
+int w2v2_asp_bn_batch_stats(const float* z, int64_t rows, int A, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, double* sums_ws, float* scale,
+                            float* shift, float* mean, float* rstd, void* stream);
+int w2v2_asp_pool_bwd(const float* x, const float* logits, const float* out, const float* dout, void* dlogits16, float* dx,
+                      int B, int T, int H, void* stream);
+int w2v2_asp_act_bwd(const float* dh, const float* z, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, int batch_stats, double* sums_ws, void* dz16, float* dgamma, float* dbeta,
+                     float grad_scale, int64_t rows, int A, void* stream);
+int w2v2_asp_front_bwd(const float* x, const float* dcat, int64_t ldc, float* dx, int B, int T, int H, void* stream);
+
+/* ---- native launch schedules of one encoder layer (HF:592-609) ------------------------------------------
+ * One call issues every kernel of a transformer layer (forward: 8-10 launches, backward: ~17) on `stream`
+ * into caller-owned buffers; they exist because 300 interpreter -> C round trips per training step cost as
+ * much host time as the step takes on the device.  All pointers are device pointers; f16 buffers are
+ * row-major with the natural pitch ([B*T, H], [B*T, 3H], [B*T, FF]).  Dropout seeds are derived from `seed`
+ * and `layer` exactly as the python schedule did (attention seed+100+l, LN1 branch +200+l, LN2 branch
+ * +300+l, activation +400+l), so forward and backward regenerate the same masks.
+ * Forward: z16 == NULL selects inference (GELU fused into the FFN1 epilogue, lse may be NULL). */
+typedef struct {
+  int B, T, H, heads, FF, layer;
+  float eps, p_hidden, p_attn, p_act;
+  uint64_t seed;
+  const void* wqkv;   /* f16 [3H, H], q rows pre-scaled by d^-0.5 */
+  const float* bqkv;  /* f32 [3H] */
+  const void* wo;     /* f16 [H, H] */
+  const float* bo;
+  const float* ln1_g;
+  const float* ln1_b;
+  const void* w1;     /* f16 [FF, H] */
+  const float* b1;
+  const void* w2;     /* f16 [H, FF] */
+  const float* b2;
+  const float* ln2_g;
+  const float* ln2_b;
+  const float* h_in32; /* f32 [B*T, H] residual stream */
+  const void* h_in16;  /* its f16 copy */
+  void* qkv16;
+  void* att16;
+  float* lse;          /* f32 [B, heads, T] */
+  float* o32;
+  float* h1_32;
+  void* h1_16;
+  void* z16;           /* f16 [B*T, FF] pre-activation (training) or NULL */
+  void* g16;           /* f16 [B*T, FF] gelu(z) */
+  float* f2_32;
+  float* h2_32;        /* layer output */
+  void* h2_16;
+} w2v2_layer_fwd_args;
+int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* args, void* stream);
+
+/* Backward of the same layer.  dy_a + dy_b (dy_b may be NULL) is the gradient of the layer output; on return
+ * dh_in32 + dx1_32 is the gradient of the layer input (kept as two terms: the next LayerNorm backward sums
+ * them for free).  Weight / bias / LayerNorm gradients are ACCUMULATED into the d_* buffers (fp32, natural
+ * shapes; d_wqkv / d_bqkv span q|k|v), activation gradients carry the caller's loss scale.  The remaining
+ * pointers are scratch of the sizes their names imply. */
+typedef struct {
+  int B, T, H, heads, FF, layer;
+  float eps, p_hidden, p_attn, p_act, qscale;
+  uint64_t seed;
+  const void* wqkvT;  /* f16 [H, 3H] */
+  const void* woT;    /* f16 [H, H] */
+  const void* w1T;    /* f16 [H, FF] */
+  const void* w2T;    /* f16 [FF, H] */
+  const float* bo;
+  const float* b2;
+  const float* ln1_g;
+  const float* ln2_g;
+  const float* h_in32;
+  const void* h_in16;
+  const void* qkv16;
+  const void* att16;
+  const float* lse;
+  const float* o32;
+  const float* h1_32;
+  const void* h1_16;
+  const void* z16;
+  const void* g16;
+  const float* f2_32;
+  const float* dy_a;
+  const float* dy_b;
+  float* d_wqkv;
+  float* d_bqkv;
+  float* d_wo;
+  float* d_bo;
+  float* d_ln1_g;
+  float* d_ln1_b;
+  float* d_w1;
+  float* d_b1;
+  float* d_w2;
+  float* d_b2;
+  float* d_ln2_g;
+  float* d_ln2_b;
+  float* dx2_32;      /* scratch f32 [B*T, H] */
+  void* dx2_16;       /* scratch f16 [B*T, H] */
+  void* dg16;         /* scratch f16 [B*T, FF] */
+  void* dz16;         /* scratch f16 [B*T, FF] */
+  float* dh1_32;      /* scratch f32 [B*T, H] */
+  void* dx1_16;       /* scratch f16 [B*T, H] */
+  void* datt16;       /* scratch f16 [B*T, H] */
+  void* dqkv16;       /* scratch f16 [B*T, 3H] */
+  float* dx1_32;      /* out: residual-path term of the input gradient */
+  float* dh_in32;     /* out: term through the q/k/v projections */
+} w2v2_layer_bwd_args;
+int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* args, void* stream);
+
+/* Optional timing of every tensor-core GEMM launch (tap-GEMM and wgrad) between start and stop: CUDA events
+ * on the launching stream; stop synchronises the device and returns summed milliseconds, FLOPs (from the
+ * launch arguments) and the number of launches.  Measurement aid of bench.py's roofline figure. */
+int w2v2_gemm_profile_start(void);
+int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int* launches);
+
 /* ---- utility ---------------------------------------------------------------------------------- */
 /* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */
 int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream);

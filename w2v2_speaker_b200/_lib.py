@@ -17,6 +17,16 @@ LIB_PATH = os.path.join(_HERE, "libw2v2_b200.so")
 # name -> (restype, argtypes); must list every symbol declared in include/w2v2_b200.h
 SIGNATURES = {
     "w2v2_last_error": (c_char_p, []),
+    "w2v2_gemm_profile_start": (c_int, []),
+    "w2v2_gemm_profile_stop": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "w2v2_encoder_layer_fwd": (c_int, [c_void_p, c_void_p]),
+    "w2v2_encoder_layer_bwd": (c_int, [c_void_p, c_void_p]),
+    "w2v2_asp_bn_batch_stats": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "w2v2_asp_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_asp_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_float, c_int64, c_int, c_void_p]),
+    "w2v2_asp_front_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_abi_version": (c_int, []),
     "w2v2_sm_count": (c_int, []),
     "w2v2_launch_count": (c_int64, []),
@@ -75,6 +85,7 @@ SIGNATURES = {
     "w2v2_stat_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_asp_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_asp_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "w2v2_asp_concat_split3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_asp_relu_bn_tanh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "w2v2_softmax_ce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "w2v2_aam_softmax_ce": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
@@ -118,7 +129,14 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """torch's current stream of the current device as a raw cudaStream_t (the fast C accessor: the
+    python-level torch.cuda.current_stream() costs several microseconds per kernel launch)."""
+    if _raw_stream is not None:
+        return c_void_p(_raw_stream(torch.cuda.current_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -577,6 +577,29 @@ static int dispatch_epilogue(const GemmParams& p, int act, cudaStream_t stream) 
   return epi ? launch_gemm<BN, OUT_F32, 0, 1, CL>(p, stream) : launch_gemm<BN, OUT_F32, 0, 0, CL>(p, stream);
 }
 
+// ---- optional per-launch timing of the tensor-core GEMMs (bench.py's roofline figure) ---------------------
+// Between w2v2_gemm_profile_start() and w2v2_gemm_profile_stop() every tap-GEMM / wgrad launch is bracketed
+// by CUDA events on its own stream; stop() synchronises and returns the summed time and FLOPs.
+struct ProfRec {
+  cudaEvent_t s, e;
+  double flops;
+};
+static bool g_prof_on = false;
+static ProfRec g_prof[4096];
+static int g_prof_n = 0;
+
+int gemm_prof_begin(double flops, cudaStream_t stream) {
+  if (!g_prof_on || g_prof_n >= 4096) return -1;
+  ProfRec& r = g_prof[g_prof_n];
+  if (cudaEventCreate(&r.s) != cudaSuccess || cudaEventCreate(&r.e) != cudaSuccess) return -1;
+  r.flops = flops;
+  cudaEventRecord(r.s, stream);
+  return g_prof_n++;
+}
+void gemm_prof_end(int slot, cudaStream_t stream) {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e, stream);
+}
+
 int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch, int ntaps,
                   int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N, const float* bias,
                   const float* shift, int act, void* out, int out_dtype, int64_t ldo, int64_t out_batch_stride,
@@ -611,14 +634,45 @@ int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
   p.batch = batch;
   p.N = N;
   p.rows = a_rows;
-  if (CL == 2) return out_dtype == 1 ? dispatch_epilogue<256, true, 2>(p, act, stream) : dispatch_epilogue<256, false, 2>(p, act, stream);
-  if (BN == 256) return out_dtype == 1 ? dispatch_epilogue<256, true, 1>(p, act, stream) : dispatch_epilogue<256, false, 1>(p, act, stream);
-  return out_dtype == 1 ? dispatch_epilogue<128, true, 1>(p, act, stream) : dispatch_epilogue<128, false, 1>(p, act, stream);
+  const int slot = gemm_prof_begin(2.0 * double(a_rows) * batch * ntaps * cin * N, stream);
+  if (CL == 2) rc = out_dtype == 1 ? dispatch_epilogue<256, true, 2>(p, act, stream) : dispatch_epilogue<256, false, 2>(p, act, stream);
+  else if (BN == 256) rc = out_dtype == 1 ? dispatch_epilogue<256, true, 1>(p, act, stream) : dispatch_epilogue<256, false, 1>(p, act, stream);
+  else rc = out_dtype == 1 ? dispatch_epilogue<128, true, 1>(p, act, stream) : dispatch_epilogue<128, false, 1>(p, act, stream);
+  gemm_prof_end(slot, stream);
+  return rc;
 }
 
 }  // namespace w2v2
 
 using namespace w2v2;
+
+extern "C" int w2v2_gemm_profile_start(void) {
+  for (int i = 0; i < g_prof_n; ++i) {
+    cudaEventDestroy(g_prof[i].s);
+    cudaEventDestroy(g_prof[i].e);
+  }
+  g_prof_n = 0;
+  g_prof_on = true;
+  return 0;
+}
+
+extern "C" int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int* launches) {
+  g_prof_on = false;
+  W2V2_CHECK_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0, fl = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof[i].s, g_prof[i].e) == cudaSuccess) ms += t;
+    fl += g_prof[i].flops;
+    cudaEventDestroy(g_prof[i].s);
+    cudaEventDestroy(g_prof[i].e);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = g_prof_n;
+  g_prof_n = 0;
+  return 0;
+}
 
 extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,
                              int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N,

@@ -212,6 +212,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
   }
 }
 
+int gemm_prof_begin(double flops, cudaStream_t stream);
+void gemm_prof_end(int slot, cudaStream_t stream);
+
 }  // namespace w2v2
 
 using namespace w2v2;
@@ -233,11 +236,23 @@ extern "C" int w2v2_gemm_wgrad_f16(const void* dY, int64_t ldy, const void* X, i
   p.kblocks = int((M + WG_BK - 1) / WG_BK);
   const int out_tiles = p.n_tiles * p.k_tiles;
   const int sms = device_sm_count();
-  // split the contraction so that about one wave of work items exists, at least 8 k-blocks per item
-  int splits = (sms + out_tiles - 1) / out_tiles;
+  // Split the contraction: pick the split count that minimises (waves of work items) x (k-blocks per item
+  // + a fixed per-item cost for pipeline fill and the reduce-add epilogue).  "About one wave" is not good
+  // enough: 72 output tiles x 3 splits = 216 items are two waves of 50 k-blocks, 72 x 2 = 144 items one
+  // wave of 75.
   const int max_splits = (p.kblocks + 7) / 8;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  int splits = 1;
+  long long best = -1;
+  for (int s = 1; s <= max_splits; ++s) {
+    const int per = (p.kblocks + s - 1) / s;
+    const int real = (p.kblocks + per - 1) / per;                  // no empty split
+    const long long waves = (static_cast<long long>(out_tiles) * real + sms - 1) / sms;
+    const long long cost = waves * (per + 6);
+    if (best < 0 || cost < best) {
+      best = cost;
+      splits = real;
+    }
+  }
   p.kblocks_per_split = (p.kblocks + splits - 1) / splits;
   p.splits = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;      // no empty split
   p.N = N;
@@ -249,7 +264,9 @@ extern "C" int w2v2_gemm_wgrad_f16(const void* dY, int64_t ldy, const void* X, i
   }
   const int items = out_tiles * p.splits;
   const int grid = items < sms ? items : sms;
+  const int slot = gemm_prof_begin(2.0 * double(M) * N * K, stream);
   gemm_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(p);
+  gemm_prof_end(slot, stream);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

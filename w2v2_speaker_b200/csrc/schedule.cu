@@ -1,0 +1,78 @@
+// Native launch schedules of one transformer encoder layer (HF:592-609): the ~10 (forward) / ~20 (backward)
+// kernel launches of a layer issued from ONE C call, all on the caller's stream, into caller-owned buffers.
+// The host side of the training step was the bottleneck (300 python -> ctypes round trips of ~35 us each
+// against ~11 ms of device time); these entry points are the same launches without the interpreter in
+// between.  Nothing here computes: every line is one of the C-ABI kernels of this library.
+//
+//   forward :  qkv = h Wqkv^T + b ; att = softmax(q k^T) v ; o = att Wo^T ; h1 = LN1(drop(o + bo) + h)
+//              z = h1 W1^T + b1 ; g = gelu(z) ; f2 = g W2^T ; h2 = LN2(drop(f2 + b2) + h1)
+//   backward:  the reverse, with the weight gradients accumulated into the caller's flat fp32 buffer.
+#include <string.h>
+
+#include "common.cuh"
+#include "w2v2_b200.h"
+
+#define W2V2_TRY(expr)     \
+  do {                     \
+    const int _rc = (expr); \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream) {
+  W2V2_REQUIRE(a != nullptr, "w2v2_encoder_layer_fwd: null argument block");
+  const int64_t M = int64_t(a->B) * a->T;
+  const int H = a->H, FF = a->FF;
+  const uint64_t seed = a->seed;
+  const int l = a->layer;
+  // attention block
+  W2V2_TRY(w2v2_gemm_f16(a->h_in16, M, H, 0, 1, 1, 0, H, a->wqkv, H, 3 * H, a->bqkv, 0, a->qkv16, 0, 3 * H, 0, stream));
+  W2V2_TRY(w2v2_attention_ex(a->qkv16, a->att16, a->lse, a->B, a->T, H, a->heads, a->p_attn, seed + 100 + l, stream));
+  W2V2_TRY(w2v2_gemm_f16(a->att16, M, H, 0, 1, 1, 0, H, a->wo, H, H, nullptr, 0, a->o32, 1, H, 0, stream));
+  W2V2_TRY(w2v2_layernorm_ex(a->o32, 1, a->bo, a->h_in32, a->ln1_g, a->ln1_b, a->eps, a->h1_32, a->h1_16, M, H, a->p_hidden,
+                             seed + 200 + l, stream));
+  // feed-forward block
+  if (a->z16 != nullptr) {      // training: keep the pre-activation, GELU as its own pass
+    W2V2_TRY(w2v2_gemm_f16(a->h1_16, M, H, 0, 1, 1, 0, H, a->w1, H, FF, a->b1, 0, a->z16, 0, FF, 0, stream));
+    W2V2_TRY(w2v2_gelu_fwd(a->z16, 0, a->g16, 0, nullptr, M * FF, stream));
+    if (a->p_act > 0.f)
+      W2V2_TRY(w2v2_dropout(a->g16, 0, nullptr, FF, a->g16, nullptr, M * FF, a->p_act, seed + 400 + l, stream));
+  } else {                      // inference: GELU in the GEMM epilogue
+    W2V2_TRY(w2v2_gemm_f16(a->h1_16, M, H, 0, 1, 1, 0, H, a->w1, H, FF, a->b1, 1, a->g16, 0, FF, 0, stream));
+  }
+  W2V2_TRY(w2v2_gemm_f16(a->g16, M, FF, 0, 1, 1, 0, FF, a->w2, FF, H, nullptr, 0, a->f2_32, 1, H, 0, stream));
+  W2V2_TRY(w2v2_layernorm_ex(a->f2_32, 1, a->b2, a->h1_32, a->ln2_g, a->ln2_b, a->eps, a->h2_32, a->h2_16, M, H, a->p_hidden,
+                             seed + 300 + l, stream));
+  return 0;
+}
+
+extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream) {
+  W2V2_REQUIRE(a != nullptr, "w2v2_encoder_layer_bwd: null argument block");
+  const int64_t M = int64_t(a->B) * a->T;
+  const int H = a->H, FF = a->FF;
+  const uint64_t seed = a->seed;
+  const int l = a->layer;
+  // LN2:  h2 = LN(drop(f2 + b2) + h1); dx2_16 is the gradient of the dropped branch, the residual keeps dx2_32
+  W2V2_TRY(w2v2_layernorm_bwd_ex(a->dy_a, a->dy_b, a->f2_32, 1, a->b2, a->h1_32, a->ln2_g, a->eps, a->dx2_32, a->dx2_16,
+                                 a->d_ln2_g, a->d_ln2_b, a->d_b2, M, H, a->p_hidden, seed + 300 + l, stream));
+  W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx2_16, H, a->g16, FF, M, H, FF, a->d_w2, FF, stream));
+  W2V2_TRY(w2v2_gemm_f16(a->dx2_16, M, H, 0, 1, 1, 0, H, a->w2T, H, FF, nullptr, 0, a->dg16, 0, FF, 0, stream));
+  if (a->p_act > 0.f)
+    W2V2_TRY(w2v2_dropout(a->dg16, 0, nullptr, FF, a->dg16, nullptr, M * FF, a->p_act, seed + 400 + l, stream));
+  W2V2_TRY(w2v2_gelu_bwd_colsum(a->dg16, a->z16, a->dz16, M, FF, a->d_b1, stream));
+  W2V2_TRY(w2v2_gemm_wgrad_f16(a->dz16, FF, a->h1_16, H, M, FF, H, a->d_w1, H, stream));
+  W2V2_TRY(w2v2_gemm_f16(a->dz16, M, FF, 0, 1, 1, 0, FF, a->w1T, FF, H, nullptr, 0, a->dh1_32, 1, H, 0, stream));
+  // LN1:  h1 = LN(drop(o + bo) + h_in)
+  W2V2_TRY(w2v2_layernorm_bwd_ex(a->dh1_32, a->dx2_32, a->o32, 1, a->bo, a->h_in32, a->ln1_g, a->eps, a->dx1_32, a->dx1_16,
+                                 a->d_ln1_g, a->d_ln1_b, a->d_bo, M, H, a->p_hidden, seed + 200 + l, stream));
+  W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx1_16, H, a->att16, H, M, H, H, a->d_wo, H, stream));
+  W2V2_TRY(w2v2_gemm_f16(a->dx1_16, M, H, 0, 1, 1, 0, H, a->woT, H, H, nullptr, 0, a->datt16, 0, H, 0, stream));
+  W2V2_TRY(w2v2_attention_bwd_ex(a->qkv16, a->att16, a->datt16, a->lse, a->dqkv16, a->B, a->T, H, a->heads, a->p_attn,
+                                 seed + 100 + l, stream));
+  W2V2_TRY(w2v2_colsum(a->dqkv16, 0, M, 3 * H, 3 * H, 1.0f, a->d_bqkv, stream));
+  W2V2_TRY(w2v2_gemm_wgrad_f16(a->dqkv16, 3 * H, a->h_in16, H, M, 3 * H, H, a->d_wqkv, H, stream));
+  // the q projection was used pre-scaled by d^-0.5: chain rule for the unscaled parameters
+  W2V2_TRY(w2v2_scale_f32(a->d_wqkv, int64_t(H) * H, a->qscale, stream));
+  W2V2_TRY(w2v2_scale_f32(a->d_bqkv, H, a->qscale, stream));
+  W2V2_TRY(w2v2_gemm_f16(a->dqkv16, M, 3 * H, 0, 1, 1, 0, 3 * H, a->wqkvT, 3 * H, H, nullptr, 0, a->dh_in32, 1, H, 0, stream));
+  return 0;
+}

@@ -238,17 +238,27 @@ class EncoderEngine:
         h32, h16 = ops.layernorm(pos.view(M, H), w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0.view(M, H))
         if hidden_states is not None:
             hidden_states.append(h32.view(B, T, H))
-        for lw in w.layers:
-            qkv = ops.gemm_f16(h16, lw["wqkv"], lw["bqkv"], 0, F16)
-            att = ops.attention(qkv, B, T, H, a.heads)
-            o = ops.gemm_f16(att, lw["wo"], None, 0, F32)
-            h32, h16 = ops.layernorm(o, lw["ln1_g"], lw["ln1_b"], a.eps, bias=lw["bo"], residual=h32)
-            f1 = ops.gemm_f16(h16, lw["w1"], lw["b1"], 1, F16)
-            f2 = ops.gemm_f16(f1, lw["w2"], None, 0, F32)
-            h32, h16 = ops.layernorm(f2, lw["ln2_g"], lw["ln2_b"], a.eps, bias=lw["b2"], residual=h32)
-            if hidden_states is not None:
-                hidden_states.append(h32.view(B, T, H))
-        return h32.view(B, T, H)
+        # one native schedule call per layer (csrc/schedule.cu); the intermediates are shared by all layers,
+        # the residual stream ping-pongs between two buffer pairs (kept per layer when hidden states are traced)
+        from . import schedule as sched
+        sizes = sched.layer_buffer_sizes(B, T, H, a.heads, a.ffn, False)
+        keep = hidden_states is not None
+        n_out = len(w.layers) if keep else 2
+        for i in range(n_out):
+            sizes[f"h32.{i}"] = M * H * 4
+            sizes[f"h16.{i}"] = M * H * 2
+        ar = sched.Arena(sizes, h0.device)
+        p32, p16 = h32.data_ptr(), h16.data_ptr()
+        out = h32.view(B, T, H)
+        for l, lw in enumerate(w.layers):
+            i = l if keep else (l & 1)
+            sched.run_layer_fwd(sched.fwd_args(a, B, T, l, lw, p32, p16, ar, False,
+                                               out32=ar.ptr(f"h32.{i}"), out16=ar.ptr(f"h16.{i}")))
+            p32, p16 = ar.ptr(f"h32.{i}"), ar.ptr(f"h16.{i}")
+            out = ar.tensor(f"h32.{i}", F32, (B, T, H))
+            if keep:
+                hidden_states.append(out)
+        return out
 
     # -- HF:1327-1383 --------------------------------------------------------------------------
     def forward(self, wav: torch.Tensor, trace: Optional[dict] = None) -> torch.Tensor:

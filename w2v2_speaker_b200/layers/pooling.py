@@ -104,15 +104,17 @@ class _AttentiveStatisticsPooling(nn.Module):
         return self.forward_btc(x_ncl.transpose(1, 2).contiguous()).unsqueeze(2)
 
     def forward_btc(self, x: torch.Tensor) -> torch.Tensor:
-        if self.training or (torch.is_grad_enabled() and x.requires_grad):
-            raise NotImplementedError("attentive pooling in training (batch-statistics BatchNorm, backward) is not "
-                                      "implemented in the sm_100a path yet; call .eval() under torch.no_grad()")
+        c1, bn, c2 = self.tdnn.conv.conv, self.tdnn.norm.norm, self.conv.conv
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(q.requires_grad for q in self.parameters()))
+        if self.training or needs_grad:
+            # batch-statistics BatchNorm and / or a backward pass: the autograd Function over the same kernels
+            from ..training import AspPoolFn
+            return AspPoolFn.apply(x.float().contiguous(), c1.weight, c1.bias, bn.weight, bn.bias, c2.weight, c2.bias, self)
         B, T, C = x.shape
         x = x.float().contiguous()
-        c1, bn, c2 = self.tdnn.conv.conv, self.tdnn.norm.norm, self.conv.conv
-        cat16 = ops.asp_concat(x)                                            # [B*T, 3C] fp16
-        z = ops.gemm_f16(cat16, ops.cast_f16(c1.weight.detach().view(self.attention_channels, 3 * C)),
-                         c1.bias.detach().float(), 0, torch.float32)           # Conv1d k=1
+        cat3 = ops.asp_concat_split3(x)                                      # [B*T, 9C] fp16: [hi | lo | hi]
+        w1 = c1.weight.detach().float().reshape(self.attention_channels, 3 * C).contiguous()
+        z = ops.gemm_f16(cat3, ops.split3_rows(w1, 1), c1.bias.detach().float(), 0, torch.float32)    # Conv1d k=1
         scale = (bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
         shift = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
         y16 = ops.asp_relu_bn_tanh(z.contiguous(), scale, shift)             # tanh(BN(ReLU(.)))

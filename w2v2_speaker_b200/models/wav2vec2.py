@@ -123,8 +123,20 @@ class Wav2Vec2ModelB200(nn.Module):
         self._prepared_sig = None
 
     # ---- weights in kernel form, rebuilt when any parameter changed -------------------------
+    def _items(self):
+        """(names, parameters, name -> parameter) cached: walking the module tree costs ~1 ms per call and
+        the training step needs it several times.  The Parameter objects never change after construction
+        (``.to()`` / optimizers mutate ``.data``)."""
+        c = self.__dict__.get("_items_cache")
+        if c is None:
+            named = list(self.named_parameters())
+            c = ([n for n, _ in named], [q for _, q in named], dict(named),
+                 [q for n, q in named if n.startswith("feature_extractor.")])
+            self.__dict__["_items_cache"] = c
+        return c
+
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in self._items()[1])
 
     def refresh(self) -> None:
         """Call after the parameters were updated in place behind autograd's back (fused optimizer):
@@ -138,7 +150,7 @@ class Wav2Vec2ModelB200(nn.Module):
         self._prepared = None
 
     def _engine(self) -> EncoderEngine:
-        if any(not p.is_cuda for p in self.parameters()):
+        if any(not p.is_cuda for p in self._items()[1]):
             raise RuntimeError("Wav2Vec2ModelB200 runs on a CUDA device only: move the module with .cuda() "
                                "(there is no CPU path)")
         sig = self._signature()
@@ -155,7 +167,7 @@ class Wav2Vec2ModelB200(nn.Module):
         return eng._train_weights
 
     def _needs_grad(self) -> bool:
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self._items()[1])
 
     def _stochastic(self) -> bool:
         r = self.reg_cfg
@@ -171,7 +183,14 @@ class Wav2Vec2ModelB200(nn.Module):
         if getattr(self, "_rng", None) is None:
             self._rng = np.random.default_rng(torch.initial_seed() % (1 << 63))
         T = self.arch.conv_lengths(wav.shape[1])[-1]
-        return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device)
+        # ring of pinned staging buffers for the SpecAugment mask (the host may run a few steps ahead of the device)
+        ring = self.__dict__.setdefault("_mask_ring", {})
+        key = (wav.shape[0], T)
+        if key not in ring:
+            ring[key] = [[torch.empty(wav.shape[0] * T, dtype=torch.uint8).pin_memory() for _ in range(8)], 0]
+        bufs, i = ring[key]
+        ring[key][1] = (i + 1) % len(bufs)
+        return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device, bufs[i])
 
     def _check_mode(self):
         if self.reg_cfg.mask_feature_prob > 0 and self.training:
@@ -181,7 +200,7 @@ class Wav2Vec2ModelB200(nn.Module):
             raise NotImplementedError(
                 "train-mode regularisation is implemented on the training path only: enable gradients, or call "
                 ".eval() for inference")
-        if self._needs_grad() and any(p.requires_grad for p in self.feature_extractor.parameters()):
+        if self._needs_grad() and any(p.requires_grad for p in self._items()[3]):
             raise NotImplementedError(
                 "the backward of the CNN feature extractor is not implemented yet: freeze it with "
                 "model.feature_extractor.requires_grad_(False) (the reference default, "
@@ -195,8 +214,8 @@ class Wav2Vec2ModelB200(nn.Module):
             if output_hidden_states:
                 raise NotImplementedError("output_hidden_states is only available without gradients")
             from ..training import EncoderFn
-            names = [n for n, _ in self.named_parameters()]
-            out = EncoderFn.apply(input_values.float(), self, names, *[p for _, p in self.named_parameters()])
+            names, params = self._items()[:2]
+            out = EncoderFn.apply(input_values.float(), self, names, *params)
             return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         eng = self._engine()
         trace = {} if output_hidden_states else None

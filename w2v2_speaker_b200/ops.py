@@ -277,6 +277,14 @@ def asp_concat(x: torch.Tensor) -> torch.Tensor:
     return cat
 
 
+def asp_concat_split3(x: torch.Tensor) -> torch.Tensor:
+    """[x | mean | std] as error-compensated operand [hi | lo | hi], f16 [B*T, 9H] (pairs with split3_rows(W, 1))."""
+    B, T, H = x.shape
+    cat = torch.empty(B * T, 9 * H, dtype=F16, device=x.device)
+    call("w2v2_asp_concat_split3", ptr(x), ptr(cat), B, T, H, stream_ptr())
+    return cat
+
+
 def asp_relu_bn_tanh(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
     rows, A = z.shape
     y = torch.empty(rows, A, dtype=F16, device=z.device)
@@ -427,4 +435,44 @@ def l2norm_rows_bwd(x: torch.Tensor, dxh: torch.Tensor, scale: float = 1.0) -> t
     dx = torch.empty(rows, E, dtype=F32, device=x.device)
     call("w2v2_l2norm_rows_bwd", ptr(x.contiguous()), ptr(dxh), dxh.stride(0), ptr(dx), rows, E, float(scale), 0,
          stream_ptr())
+    return dx
+
+
+# ---- attentive-statistics pooling, training ------------------------------------------------------
+
+
+def asp_bn_batch_stats(z: torch.Tensor, gamma, beta, eps: float, momentum: float, running_mean, running_var):
+    """Training-mode BatchNorm1d over the rows of relu(z) -> (scale, shift, mean, rstd); updates the running stats."""
+    rows, A = z.shape
+    dev = z.device
+    ws = torch.empty(2 * A, dtype=torch.float64, device=dev)
+    scale, shift, mean, rstd = (torch.empty(A, dtype=F32, device=dev) for _ in range(4))
+    call("w2v2_asp_bn_batch_stats", ptr(z), rows, A, ptr(gamma), ptr(beta), float(eps), float(momentum), ptr(running_mean),
+         ptr(running_var), ptr(ws), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), stream_ptr())
+    return scale, shift, mean, rstd
+
+
+def asp_pool_bwd(x: torch.Tensor, logits: torch.Tensor, out: torch.Tensor, dout: torch.Tensor):
+    """-> (dlogits f16 [B*T, C], dx_direct f32 [B,T,C])."""
+    B, T, C = x.shape
+    dlg = torch.empty(B * T, C, dtype=F16, device=x.device)
+    dx = torch.empty_like(x)
+    call("w2v2_asp_pool_bwd", ptr(x), ptr(logits), ptr(out), ptr(dout.contiguous()), ptr(dlg), ptr(dx), B, T, C, stream_ptr())
+    return dlg, dx
+
+
+def asp_act_bwd(dh: torch.Tensor, z: torch.Tensor, scale, shift, mean, rstd, batch_stats: bool, dgamma, dbeta,
+                grad_scale: float) -> torch.Tensor:
+    rows, A = z.shape
+    ws = torch.empty(2 * A, dtype=torch.float64, device=z.device)
+    dz = torch.empty(rows, A, dtype=F16, device=z.device)
+    call("w2v2_asp_act_bwd", ptr(dh), ptr(z), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), int(batch_stats), ptr(ws), ptr(dz),
+         ptr(dgamma), ptr(dbeta), float(grad_scale), rows, A, stream_ptr())
+    return dz
+
+
+def asp_front_bwd_(x: torch.Tensor, dcat: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
+    B, T, C = x.shape
+    assert dcat.stride(1) == 1 and dcat.shape == (B * T, 3 * C)
+    call("w2v2_asp_front_bwd", ptr(x), ptr(dcat), dcat.stride(0), ptr(dx), B, T, C, stream_ptr())
     return dx

@@ -67,13 +67,18 @@ class FlatAdamTrainer:
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._overlapped = []
+        self._refreshable = None
         if seg0 and self.world > 1:
             self.model._grad_ready_hook = self._reduce_span      # spans of flat_g[:n0] == GradBook offsets
 
     def _refresh_module_weights(self):
-        for m in self.module.modules():
-            if hasattr(m, "refresh"):
-                m.refresh()
+        if self._refreshable is None:          # the module tree is fixed: walk it once
+            mods = list(self.module.modules())
+            self._refreshable = ([m for m in mods if hasattr(m, "refresh")],
+                                 [m for m in mods if hasattr(m, "_w_split") or hasattr(m, "_w_sig")])
+        for m in self._refreshable[0]:
+            m.refresh()
+        for m in self._refreshable[1]:
             for attr in ("_w_split", "_w_sig"):
                 if hasattr(m, attr):
                     setattr(m, attr, None)

@@ -18,6 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
+from . import schedule as sched
 from .engine import ArchConfig, EncoderEngine, PreparedWeights
 
 F16, F32 = torch.float16, torch.float32
@@ -70,7 +71,7 @@ class RegPlan:
     (HF:701-713) and the SpecAugment time mask (HF:101-217, 1280-1324; spans of `mask_time_length`
     frames, at least two per utterance), all drawn on the host like the reference does."""
 
-    def __init__(self, reg, layers: int, B: int, T: int, rng, device):
+    def __init__(self, reg, layers: int, B: int, T: int, rng, device, pinned: Optional[torch.Tensor] = None):
         self.p_feat = float(reg.feat_proj_dropout)
         self.p_hidden = float(reg.hidden_dropout)
         self.p_attn = float(reg.attention_dropout)
@@ -79,7 +80,12 @@ class RegPlan:
         self.skip = [bool(rng.random() < reg.layerdrop) for _ in range(layers)]
         self.mask = None
         if reg.mask_time_prob > 0:
-            self.mask = torch.from_numpy(compute_time_mask(B, T, reg.mask_time_prob, reg.mask_time_length, 2, rng)).to(device)
+            m = torch.from_numpy(compute_time_mask(B, T, reg.mask_time_prob, reg.mask_time_length, 2, rng))
+            if pinned is not None:               # staging buffer owned by the model: asynchronous upload
+                pinned.copy_(m)
+                self.mask = pinned.to(device, non_blocking=True)
+            else:
+                self.mask = m.to(device)
 
     @property
     def any(self) -> bool:
@@ -129,29 +135,24 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
     h32, h16 = ops.layernorm(pos, w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0)
     if ph > 0:
         h32, h16 = ops.dropout_(h32, ph, seed + 2, want16=True)          # HF:693
-    S.update(B=B, T=T, feat=feat2, n16=n16, h0=h0, x16=x16, pos=pos, zpos16=zpos16, layers=[])
+    S.update(B=B, T=T, feat=feat2, n16=n16, h0=h0, x16=x16, pos=pos, zpos16=zpos16, layers=[], top=(h32, h16))
+    # transformer layers: one native schedule call per layer (csrc/schedule.cu), buffers from one arena each
+    sizes = sched.layer_buffer_sizes(B, T, H, a.heads, a.ffn, True)
+    p32, p16 = h32.data_ptr(), h16.data_ptr()
+    last = None
     for l, lw in enumerate(w.layers):
         if plan is not None and plan.skip[l]:                            # LayerDrop (HF:701-713)
             S["layers"].append(None)
             continue
-        L = dict(h_in32=h32, h_in16=h16)
-        L["qkv"] = ops.gemm_f16(h16, lw["wqkv"], lw["bqkv"], 0, F16)
-        L["att"], L["lse"] = ops.attention(L["qkv"], B, T, H, a.heads, want_lse=True,
-                                           drop_p=plan.p_attn if plan is not None else 0.0, drop_seed=seed + 100 + l)
-        L["o"] = ops.gemm_f16(L["att"], lw["wo"], None, 0, F32).contiguous()
-        # x1 = h_in + drop(o + bo) (HF:546-549), the dropout is generated inside the LayerNorm kernel
-        h32, h16 = ops.layernorm(L["o"], lw["ln1_g"], lw["ln1_b"], a.eps, bias=lw["bo"], residual=L["h_in32"],
-                                 drop_p=ph, drop_seed=seed + 200 + l)
-        L["h1_32"], L["h1_16"] = h32, h16
-        L["z"] = ops.gemm_f16(h16, lw["w1"], lw["b1"], 0, F16).contiguous()
-        L["g"], _ = ops.gelu_fwd(L["z"], F16)
-        if plan is not None and plan.p_act > 0:
-            ops.dropout_(L["g"], plan.p_act, seed + 400 + l)             # HF:568
-        L["f2"] = ops.gemm_f16(L["g"], lw["w2"], None, 0, F32).contiguous()
-        h32, h16 = ops.layernorm(L["f2"], lw["ln2_g"], lw["ln2_b"], a.eps, bias=lw["b2"], residual=L["h1_32"],
-                                 drop_p=ph, drop_seed=seed + 300 + l)                      # HF:572-574
-        S["layers"].append(L)
-    return h32.view(B, T, H), S
+        ar = sched.Arena(sizes, h32.device)
+        sched.run_layer_fwd(sched.fwd_args(a, B, T, l, lw, p32, p16, ar, True, ph,
+                                           plan.p_attn if plan is not None else 0.0,
+                                           plan.p_act if plan is not None else 0.0, seed))
+        S["layers"].append(dict(arena=ar, h_in32=p32, h_in16=p16))
+        p32, p16 = ar.ptr("h2_32"), ar.ptr("h2_16")
+        last = ar
+    out = last.tensor("h2_32", F32, (B, T, H)) if last is not None else h32.view(B, T, H)
+    return out, S
 
 
 class GradBook:
@@ -223,42 +224,49 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
             hi = G.offsets[f"encoder.layers.{l + 1}.attention.q_proj.weight"] if l + 1 < a.layers else G.numel
             on_layer_done(lo, hi)
 
+    # transformer layers in reverse: one native schedule call per layer; the scratch arena is shared by all
+    # layers, the two terms of the input gradient ping-pong between two buffer pairs
+    scr = sched.Arena(sched.bwd_scratch_sizes(B, T, H, FF), dev)
+    gbase = G.flat.data_ptr()
+    pa, pb, pp = dy_a.data_ptr(), None, 0
+    ran = False
     for l in reversed(range(a.layers)):
         L = S["layers"][l]
         if L is None:                                   # LayerDrop: identity in forward, identity in backward
             layer_done(l)
             continue
         pre = f"encoder.layers.{l}."
-        lw, tl = w.layers[l], tw.layers[l]
-        # LN2:  h2 = LN(drop(f2 + b2) + h1); dx2_16 is the gradient of the dropped branch, the residual keeps dx2_32
-        dx2_32, dx2_16 = ops.layernorm_bwd(dy_a, L["f2"], lw["ln2_g"], a.eps, dy_b=dy_b, bias=lw["b2"],
-                                           residual=L["h1_32"], dgamma=G.view(pre + "final_layer_norm.weight"),
-                                           dbeta=G.view(pre + "final_layer_norm.bias"), drop_p=ph, drop_seed=seed + 300 + l,
-                                           dbias=G.view(pre + "feed_forward.output_dense.bias"))
-        ops.gemm_wgrad_f16(dx2_16, L["g"], G.view(pre + "feed_forward.output_dense.weight"))
-        dg16 = ops.gemm_f16(dx2_16, tl["w2T"], None, 0, F16).contiguous()       # [M, FF]
-        if plan is not None and plan.p_act > 0:
-            ops.dropout_(dg16, plan.p_act, seed + 400 + l)
-        dz16 = ops.gelu_bwd(dg16, L["z"], dbias=G.view(pre + "feed_forward.intermediate_dense.bias"))
-        ops.gemm_wgrad_f16(dz16, L["h1_16"], G.view(pre + "feed_forward.intermediate_dense.weight"))
-        dh1_a = ops.gemm_f16(dz16, tl["w1T"], None, 0, F32)                      # [M, H]
-        # LN1:  h1 = LN(drop(o + bo) + h_in)
-        dx1_32, dx1_16 = ops.layernorm_bwd(dh1_a, L["o"], lw["ln1_g"], a.eps, dy_b=dx2_32, bias=lw["bo"],
-                                           residual=L["h_in32"], dgamma=G.view(pre + "layer_norm.weight"),
-                                           dbeta=G.view(pre + "layer_norm.bias"), drop_p=ph, drop_seed=seed + 200 + l,
-                                           dbias=G.view(pre + "attention.out_proj.bias"))
-        ops.gemm_wgrad_f16(dx1_16, L["att"], G.view(pre + "attention.out_proj.weight"))
-        datt16 = ops.gemm_f16(dx1_16, tl["woT"], None, 0, F16)
-        dqkv16 = ops.attention_bwd(L["qkv"], L["att"], datt16, L["lse"], B, T, H, a.heads,
-                                   drop_p=plan.p_attn if plan is not None else 0.0, drop_seed=seed + 100 + l)
-        ops.colsum(dqkv16, G.span(pre + "attention.q_proj.bias", 1, 3 * H).view(3 * H))
-        ops.gemm_wgrad_f16(dqkv16, L["h_in16"], G.span(pre + "attention.q_proj.weight", 3 * H, H))
-        # the q projection was used pre-scaled by d^-0.5: chain rule for the unscaled parameters
-        ops.scale_f32_(G.view(pre + "attention.q_proj.weight"), qscale)
-        ops.scale_f32_(G.view(pre + "attention.q_proj.bias"), qscale)
-        dy_a = ops.gemm_f16(dqkv16, tl["wqkvT"], None, 0, F32)                   # d h_in via qkv
-        dy_b = dx1_32                                                            # + residual path
+        lw, tl, ar = w.layers[l], tw.layers[l], L["arena"]
+        g = lambda k: gbase + 4 * G.offsets[pre + k]
+        b = sched.LayerBwdArgs()
+        b.B, b.T, b.H, b.heads, b.FF, b.layer = B, T, H, a.heads, FF, l
+        b.eps, b.p_hidden, b.qscale = a.eps, ph, qscale
+        b.p_attn = plan.p_attn if plan is not None else 0.0
+        b.p_act = plan.p_act if plan is not None else 0.0
+        b.seed = seed
+        b.wqkvT, b.woT, b.w1T, b.w2T = (tl[k].data_ptr() for k in ("wqkvT", "woT", "w1T", "w2T"))
+        b.bo, b.b2, b.ln1_g, b.ln2_g = (lw[k].data_ptr() for k in ("bo", "b2", "ln1_g", "ln2_g"))
+        b.h_in32, b.h_in16 = L["h_in32"], L["h_in16"]
+        for k in ("qkv16", "att16", "lse", "o32", "h1_32", "h1_16", "z16", "g16", "f2_32"):
+            setattr(b, k, ar.ptr(k))
+        b.dy_a, b.dy_b = pa, pb
+        b.d_wqkv, b.d_bqkv = g("attention.q_proj.weight"), g("attention.q_proj.bias")
+        b.d_wo, b.d_bo = g("attention.out_proj.weight"), g("attention.out_proj.bias")
+        b.d_ln1_g, b.d_ln1_b = g("layer_norm.weight"), g("layer_norm.bias")
+        b.d_w1, b.d_b1 = g("feed_forward.intermediate_dense.weight"), g("feed_forward.intermediate_dense.bias")
+        b.d_w2, b.d_b2 = g("feed_forward.output_dense.weight"), g("feed_forward.output_dense.bias")
+        b.d_ln2_g, b.d_ln2_b = g("final_layer_norm.weight"), g("final_layer_norm.bias")
+        for k in ("dx2_32", "dx2_16", "dg16", "dz16", "dh1_32", "dx1_16", "datt16", "dqkv16"):
+            setattr(b, k, scr.ptr(k))
+        b.dx1_32, b.dh_in32 = scr.ptr(f"dx1_32.{pp}"), scr.ptr(f"dh_in32.{pp}")
+        sched.run_layer_bwd(b)
+        pa, pb = b.dh_in32, b.dx1_32
+        ran, last_pp = True, pp
+        pp ^= 1
         layer_done(l)
+    if ran:
+        dy_a = scr.tensor(f"dh_in32.{last_pp}", F32, (M, H))                     # d h_in via qkv
+        dy_b = scr.tensor(f"dx1_32.{last_pp}", F32, (M, H))                      # + residual path
     # encoder top:  h_e = drop(LN(pos + h0)),  pos = GELU(zpos),  zpos = posconv(h0) + b
     if ph > 0:
         dy_a, _ = ops.add2_cast(dy_a, dy_b, want16=False)
@@ -310,7 +318,7 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dh):
         model, names, eng = ctx.model, ctx.names, ctx.eng
-        pd = dict(model.named_parameters())
+        pd = model._items()[2]
         tw = model._train_weights(eng)
         sink = getattr(model, "_grad_sink", None)
         G = encoder_backward(eng, tw, pd, ctx.saved, dh.float(), sink,
@@ -437,3 +445,72 @@ class AamSoftmaxFn(torch.autograd.Function):
         ops.gemm_wgrad_f16(dc16[:, :S], xh16, dwh)                                # d(W_hat) [S, E]
         dW = ops.l2norm_rows_bwd(Wf, dwh, 1.0 / LOSS_SCALE)
         return dx, dW, None, None, None, None, None
+
+
+class AspPoolFn(torch.autograd.Function):
+    """[mean || std] of attentive-statistics pooling (R:src/layers/pooling.py:87-106) with its backward.
+    `layer` is the parameter holder (layers.pooling._AttentiveStatisticsPooling): training-mode BatchNorm
+    uses (and updates) batch statistics exactly like torch's BatchNorm1d.  The incoming gradient carries
+    LOSS_SCALE and so does the returned d x; parameter gradients are unscaled."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, gamma, beta, w2, b2, layer):
+        bn = layer.tdnn.norm.norm
+        A = layer.attention_channels
+        x = x.detach().float().contiguous()
+        B, T, C = x.shape
+        cat3 = ops.asp_concat_split3(x)                                              # [B*T, 9C] f16: [hi | lo | hi]
+        cat16 = cat3[:, :3 * C]                                                      # the plain fp16 cat (row pitch 9C)
+        w1f = w1.detach().float().reshape(A, 3 * C).contiguous()
+        w2f = w2.detach().float().reshape(C, A).contiguous()
+        # Conv1d k=1 with error-compensated operands: the ReLU that follows makes the TDNN gradient sensitive to z
+        z = ops.gemm_f16(cat3, ops.split3_rows(w1f, 1), b1.detach().float(), 0, F32).contiguous()
+        g, bt = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        batch_stats = bool(bn.training)
+        if batch_stats:
+            momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+            track = bn.track_running_stats and bn.running_mean is not None
+            scale, shift, mean, rstd = ops.asp_bn_batch_stats(z, g, bt, bn.eps, momentum,
+                                                              bn.running_mean if track else None,
+                                                              bn.running_var if track else None)
+            if track and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+            scale = (g * rstd).contiguous()
+            mean = bn.running_mean.float().contiguous()
+            shift = (bt - mean * scale).contiguous()
+        y16 = ops.asp_relu_bn_tanh(z, scale, shift)                                  # tanh(BN(ReLU(.)))
+        logits = ops.gemm_f16(y16, ops.cast_f16(w2f), b2.detach().float(), 0, F32).contiguous()
+        out = ops.asp_pool(x, logits.view(B, T, C))
+        ctx.save_for_backward(x, cat16, z, y16, logits, out, scale, shift, mean, rstd, w1f, w2f)
+        ctx.batch_stats = batch_stats
+        ctx.shapes = (w1.shape, w2.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, cat16, z, y16, logits, out, scale, shift, mean, rstd, w1f, w2f = ctx.saved_tensors
+        B, T, C = x.shape
+        A = z.shape[1]
+        dev = x.device
+        inv_ls = 1.0 / LOSS_SCALE
+        dlg16, dx = ops.asp_pool_bwd(x, logits.view(B, T, C), out, dout.float())
+        dW2 = torch.zeros(C, A, dtype=F32, device=dev)
+        ops.gemm_wgrad_f16(dlg16, y16, dW2)
+        db2 = torch.zeros(C, dtype=F32, device=dev)
+        ops.colsum(dlg16, db2, inv_ls)
+        dh = ops.gemm_f16(dlg16, ops.cast_f16_transpose(w2f, C), None, 0, F32).contiguous()       # [B*T, A]
+        dgamma = torch.empty(A, dtype=F32, device=dev)
+        dbeta = torch.empty(A, dtype=F32, device=dev)
+        dz16 = ops.asp_act_bwd(dh, z, scale, shift, mean, rstd, ctx.batch_stats, dgamma, dbeta, inv_ls)
+        dW1 = torch.zeros(A, 3 * C, dtype=F32, device=dev)
+        ops.gemm_wgrad_f16(dz16, cat16, dW1)
+        db1 = torch.zeros(A, dtype=F32, device=dev)
+        ops.colsum(dz16, db1, inv_ls)
+        dcat = ops.gemm_f16(dz16, ops.cast_f16_transpose(w1f, A), None, 0, F32)                    # [B*T, 3C]
+        ops.asp_front_bwd_(x, dcat, dx)
+        ops.scale_f32_(dW1, inv_ls)
+        ops.scale_f32_(dW2, inv_ls)
+        s1, s2 = ctx.shapes
+        return dx, dW1.view(s1), db1, dgamma, dbeta, dW2.view(s2), db2, None
