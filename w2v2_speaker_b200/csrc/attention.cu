@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, cg = warp >> 2;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&p.tmQ);
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_tma, 16384 + 2 * kv_bytes);
@@ -247,7 +249,7 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
     configured_smem = smem;
   }
   dim3 grid((T + 127) / 128, heads, B);
-  attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(p);
+  W2V2_CHECK_CUDA(launch_k(attention_kernel, grid, dim3(ATT_THREADS), smem, stream, 1, p));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, cg = warp >> 2;
   const int row = quarter * 32 + lane;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&p.tmQ);
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
+  pdl_wait();
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_tma, (p.resident ? 2 * p.qtiles * 16384 : 0) + 2 * TK * 128);
@@ -393,7 +395,7 @@ extern "C" int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const v
     configured = smem;
   }
   dim3 grid(heads, B);
-  attention_bwd_kernel<<<grid, AB_THREADS, smem, stream>>>(p);
+  W2V2_CHECK_CUDA(launch_k(attention_bwd_kernel, grid, dim3(AB_THREADS), smem, stream, 1, p));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, cg = warp >> 2;
   const int row = quarter * 32 + lane;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&p.tmQ0);
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
+  pdl_wait();
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_tma, 3 * 16384 + (p.qtiles > 1 ? 3 * 4096 : 0) + 2 * TK * 128);
@@ -402,7 +404,7 @@ int attention_bwd_fused_launch(const void* qkv16, const void* o16, const void* d
     configured = true;
   }
   dim3 grid(heads, B);
-  attention_bwd_fused_kernel<<<grid, AF_THREADS, AF_SMEM, stream>>>(p);
+  W2V2_CHECK_CUDA(launch_k(attention_bwd_fused_kernel, grid, dim3(AF_THREADS), size_t(AF_SMEM), stream, 1, p));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
                                                             float* __restrict__ dbias,
                                                             int64_t rows, int H, uint32_t thr, float inv_keep,
                                                             uint64_t seed) {
+  pdl_trigger();
+  pdl_wait();
   // MAXV = ceil(H / 128) float4 slots per lane (4: H <= 512, 6: H <= 768, 8: H <= 1024)
   // strips: 0 = dgamma, 1 = dbeta, 2 = dbias (column sums of the branch gradient, i.e. the bias gradient of
   // the Linear that produced xa)
@@ -227,6 +229,8 @@ __global__ void gelu_bwd_kernel(const __half* __restrict__ dg, const __half* __r
 __global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const __half* __restrict__ dg, const __half* __restrict__ z,
                                                               __half* __restrict__ dz, int64_t rows, int cols,
                                                               float* __restrict__ dbias) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[8][256 + 8];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + cl * 8;
@@ -295,6 +299,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_
 // fp16 fast path: 16-byte loads, a warp covers 256 consecutive columns of one row, 8 rows per block pass
 __global__ void __launch_bounds__(256) colsum_f16_vec_kernel(const __half* __restrict__ x, int64_t rows, int cols,
                                                              int64_t ld, float scale, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sm[8][256 + 8];
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -400,7 +406,7 @@ int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, 
   const int grid = int((want + per_warp - 1) / per_warp);
   cudaStream_t st = (cudaStream_t)stream;
 #define W2V2_LNB(F32, NV, EX) \
-  layernorm_bwd_kernel<F32, NV, EX><<<grid, LNB_WARPS * 32, 0, st>>>(dy_a, dy_b, xa, bias, residual, gamma, eps, dx32, (__half*)dx16, dgamma, dbeta, dbias, rows, H, thr, inv_keep, drop_seed)
+  launch_k(layernorm_bwd_kernel<F32, NV, EX>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, 1, dy_a, dy_b, xa, bias, residual, gamma, eps, dx32, (__half*)dx16, dgamma, dbeta, dbias, rows, H, thr, inv_keep, drop_seed)
   if (xa_dtype == 1) {
     if (H == 512) W2V2_LNB(true, 4, true); else if (H == 768) W2V2_LNB(true, 6, true);
     else if (H == 1024) W2V2_LNB(true, 8, true); else W2V2_LNB(true, 8, false);
@@ -431,8 +437,8 @@ int w2v2_gelu_bwd_colsum(const void* dg16, const void* z16, void* dz16, int64_t 
   dim3 grid((cols + 255) / 256, 1);
   int64_t want = (int64_t(device_sm_count()) * 6 + grid.x - 1) / grid.x, cap = (rows + 7) / 8;
   grid.y = unsigned(want < cap ? want : cap);
-  gelu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)dg16, (const __half*)z16, (__half*)dz16, rows,
-                                                                cols, dbias);
+  W2V2_CHECK_CUDA(launch_k(gelu_bwd_colsum_kernel, grid, dim3(256), 0, (cudaStream_t)stream, 1, (const __half*)dg16,
+                           (const __half*)z16, (__half*)dz16, rows, cols, dbias));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -444,7 +450,8 @@ int w2v2_colsum(const void* x, int x_dtype, int64_t rows, int cols, int64_t ld, 
     dim3 vgrid((cols + 255) / 256, (unsigned)grid_cap((rows + 63) / 64, 1));
     const unsigned want = (unsigned)(2 * device_sm_count() / vgrid.x + 1);
     if (vgrid.y > want) vgrid.y = want;
-    colsum_f16_vec_kernel<<<vgrid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, rows, cols, ld, scale, out);
+    W2V2_CHECK_CUDA(launch_k(colsum_f16_vec_kernel, vgrid, dim3(256), 0, (cudaStream_t)stream, 1, (const __half*)x, rows, cols,
+                             ld, scale, out));
     count_launches(1);
     W2V2_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -44,6 +44,8 @@ __global__ void cast_f16_rows_kernel(const float* __restrict__ x, int64_t ldx, _
 }
 
 __global__ void scale_f32_kernel(float* __restrict__ x, int64_t n, float s) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) x[i] *= s;
 }
 
@@ -84,7 +86,7 @@ int w2v2_cast_f16_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int6
 
 int w2v2_scale_f32(float* x, int64_t n, float s, void* stream) {
   if (n == 0) return 0;
-  scale_f32_kernel<<<mgrid(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, n, s);
+  W2V2_CHECK_CUDA(launch_k(scale_f32_kernel, dim3(mgrid(n, 256, 8)), dim3(256), 0, (cudaStream_t)stream, 1, x, n, s));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -18,6 +18,8 @@ static inline int pgrid(int64_t n, int per_block, int per_sm) {
 template <bool IN_F32, bool OUT_F32>
 __global__ void gelu_fwd_kernel(const void* __restrict__ x_, void* __restrict__ y_, __half* __restrict__ x16_copy,
                                 int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   // n % 4 == 0.  Optionally also writes the (rounded) input as f16 (saved pre-activation).
   int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
@@ -118,10 +120,10 @@ int w2v2_gelu_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* x16_co
   const int grid = pgrid(n / 4, 256, 8);
   cudaStream_t st = (cudaStream_t)stream;
   __half* c = (__half*)x16_copy;
-  if (x_dtype == 1 && y_dtype == 1) gelu_fwd_kernel<true, true><<<grid, 256, 0, st>>>(x, y, c, n);
-  else if (x_dtype == 1) gelu_fwd_kernel<true, false><<<grid, 256, 0, st>>>(x, y, c, n);
-  else if (y_dtype == 1) gelu_fwd_kernel<false, true><<<grid, 256, 0, st>>>(x, y, c, n);
-  else gelu_fwd_kernel<false, false><<<grid, 256, 0, st>>>(x, y, c, n);
+  if (x_dtype == 1 && y_dtype == 1) launch_k(gelu_fwd_kernel<true, true>, dim3(grid), dim3(256), 0, st, 1, x, y, c, n);
+  else if (x_dtype == 1) launch_k(gelu_fwd_kernel<true, false>, dim3(grid), dim3(256), 0, st, 1, x, y, c, n);
+  else if (y_dtype == 1) launch_k(gelu_fwd_kernel<false, true>, dim3(grid), dim3(256), 0, st, 1, x, y, c, n);
+  else launch_k(gelu_fwd_kernel<false, false>, dim3(grid), dim3(256), 0, st, 1, x, y, c, n);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float* __restrict__ y32, __half* __restrict__ y16,
                                                         int64_t rows, int H, uint32_t thr, float inv_keep, uint64_t seed) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -638,7 +640,7 @@ int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float
   const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
   const int grid = int((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define W2V2_LN(F32, NV, EX) layernorm_kernel<F32, NV, EX><<<grid, 256, 0, st>>>(x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed)
+#define W2V2_LN(F32, NV, EX) launch_k(layernorm_kernel<F32, NV, EX>, dim3(grid), dim3(256), 0, st, 1, x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed)
   if (x_dtype == 1) {
     if (H == 512) W2V2_LN(true, 4, true); else if (H == 768) W2V2_LN(true, 6, true);
     else if (H == 1024) W2V2_LN(true, 8, true); else W2V2_LN(true, 8, false);

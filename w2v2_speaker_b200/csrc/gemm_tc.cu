@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_trigger();
   uint8_t* wstage = smem + STAGES * Cfg::STAGE_BYTES;
   float* sbias = reinterpret_cast<float*>(wstage + EPI_WARPS * WSTAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + Cfg::BIAS_BYTES);
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -499,6 +501,15 @@ int device_sm_count() {
   return sms;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("W2V2_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // W2V2_STREAMK=0 disables the stream-K schedule (A/B measurements, tools/time_ops.py)
 static bool sk_enabled() {
   static int v = -1;
@@ -542,24 +553,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
       q.sk_flags = flags + (slot++ % SK_RING) * SK_MAX_TILES;
     }
   }
-  if constexpr (CL == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid * 2);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    W2V2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
-  } else {
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(q);
-  }
+  W2V2_CHECK_CUDA(launch_k(kern, dim3(grid * CL), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, CL, q));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

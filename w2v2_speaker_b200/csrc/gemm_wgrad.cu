@@ -53,6 +53,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const 
 __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  pdl_trigger();
   uint8_t* wstage = smem + WG_STAGES * WG_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(wstage + WG_EPI_WARPS * WG_WSTAGE);
   uint64_t* empty_bar = full_bar + WG_STAGES;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // item -> (split, output row tile, output column tile); split fastest so the CTAs that run together
   // reduce into different addresses as little as possible... they do not: they share the tile, which is
@@ -265,7 +267,7 @@ extern "C" int w2v2_gemm_wgrad_f16(const void* dY, int64_t ldy, const void* X, i
   const int items = out_tiles * p.splits;
   const int grid = items < sms ? items : sms;
   const int slot = gemm_prof_begin(2.0 * double(M) * N * K, stream);
-  gemm_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(p);
+  W2V2_CHECK_CUDA(launch_k(gemm_wgrad_kernel, dim3(grid), dim3(WG_THREADS), WG_SMEM, stream, 1, p));
   gemm_prof_end(slot, stream);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());

@@ -18,6 +18,8 @@ static inline int rgrid(int64_t n, int per_block, int per_sm) {
 template <bool F32>
 __global__ void dropout_kernel(const void* __restrict__ x_, const float* __restrict__ bias, int H, void* __restrict__ y_,
                                __half* __restrict__ y16, int64_t n, uint32_t thr, float inv_keep, uint64_t seed) {
+  pdl_trigger();
+  pdl_wait();
   // two elements (one hash) per thread iteration; n % 2 == 0
   const DropKeys dkeys = drop_keys(seed);
   for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < n;
@@ -82,8 +84,8 @@ int w2v2_dropout(const void* x, int dtype, const float* bias, int H, void* y, vo
   const uint32_t thr = uint32_t(p * 65536.0f + 0.5f);
   const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
   const int grid = rgrid(n / 2, 256, 8);
-  if (dtype == 1) dropout_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
-  else dropout_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
+  if (dtype == 1) launch_k(dropout_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
+  else launch_k(dropout_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
