@@ -6,6 +6,8 @@
 
 Workload = configs[1] of BASELINE.json: wav2vec2-base + mean pool + Linear(768->5994) + CE on synthetic
 3 s utterances, 64 per GPU, driven through the public module API (w2v2_speaker_b200/speaker_module.py).
+--workload cfg2|cfg3|cfg4 selects the other BASELINE.json configurations (attentive pooling + AAM, mean+std +
+AAM, wav2vec2-large 5 s) for both arms; cfg1 stays the default the metric is quoted on.
 
   --mode train   (default) one step = forward + backward + gradient all-reduce (N > 1) + Adam update
                  (w2v2_speaker_b200/trainer.py); CNN feature extractor frozen and dropout 0.1 (feature
@@ -44,6 +46,21 @@ SAMPLES = 48000
 BATCH = 64
 DEFAULT_MODE = "train"
 
+# BASELINE.json configs[1..4]; cfg1 is the one the metric is quoted on (the default).  The others are selectable
+# with --workload so that every configuration has a measured line (profiles/).
+WORKLOADS = {
+    "cfg1": dict(hf_id="facebook/wav2vec2-base", arch="base", pooling="mean", loss="ce", samples=48000, batch=64,
+                 desc="cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU"),
+    "cfg2": dict(hf_id="facebook/wav2vec2-base", arch="base", pooling="attentive", loss="aam", samples=48000, batch=64,
+                 desc="cfg2: wav2vec2-base + attentive-stat-pool + AAM-softmax(m=0.2, s=30), 3 s@16 kHz, batch 64 per GPU"),
+    "cfg3": dict(hf_id="facebook/wav2vec2-base", arch="base", pooling="mean+std", loss="aam", samples=48000, batch=64,
+                 desc="cfg3: wav2vec2-base + mean+std pool (reference default) + AAM-softmax(m=0.2, s=30), 3 s@16 kHz, "
+                      "batch 64 per GPU (global batch 512 at 8 GPUs)"),
+    "cfg4": dict(hf_id="facebook/wav2vec2-large", arch="large", pooling="mean+std", loss="ce", samples=80000, batch=32,
+                 desc="cfg4: wav2vec2-large (24 layers) + mean+std pool + CE(5994), 5 s@16 kHz, batch 32 per GPU"),
+}
+WL = WORKLOADS["cfg1"]
+
 
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -51,12 +68,10 @@ def dist_env():
 
 def workload_name(mode: str, reg: bool = True) -> str:
     if mode == "train":
-        return ("cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, TRAIN step = forward + "
-                "backward + grad all-reduce + Adam; CNN frozen, " +
+        return (WL["desc"] + ", TRAIN step = forward + backward + grad all-reduce + Adam; CNN frozen, " +
                 ("dropout 0.1 / LayerDrop 0.05 / SpecAugment 0.05 on (reference defaults)" if reg else
                  "regularisation probabilities 0"))
-    return ("cfg1: wav2vec2-base + mean-pool + CE(5994), 3 s@16 kHz, batch 64 per GPU, eval forward "
-            "(embedding + logits + softmax/loss)")
+    return WL["desc"] + ", eval forward (embedding + logits + softmax/loss)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -118,22 +133,39 @@ class ClockSampler:
 
 def cpu_reference_step_fn(batch: int, mode: str):
     from oracle import w2v2_oracle as O
-    from oracle.params import BASE, make_head_params, make_inputs, make_params
-    p = make_params(BASE, seed=0)
-    hp = make_head_params(768, NUM_SPEAKERS, seed=1)
-    wav, labels = make_inputs(batch, SAMPLES, NUM_SPEAKERS, seed=1234)
-    if mode == "train":
+    from oracle import params as OP
+    arch = OP.LARGE if WL["arch"] == "large" else OP.BASE
+    p = OP.make_params(arch, seed=0)
+    E = arch.hidden * (1 if WL["pooling"] == "mean" else 2)
+    hp = OP.make_head_params(E, NUM_SPEAKERS, seed=1)
+    asp = OP.make_asp_params(arch.hidden, seed=2) if WL["pooling"] == "attentive" else None
+    wav, labels = OP.make_inputs(batch, WL["samples"], NUM_SPEAKERS, seed=1234)
+    train = mode == "train"
+
+    def embed():
+        h = O.wav2vec2_forward(wav, p, arch)
+        if WL["pooling"] == "attentive":
+            return O.attentive_stat_pool(h, asp, training=train)
+        return O.mean_pool(h) if WL["pooling"] == "mean" else O.mean_std_pool(h)
+
+    def head(emb):
+        if WL["loss"] == "aam":
+            return O.aam_softmax(emb, hp["aam.fc_weights"], labels, 0.2, 30.0)
+        return O.cross_entropy_head(emb, hp["fc.weight"], hp["fc.bias"], labels)
+
+    if train:
         O.TRAIN_REG = {"feat": 0.1, "hidden": 0.1, "attn": 0.1, "layerdrop": 0.05}     # reference defaults
-        train = [k for k in p if not k.startswith("feature_extractor") and k != "masked_spec_embed"]
-        for k in train:
-            p[k].requires_grad_(True)
-        fw, fb = hp["fc.weight"].requires_grad_(True), hp["fc.bias"].requires_grad_(True)
-        opt = torch.optim.Adam([p[k] for k in train] + [fw, fb], lr=1e-4)
+        tr = [p[k] for k in p if not k.startswith("feature_extractor") and k != "masked_spec_embed"]
+        tr += [hp["aam.fc_weights"]] if WL["loss"] == "aam" else [hp["fc.weight"], hp["fc.bias"]]
+        if asp is not None:
+            tr += [v for k, v in asp.items() if "running" not in k]
+        for t in tr:
+            t.requires_grad_(True)
+        opt = torch.optim.Adam(tr, lr=1e-4)
 
         def step():
             opt.zero_grad()
-            emb = O.speaker_embedding(wav, p, "mean")
-            logits, loss, sm = O.cross_entropy_head(emb, fw, fb, labels)
+            _, loss, _ = head(embed())
             loss.backward()
             opt.step()
             return float(loss)
@@ -143,8 +175,7 @@ def cpu_reference_step_fn(batch: int, mode: str):
 
     def step():
         with torch.no_grad():
-            emb = O.speaker_embedding(wav, p, "mean")
-            logits, loss, sm = O.cross_entropy_head(emb, hp["fc.weight"], hp["fc.bias"], labels)
+            _, loss, _ = head(embed())
         return float(loss)
     return step
 
@@ -209,14 +240,15 @@ def run_reference_arm(args):
 
 
 def build_module(device, train: bool, reg: bool = True):
-    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
     from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
     torch.manual_seed(0)
     kw = dict(activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
               mask_time_prob=0.0, mask_feature_prob=0.0) if (train and not reg) else {}
-    cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id="facebook/wav2vec2-base", stat_pooling_type="mean",
-                                 test_stat_pooling_type="mean", **kw)
-    m = Wav2vec2FCModule(cfg, NUM_SPEAKERS, CrossEntropyLoss).to(device)
+    cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id=WL["hf_id"], stat_pooling_type=WL["pooling"],
+                                 test_stat_pooling_type=WL["pooling"], **kw)
+    loss = CrossEntropyLoss if WL["loss"] == "ce" else (lambda: AngularAdditiveMarginSoftMaxLoss(1, 1, margin=0.2, scale=30))
+    m = Wav2vec2FCModule(cfg, NUM_SPEAKERS, loss).to(device)
     if train:
         m.train()
         m.wav2vec.model.feature_extractor.requires_grad_(False)       # R:.../wav2vec2_fc.py:346-347
@@ -263,10 +295,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=DEFAULT_MODE, choices=["train", "forward"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration (cfg1 = the one the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reg", action="store_true", help="train mode without dropout / LayerDrop / SpecAugment")
     args = ap.parse_args()
+    global WL
+    WL = WORKLOADS[args.workload]
+    if args.batch is None:
+        args.batch = WL["batch"]
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -292,7 +330,7 @@ def main():
     if train:
         from w2v2_speaker_b200.trainer import FlatAdamTrainer
         trainer = FlatAdamTrainer(module, lr=1e-4)
-    wav_cpu, labels_cpu = make_inputs(B, SAMPLES, NUM_SPEAKERS, seed=1234 + rank)
+    wav_cpu, labels_cpu = make_inputs(B, WL["samples"], NUM_SPEAKERS, seed=1234 + rank)
     wav_pin = wav_cpu[:, None, :].contiguous().pin_memory()          # [B,1,N] as the reference batches
     labels_pin = labels_cpu.pin_memory()
     wav_dev = wav_pin.to(dev)
@@ -310,7 +348,8 @@ def main():
     def step_device():
         return run(wav_dev, labels_dev)
 
-    emb_host = torch.empty(B, 768, dtype=torch.float32).pin_memory()
+    emb_dim = (1024 if WL["arch"] == "large" else 768) * (1 if WL["pooling"] == "mean" else 2)
+    emb_host = torch.empty(B, emb_dim, dtype=torch.float32).pin_memory()
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     arg_host = torch.empty(B, dtype=torch.int64).pin_memory()
 
@@ -376,11 +415,16 @@ def main():
             fl = t["gemm_flops"]
             ach = fl / (g_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel + gemm_wgrad_kernel (tcgen05), all launches of one step",
-                    "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak, "traffic": None,
+                    "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the largest single instance (FFN2: M=9536, N=768,
+                    # K=3072, f32 out; algorithmic 92.6 MB, part of the output still sits in L2 when the kernel ends),
+                    # ncu --set full capture in profiles/r01_e_gemm_pair_full.txt
+                    "traffic": 76.79e6 if WL is WORKLOADS["cfg1"] else None,
+                    "traffic_note": "bytes per launch of the FFN2 GEMM instance (profiles/r01_e_gemm_pair_full.txt)",
                     "peak_source": peak_src, "launches": t["gemm_launches"], "ms_per_step": g_ms, "tflop_per_step": fl / 1e12}
         roof_hbm = None
         if t["conv0"]:
-            c0_bytes = B * (SAMPLES * 4 * 2 + 9599 * 512 * 2)
+            c0_bytes = B * (WL["samples"] * 4 * 2 + ((WL["samples"] - 10) // 5 + 1) * 512 * 2)
             c_ms = sum(t["conv0"])
             ach = c0_bytes / (c_ms * 1e-3) / 1e9
             roof_hbm = {"bound": "hbm", "kernel": "conv0+GroupNorm+GELU stage (moments, stats, im2col, tensor-core GEMM "
@@ -402,8 +446,8 @@ def main():
                                                        " (independent utterances, no collective)"),
                        "l2": "per-step working set (> 1.5 GB activations + 0.19 GB fp16 weights) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": B * SAMPLES * 4 + B * 8,
-                    "d2h_bytes_per_step": (0 if train else B * 768 * 4) + 4 + B * 8},
+                    "h2d_bytes_per_step": B * WL["samples"] * 4 + B * 8,
+                    "d2h_bytes_per_step": (0 if train else B * emb_dim * 4) + 4 + B * 8},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
             "cpu_baseline": cpu,
         }
