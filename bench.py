@@ -60,6 +60,7 @@ WORKLOADS = {
                  desc="cfg4: wav2vec2-large (24 layers) + mean+std pool + CE(5994), 5 s@16 kHz, batch 32 per GPU"),
 }
 WL = WORKLOADS["cfg1"]
+TRAIN_CNN = False
 
 
 def dist_env():
@@ -68,7 +69,8 @@ def dist_env():
 
 def workload_name(mode: str, reg: bool = True) -> str:
     if mode == "train":
-        return (WL["desc"] + ", TRAIN step = forward + backward + grad all-reduce + Adam; CNN frozen, " +
+        return (WL["desc"] + ", TRAIN step = forward + backward + grad all-reduce + Adam; " +
+                ("CNN UNFROZEN, " if TRAIN_CNN else "CNN frozen, ") +
                 ("dropout 0.1 / LayerDrop 0.05 / SpecAugment 0.05 on (reference defaults)" if reg else
                  "regularisation probabilities 0"))
     return WL["desc"] + ", eval forward (embedding + logits + softmax/loss)"
@@ -239,7 +241,7 @@ def run_reference_arm(args):
 # our arm
 
 
-def build_module(device, train: bool, reg: bool = True):
+def build_module(device, train: bool, reg: bool = True, train_cnn: bool = False):
     from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
     from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
     torch.manual_seed(0)
@@ -251,7 +253,7 @@ def build_module(device, train: bool, reg: bool = True):
     m = Wav2vec2FCModule(cfg, NUM_SPEAKERS, loss).to(device)
     if train:
         m.train()
-        m.wav2vec.model.feature_extractor.requires_grad_(False)       # R:.../wav2vec2_fc.py:346-347
+        m.wav2vec.model.feature_extractor.requires_grad_(train_cnn)   # R:.../wav2vec2_fc.py:346-347 (default: frozen)
     else:
         m.eval()
     return m
@@ -300,9 +302,12 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reg", action="store_true", help="train mode without dropout / LayerDrop / SpecAugment")
+    ap.add_argument("--train-cnn", action="store_true",
+                    help="train mode with the CNN feature extractor unfrozen (completely_freeze_feature_extractor: false)")
     args = ap.parse_args()
-    global WL
+    global WL, TRAIN_CNN
     WL = WORKLOADS[args.workload]
+    TRAIN_CNN = bool(args.train_cnn)
     if args.batch is None:
         args.batch = WL["batch"]
     if args.impl == "reference":
@@ -325,7 +330,7 @@ def main():
     B = args.batch
     K, W = args.steps, max(3, args.warmup)
     train = args.mode == "train"
-    module = build_module(dev, train, not args.no_reg)
+    module = build_module(dev, train, not args.no_reg, args.train_cnn)
     trainer = None
     if train:
         from w2v2_speaker_b200.trainer import FlatAdamTrainer

@@ -359,6 +359,30 @@ int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* args, void* stream);
 int w2v2_gemm_profile_start(void);
 int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int* launches);
 
+/* ---- backward of the CNN feature extractor (HF:254-323; the reference trains it when
+ * completely_freeze_feature_extractor is false) ------------------------------------------------------------
+ * w2v2_conv0_gn_ex: w2v2_conv0_gn_gelu with the GELU optional (act 0: the GroupNorm output, which the
+ *   training forward keeps as the pre-activation); w2v2_conv0_workspace_offsets: where the per-(b, c) affine
+ *   (scale = gamma * rstd, shift) and the error-compensated im2col operand ([B*L0, 64] f16, columns
+ *   [x_hi(10) | x_lo(10) | x_hi(10) | 0]) live inside that workspace -- the backward reads both.
+ * w2v2_gemm_f16_taps: tap-GEMM whose taps are ROW offsets into one activation (may be negative; rows outside
+ *   [0, a_extent) read as zero): out[b, r, n] = sum_t sum_c A[b, r + tap_row[t], c] W[n, t*cin + c].  The data
+ *   gradient of a stride-2 Conv1d is two of these (even / odd input rows), written through ldo = 2 * Cin.
+ * w2v2_gemm_wgrad_f16_batched: dW[n, k] += sum_b sum_{r<rows} dY[b][r, n] X[b][r, k] with independent row
+ *   pitches / batch strides (X = every stride-th input frame of one tap).
+ * w2v2_groupnorm_bwd: per-(b, c) GroupNorm backward over time of conv layer 0 (see csrc/backward_cnn.cu). */
+int w2v2_conv0_gn_ex(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
+                     void* workspace, void* out_f16, int C, int act, void* stream);
+int w2v2_conv0_workspace_offsets(int B, int N, int C, int64_t* scale_off, int64_t* shift_off, int64_t* im2col_off);
+int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
+                       int64_t a_batch_stride, int batch, int ntaps, int cin, const void* W, int64_t ldw, int N, void* out,
+                       int out_dtype, int64_t ldo, int64_t out_batch_stride, void* stream);
+int w2v2_gemm_wgrad_f16_batched(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* X, int64_t ldx,
+                                int64_t x_batch_stride, int64_t rows, int batch, int N, int K, float* dW, int64_t ldw,
+                                void* stream);
+int w2v2_groupnorm_bwd(const void* dy16, const void* y16, const float* gamma, const float* beta, const float* scale,
+                       void* dc16, float* dgamma, float* dbeta, float grad_scale, int B, int L, int C, void* stream);
+
 /* ---- utility ---------------------------------------------------------------------------------- */
 /* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */
 int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream);

@@ -17,6 +17,15 @@ LIB_PATH = os.path.join(_HERE, "libw2v2_b200.so")
 # name -> (restype, argtypes); must list every symbol declared in include/w2v2_b200.h
 SIGNATURES = {
     "w2v2_last_error": (c_char_p, []),
+    "w2v2_conv0_gn_ex": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                                 c_int, c_void_p]),
+    "w2v2_conv0_workspace_offsets": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "w2v2_gemm_f16_taps": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
+                                   c_int64, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "w2v2_gemm_wgrad_f16_batched": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int,
+                                            c_int, c_void_p, c_int64, c_void_p]),
+    "w2v2_groupnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                   c_int, c_int, c_int, c_void_p]),
     "w2v2_gemm_profile_start": (c_int, []),
     "w2v2_gemm_profile_stop": (c_int, [c_void_p, c_void_p, c_void_p]),
     "w2v2_encoder_layer_fwd": (c_int, [c_void_p, c_void_p]),

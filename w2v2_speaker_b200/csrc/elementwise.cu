@@ -596,9 +596,24 @@ static Conv0Ws conv0_ws(int B, int N, int C) {
 
 int64_t w2v2_conv0_workspace_bytes(int B, int N, int C) { return N >= C0_K ? conv0_ws(B, N, C).total : 0; }
 
+int w2v2_conv0_workspace_offsets(int B, int N, int C, int64_t* scale_off, int64_t* shift_off, int64_t* im2col_off) {
+  W2V2_REQUIRE(N >= C0_K, "w2v2_conv0_workspace_offsets: N=%d too short", N);
+  const Conv0Ws ws = conv0_ws(B, N, C);
+  if (scale_off) *scale_off = ws.scale;
+  if (shift_off) *shift_off = ws.shift;
+  if (im2col_off) *im2col_off = ws.a;
+  return 0;
+}
+
 int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
                        void* workspace, void* out_f16, int C, void* stream_) {
+  return w2v2_conv0_gn_ex(wav, B, N, w, gamma, beta, eps, workspace, out_f16, C, 1, stream_);
+}
+
+int w2v2_conv0_gn_ex(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
+                     void* workspace, void* out_f16, int C, int act, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  W2V2_REQUIRE(act == 0 || act == 1, "w2v2_conv0_gn_ex: act must be 0 (GroupNorm output) or 1 (+ GELU)");
   W2V2_REQUIRE(B > 0 && N >= C0_K, "w2v2_conv0_gn_gelu: need B>0 and N>=10 (got B=%d N=%d)", B, N);
   W2V2_REQUIRE(C > 128 && C % 8 == 0, "w2v2_conv0_gn_gelu: C=%d must be a multiple of 8 and > 128", C);
   W2V2_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "w2v2_conv0_gn_gelu: workspace must be 256-byte aligned");
@@ -621,7 +636,7 @@ int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const flo
   count_launches(4);
   W2V2_CHECK_CUDA(cudaGetLastError());
   // y = GELU(conv * scale[b,c] + shift[b,c]) on the tensor cores, fp16 channels-last out
-  return gemm_f16_impl(a16, L, C0_KP, int64_t(L) * C0_KP, B, 1, 0, C0_KP, w16, C0_KP, C, scale, shift, 1, out_f16, 0, C,
+  return gemm_f16_impl(a16, L, C0_KP, int64_t(L) * C0_KP, B, 1, 0, C0_KP, w16, C0_KP, C, scale, shift, act, out_f16, 0, C,
                        int64_t(L) * C, stream);
 }
 

@@ -45,6 +45,7 @@ struct alignas(64) GemmParams {
   const float* bias;             // EPI 1: [N];  EPI 2: per-(batch, column) scale [batch, N]
   const float* shift;            // EPI 2: per-(batch, column) shift [batch, N]
   int ntaps, kblocks_per_tap;
+  int tap_row[3];                // row-coordinate offset of each tap (may be negative: rows before the first are zero-filled)
   int m_tiles, n_tiles, batch;
   int N;
   long long rows;                // valid rows per batch element
@@ -217,11 +218,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             // both CTAs load their halves; the bytes of both are counted on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            tma_load_3d_2sm(sa, &p.tmA[tap], lead_bar, kb * BK, (mt * 2 + cta_rank) * BM, b);
+            tma_load_3d_2sm(sa, &p.tmA[tap], lead_bar, kb * BK, (mt * 2 + cta_rank) * BM + p.tap_row[tap], b);
             tma_load_3d_2sm(sb, &p.tmB, lead_bar, (tap * p.kblocks_per_tap + kb) * BK, nt * BN + cta_rank * (BN / 2), 0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_3d(sa, &p.tmA[tap], &full_bar[stage], kb * BK, mt * BM, b);
+            tma_load_3d(sa, &p.tmA[tap], &full_bar[stage], kb * BK, mt * BM + p.tap_row[tap], b);
             tma_load_3d(sb, &p.tmB, &full_bar[stage], (tap * p.kblocks_per_tap + kb) * BK, nt * BN, 0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -563,7 +564,9 @@ template <int BN, bool OUT_F32, int CL>
 static int dispatch_epilogue(const GemmParams& p, int act, cudaStream_t stream) {
   const int epi = p.shift != nullptr ? 2 : (p.bias != nullptr ? 1 : 0);
   if (epi == 2) {
-    if constexpr (!OUT_F32 && BN == 256) return launch_gemm<256, false, 1, 2, CL>(p, stream);   // conv0: GN affine + GELU -> f16
+    if constexpr (!OUT_F32 && BN == 256) {      // conv0: GN affine (+ GELU) -> f16
+      return act == 1 ? launch_gemm<256, false, 1, 2, CL>(p, stream) : launch_gemm<256, false, 0, 2, CL>(p, stream);
+    }
     set_last_error("w2v2 gemm: the per-batch affine epilogue is built for f16 output, N > 128");
     return -1;
   }
@@ -594,10 +597,25 @@ void gemm_prof_end(int slot, cudaStream_t stream) {
   if (slot >= 0) cudaEventRecord(g_prof[slot].e, stream);
 }
 
+int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
+                   int64_t a_batch_stride, int batch, int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw,
+                   int N, const float* bias, const float* shift, int act, void* out, int out_dtype, int64_t ldo,
+                   int64_t out_batch_stride, cudaStream_t stream);
+
 int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch, int ntaps,
                   int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N, const float* bias,
                   const float* shift, int act, void* out, int out_dtype, int64_t ldo, int64_t out_batch_stride,
                   cudaStream_t stream) {
+  return gemm_f16_impl2(A, a_rows, a_rows, nullptr, a_row_stride, a_batch_stride, batch, ntaps, a_tap_stride, cin, W, ldw, N,
+                        bias, shift, act, out, out_dtype, ldo, out_batch_stride, stream);
+}
+
+// a_rows: output rows per batch element; a_extent: rows of A that exist per batch element (rows outside
+// [0, a_extent) read as zero); tap_row[t]: row offset of tap t relative to the output row (nullptr = 0).
+int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
+                   int64_t a_batch_stride, int batch, int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw,
+                   int N, const float* bias, const float* shift, int act, void* out, int out_dtype, int64_t ldo,
+                   int64_t out_batch_stride, cudaStream_t stream) {
   W2V2_REQUIRE(ntaps >= 1 && ntaps <= 3, "w2v2_gemm_f16: ntaps=%d not in [1,3]", ntaps);
   W2V2_REQUIRE(cin % BK == 0, "w2v2_gemm_f16: cin=%d must be a multiple of %d", cin, BK);
   W2V2_REQUIRE(out_dtype == 0 || out_dtype == 1, "w2v2_gemm_f16: out_dtype must be 0 (f16) or 1 (f32)");
@@ -608,11 +626,12 @@ int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
   const int BN = (N <= 128) ? 128 : 256;
   const int CL = (BN == 256 && pair_enabled()) ? 2 : 1;         // CTA pairs for every wide GEMM
   const int osz = out_dtype == 1 ? 4 : 2;
-  const uint64_t a_bstride = batch > 1 ? uint64_t(a_batch_stride) * 2 : uint64_t(a_rows) * uint64_t(a_row_stride) * 2;
+  const uint64_t a_bstride = batch > 1 ? uint64_t(a_batch_stride) * 2 : uint64_t(a_extent) * uint64_t(a_row_stride) * 2;
   for (int t = 0; t < ntaps; ++t) {
     const __half* base = static_cast<const __half*>(A) + t * a_tap_stride;
-    int rc = make_tmap_3d(&p.tmA[t], base, 2, cin, a_rows, batch, uint64_t(a_row_stride) * 2, a_bstride, BK, BM, 1, 128);
+    int rc = make_tmap_3d(&p.tmA[t], base, 2, cin, a_extent, batch, uint64_t(a_row_stride) * 2, a_bstride, BK, BM, 1, 128);
     if (rc) return rc;
+    p.tap_row[t] = tap_row != nullptr ? tap_row[t] : 0;
   }
   int rc = make_tmap_3d(&p.tmB, W, 2, uint64_t(ntaps) * cin, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, BN / CL, 1, 128);
   if (rc) return rc;
@@ -666,6 +685,14 @@ extern "C" int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int
   if (launches) *launches = g_prof_n;
   g_prof_n = 0;
   return 0;
+}
+
+extern "C" int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
+                                  int64_t a_batch_stride, int batch, int ntaps, int cin, const void* W, int64_t ldw, int N,
+                                  void* out, int out_dtype, int64_t ldo, int64_t out_batch_stride, void* stream_) {
+  W2V2_REQUIRE(tap_row != nullptr, "w2v2_gemm_f16_taps: tap_row is required");
+  return gemm_f16_impl2(A, out_rows, a_extent, tap_row, a_row_stride, a_batch_stride, batch, ntaps, 0, cin, W, ldw, N, nullptr,
+                        nullptr, 0, out, out_dtype, ldo, out_batch_stride, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,

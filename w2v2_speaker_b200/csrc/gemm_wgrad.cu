@@ -40,6 +40,7 @@ struct alignas(64) WgradParams {
   CUtensorMap tmOut;    // dW [N, K] f32: dims {K, N, 1}, box {32, 32, 1}
   int n_tiles, k_tiles, splits;
   int kblocks, kblocks_per_split;
+  int kb_per_batch;     // contraction blocks per batch element (rows of one element never share a block with the next)
   int N, K;
 };
 
@@ -115,9 +116,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_kernel(const __grid_
           uint8_t* sb = sa + WG_A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
 #pragma unroll
-          for (int i = 0; i < WG_BM / 64; ++i) tma_load_3d(sa + i * 8192, &p.tmA, &full_bar[stage], nt * WG_BM + i * 64, kb * WG_BK, 0);
+          const int bi = kb / p.kb_per_batch, r0 = (kb - bi * p.kb_per_batch) * WG_BK;
 #pragma unroll
-          for (int i = 0; i < WG_BN / 64; ++i) tma_load_3d(sb + i * 8192, &p.tmB, &full_bar[stage], kt * WG_BN + i * 64, kb * WG_BK, 0);
+          for (int i = 0; i < WG_BM / 64; ++i) tma_load_3d(sa + i * 8192, &p.tmA, &full_bar[stage], nt * WG_BM + i * 64, r0, bi);
+#pragma unroll
+          for (int i = 0; i < WG_BN / 64; ++i) tma_load_3d(sb + i * 8192, &p.tmB, &full_bar[stage], kt * WG_BN + i * 64, r0, bi);
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -221,21 +224,39 @@ void gemm_prof_end(int slot, cudaStream_t stream);
 
 using namespace w2v2;
 
+static int wgrad_impl(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* X, int64_t ldx, int64_t x_batch_stride,
+                      int64_t rows, int batch, int N, int K, float* dW, int64_t ldw, cudaStream_t stream);
+
 extern "C" int w2v2_gemm_wgrad_f16(const void* dY, int64_t ldy, const void* X, int64_t ldx, int64_t M, int N, int K,
                                    float* dW, int64_t ldw, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  W2V2_REQUIRE(M > 0 && N > 0 && K > 0, "w2v2_gemm_wgrad_f16: empty problem");
+  return wgrad_impl(dY, ldy, M * ldy, X, ldx, M * ldx, M, 1, N, K, dW, ldw, static_cast<cudaStream_t>(stream_));
+}
+
+// Batched contraction: dW[n, k] += sum_b sum_{r < rows} dY[b][r, n] * X[b][r, k], each operand with its own row pitch and
+// batch stride (strided Conv1d weight gradient: X rows are every `stride`-th input frame of one tap).
+extern "C" int w2v2_gemm_wgrad_f16_batched(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* X, int64_t ldx,
+                                           int64_t x_batch_stride, int64_t rows, int batch, int N, int K, float* dW,
+                                           int64_t ldw, void* stream_) {
+  return wgrad_impl(dY, ldy, dy_batch_stride, X, ldx, x_batch_stride, rows, batch, N, K, dW, ldw,
+                    static_cast<cudaStream_t>(stream_));
+}
+
+static int wgrad_impl(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* X, int64_t ldx, int64_t x_batch_stride,
+                      int64_t rows, int batch, int N, int K, float* dW, int64_t ldw, cudaStream_t stream) {
+  const int64_t M = rows * batch;
+  W2V2_REQUIRE(rows > 0 && batch > 0 && N > 0 && K > 0, "w2v2_gemm_wgrad_f16: empty problem");
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  int rc = make_tmap_3d(&p.tmA, dY, 2, N, M, 1, uint64_t(ldy) * 2, uint64_t(M) * ldy * 2, 64, WG_BK, 1, 128);
+  int rc = make_tmap_3d(&p.tmA, dY, 2, N, rows, batch, uint64_t(ldy) * 2, uint64_t(dy_batch_stride) * 2, 64, WG_BK, 1, 128);
   if (rc) return rc;
-  rc = make_tmap_3d(&p.tmB, X, 2, K, M, 1, uint64_t(ldx) * 2, uint64_t(M) * ldx * 2, 64, WG_BK, 1, 128);
+  rc = make_tmap_3d(&p.tmB, X, 2, K, rows, batch, uint64_t(ldx) * 2, uint64_t(x_batch_stride) * 2, 64, WG_BK, 1, 128);
   if (rc) return rc;
   rc = make_tmap_3d(&p.tmOut, dW, 4, K, N, 1, uint64_t(ldw) * 4, uint64_t(N) * ldw * 4, 32, 32, 1, 128);
   if (rc) return rc;
   p.n_tiles = (N + WG_BM - 1) / WG_BM;
   p.k_tiles = (K + WG_BN - 1) / WG_BN;
-  p.kblocks = int((M + WG_BK - 1) / WG_BK);
+  p.kb_per_batch = int((rows + WG_BK - 1) / WG_BK);
+  p.kblocks = p.kb_per_batch * batch;
   const int out_tiles = p.n_tiles * p.k_tiles;
   const int sms = device_sm_count();
   // Split the contraction: pick the split count that minimises (waves of work items) x (k-blocks per item

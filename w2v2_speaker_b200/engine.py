@@ -127,6 +127,10 @@ class PreparedWeights:
         self.gn_b = f("feature_extractor.conv_layers.0.layer_norm.bias")
         self.conv_w = [None] + [ops.conv_weight_tapmajor(f(f"feature_extractor.conv_layers.{i}.conv.weight"))
                                 for i in range(1, len(arch.conv_kernel))]
+        # trainable feature extractor: remember the live fp32 sources so update() can re-derive conv_w
+        # (conv0_w / gn_g / gn_b alias the parameters and follow them without a copy)
+        names = [f"feature_extractor.conv_layers.{i}.conv.weight" for i in range(1, len(arch.conv_kernel))]
+        self._cnn_sources = ([None] + [f(n) for n in names]) if any(p[n].requires_grad for n in names) else None
         self.fp_ln_g = f("feature_projection.layer_norm.weight")
         self.fp_ln_b = f("feature_projection.layer_norm.bias")
         self.fp_b = f("feature_projection.projection.bias")
@@ -181,6 +185,10 @@ class PreparedWeights:
             return False
         self.prep.run()
         self._pos_w.clear()
+        if self._cnn_sources is not None:      # unfrozen feature extractor: its tap-major fp16 weights change too
+            for i, src in enumerate(self._cnn_sources):
+                if src is not None:
+                    self.conv_w[i] = ops.conv_weight_tapmajor(src)
         return True
 
 

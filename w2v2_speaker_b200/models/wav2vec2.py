@@ -200,11 +200,6 @@ class Wav2Vec2ModelB200(nn.Module):
             raise NotImplementedError(
                 "train-mode regularisation is implemented on the training path only: enable gradients, or call "
                 ".eval() for inference")
-        if self._needs_grad() and any(p.requires_grad for p in self._items()[3]):
-            raise NotImplementedError(
-                "the backward of the CNN feature extractor is not implemented yet: freeze it with "
-                "model.feature_extractor.requires_grad_(False) (the reference default, "
-                "completely_freeze_feature_extractor: true)")
 
     def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, **_):
         """HF:1327-1383.  input_values f32 [B,N].  With gradients enabled the forward keeps what the

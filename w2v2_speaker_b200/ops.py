@@ -476,3 +476,61 @@ def asp_front_bwd_(x: torch.Tensor, dcat: torch.Tensor, dx: torch.Tensor) -> tor
     assert dcat.stride(1) == 1 and dcat.shape == (B * T, 3 * C)
     call("w2v2_asp_front_bwd", ptr(x), ptr(dcat), dcat.stride(0), ptr(dx), B, T, C, stream_ptr())
     return dx
+
+
+# ---- CNN feature extractor, training ---------------------------------------------------------------
+
+
+def conv0_gn(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, act: int):
+    """conv layer 0 + GroupNorm (+ GELU if act) -> (f16 channels-last [B, L0, C], workspace tensor, (scale, im2col) views).
+    The workspace keeps the per-(b, c) affine and the im2col operand the backward needs."""
+    import ctypes
+    _chk(wav, F32, "wav")
+    B, N = wav.shape
+    C = w.shape[0]
+    L0 = (N - 10) // 5 + 1
+    lib = _lib.load()
+    ws = torch.empty(lib.w2v2_conv0_workspace_bytes(B, N, C), dtype=torch.uint8, device=wav.device)
+    out = torch.empty(B, L0, C, dtype=F16, device=wav.device)
+    call("w2v2_conv0_gn_ex", ptr(wav.contiguous()), B, N, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps, ptr(ws), ptr(out), C,
+         int(act), stream_ptr())
+    so, sho, ao = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    call("w2v2_conv0_workspace_offsets", B, N, C, ctypes.byref(so), ctypes.byref(sho), ctypes.byref(ao))
+    scale = ws[so.value:so.value + B * C * 4].view(F32).view(B, C)
+    im2col = ws[ao.value:ao.value + B * L0 * 64 * 2].view(F16).view(B, L0, 64)
+    return out, ws, scale, im2col
+
+
+def gemm_f16_taps(a16: torch.Tensor, tap_rows, w16: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[b, r, :] = sum_t a16[b, r + tap_rows[t], :] @ w16[:, t*C:(t+1)*C]^T  (rows outside a16 read as zero).
+    a16 f16 [B, L, C] contiguous; w16 f16 [N, ntaps*C]; out [B, R, N] with stride(2) == 1 (rows may be strided)."""
+    import ctypes
+    _chk(a16, F16, "a16"); _chk(w16, F16, "w16")
+    B, L, C = a16.shape
+    assert a16.is_contiguous() and out.stride(2) == 1 and out.shape[0] == B
+    nt = len(tap_rows)
+    N = w16.shape[0]
+    assert w16.shape[1] == nt * C and out.shape[2] == N
+    taps = (ctypes.c_int * 3)(*(list(tap_rows) + [0] * (3 - nt)))
+    call("w2v2_gemm_f16_taps", ptr(a16), out.shape[1], L, taps, C, L * C, B, nt, C, ptr(w16), w16.stride(0), N, ptr(out),
+         1 if out.dtype == F32 else 0, out.stride(1), out.stride(0), stream_ptr())
+    return out
+
+
+def gemm_wgrad_f16_batched(dy16: torch.Tensor, x16: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+    """dw[N, K] (f32, accumulated) += sum_b dy16[b]^T @ x16[b];  dy16 [B, R, N], x16 [B, R, K] (any row / batch strides)."""
+    _chk(dy16, F16, "dy16"); _chk(x16, F16, "x16"); _chk(dw, F32, "dw")
+    B, R, N = dy16.shape
+    K = x16.shape[2]
+    assert x16.shape[:2] == (B, R) and dy16.stride(2) == 1 and x16.stride(2) == 1 and dw.shape == (N, K) and dw.stride(1) == 1
+    call("w2v2_gemm_wgrad_f16_batched", ptr(dy16), dy16.stride(1), dy16.stride(0), ptr(x16), x16.stride(1), x16.stride(0), R, B,
+         N, K, ptr(dw), dw.stride(0), stream_ptr())
+    return dw
+
+
+def groupnorm_bwd(dy16, y16, gamma, beta, scale, dgamma, dbeta, grad_scale: float) -> torch.Tensor:
+    B, L, C = y16.shape
+    dc = torch.empty(B, L, C, dtype=F16, device=y16.device)
+    call("w2v2_groupnorm_bwd", ptr(dy16), ptr(y16), ptr(gamma), ptr(beta), ptr(scale), ptr(dc), ptr(dgamma), ptr(dbeta),
+         float(grad_scale), B, L, C, stream_ptr())
+    return dc

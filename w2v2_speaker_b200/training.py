@@ -111,15 +111,95 @@ def compute_time_mask(B: int, T: int, mask_prob: float, mask_length: int, min_ma
     return mask.reshape(-1)
 
 
+def cnn_forward_train(eng: EncoderEngine, wav: torch.Tensor):
+    """Feature extractor (HF:409-419) keeping what its backward needs: the pre-GELU activation of every layer
+    (the GELUs run as separate passes) and the GroupNorm affine / im2col operand of layer 0.
+    -> (features f32 [B, T, C], saved)."""
+    a, w = eng.arch, eng.w
+    y0, ws, scale, im2col = ops.conv0_gn(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps, act=0)      # GroupNorm output, f16
+    h, _ = ops.gelu_fwd(y0, F16)
+    saved = dict(ws=ws, scale=scale, im2col=im2col, zs=[y0], outs=[h])
+    n = len(a.conv_kernel)
+    for i in range(1, n):
+        last = i == n - 1
+        z = ops.conv1d_cl_f16(h, w.conv_w[i], a.conv_kernel[i], a.conv_stride[i], act=0, out_dtype=F32 if last else F16)
+        if last:
+            h, z16 = ops.gelu_fwd(z, F32, want_x16=True)          # f32 features (they feed a LayerNorm), f16 copy of z
+        else:
+            h, z16 = ops.gelu_fwd(z, F16)[0], z
+        saved["zs"].append(z16)
+        saved["outs"].append(h)
+    return h, saved
+
+
+def cnn_dgrad_weights(params: Dict[str, torch.Tensor], arch: ArchConfig):
+    """fp16 operands of the data-gradient tap-GEMMs of conv layers 1..6 (stride 2): for the even input rows
+    [W_0^T | W_2^T] (k = 3) or W_0^T (k = 2), for the odd rows W_1^T; W_j = weight[:, :, j] ([Cout, Cin]).
+    A re-layout of 6 x 0.8 M parameters per optimizer step (torch indexing: plumbing, no arithmetic)."""
+    out = [None]
+    for i in range(1, len(arch.conv_kernel)):
+        wt = params[f"feature_extractor.conv_layers.{i}.conv.weight"].detach()      # [Cout, Cin, k]
+        k = arch.conv_kernel[i]
+        assert arch.conv_stride[i] == 2 and k in (2, 3), "data gradient built for the stride-2, k in {2, 3} layers"
+        t = [wt[:, :, j].t() for j in range(k)]                                      # [Cin, Cout] each
+        even = torch.cat([t[0], t[2]], dim=1) if k == 3 else t[0]
+        out.append((even.contiguous().to(F16), t[1].contiguous().to(F16)))
+    return out
+
+
+def cnn_backward(eng: EncoderEngine, params: Dict[str, torch.Tensor], S: dict, dfeat: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """dfeat: f32 [B, T, C] gradient of the extracted features (carrying LOSS_SCALE).  Returns the UNSCALED
+    gradients of the feature-extractor parameters under their HF names."""
+    a, w = eng.arch, eng.w
+    C = a.conv_dim
+    dev = dfeat.device
+    inv_ls = 1.0 / LOSS_SCALE
+    grads: Dict[str, torch.Tensor] = {}
+    wd = cnn_dgrad_weights(params, a)
+    d = ops.cast_f16(dfeat.contiguous())                                            # d out_6
+    B = d.shape[0]
+    for i in reversed(range(1, len(a.conv_kernel))):
+        k, s = a.conv_kernel[i], a.conv_stride[i]
+        dz = ops.gelu_bwd(d, S["zs"][i])                                            # [B, Lout, C]
+        x_in = S["outs"][i - 1]                                                     # [B, Lin, C] f16
+        Lin, Lout = x_in.shape[1], dz.shape[1]
+        # weight gradient, tap by tap, into the tap-major [Cout, k*Cin] layout
+        dwt = torch.zeros(C, k * C, dtype=F32, device=dev)
+        for j in range(k):
+            ops.gemm_wgrad_f16_batched(dz, x_in[:, j:j + s * (Lout - 1) + 1:s, :], dwt[:, j * C:(j + 1) * C])
+        ops.scale_f32_(dwt, inv_ls)
+        grads[f"feature_extractor.conv_layers.{i}.conv.weight"] = dwt.view(C, k, C).permute(0, 2, 1).contiguous()
+        # data gradient: input row u receives dz[(u - j) / 2] W_j for every tap j of u's parity
+        d_in = torch.empty(B, Lin, C, dtype=F16, device=dev)
+        ops.gemm_f16_taps(dz, [0, -1] if k == 3 else [0], wd[i][0], d_in[:, 0::2, :])
+        ops.gemm_f16_taps(dz, [0], wd[i][1], d_in[:, 1::2, :])
+        d = d_in
+    # layer 0: GELU, GroupNorm, conv (no data gradient: the input is the waveform)
+    dy = ops.gelu_bwd(d, S["zs"][0])
+    dgam = torch.zeros(C, dtype=F32, device=dev)
+    dbet = torch.zeros(C, dtype=F32, device=dev)
+    dc = ops.groupnorm_bwd(dy, S["zs"][0], w.gn_g, w.gn_b, S["scale"], dgam, dbet, inv_ls)
+    o = torch.zeros(C, 64, dtype=F32, device=dev)
+    ops.gemm_wgrad_f16_batched(dc, S["im2col"], o)                                  # columns [x_hi | x_lo | x_hi | 0]
+    ops.scale_f32_(o, inv_ls)
+    grads["feature_extractor.conv_layers.0.conv.weight"] = (o[:, :10] + o[:, 10:20]).reshape(C, 1, 10)
+    grads["feature_extractor.conv_layers.0.layer_norm.weight"] = dgam
+    grads["feature_extractor.conv_layers.0.layer_norm.bias"] = dbet
+    return grads
+
+
 def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[RegPlan] = None,
-                          mask_embed: Optional[torch.Tensor] = None):
+                          mask_embed: Optional[torch.Tensor] = None, train_cnn: bool = False):
     """Same arithmetic as EncoderEngine.forward (the GELUs run as separate passes so the pre-activations
     can be kept) plus the train-mode regularisation of `plan`; returns (last_hidden_state f32 [B,T,H], saved)."""
     a, w = eng.arch, eng.w
     S = {"plan": plan}
     ph = plan.p_hidden if plan is not None else 0.0
     seed = plan.seed if plan is not None else 0
-    feat = eng.feature_extractor(wav)                         # frozen CNN: nothing saved from inside
+    if train_cnn:
+        feat, S["cnn"] = cnn_forward_train(eng, wav)          # unfrozen CNN: pre-activations kept
+    else:
+        feat = eng.feature_extractor(wav)                     # frozen CNN: nothing saved from inside
     B, T, C = feat.shape
     H, M = a.hidden, B * T
     feat2 = feat.contiguous().view(M, C)
@@ -295,8 +375,10 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
     ops.colsum(dh0_16, G.view("feature_projection.projection.bias"))
     ops.gemm_wgrad_f16(dh0_16, S["n16"], G.view("feature_projection.projection.weight"))
     dn32 = ops.gemm_f16(dh0_16, tw.fp_wT, None, 0, F32)                           # [M, 512]
-    ops.layernorm_bwd(dn32, S["feat"], w.fp_ln_g, a.eps, dgamma=G.view("feature_projection.layer_norm.weight"),
-                      dbeta=G.view("feature_projection.layer_norm.bias"), want32=False, want16=False)
+    dfeat, _ = ops.layernorm_bwd(dn32, S["feat"], w.fp_ln_g, a.eps, dgamma=G.view("feature_projection.layer_norm.weight"),
+                                 dbeta=G.view("feature_projection.layer_norm.bias"), want32="cnn" in S, want16=False)
+    if "cnn" in S:                                     # unfrozen feature extractor: its gradients are returned unscaled
+        G.cnn_grads = cnn_backward(eng, params, S["cnn"], dfeat.view(B, T, -1))
     return G
 
 
@@ -311,7 +393,8 @@ class EncoderFn(torch.autograd.Function):
     def forward(ctx, wav, model, names, *params):
         eng = model._engine()
         plan = model._draw_reg_plan(wav, eng)
-        out, saved = encoder_forward_train(eng, wav, plan, model.masked_spec_embed.detach())
+        train_cnn = any(q.requires_grad for q in model._items()[3])
+        out, saved = encoder_forward_train(eng, wav, plan, model.masked_spec_embed.detach(), train_cnn)
         ctx.model, ctx.names, ctx.saved, ctx.eng = model, names, saved, eng
         return out
 
@@ -324,13 +407,21 @@ class EncoderFn(torch.autograd.Function):
         G = encoder_backward(eng, tw, pd, ctx.saved, dh.float(), sink,
                              getattr(model, "_grad_ready_hook", None) if sink is not None else None)
         ctx.saved = None
+        cnn = getattr(G, "cnn_grads", None) or {}
+        G.cnn_grads = None
         if sink is not None:
-            # the trainer owns the (loss-scaled) flat gradient: nothing goes back through autograd
-            return (None, None, None, *([None] * len(names)))
+            # the trainer owns the (loss-scaled) flat gradient of everything behind the CNN: only the feature
+            # extractor's (unscaled) gradients go back through autograd
+            return (None, None, None, *[cnn.get(n) if pd[n].requires_grad else None for n in names])
         ops.scale_f32_(G.flat, 1.0 / LOSS_SCALE)
         grads = []
         for n in names:
-            grads.append(G.view(n) if (n in G.offsets and pd[n].requires_grad) else None)
+            if not pd[n].requires_grad:
+                grads.append(None)
+            elif n in G.offsets:
+                grads.append(G.view(n))
+            else:
+                grads.append(cnn.get(n))
         return (None, None, None, *grads)
 
 
