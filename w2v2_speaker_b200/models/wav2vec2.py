@@ -7,8 +7,8 @@ C ABI.  Parameters are ``nn.Parameter``s under HF's state_dict names, so ``param
 ``state_dict()``, ``load_state_dict(strict=False)`` and ``requires_grad_`` keep working
 (SURVEY 8b).
 
-This round ships the eval-mode forward; a grad-requiring training forward raises (there is no
-PyTorch fallback to fall into).
+With gradients enabled the forward runs through ``training.EncoderFn`` (hand-written backward, frozen or
+unfrozen CNN, train-mode regularisation); there is no PyTorch fallback to fall into.
 """
 from __future__ import annotations
 

@@ -3,9 +3,10 @@ sm_100a kernels, and the torch.autograd.Function wrappers that make ``loss.backw
 reference-facing modules (the reference trains through Lightning's automatic optimisation,
 R:src/lightning_modules/speaker/speaker_recognition_module.py:148-220).
 
-Scope of this round: wav2vec2-base/large encoder with the CNN feature extractor frozen (the reference
-default ``completely_freeze_feature_extractor: true``, R:config/network/wav2vec2_fc.yaml:16), all
-stochastic regularisation at probability 0 (dropout / LayerDrop / SpecAugment), mean pooling + CE head.
+Scope: wav2vec2-base/large encoder with the CNN feature extractor frozen (the reference default
+``completely_freeze_feature_extractor: true``, R:config/network/wav2vec2_fc.yaml:16) or trained, the
+reference's train-mode regularisation (dropout / LayerDrop / SpecAugment), mean / mean+std / attentive
+pooling, CE and AAM-softmax heads.
 
 Gradient convention between the Functions of this module: activation gradients carry ``LOSS_SCALE``
 (their fp16 copies feed the tensor cores), parameter gradients are unscaled before they are returned
