@@ -358,15 +358,41 @@ def main():
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     arg_host = torch.empty(B, dtype=torch.int64).pin_memory()
 
+    # End-to-end step: the batch comes from pinned host memory and the result (loss / arg-max, and the embedding in
+    # forward mode) is read back every step.  Like a data loader with pinned memory would, the upload of the NEXT
+    # batch is issued on a copy stream before this step's kernels are enqueued, so it runs under them; every step
+    # still uploads exactly one batch and ends with the host holding that step's result.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [dict(w=torch.empty_like(wav_dev), l=torch.empty_like(labels_dev),
+                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    state = {"i": 0, "primed": False}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot["free"])          # the step that last used this slot has consumed it
+            slot["w"].copy_(wav_pin, non_blocking=True)
+            slot["l"].copy_(labels_pin, non_blocking=True)
+            slot["ready"].record(copy_stream)
+
     def step_e2e():
-        w = wav_pin.to(dev, non_blocking=True)
-        l = labels_pin.to(dev, non_blocking=True)
-        emb, loss, prob = run(w, l)
+        cur = torch.cuda.current_stream()
+        i = state["i"]
+        if not state["primed"]:
+            for sl in slots:
+                sl["free"].record(cur)
+            upload(slots[i % 2])                          # nothing was prefetched for the first step
+            state["primed"] = True
+        sl = slots[i % 2]
+        upload(slots[(i + 1) % 2])                        # next step's batch, under this step's compute
+        cur.wait_event(sl["ready"])
+        emb, loss, prob = run(sl["w"], sl["l"])
+        sl["free"].record(cur)
         if emb is not None:
             emb_host.copy_(emb, non_blocking=True)
         loss_host.copy_(loss.view(1), non_blocking=True)
         arg_host.copy_(prob.argmax(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the user reads the step's result on the host
+        state["i"] = i + 1
+        cur.synchronize()                                 # the user reads the step's result on the host
 
     def barrier():
         if use_dist:

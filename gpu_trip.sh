@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
 T0=$(date +%s)
-timeout -k 5 600 python -m pytest tests/test_gpu_training.py -m gpu -x -q -s -k "unfrozen" > gpurun_out/t33_cnn.log 2>&1; grep -E "unfrozen-CNN|passed|failed|Error|error" gpurun_out/t33_cnn.log | cut -c1-1500 | head -20
-echo "cnn tests done $(( $(date +%s) - T0 )) s"
-timeout -k 5 900 python -m pytest tests -m gpu -x -q > gpurun_out/t33_tests.log 2>&1; tail -5 gpurun_out/t33_tests.log
+NG=$(nvidia-smi -L | wc -l)
+timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $NG --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/t37_train$NG.log 2>&1; tail -1 gpurun_out/t37_train$NG.log | cut -c1-330
+echo "train$NG done $(( $(date +%s) - T0 )) s"
+timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus $NG --mode forward --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/t37_fwd$NG.log 2>&1; tail -1 gpurun_out/t37_fwd$NG.log | cut -c1-330
 echo "all done $(( $(date +%s) - T0 )) s"

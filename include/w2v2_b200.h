@@ -231,6 +231,9 @@ int w2v2_softmax_ce_bwd_f32(const float* prob, const int64_t* labels, const floa
  * (undoes the loss scale and applies the 1/world_size of the data-parallel mean). */
 int w2v2_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                    int step, float grad_scale, void* stream);
+/* Same, optionally clearing the gradient in the same pass (zero_grad != 0): the next backward re-accumulates it. */
+int w2v2_adam_step_ex(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      int step, float grad_scale, int zero_grad, void* stream);
 
 /* ---- attentive-statistics pooling in training (R:src/layers/pooling.py:87-106; speechbrain
  * AttentiveStatisticsPooling, restated in oracle/w2v2_oracle.py::attentive_stat_pool) -------------------

@@ -257,9 +257,9 @@ def mean_pool_bwd(demb, T: int):
     return dh
 
 
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, step: int, grad_scale: float = 1.0):
-    call("w2v2_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
-         int(step), float(grad_scale), stream_ptr())
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step: int, grad_scale: float = 1.0, zero_grad: bool = False):
+    call("w2v2_adam_step_ex", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         int(step), float(grad_scale), int(zero_grad), stream_ptr())
 
 
 def stat_pool(x: torch.Tensor, mode: int) -> torch.Tensor:

@@ -11,6 +11,11 @@ R:config/trainer/trainer.yaml:6-9) amount to.  The encoder's backward writes its
 straight into the flat buffer (``model._grad_sink``), so no per-parameter accumulation pass exists;
 they stay loss-scaled and Adam undoes the scale.  Unused / LayerDrop-skipped parameters keep a zero
 gradient.
+
+The optimizer runs on its own stream: Adam, the re-derivation of the fp16 operand copies and the zeroing of
+the gradient buffer are HBM-bound and depend on nothing of the next step's CNN forward (frozen feature
+extractor: its weights do not change), which is tensor-bound -- so step n's update overlaps step n+1's
+feature extractor.  The encoder waits for the update right after the CNN (``model._pre_encoder_hook``).
 """
 from __future__ import annotations
 
@@ -68,6 +73,14 @@ class FlatAdamTrainer:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self._overlapped = []
         self._refreshable = None
+        # optimizer stream (see module docstring); with a trainable CNN the update must finish before the next forward
+        self.opt_stream = torch.cuda.Stream(device=dev)
+        cnn_trainable = self.model is not None and any(q.requires_grad for q in self.model._items()[3])
+        import os
+        self._overlap_update = (self.model is not None and not cnn_trainable and
+                                os.environ.get("W2V2_OPT_STREAM", "1") != "0")        # =0: update in stream order (A/B)
+        if self._overlap_update:
+            self.model._pre_encoder_hook = self._join_update
         if seg0 and self.world > 1:
             self.model._grad_ready_hook = self._reduce_span      # spans of flat_g[:n0] == GradBook offsets
 
@@ -107,21 +120,37 @@ class FlatAdamTrainer:
         self._overlapped = []
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
+    def _join_update(self):
+        """Called by the encoder right after the CNN forward: everything from here on reads updated parameters
+        (and, in the backward, writes the gradient buffer the optimizer stream has just zeroed)."""
+        torch.cuda.current_stream().wait_stream(self.opt_stream)
+
+    def synchronize(self):
+        """Make the current stream wait for the pending parameter update (call before reading parameters
+        outside step(): evaluation, checkpointing)."""
+        torch.cuda.current_stream().wait_stream(self.opt_stream)
+
     def step(self, wav: torch.Tensor, labels: torch.Tensor):
         """One optimisation step; returns (loss, softmax) like the reference's training_step uses them."""
-        self.flat_g.zero_()
+        cur = torch.cuda.current_stream()
+        if not self._overlap_update:
+            cur.wait_stream(self.opt_stream)
         emb, pred = self.module(wav)
+        cur.wait_stream(self.opt_stream)          # no-op if the encoder already joined (it always does when it runs)
         loss, prob = self.module.loss_fn(pred, labels)
         loss.backward()
         self.allreduce_grads()
         self.step_count += 1
         b1, b2 = self.betas
         n0, n = self.n0, self.flat_p.numel()
-        if n0:
-            ops.adam_step(self.flat_p[:n0], self.flat_g[:n0], self.m[:n0], self.v[:n0], self.lr, b1, b2, self.eps,
-                          self.step_count, grad_scale=1.0 / (LOSS_SCALE * self.world))
-        if n > n0:
-            ops.adam_step(self.flat_p[n0:], self.flat_g[n0:], self.m[n0:], self.v[n0:], self.lr, b1, b2, self.eps,
-                          self.step_count, grad_scale=1.0 / self.world)
-        self._refresh_module_weights()
+        opt_stream = self.opt_stream if self._overlap_update else cur
+        opt_stream.wait_stream(cur)
+        with torch.cuda.stream(opt_stream):
+            if n0:
+                ops.adam_step(self.flat_p[:n0], self.flat_g[:n0], self.m[:n0], self.v[:n0], self.lr, b1, b2, self.eps,
+                              self.step_count, grad_scale=1.0 / (LOSS_SCALE * self.world), zero_grad=True)
+            if n > n0:
+                ops.adam_step(self.flat_p[n0:], self.flat_g[n0:], self.m[n0:], self.v[n0:], self.lr, b1, b2, self.eps,
+                              self.step_count, grad_scale=1.0 / self.world, zero_grad=True)
+            self._refresh_module_weights()         # (the gradient buffer was cleared by the Adam pass itself)
         return loss.detach(), prob
