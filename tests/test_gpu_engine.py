@@ -81,3 +81,22 @@ def test_five_second_utterances_use_the_wide_tiles(engine, base_params):
         ref = O.wav2vec2_forward(wav, base_params, BASE)
     assert h.shape == ref.shape == (1, 249, 768)
     assert rel_rows(h.mean(1), ref.mean(1)) < 1e-3
+
+
+@pytest.mark.parametrize("N", [160400, 99000])
+def test_full_utterance_forward_matches_oracle(engine, base_params, N):
+    """Full-utterance evaluation: ~10 s -> 501 frames, ~6.2 s -> 309 frames: key-tiled attention and the
+    chunked positional conv against the CPU oracle."""
+    from oracle import w2v2_oracle as O
+    from oracle.params import BASE, make_inputs
+    torch.set_num_threads(8)
+    wav, _ = make_inputs(1, N, seed=8)
+    h = engine.forward(wav.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.wav2vec2_forward(wav, base_params, BASE)
+    T = BASE.conv_lengths(N)[-1]
+    assert h.shape == ref.shape == (1, T, 768) and T > 256
+    assert rel_rows(h.mean(1), ref.mean(1)) < 1e-3
+    r = ((h.cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+    assert r < 1.5e-3, r

@@ -227,11 +227,28 @@ def test_attention(ops, B, T, H, heads):
     assert rel(out.float(), ref) < 1.5e-3
 
 
-def test_attention_rejects_long_sequences(ops):
+@pytest.mark.parametrize("B,T,H,heads", [(2, 300, 768, 12), (1, 513, 768, 12), (1, 1000, 1024, 16), (3, 257, 768, 12),
+                                         (1, 384, 768, 12)])
+def test_attention_long_sequences(ops, B, T, H, heads):
+    """T > 256 (full-utterance evaluation): the key-tiled two-pass kernel, output and log-sum-exp."""
+    qkv = _rand((B * T, 3 * H), 31, 1.0).half()
+    qkv[:, :H] *= 0.35
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True)
+    torch.cuda.synchronize()
+    d = H // heads
+    q, k, v = (qkv[:, i * H:(i + 1) * H].float().view(B, T, heads, d).transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(2, 3)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, H)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out.float(), ref) < 1.5e-3
+    assert rel(lse, torch.logsumexp(s, -1)) < 1e-3
+
+
+def test_attention_dropout_rejects_long_sequences(ops):
     from w2v2_speaker_b200._lib import W2V2Error
     qkv = torch.zeros(300, 3 * 768, dtype=torch.float16, device="cuda")
     with pytest.raises(W2V2Error):
-        ops.attention(qkv, 1, 300, 768, 12)
+        ops.attention(qkv, 1, 300, 768, 12, drop_p=0.1, drop_seed=1)
 
 
 @pytest.mark.parametrize("B,T,H,G", [(2, 49, 768, 16), (5, 149, 768, 16), (3, 249, 1024, 16), (1, 7, 768, 16), (9, 35, 768, 16)])

@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   }
 }
 
+int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, cudaStream_t stream);
+
 }  // namespace w2v2
 
 using namespace w2v2;
@@ -221,10 +223,12 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
                                  uint64_t drop_seed, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * ATT_D, "w2v2_attention: head dim must be 64 (H=%d heads=%d)", H, heads);
-  W2V2_REQUIRE(T >= 1 && T <= 256,
-               "w2v2_attention: T=%d frames not supported (single-tile kernel handles T <= 256; longer "
-               "utterances need the tiled variant)", T);
+  W2V2_REQUIRE(T >= 1, "w2v2_attention: empty sequence");
   W2V2_REQUIRE(B >= 1 && B <= 65535, "w2v2_attention: bad batch %d", B);
+  if (T > 256) {       // full-utterance evaluation: key-tiled two-pass kernel (attention_long.cu), no dropout
+    W2V2_REQUIRE(drop_p == 0.f, "w2v2_attention: attention dropout is only built for T <= 256 (training crops)");
+    return attention_long_launch(qkv16, out16, lse, B, T, H, heads, stream);
+  }
   AttnParams p;
   const int TK = (T + 15) / 16 * 16;
   int rc = make_tmap_3d(&p.tmQ, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, ATT_D, 128, 1, 128);

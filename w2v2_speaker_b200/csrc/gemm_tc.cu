@@ -95,11 +95,13 @@ struct WorkIter {
 
 // CL = CTAs per MMA: 1 (tcgen05.mma.cta_group::1, tile 128 x BN) or 2 (a CTA pair, cta_group::2, tile 256 x BN:
 // each CTA stages its 128 rows of A and BN/2 columns of B)
-template <int BN, int CL = 1>
+// MINB = CTAs per SM the kernel is built for: 2 only for the epilogue-bound conv0 GEMM (K = 64: one k-block per
+// tile, so two pipeline stages are plenty and two CTAs -- 16 epilogue warps -- share an SM)
+template <int BN, int CL = 1, int MINB = 1>
 struct GemmCfg {
   static constexpr int B_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256 && CL == 1) ? 4 : 6;
+  static constexpr int STAGES = MINB == 2 ? 2 : ((BN == 256 && CL == 1) ? 4 : 6);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias tile
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE_BYTES + BIAS_BYTES + 256 /*barriers*/;
@@ -108,9 +110,9 @@ struct GemmCfg {
 };
 
 // EPI: 0 = none, 1 = + bias[n], 2 = * scale[b, n] + shift[b, n]  (GroupNorm affine of conv layer 0)
-template <int BN, bool OUT_F32, int ACT, int EPI, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, CL>;
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1>
+__global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN, CL, MINB>;
   constexpr int STAGES = Cfg::STAGES;
   // the 128B-swizzled tiles need a 1024-byte aligned base; the kernel has no static shared memory, so
   // the dynamic window starts at the CTA's (1024-aligned) shared base -- verified, not assumed
@@ -531,17 +533,17 @@ static bool pair_enabled() {
   return v == 1;
 }
 
-template <int BN, bool OUT_F32, int ACT, int EPI, int CL>
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, MINB>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI, CL>;
+  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI, CL, MINB>;
   if (!configured) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.batch;          // scheduling units: CTAs (CL = 1) or CTA pairs
-  const int units = device_sm_count() / CL;
+  const int units = device_sm_count() / CL * MINB;
   const int grid = tiles < units ? tiles : units;
   GemmParams q = p;
   if constexpr (OUT_F32 && ACT == 0 && EPI != 2) {
@@ -567,7 +569,10 @@ static int dispatch_epilogue(const GemmParams& p, int act, cudaStream_t stream) 
     if constexpr (!OUT_F32 && BN == 256) {      // conv0: GN affine (+ GELU) -> f16
       return act == 1 ? launch_gemm<256, false, 1, 2, CL>(p, stream) : launch_gemm<256, false, 0, 2, CL>(p, stream);
     }
-    set_last_error("w2v2 gemm: the per-batch affine epilogue is built for f16 output, N > 128");
+    if constexpr (!OUT_F32 && BN == 128 && CL == 1) {   // same, 128-wide tiles, two CTAs per SM (W2V2_CONV0_2CTA)
+      return act == 1 ? launch_gemm<128, false, 1, 2, 1, 2>(p, stream) : launch_gemm<128, false, 0, 2, 1, 2>(p, stream);
+    }
+    set_last_error("w2v2 gemm: the per-batch affine epilogue is built for f16 output");
     return -1;
   }
   if (act == 1) return epi ? launch_gemm<BN, OUT_F32, 1, 1, CL>(p, stream) : launch_gemm<BN, OUT_F32, 1, 0, CL>(p, stream);
@@ -623,7 +628,11 @@ int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* t
   W2V2_REQUIRE(a_rows > 0 && batch > 0 && N > 0, "w2v2_gemm_f16: empty problem");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int BN = (N <= 128) ? 128 : 256;
+  static const bool conv0_2cta = []() { const char* e = getenv("W2V2_CONV0_2CTA"); return !(e != nullptr && e[0] == '0'); }();
+  // the GroupNorm-affine + GELU epilogue of conv layer 0 is issue-bound, not tensor-bound: 128-wide tiles with two
+  // CTAs (16 epilogue warps) per SM instead of one pair-CTA with 8
+  const bool small_tiles = shift != nullptr && out_dtype == 0 && cin == BK && ntaps == 1 && conv0_2cta;
+  const int BN = (N <= 128 || small_tiles) ? 128 : 256;
   const int CL = (BN == 256 && pair_enabled()) ? 2 : 1;         // CTA pairs for every wide GEMM
   const int osz = out_dtype == 1 ? 4 : 2;
   const uint64_t a_bstride = batch > 1 ? uint64_t(a_batch_stride) * 2 : uint64_t(a_extent) * uint64_t(a_row_stride) * 2;

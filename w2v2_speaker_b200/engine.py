@@ -234,6 +234,25 @@ class EncoderEngine:
         h0 = ops.gemm_f16(n16, w.fp_w, w.fp_b, 0, F32)
         return h0.view(B, T, a.hidden)
 
+    POS_SINGLE_SLAB = 256      # frames the shifted-slab positional-conv kernel holds in shared memory at once
+
+    def _posconv_long(self, x16: torch.Tensor) -> torch.Tensor:
+        """Positional conv embedding (HF:326-379) of a sequence longer than one slab (full-utterance evaluation):
+        the time axis is cut into chunks of 128 frames, each handed to the slab kernel as its own 'utterance'
+        together with a real-data halo of K/2 = 64 frames on both sides (zeros beyond the ends of the sequence,
+        which is exactly the conv's own padding); only the middle 128 outputs of a chunk are kept -- they depend on
+        nothing outside it.  The gather is strided-copy plumbing; the arithmetic is the same tcgen05 kernel."""
+        a, w = self.arch, self.w
+        B, T, H = x16.shape
+        K = a.pos_kernel
+        halo, tc = K // 2, self.POS_SINGLE_SLAB - K
+        n = (T + tc - 1) // tc
+        xp = torch.zeros(B, n * tc + K, H, dtype=F16, device=x16.device)
+        xp[:, halo:halo + T] = x16
+        chunks = xp.as_strided((B, n, tc + K, H), (xp.stride(0), tc * H, H, 1)).contiguous().view(B * n, tc + K, H)
+        out = ops.posconv(chunks, w.pos_w(tc + K), w.pos_b, a.pos_groups, K)              # [B*n, tc+K, H] f32
+        return out.view(B, n, tc + K, H)[:, :, halo:halo + tc].reshape(B, n * tc, H)[:, :T].contiguous()
+
     # -- HF:668-727 ----------------------------------------------------------------------------
     def encoder(self, h0: torch.Tensor, hidden_states: Optional[list] = None) -> torch.Tensor:
         """h0 f32 [B,T',H] (any sequence, e.g. with a CLS frame prepended) -> last_hidden_state f32."""
@@ -242,7 +261,10 @@ class EncoderEngine:
         M = B * T
         h0 = h0.contiguous()
         x16 = ops.cast_f16(h0)
-        pos = ops.posconv(x16, w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel)
+        if T <= self.POS_SINGLE_SLAB:
+            pos = ops.posconv(x16, w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel)
+        else:
+            pos = self._posconv_long(x16)
         h32, h16 = ops.layernorm(pos.view(M, H), w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0.view(M, H))
         if hidden_states is not None:
             hidden_states.append(h32.view(B, T, H))
