@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
 T0=$(date +%s)
-timeout -k 5 300 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py -m gpu -x -q -k "attention or full_utterance or posconv" > gpurun_out/t39_tests.log 2>&1; tail -12 gpurun_out/t39_tests.log
+timeout -k 5 900 python -m pytest tests -m gpu -x -q > gpurun_out/t41_tests.log 2>&1; tail -6 gpurun_out/t41_tests.log
 echo "tests done $(( $(date +%s) - T0 )) s"
+timeout -k 5 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/t41_train1.log 2>&1; tail -1 gpurun_out/t41_train1.log | cut -c1-200
+echo "all done $(( $(date +%s) - T0 )) s"

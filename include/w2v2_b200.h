@@ -216,6 +216,12 @@ int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int B, int T, 
                       uint64_t drop_seed, void* stream);
 int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
                           int T, int H, int heads, float drop_p, uint64_t drop_seed, void* stream);
+/* Same, with the chain rule of the folded softmax scale and the bias gradients done on the way out of TMEM:
+ * dq is multiplied by qscale before it is stored, and dbias (f32 [3H], NULL = skip) accumulates the column
+ * sums of (dq * qscale | dk | dv) -- the q/k/v projection bias gradients. */
+int w2v2_attention_bwd_ex2(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
+                           int T, int H, int heads, float drop_p, uint64_t drop_seed, float qscale, float* dbias,
+                           void* stream);
 int w2v2_time_mask_apply(float* h, const uint8_t* mask, const float* embed, int64_t rows, int H, void* stream);
 int w2v2_time_mask_bwd(float* dh, const uint8_t* mask, float* dembed, int64_t rows, int H, float scale, void* stream);
 /* Gradient plumbing: out = a + b (b may be NULL) as f32 and/or f16 (n % 4 == 0); row-wise f32 -> f16 cast
@@ -310,7 +316,7 @@ typedef struct {
   int B, T, H, heads, FF, layer;
   float eps, p_hidden, p_attn, p_act, qscale;
   uint64_t seed;
-  const void* wqkvT;  /* f16 [H, 3H] */
+  const void* wqkvT;  /* f16 [H, 3H]; the q block is the UNSCALED Wq^T (dq arrives multiplied by qscale) */
   const void* woT;    /* f16 [H, H] */
   const void* w1T;    /* f16 [H, FF] */
   const void* w2T;    /* f16 [FF, H] */
@@ -402,7 +408,7 @@ typedef struct {
   int32_t R, C;
   int32_t ld, ldt;      /* row pitch (elements) of dst16 / dst32, and of dstT16 */
   float scale;
-  int32_t pad_;
+  float scale_t;       /* scale of the transposed copy relative to src (the plain copies use `scale`) */
   int64_t tile_begin;
 } w2v2_prep_job;
 int w2v2_prepare_weights(const w2v2_prep_job* jobs_dev, int njobs, int64_t total_tiles, void* stream);

@@ -141,6 +141,27 @@ def test_attention_bwd(ops, B, T, H, heads):
             assert rel(got, want) < 4e-3, name
 
 
+@pytest.mark.parametrize("B,T,H,heads", [(3, 149, 768, 12), (2, 249, 1024, 16)])
+def test_attention_bwd_scaled_dq_and_bias_gradients(ops, B, T, H, heads):
+    """w2v2_attention_bwd_ex2: dq multiplied by qscale on the way out, q/k/v bias gradients = column sums of dqkv."""
+    qkv = _rand((B * T, 3 * H), 40).half()
+    qkv[:, :H] *= 0.35
+    d_o = _rand((B * T, H), 41, 0.7).half()
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True)
+    base = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads).float()
+    dbias = torch.zeros(3 * H, device="cuda")
+    got = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads, qscale=0.125, dbias=dbias).float()
+    torch.cuda.synchronize()
+    want = base.clone()
+    want[:, :H] *= 0.125
+    assert rel(got, want) < 1e-3
+    ref_b = want.double().sum(0)
+    ref_b[H:2 * H] = 0           # the key-bias gradient is exactly 0 in exact arithmetic: compare it against the others' scale
+    assert (dbias.double()[:H] - ref_b[:H]).norm() / ref_b[:H].norm() < 2e-3
+    assert (dbias.double()[2 * H:] - ref_b[2 * H:]).norm() / ref_b[2 * H:].norm() < 2e-3
+    assert dbias[H:2 * H].double().norm() < 1e-2 * ref_b[2 * H:].norm()
+
+
 def test_adam_matches_torch(ops):
     n = 100003
     p0 = _rand((n,), 22)

@@ -105,10 +105,17 @@ def test_wrapper_cls_token_and_lite_paths(base_params):
     assert ((f.cpu().double() - feat.transpose(1, 2).double()).norm() / feat.double().norm()).item() < 2e-3
 
 
-def test_long_utterance_fails_loudly(base_params):
+def test_long_utterance_evaluates_and_training_on_it_fails_loudly(base_params):
+    """Utterances longer than 256 frames: the evaluation forward handles any length (full-utterance test_step);
+    TRAINING on them is not built (the reference trains on 3 s crops) and must raise, not fall back."""
     _need_cuda()
     from w2v2_speaker_b200._lib import W2V2Error
     from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
     w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False).cuda().eval()
-    with torch.no_grad(), pytest.raises(W2V2Error):
-        w(torch.zeros(1, 16000 * 6, device="cuda"))              # 299 frames > 256
+    with torch.no_grad():
+        out = w(torch.randn(1, 16000 * 6, device="cuda"))           # 299 frames > 256
+    assert out.shape == (1, 768, 299) and torch.isfinite(out).all()
+    w.train()
+    w.model.feature_extractor.requires_grad_(False)
+    with pytest.raises(W2V2Error):
+        w(torch.randn(1, 16000 * 6, device="cuda")).sum().backward()

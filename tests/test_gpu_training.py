@@ -376,7 +376,10 @@ def test_inplace_weight_refresh_equals_rebuild(base_params):
         ref = torch.cat([named[pre + "attention.q_proj.weight"] * scale, named[pre + "attention.k_proj.weight"],
                          named[pre + "attention.v_proj.weight"]], 0).half()
         assert torch.equal(eng.w.layers[l]["wqkv"], ref)
-        assert torch.equal(tw.layers[l]["wqkvT"], ref.t())
+        # the transposed (data-gradient) copy keeps the q block UNSCALED: the attention backward scales dq instead
+        ref_t = torch.cat([named[pre + "attention.q_proj.weight"], named[pre + "attention.k_proj.weight"],
+                           named[pre + "attention.v_proj.weight"]], 0).half()
+        assert torch.equal(tw.layers[l]["wqkvT"], ref_t.t())
         assert torch.equal(tw.layers[l]["w2T"], named[pre + "feed_forward.output_dense.weight"].half().t())
     assert torch.equal(eng.w.fp_w, named["feature_projection.projection.weight"].half())
     assert torch.equal(tw.fp_wT, eng.w.fp_w.t())

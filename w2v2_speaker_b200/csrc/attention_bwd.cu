@@ -38,6 +38,8 @@ struct alignas(64) AttnBwdParams {
   int pblocks;         // 64-key blocks of P / dS
   int resident;        // 1: every Q / dO tile stays in smem; 0: one tile buffer, reloaded per query tile
   int col_dq;          // TMEM column of dQ
+  float qscale;        // dq is multiplied by this (chain rule of the d^-0.5 folded into Wq); 1 = leave as is
+  float* dbias;        // f32 [3H] (+)= column sums of (dq * qscale | dk | dv), or nullptr
   uint32_t drop_thr;
   float drop_inv_keep;
   unsigned long long drop_seed;
@@ -289,6 +291,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
       uint32_t r[32];
       tmem_ld_32x32b_x32(t_row + p.col_dq + cg * 32, r);
       tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = __uint_as_float(r[j]) * p.qscale;
+        r[j] = __float_as_uint(v[j]);
+      }
       if (valid) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
           *reinterpret_cast<uint4*>(dst + 8 * c) = q;
         }
       }
+      if (p.dbias != nullptr) warp_colsum_atomic<32>(v, valid, 1.0f, p.dbias + h * AB_D + cg * 32);
     }
     // all threads must be done with S/dP and dQ columns before the next tile's MMAs overwrite them
     tc_fence_before();
@@ -330,6 +339,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
           *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * c) = q;
         }
       }
+      if (p.dbias != nullptr) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        warp_colsum_atomic<32>(v, kvalid, 1.0f, p.dbias + (cg == 0 ? p.H : 2 * p.H) + h * AB_D + hh * 32);
+      }
     }
   }
   tc_fence_before();
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
 
 int attention_bwd_fused_launch(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
                                int T, int H, int heads, uint32_t drop_thr, float drop_inv_keep, uint64_t drop_seed,
-                               cudaStream_t stream);
+                               float qscale, float* dbias, cudaStream_t stream);
 
 }  // namespace w2v2
 
@@ -350,6 +365,12 @@ using namespace w2v2;
 
 extern "C" int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16,
                                      int B, int T, int H, int heads, float drop_p, uint64_t drop_seed, void* stream_) {
+  return w2v2_attention_bwd_ex2(qkv16, o16, do16, lse, dqkv16, B, T, H, heads, drop_p, drop_seed, 1.0f, nullptr, stream_);
+}
+
+extern "C" int w2v2_attention_bwd_ex2(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16,
+                                      int B, int T, int H, int heads, float drop_p, uint64_t drop_seed, float qscale,
+                                      float* dbias, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * AB_D, "w2v2_attention_bwd: head dim must be 64 (H=%d heads=%d)", H, heads);
   W2V2_REQUIRE(T >= 1 && T <= 256,
@@ -362,7 +383,7 @@ extern "C" int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const v
   if (TK <= 160) {     // 3 s utterances: the short-chain kernel (attention_bwd_fused.cu)
     const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
     return attention_bwd_fused_launch(qkv16, o16, do16, lse, dqkv16, B, T, H, heads, thr,
-                                      1.0f / (1.0f - float(thr) / 65536.0f), drop_seed, stream);
+                                      1.0f / (1.0f - float(thr) / 65536.0f), drop_seed, qscale, dbias, stream);
   }
   int rc = make_tmap_3d(&p.tmQ, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AB_D, 128, 1, 128);
   if (rc) return rc;
@@ -379,6 +400,8 @@ extern "C" int w2v2_attention_bwd_ex(const void* qkv16, const void* o16, const v
   p.pblocks = (TK + 63) / 64;
   p.resident = TK <= 192 ? 1 : 0;
   p.col_dq = TK <= 192 ? 192 : 0;
+  p.qscale = qscale;
+  p.dbias = dbias;
   W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention_bwd: dropout p=%f out of [0,1)", drop_p);
   p.drop_thr = uint32_t(drop_p * 65536.0f + 0.5f);
   p.drop_inv_keep = 1.0f / (1.0f - float(p.drop_thr) / 65536.0f);

@@ -63,6 +63,8 @@ struct alignas(64) AttnBwdFusedParams {
   const float* lse;    // [B, heads, T]
   __half* dqkv;        // [B*T, 3H]
   int T, TK, H, heads, qtiles;
+  float qscale;        // dq is multiplied by this (chain rule of the d^-0.5 folded into Wq); 1 = leave as is
+  float* dbias;        // f32 [3H] (+)= column sums of (dq * qscale | dk | dv), or nullptr
   uint32_t drop_thr;
   float drop_inv_keep;
   unsigned long long drop_seed;
@@ -249,13 +251,20 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
       *reinterpret_cast<uint4*>(dsrow + o1) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
     }
   };
-  // 16 of the 64 dQ columns of this thread's row -> global
+  // 16 of the 64 dQ columns of this thread's row -> global (x qscale), and their share of the q-bias gradient
   auto drain_dq = [&](int qt) {
     const int t = qt * 128 + row;
     uint32_t r[16];
     tmem_ld_32x32b_x16(t_row + (qt == 0 ? AF_COL_DQ0 : AF_COL_DQ1) + cg * 16, r);
     tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = __uint_as_float(r[j]) * p.qscale;
+      r[j] = __float_as_uint(v[j]);
+    }
     if (t < p.T) store_row_f16x16(p.dqkv + (int64_t(b) * p.T + t) * 3 * p.H + h * AF_D + cg * 16, r);
+    if (p.dbias != nullptr) warp_colsum_atomic<16>(v, t < p.T, 1.0f, p.dbias + h * AF_D + cg * 16);
   };
   auto commit_and_wait = [&]() {
     if (threadIdx.x == 0) umma_commit(bar_mma);
@@ -361,6 +370,12 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
         *reinterpret_cast<uint4*>(dst + 8 * c) = q;
       }
     }
+    if (p.dbias != nullptr) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      warp_colsum_atomic<32>(v, key < p.T, 1.0f, p.dbias + (which == 0 ? p.H : 2 * p.H) + h * AF_D + half * 32);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attention_bwd_fused_kernel(cons
 
 int attention_bwd_fused_launch(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
                                int T, int H, int heads, uint32_t drop_thr, float drop_inv_keep, uint64_t drop_seed,
-                               cudaStream_t stream) {
+                               float qscale, float* dbias, cudaStream_t stream) {
   AttnBwdFusedParams p;
   const int TK = (T + 15) / 16 * 16;
   W2V2_REQUIRE(TK <= AF_MAX_TK, "attention_bwd_fused: T=%d exceeds %d", T, AF_MAX_TK);
@@ -395,6 +410,8 @@ int attention_bwd_fused_launch(const void* qkv16, const void* o16, const void* d
   p.dqkv = static_cast<__half*>(dqkv16);
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   p.qtiles = (T + 127) / 128;
+  p.qscale = qscale;
+  p.dbias = dbias;
   p.drop_thr = drop_thr;
   p.drop_inv_keep = drop_inv_keep;
   p.drop_seed = drop_seed;

@@ -442,6 +442,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Column sums over the 32 rows a warp holds (lane = row, v[j] = that row's j-th column): lane j adds the sum of
+// column j to dst[j].  Used by the attention backward to emit the q/k/v bias gradients while draining TMEM.
+template <int N>
+__device__ __forceinline__ void warp_colsum_atomic(const float (&v)[N], bool row_valid, float scale, float* dst) {
+  static_assert(N <= 32, "one lane per column");
+  const int lane = threadIdx.x & 31;
+  float mine = 0.f;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float s = warp_sum(row_valid ? v[j] : 0.f);
+    if (lane == j) mine = s;
+  }
+  if (lane < N) atomicAdd(dst + lane, mine * scale);
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

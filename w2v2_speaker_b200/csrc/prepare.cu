@@ -42,9 +42,11 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(const w2v2_prep_jo
     const int r = r0 + i, c = c0 + tx;
     float v = 0.f;
     if (r < j.R && c < j.C) {
-      v = src[int64_t(r) * j.C + c] * j.scale;
+      const float raw = src[int64_t(r) * j.C + c];
+      v = raw * j.scale;
       if (d16 != nullptr) d16[int64_t(r) * j.ld + c] = __float2half_rn(v);
       if (d32 != nullptr) d32[int64_t(r) * j.ld + c] = v;
+      v = raw * j.scale_t;
     }
     tile[i][tx] = v;
   }

@@ -66,13 +66,12 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
                                  a->d_ln1_g, a->d_ln1_b, a->d_bo, M, H, a->p_hidden, seed + 200 + l, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx1_16, H, a->att16, H, M, H, H, a->d_wo, H, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dx1_16, M, H, 0, 1, 1, 0, H, a->woT, H, H, nullptr, 0, a->datt16, 0, H, 0, stream));
-  W2V2_TRY(w2v2_attention_bwd_ex(a->qkv16, a->att16, a->datt16, a->lse, a->dqkv16, a->B, a->T, H, a->heads, a->p_attn,
-                                 seed + 100 + l, stream));
-  W2V2_TRY(w2v2_colsum(a->dqkv16, 0, M, 3 * H, 3 * H, 1.0f, a->d_bqkv, stream));
+  // The q projection was used pre-scaled by d^-0.5: the attention backward multiplies dq by the same factor (chain
+  // rule for the unscaled parameters) and emits the q/k/v bias gradients while it drains TMEM; wqkvT holds the
+  // UNSCALED Wq^T, so neither the weight gradient nor the data gradient needs a correction pass.
+  W2V2_TRY(w2v2_attention_bwd_ex2(a->qkv16, a->att16, a->datt16, a->lse, a->dqkv16, a->B, a->T, H, a->heads, a->p_attn,
+                                  seed + 100 + l, a->qscale, a->d_bqkv, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dqkv16, 3 * H, a->h_in16, H, M, 3 * H, H, a->d_wqkv, H, stream));
-  // the q projection was used pre-scaled by d^-0.5: chain rule for the unscaled parameters
-  W2V2_TRY(w2v2_scale_f32(a->d_wqkv, int64_t(H) * H, a->qscale, stream));
-  W2V2_TRY(w2v2_scale_f32(a->d_bqkv, H, a->qscale, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dqkv16, M, 3 * H, 0, 1, 1, 0, 3 * H, a->wqkvT, 3 * H, H, nullptr, 0, a->dh_in32, 1, H, 0, stream));
   return 0;
 }

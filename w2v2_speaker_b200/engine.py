@@ -33,7 +33,7 @@ class WeightPrep:
     + folded scalar), every fused bias -> assembled fp32 vector, all in ONE launch per optimizer step."""
 
     DT = np.dtype([("src", "<u8"), ("dst16", "<u8"), ("dstT16", "<u8"), ("dst32", "<u8"), ("R", "<i4"), ("C", "<i4"),
-                   ("ld", "<i4"), ("ldt", "<i4"), ("scale", "<f4"), ("pad", "<i4"), ("tile_begin", "<i8")])
+                   ("ld", "<i4"), ("ldt", "<i4"), ("scale", "<f4"), ("scale_t", "<f4"), ("tile_begin", "<i8")])
 
     def __init__(self):
         self.jobs: Dict[str, dict] = {}
@@ -48,12 +48,15 @@ class WeightPrep:
         d2 = d if d.dim() == 2 else d.view(1, -1)
         assert d2.shape == src2.shape and d2.stride(-1) == 1
         self.jobs[key] = dict(src=src2, dst16=d2 if dst16 is not None else None, dst32=d2 if dst32 is not None else None,
-                              dstT=None, scale=float(scale))
+                              dstT=None, scale=float(scale), scale_t=float(scale))
         self._table = None
 
-    def add_transposed(self, key: str, dstT: torch.Tensor):
-        """dstT: f16 view [C, R] (row pitch = ldt) receiving the transpose of job `key`."""
+    def add_transposed(self, key: str, dstT: torch.Tensor, scale: Optional[float] = None):
+        """dstT: f16 view [C, R] (row pitch = ldt) receiving the transpose of job `key` (x `scale` of the source
+        if given, else the job's own scale)."""
         j = self.jobs[key]
+        if scale is not None:
+            j["scale_t"] = float(scale)
         assert dstT.shape == (j["src"].shape[1], j["src"].shape[0]) and dstT.stride(1) == 1
         j["dstT"] = dstT
         self._table = None
@@ -68,7 +71,7 @@ class WeightPrep:
                           j["dstT"].data_ptr() if j["dstT"] is not None else 0,
                           j["dst32"].data_ptr() if j["dst32"] is not None else 0, R, C,
                           (j["dst16"] if j["dst16"] is not None else j["dst32"]).stride(0) if R > 1 else C,
-                          j["dstT"].stride(0) if j["dstT"] is not None else 0, j["scale"], 0, t)
+                          j["dstT"].stride(0) if j["dstT"] is not None else 0, j["scale"], j["scale_t"], t)
                 t += ((R + 31) // 32) * ((C + 31) // 32)
             dev = next(iter(self.jobs.values()))["src"].device
             self._table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)

@@ -178,10 +178,11 @@ def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, want_lse:
 
 
 def attention_bwd(qkv16, o16, do16, lse, B: int, T: int, H: int, heads: int, drop_p: float = 0.0,
-                  drop_seed: int = 0) -> torch.Tensor:
+                  drop_seed: int = 0, qscale: float = 1.0, dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """-> dqkv f16 [B*T, 3H] with the q block multiplied by `qscale`; `dbias` (f32 [3H]) accumulates its column sums."""
     dqkv = torch.empty(B * T, 3 * H, dtype=F16, device=qkv16.device)
-    call("w2v2_attention_bwd_ex", ptr(qkv16), ptr(o16), ptr(do16), ptr(lse), ptr(dqkv), B, T, H, heads, float(drop_p),
-         int(drop_seed), stream_ptr())
+    call("w2v2_attention_bwd_ex2", ptr(qkv16), ptr(o16), ptr(do16), ptr(lse), ptr(dqkv), B, T, H, heads, float(drop_p),
+         int(drop_seed), float(qscale), ptr(dbias), stream_ptr())
     return dqkv
 
 

@@ -44,8 +44,10 @@ class TrainWeights:
         for l in range(a.layers):
             pre = f"encoder.layers.{l}."
             L = dict(wqkvT=tbuf(H, 3 * H), woT=tbuf(H, H), w1T=tbuf(H, FF), w2T=tbuf(FF, H))
-            for i, n in enumerate("qkv"):                                                      # folded, [H, 3H]
-                prep.add_transposed(pre + f"attention.{n}_proj.weight", L["wqkvT"][:, i * H:(i + 1) * H])
+            # [H, 3H]; the q block UNSCALED: the attention backward already multiplies dq by d^-0.5 (chain rule of the
+            # folded scale), so dX = dq_scaled Wq and dWq / dbq need no further correction
+            for i, n in enumerate("qkv"):
+                prep.add_transposed(pre + f"attention.{n}_proj.weight", L["wqkvT"][:, i * H:(i + 1) * H], scale=1.0)
             prep.add_transposed(pre + "attention.out_proj.weight", L["woT"])
             prep.add_transposed(pre + "feed_forward.intermediate_dense.weight", L["w1T"])
             prep.add_transposed(pre + "feed_forward.output_dense.weight", L["w2T"])
