@@ -108,6 +108,62 @@ __global__ void wnorm_bwd_apply_kernel(const float* __restrict__ dw, const float
   }
 }
 
+// Coalesced forms of the two kernels above.  dW arrives as [H][K][I] (taps outer), v and dv are [H][I][K] (taps
+// inner): one block per output channel o stages dW[o] transposed in shared memory (padded rows), so both global
+// streams are read / written along their contiguous axis.
+float* posconv_partial_buffer();
+constexpr int WN_BLOCKS = 128;
+
+__global__ void __launch_bounds__(256) wnorm_bwd_reduce_tiled_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                                     float* __restrict__ partial, int H, int I, int K) {
+  extern __shared__ float dwt[];                          // [I][K + 1]
+  __shared__ float red[256];
+  const int k = threadIdx.x % K, hl = threadIdx.x / K, nhl = 256 / K;
+  float s = 0.f;
+  for (int o = blockIdx.x; o < H; o += gridDim.x) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < K * I; idx += 256) {       // dW[o][kk][i], i fastest
+      const int i = idx % I, kk = idx / I;
+      dwt[i * (K + 1) + kk] = dw[int64_t(o) * K * I + idx];
+    }
+    __syncthreads();
+    for (int i = hl; i < I; i += nhl) s = fmaf(dwt[i * (K + 1) + k], v[(int64_t(o) * I + i) * K + k], s);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (hl == 0) {
+    for (int j = 1; j < nhl; ++j) s += red[j * K + k];
+    partial[blockIdx.x * K + k] = s;
+  }
+}
+__global__ void posconv_partial_sum_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[b * K + k];
+  out[k] = s;
+}
+__global__ void __launch_bounds__(256) wnorm_bwd_apply_tiled_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                                    const float* __restrict__ g, const float* __restrict__ norm,
+                                                                    const float* __restrict__ S, float scale,
+                                                                    float* __restrict__ dv, float* __restrict__ dg, int H, int I,
+                                                                    int K) {
+  extern __shared__ float dwt[];                          // [I][K + 1]
+  const int o = blockIdx.x;
+  for (int idx = threadIdx.x; idx < K * I; idx += 256) {
+    const int i = idx % I, kk = idx / I;
+    dwt[i * (K + 1) + kk] = dw[int64_t(o) * K * I + idx];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < I * K; idx += 256) {       // dv[o][i][k], k fastest
+    const int k = idx % K, i = idx / K;
+    const float nk = norm[k];
+    const int64_t at = (int64_t(o) * I + i) * K + k;
+    dv[at] += scale * (g[k] / nk) * (dwt[i * (K + 1) + k] - v[at] * S[k] / (nk * nk));
+  }
+  if (o == 0 && int(threadIdx.x) < K) dg[threadIdx.x] += scale * S[threadIdx.x] / norm[threadIdx.x];
+}
+
 }  // namespace w2v2
 
 using namespace w2v2;
@@ -146,10 +202,19 @@ int w2v2_weight_norm_bwd(const float* dw_hki, const float* v, const float* g, fl
   float* norm = scratch_2k;
   float* S = scratch_2k + K;
   posconv_tap_norms(v, norm, H, I, K, stream);      // ||v[:,:,k]||
-  wnorm_bwd_reduce_kernel<<<K, 256, 0, stream>>>(dw_hki, v, S, H, I, K);
-  const int64_t n = int64_t(H) * I * K;
-  wnorm_bwd_apply_kernel<<<pgrid(n, 256, 8), 256, 0, stream>>>(dw_hki, v, g, norm, S, scale, dv, dg, H, I, K);
-  count_launches(3);
+  const size_t smem = size_t(I) * (K + 1) * sizeof(float);
+  if (K <= 256 && 256 % K == 0 && smem <= 48 * 1024) {
+    float* partial = posconv_partial_buffer();      // the norm kernels are done with it (same stream)
+    const int nb = H < WN_BLOCKS ? H : WN_BLOCKS;
+    wnorm_bwd_reduce_tiled_kernel<<<nb, 256, smem, stream>>>(dw_hki, v, partial, H, I, K);
+    posconv_partial_sum_kernel<<<(K + 127) / 128, 128, 0, stream>>>(partial, S, nb, K);
+    wnorm_bwd_apply_tiled_kernel<<<H, 256, smem, stream>>>(dw_hki, v, g, norm, S, scale, dv, dg, H, I, K);
+  } else {
+    wnorm_bwd_reduce_kernel<<<K, 256, 0, stream>>>(dw_hki, v, S, H, I, K);
+    const int64_t n = int64_t(H) * I * K;
+    wnorm_bwd_apply_kernel<<<pgrid(n, 256, 8), 256, 0, stream>>>(dw_hki, v, g, norm, S, scale, dv, dg, H, I, K);
+  }
+  count_launches(5);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
