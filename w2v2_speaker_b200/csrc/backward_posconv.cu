@@ -112,7 +112,7 @@ __global__ void wnorm_bwd_apply_kernel(const float* __restrict__ dw, const float
 // inner): one block per output channel o stages dW[o] transposed in shared memory (padded rows), so both global
 // streams are read / written along their contiguous axis.
 float* posconv_partial_buffer();
-constexpr int WN_BLOCKS = 128;
+constexpr int WN_BLOCKS = 296;     // <= PN_BLOCKS (shared partial buffer), 2 per SM
 
 __global__ void __launch_bounds__(256) wnorm_bwd_reduce_tiled_kernel(const float* __restrict__ dw, const float* __restrict__ v,
                                                                      float* __restrict__ partial, int H, int I, int K) {

@@ -546,7 +546,7 @@ __global__ void posconv_fold_kernel(const float* __restrict__ v, const float* __
 // every block sums the squares of its slice of (out, in) rows per tap (lane = tap); stage 2 adds the per-block
 // partials in a fixed order.  ~6 us instead of 32 for the 4.7 M weights (the strided kernel above reads one
 // 4-byte value per 32-byte sector).
-constexpr int PN_BLOCKS = 128;
+constexpr int PN_BLOCKS = 592;     // 4 per SM: enough loads in flight for a 19 MB streaming read
 __device__ float g_pn_partial[PN_BLOCKS * 256];
 
 __global__ void __launch_bounds__(256) posconv_norm_partial_kernel(const float* __restrict__ v, float* __restrict__ partial,

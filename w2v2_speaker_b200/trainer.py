@@ -81,8 +81,11 @@ class FlatAdamTrainer:
                                 os.environ.get("W2V2_OPT_STREAM", "1") != "0")        # =0: update in stream order (A/B)
         if self._overlap_update:
             self.model._pre_encoder_hook = self._join_update
+        import os
+        self._pending = None
+        self.ar_layers = max(1, int(os.environ.get("W2V2_AR_LAYERS", "4")))    # transformer layers per all-reduce
         if seg0 and self.world > 1:
-            self.model._grad_ready_hook = self._reduce_span      # spans of flat_g[:n0] == GradBook offsets
+            self.model._grad_ready_hook = self._layer_ready      # spans of flat_g[:n0] == GradBook offsets
 
     def _refresh_module_weights(self):
         if self._refreshable is None:          # the module tree is fixed: walk it once
@@ -95,6 +98,24 @@ class FlatAdamTrainer:
             for attr in ("_w_split", "_w_sig"):
                 if hasattr(m, attr):
                     setattr(m, attr, None)
+
+    def _layer_ready(self, lo: int, hi: int):
+        """Backward hook: layer spans arrive deepest first and are contiguous; merge `ar_layers` of them into one
+        all-reduce (fewer NCCL launches competing with the backward GEMMs for SMs)."""
+        if self._pending is None:
+            self._pending = [lo, hi, 1]
+        else:
+            self._pending[0] = min(self._pending[0], lo)
+            self._pending[1] = max(self._pending[1], hi)
+            self._pending[2] += 1
+        if self._pending[2] >= self.ar_layers:
+            self._flush_pending()
+
+    def _flush_pending(self):
+        if self._pending is not None:
+            lo, hi, _ = self._pending
+            self._pending = None
+            self._reduce_span(lo, hi)
 
     def _reduce_span(self, lo: int, hi: int):
         """Enqueue the sum-all-reduce of flat_g[lo:hi] on the communication stream, ordered after everything
@@ -115,6 +136,7 @@ class FlatAdamTrainer:
         the same order."""
         if self.world == 1:
             return
+        self._flush_pending()
         for lo, hi in remaining_spans(self._overlapped, self.flat_g.numel()):
             self._reduce_span(lo, hi)
         self._overlapped = []
