@@ -383,6 +383,10 @@ int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int* launches)
 int w2v2_conv0_gn_ex(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
                      void* workspace, void* out_f16, int C, int act, void* stream);
 int w2v2_conv0_workspace_offsets(int B, int N, int C, int64_t* scale_off, int64_t* shift_off, int64_t* im2col_off);
+/* out_act = gelu(A W^T + bias), out_pre = A W^T + bias (both f16 [M, N], row pitch ldo) from ONE GEMM: the FFN1 of
+ * the training forward keeps the pre-activation for the backward. */
+int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                            const float* bias, void* out_act16, void* out_pre16, int64_t ldo, void* stream);
 int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
                        int64_t a_batch_stride, int batch, int ntaps, int cin, const void* W, int64_t ldw, int N, void* out,
                        int out_dtype, int64_t ldo, int64_t out_batch_stride, void* stream);

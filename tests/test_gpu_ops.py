@@ -91,6 +91,24 @@ def test_gemm_f16_stream_k_repeatable(ops, M, N, K, use_bias):
         assert (out - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(9536, 3072, 768), (1000, 4096, 1024), (300, 256, 64)])
+def test_gemm_dual_output_gelu(ops, M, N, K):
+    """FFN1 of the training forward: pre-activation and GELU output from one GEMM, identical to the two-pass form."""
+    a = _rand((M, K), 51).half()
+    w = _rand((N, K), 52, 1.0 / math.sqrt(K)).half()
+    bias = _rand((N,), 53)
+    act, pre = ops.gemm_f16_dual_gelu(a, w, bias)
+    torch.cuda.synchronize()
+    ref_pre = a.float() @ w.float().t() + bias
+    assert rel(pre.float(), ref_pre) < 6e-4
+    assert rel(act.float(), F.gelu(ref_pre)) < 6e-4
+    z = ops.gemm_f16(a, w, bias, 0, torch.float16)
+    assert torch.equal(pre, z)                            # same accumulation, same rounding
+    g, _ = ops.gelu_fwd(z.contiguous(), torch.float16)
+    # the fused epilogue applies the GELU to the fp32 accumulator, the two-pass form to the fp16-rounded z
+    assert rel(act.float(), g.float()) < 6e-4
+
+
 def test_gemm_rejects_bad_k(ops):
     from w2v2_speaker_b200._lib import W2V2Error
     a = torch.zeros(8, 40, dtype=torch.float16, device="cuda")

@@ -42,6 +42,7 @@ struct alignas(64) GemmParams {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
   CUtensorMap tmOut;             // box {64 (f16) | 32 (f32) columns, 32 rows, 1}
+  CUtensorMap tmOut2;            // DUAL: second f16 output, the pre-activation (bias added, before the GELU)
   const float* bias;             // EPI 1: [N];  EPI 2: per-(batch, column) scale [batch, N]
   const float* shift;            // EPI 2: per-(batch, column) shift [batch, N]
   int ntaps, kblocks_per_tap;
@@ -97,22 +98,26 @@ struct WorkIter {
 // each CTA stages its 128 rows of A and BN/2 columns of B)
 // MINB = CTAs per SM the kernel is built for: 2 only for the epilogue-bound conv0 GEMM (K = 64: one k-block per
 // tile, so two pipeline stages are plenty and two CTAs -- 16 epilogue warps -- share an SM)
-template <int BN, int CL = 1, int MINB = 1>
+// DUAL: the epilogue stores the pre-activation next to the activated output (training keeps both): twice the
+// staging, one pipeline stage less
+template <int BN, int CL = 1, int MINB = 1, bool DUAL = false>
 struct GemmCfg {
   static constexpr int B_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = MINB == 2 ? 2 : ((BN == 256 && CL == 1) ? 4 : 6);
+  static constexpr int STAGES = MINB == 2 ? 2 : ((BN == 256 && CL == 1) ? (DUAL ? 3 : 4) : (DUAL ? 5 : 6));
+  static constexpr int WSTAGE = WSTAGE_BYTES * (DUAL ? 2 : 1);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias tile
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE_BYTES + BIAS_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE + BIAS_BYTES + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
   static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area too small");
 };
 
 // EPI: 0 = none, 1 = + bias[n], 2 = * scale[b, n] + shift[b, n]  (GroupNorm affine of conv layer 0)
-template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1>
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, bool DUAL = false>
 __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, CL, MINB>;
+  using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
+  static_assert(!DUAL || (!OUT_F32 && ACT == 1), "the dual-output epilogue is the fp16 pre-activation + GELU pair");
   constexpr int STAGES = Cfg::STAGES;
   // the 128B-swizzled tiles need a 1024-byte aligned base; the kernel has no static shared memory, so
   // the dynamic window starts at the CTA's (1024-aligned) shared base -- verified, not assumed
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   pdl_trigger();
   uint8_t* wstage = smem + STAGES * Cfg::STAGE_BYTES;
-  float* sbias = reinterpret_cast<float*>(wstage + EPI_WARPS * WSTAGE_BYTES);
+  float* sbias = reinterpret_cast<float*>(wstage + EPI_WARPS * Cfg::WSTAGE);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
     constexpr int HALF_COLS = BN / 2;
     constexpr int NCHUNK = HALF_COLS / 32;      // 32-column chunks per warp per tile (4 or 2)
     constexpr int CHUNKS_PER_STORE = OUT_F32 ? 1 : 2;      // 128 bytes of output per staged row
-    uint8_t* mystage = wstage + ew * WSTAGE_BYTES;
+    uint8_t* mystage = wstage + ew * Cfg::WSTAGE;
     uint8_t* crow = mystage + lane * 128;
     const int epi_tid = threadIdx.x - 64;       // 0..255
     int acc = 0;
@@ -364,15 +369,27 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
             v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
           }
         }
-        if constexpr (ACT == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
-        }
         const int sub = c % CHUNKS_PER_STORE;            // position inside the staged 128-byte row
         if (sub == 0) {
           // staging buffer reuse: the previous TMA store of this warp must have finished reading it
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
+        }
+        if constexpr (DUAL) {                            // the pre-activation goes to the second staging buffer
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int pc = (sub * 4 + q) ^ (lane & 7);
+            uint4 w;
+            w.x = pack_half2(v[8 * q], v[8 * q + 1]);
+            w.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+            w.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
+            w.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4*>(crow + WSTAGE_BYTES + pc * 16) = w;
+          }
+        }
+        if constexpr (ACT == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
         }
         if constexpr (OUT_F32) {
 #pragma unroll
@@ -399,6 +416,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
           if (lane == 0 && row0 < p.rows && scol < p.N) {   // skip boxes that lie entirely in the M / N tail
             if (SK_OK && sk_trail) tma_reduce_add_3d(&p.tmOut, mystage, scol, row0, b);
             else tma_store_3d(&p.tmOut, mystage, scol, row0, b);
+            if constexpr (DUAL) tma_store_3d(&p.tmOut2, mystage + WSTAGE_BYTES, scol, row0, b);
             tma_store_commit();
           }
         }
@@ -533,11 +551,11 @@ static bool pair_enabled() {
   return v == 1;
 }
 
-template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1>
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, bool DUAL = false>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL, MINB>;
+  using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI, CL, MINB>;
+  auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI, CL, MINB, DUAL>;
   if (!configured) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -694,6 +712,37 @@ extern "C" int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int
   if (launches) *launches = g_prof_n;
   g_prof_n = 0;
   return 0;
+}
+
+// out_act = gelu(A W^T + bias) and out_pre = A W^T + bias, both f16 [M, N]: the FFN1 GEMM of the training forward,
+// which has to keep the pre-activation for the backward (saves the separate GELU pass over [M, FF]).
+extern "C" int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                       const float* bias, void* out_act16, void* out_pre16, int64_t ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  W2V2_REQUIRE(K % BK == 0 && N > 128 && bias != nullptr && M > 0, "w2v2_gemm_f16_dual_gelu: needs K %% 64 == 0, N > 128, a bias");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int CL = pair_enabled() ? 2 : 1;
+  int rc = make_tmap_3d(&p.tmA[0], A, 2, K, M, 1, uint64_t(lda) * 2, uint64_t(M) * lda * 2, BK, BM, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmB, W, 2, K, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, 256 / CL, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmOut, out_act16, 2, N, M, 1, uint64_t(ldo) * 2, uint64_t(M) * ldo * 2, 64, 32, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmOut2, out_pre16, 2, N, M, 1, uint64_t(ldo) * 2, uint64_t(M) * ldo * 2, 64, 32, 1, 128);
+  if (rc) return rc;
+  p.bias = bias;
+  p.ntaps = 1;
+  p.kblocks_per_tap = K / BK;
+  p.m_tiles = int((M + BM * CL - 1) / (BM * CL));
+  p.n_tiles = (N + 255) / 256;
+  p.batch = 1;
+  p.N = N;
+  p.rows = M;
+  const int slot = gemm_prof_begin(2.0 * double(M) * K * N, stream);
+  rc = CL == 2 ? launch_gemm<256, false, 1, 1, 2, 1, true>(p, stream) : launch_gemm<256, false, 1, 1, 1, 1, true>(p, stream);
+  gemm_prof_end(slot, stream);
+  return rc;
 }
 
 extern "C" int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,

@@ -32,8 +32,8 @@ extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream
                              seed + 200 + l, stream));
   // feed-forward block
   if (a->z16 != nullptr) {      // training: keep the pre-activation, GELU as its own pass
-    W2V2_TRY(w2v2_gemm_f16(a->h1_16, M, H, 0, 1, 1, 0, H, a->w1, H, FF, a->b1, 0, a->z16, 0, FF, 0, stream));
-    W2V2_TRY(w2v2_gelu_fwd(a->z16, 0, a->g16, 0, nullptr, M * FF, stream));
+    // one GEMM, two outputs: z (kept for the backward) and g = gelu(z)
+    W2V2_TRY(w2v2_gemm_f16_dual_gelu(a->h1_16, M, H, H, a->w1, H, FF, a->b1, a->g16, a->z16, FF, stream));
     if (a->p_act > 0.f)
       W2V2_TRY(w2v2_dropout(a->g16, 0, nullptr, FF, a->g16, nullptr, M * FF, a->p_act, seed + 400 + l, stream));
   } else {                      // inference: GELU in the GEMM epilogue

@@ -39,6 +39,18 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
     return out
 
 
+def gemm_f16_dual_gelu(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
+    """-> (gelu(a @ w^T + bias), a @ w^T + bias), both f16 [M, N], from one GEMM."""
+    _chk(a, F16, "a"); _chk(w, F16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    act = torch.empty(M, N, dtype=F16, device=a.device)
+    pre = torch.empty(M, N, dtype=F16, device=a.device)
+    call("w2v2_gemm_f16_dual_gelu", ptr(a), M, a.stride(0), K, ptr(w), w.stride(0), N, ptr(bias), ptr(act), ptr(pre), N,
+         stream_ptr())
+    return act, pre
+
+
 def conv1d_cl_f16(x: torch.Tensor, w_tap: torch.Tensor, ksize: int, stride: int, act: int = 1,
                   out_dtype=F16) -> torch.Tensor:
     """Strided Conv1d (no bias) + activation over a channels-last fp16 activation x[B,L,C] with the
