@@ -396,6 +396,12 @@ int w2v2_gemm_wgrad_f16_batched(const void* dY, int64_t ldy, int64_t dy_batch_st
 int w2v2_groupnorm_bwd(const void* dy16, const void* y16, const float* gamma, const float* beta, const float* scale,
                        void* dc16, float* dgamma, float* dbeta, float grad_scale, int B, int L, int C, void* stream);
 
+/* ---- evaluation: trial scoring (R:src/evaluation/speaker/cosine_distance.py:107-132, 249-262) -----------
+ * scores[p] = cosine(f(emb[idx_a[p]]), f(emb[idx_b[p]])), f(x) = (x - mean) / (std + 1e-12) when mean / std are
+ * given (the evaluator's centring), identity otherwise; torch.nn.CosineSimilarity semantics (eps 1e-8). */
+int w2v2_cosine_pairs(const float* emb, const float* mean, const float* stdv, const int32_t* idx_a, const int32_t* idx_b,
+                      float* scores, int64_t P, int E, void* stream);
+
 /* ---- utility ---------------------------------------------------------------------------------- */
 /* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */
 int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* stream);

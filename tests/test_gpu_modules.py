@@ -119,3 +119,44 @@ def test_long_utterance_evaluates_and_training_on_it_fails_loudly(base_params):
     w.model.feature_extractor.requires_grad_(False)
     with pytest.raises(W2V2Error):
         w(torch.randn(1, 16000 * 6, device="cuda")).sum().backward()
+
+
+
+@pytest.mark.parametrize("center", [False, True])
+def test_cosine_evaluator_matches_reference_formulation(center):
+    """CosineDistanceEvaluator: GPU trial scoring against torch's CosineSimilarity with the evaluator's centring, EER /
+    min-DCF against the reference's sklearn / scipy formulation (oracle/eval_oracle.py)."""
+    _need_cuda()
+    from oracle import eval_oracle as EO
+    from w2v2_speaker_b200.evaluation.speaker import CosineDistanceEvaluator, EmbeddingSample, EvaluationPair
+    g = torch.Generator().manual_seed(9)
+    n_spk, per, E = 40, 6, 1536
+    centers = torch.randn(n_spk, E, generator=g)
+    emb = (centers[:, None, :] + 5.0 * torch.randn(n_spk, per, E, generator=g) + 0.5).reshape(-1, E)
+    ids = [f"spk{s}/utt{u}" for s in range(n_spk) for u in range(per)]
+    samples = [EmbeddingSample(i, e) for i, e in zip(ids, emb)]
+    rng = np.random.default_rng(4)
+    pairs = []
+    for _ in range(3000):
+        a, b = rng.integers(0, len(ids), 2)
+        if a != b:
+            pairs.append(EvaluationPair(ids[a].split("/")[0] == ids[b].split("/")[0], ids[a], ids[b]))
+    ev = CosineDistanceEvaluator(center_before_scoring=center, length_norm_before_scoring=True, max_num_training_samples=0)
+    ev.fit_parameters(list(emb[::3]), [])
+    scores = ev.score_pairs(pairs, samples)
+    idx = {k: i for i, k in enumerate(ids)}
+    left = torch.stack([emb[idx[p.sample1_id]] for p in pairs]); right = torch.stack([emb[idx[p.sample2_id]] for p in pairs])
+    mean = std = None
+    if center:
+        std, mean = torch.std_mean(torch.stack(list(emb[::3])), dim=0)
+    ref = EO.cosine_scores(left, right, mean, std).numpy()
+    assert np.abs(scores - ref).max() < 2e-6
+    res = ev.evaluate(pairs, samples)
+    gt = [1 if p.same_speaker else 0 for p in pairs]
+    pred = np.clip((ref.astype(np.float64) + 1) / 2, 0, 1).tolist()
+    re, _ = EO.eer(gt, pred)
+    rm, _ = EO.mdc(gt, pred)
+    assert abs(res["eer"] - re) < 1e-4 and abs(res["mdc"] - rm) < 1e-3
+    assert 0.0 < res["eer"] < 0.5
+    missing = ev.evaluate([EvaluationPair(True, "nope", ids[0])], samples)
+    assert missing == {"eer": -1, "eer_threshold": -1, "mdc": -1, "mdc_threshold": -1}

@@ -114,3 +114,28 @@ def test_embedding_masker_is_identity_on_the_path():
     assert torch.equal(mk(x), x)
     with pytest.raises(ValueError):
         EmbeddingMasker(1.5, 1, 0, 1)
+
+
+@pytest.mark.parametrize("seed,n,ties", [(0, 2000, False), (1, 500, True), (2, 37, False), (3, 10000, True)])
+def test_eer_and_min_dcf_match_the_reference_formulation(seed, n, ties):
+    """eval_metrics (numpy) against the reference's sklearn / scipy / list-loop formulation (oracle/eval_oracle.py)."""
+    import numpy as np
+    from oracle import eval_oracle as EO
+    from w2v2_speaker_b200.eval_metrics import calculate_eer, calculate_mdc
+    rng = np.random.default_rng(seed)
+    gt = rng.integers(0, 2, n)
+    sc = np.clip(0.5 + 0.18 * rng.standard_normal(n) + 0.15 * (gt - 0.5) * 2, 0, 1)
+    if ties:
+        sc = np.round(sc, 2)
+    e, t = calculate_eer(gt.tolist(), sc.tolist())
+    re, rt = EO.eer(gt.tolist(), sc.tolist())
+    assert abs(e - re) < 1e-9
+    if np.isfinite(rt):
+        assert abs(t - rt) < 1e-6
+    m, mt = calculate_mdc(gt.tolist(), sc.tolist())
+    rm, rmt = EO.mdc(gt.tolist(), sc.tolist())
+    assert abs(m - rm) < 1e-9 and abs(mt - rmt) < 1e-12
+    with pytest.raises(ValueError):
+        calculate_eer([0, 2, 1], [0.1, 0.2, 0.3])
+    with pytest.raises(ValueError):
+        calculate_mdc([0, 1], [0.1])

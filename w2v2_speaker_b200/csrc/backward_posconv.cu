@@ -136,12 +136,14 @@ __global__ void __launch_bounds__(256) wnorm_bwd_reduce_tiled_kernel(const float
     partial[blockIdx.x * K + k] = s;
   }
 }
-__global__ void posconv_partial_sum_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) posconv_partial_sum_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                                  int nblocks, int K) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per tap
   if (k >= K) return;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[b * K + k];
-  out[k] = s;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) s += partial[b * K + k];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[k] = s;
 }
 __global__ void __launch_bounds__(256) wnorm_bwd_apply_tiled_kernel(const float* __restrict__ dw, const float* __restrict__ v,
                                                                     const float* __restrict__ g, const float* __restrict__ norm,
@@ -207,7 +209,7 @@ int w2v2_weight_norm_bwd(const float* dw_hki, const float* v, const float* g, fl
     float* partial = posconv_partial_buffer();      // the norm kernels are done with it (same stream)
     const int nb = H < WN_BLOCKS ? H : WN_BLOCKS;
     wnorm_bwd_reduce_tiled_kernel<<<nb, 256, smem, stream>>>(dw_hki, v, partial, H, I, K);
-    posconv_partial_sum_kernel<<<(K + 127) / 128, 128, 0, stream>>>(partial, S, nb, K);
+    posconv_partial_sum_kernel<<<(K + 7) / 8, 256, 0, stream>>>(partial, S, nb, K);
     wnorm_bwd_apply_tiled_kernel<<<H, 256, smem, stream>>>(dw_hki, v, g, norm, S, scale, dv, dg, H, I, K);
   } else {
     wnorm_bwd_reduce_kernel<<<K, 256, 0, stream>>>(dw_hki, v, S, H, I, K);

@@ -567,13 +567,15 @@ __global__ void __launch_bounds__(256) posconv_norm_partial_kernel(const float* 
     partial[blockIdx.x * K + k] = s;
   }
 }
-__global__ void posconv_partial_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks, int K,
-                                              int take_sqrt) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per tap: lanes stride over the per-block partials, then a shuffle tree (a fixed order: deterministic)
+__global__ void __launch_bounds__(256) posconv_partial_finish_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                                     int nblocks, int K, int take_sqrt) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[b * K + k];
-  out[k] = take_sqrt ? sqrtf(s) : s;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) s += partial[b * K + k];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) out[k] = take_sqrt ? sqrtf(s) : s;
 }
 
 float* posconv_partial_buffer() {
@@ -589,7 +591,7 @@ void posconv_tap_norms(const float* v, float* norm, int H, int I, int K, cudaStr
   }
   float* partial = posconv_partial_buffer();
   posconv_norm_partial_kernel<<<PN_BLOCKS, 256, 0, stream>>>(v, partial, int64_t(H) * I, K);
-  posconv_partial_finish_kernel<<<(K + 127) / 128, 128, 0, stream>>>(partial, norm, PN_BLOCKS, K, 1);
+  posconv_partial_finish_kernel<<<(K + 7) / 8, 256, 0, stream>>>(partial, norm, PN_BLOCKS, K, 1);
 }
 
 // Fold with coalesced traffic: one block per (group, 8-channel plane c, 16-tap chunk).  It gathers

@@ -547,3 +547,18 @@ def groupnorm_bwd(dy16, y16, gamma, beta, scale, dgamma, dbeta, grad_scale: floa
     call("w2v2_groupnorm_bwd", ptr(dy16), ptr(y16), ptr(gamma), ptr(beta), ptr(scale), ptr(dc), ptr(dgamma), ptr(dbeta),
          float(grad_scale), B, L, C, stream_ptr())
     return dc
+
+
+# ---- evaluation ----------------------------------------------------------------------------------
+
+
+def cosine_pairs(emb: torch.Tensor, idx_a: torch.Tensor, idx_b: torch.Tensor, mean: Optional[torch.Tensor] = None,
+                 std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores[p] = cosine similarity of (optionally centred) emb[idx_a[p]] and emb[idx_b[p]]; emb f32 [N, E], idx int32 [P]."""
+    _chk(emb, F32, "emb")
+    assert idx_a.dtype == torch.int32 and idx_b.dtype == torch.int32 and idx_a.shape == idx_b.shape
+    P = idx_a.numel()
+    scores = torch.empty(P, dtype=F32, device=emb.device)
+    call("w2v2_cosine_pairs", ptr(emb.contiguous()), ptr(mean), ptr(std), ptr(idx_a.contiguous()), ptr(idx_b.contiguous()),
+         ptr(scores), P, emb.shape[1], stream_ptr())
+    return scores
