@@ -139,3 +139,39 @@ def test_eer_and_min_dcf_match_the_reference_formulation(seed, n, ties):
         calculate_eer([0, 2, 1], [0.1, 0.2, 0.3])
     with pytest.raises(ValueError):
         calculate_mdc([0, 1], [0.1])
+
+
+def test_reference_era_checkpoints_load(wrapper):
+    """transformers 4.x key names (weight_g / weight_v), HF task-model checkpoints (wav2vec2. prefix + heads)
+    and Lightning checkpoints of the reference's Wav2vec2FCModule load into the modules of this package."""
+    import torch
+    from w2v2_speaker_b200 import checkpoint as C
+    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    sd = {k: torch.randn_like(v) for k, v in wrapper.model.state_dict().items()}
+    g5, v5 = ("encoder.pos_conv_embed.conv.parametrizations.weight.original0",
+              "encoder.pos_conv_embed.conv.parametrizations.weight.original1")
+    old = dict(sd)
+    old["encoder.pos_conv_embed.conv.weight_g"] = old.pop(g5)
+    old["encoder.pos_conv_embed.conv.weight_v"] = old.pop(v5)
+    # 1. plain load_state_dict with 4.x names (pre-hook)
+    res = wrapper.model.load_state_dict(dict(old))
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(wrapper.model.state_dict()[g5], sd[g5]) and torch.equal(wrapper.model.state_dict()[v5], sd[v5])
+    # 2. a Wav2Vec2ForCTC-style checkpoint
+    ctc = {"wav2vec2." + k: v for k, v in old.items()}
+    ctc["lm_head.weight"] = torch.zeros(32, 768)
+    conv = C.convert_hf_state_dict(ctc)
+    assert set(conv) == set(sd)
+    # 3. a Lightning checkpoint of the reference's speaker module
+    m = Wav2vec2FCModule(Wav2vec2FCModuleConfig(stat_pooling_type="mean", test_stat_pooling_type="mean"), 11, CrossEntropyLoss)
+    ours = m.state_dict()
+    ckpt = {"state_dict": {}}
+    for k, v in ours.items():
+        k4 = k.replace("parametrizations.weight.original0", "weight_g").replace("parametrizations.weight.original1", "weight_v")
+        ckpt["state_dict"][k4] = torch.randn_like(v) if v.is_floating_point() else v.clone()
+    missing, unexpected = C.load_reference_checkpoint(m, ckpt)
+    assert not list(missing) and not list(unexpected)
+    k = "wav2vec.model.encoder.pos_conv_embed.conv.parametrizations.weight.original1"
+    assert torch.equal(m.state_dict()[k], ckpt["state_dict"][k.replace("parametrizations.weight.original1", "weight_v")])
+    assert torch.equal(m.state_dict()["fc_list.0.0.weight"], ckpt["state_dict"]["fc_list.0.0.weight"])

@@ -121,6 +121,8 @@ class Wav2Vec2ModelB200(nn.Module):
             _set_param(self, name, value)
         self._prepared = None
         self._prepared_sig = None
+        from ..checkpoint import install_key_translation
+        install_key_translation(self)          # transformers 4.x checkpoints (weight_g / weight_v) load as they are
 
     # ---- weights in kernel form, rebuilt when any parameter changed -------------------------
     def _items(self):
