@@ -69,6 +69,12 @@ int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float
                       const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, float drop_p,
                       uint64_t drop_seed, void* stream);
 
+/* Same, additionally writing the per-row 1 / sqrt(var + eps) (f32 [rows], NULL = skip): with it the backward can work
+ * from the LayerNorm OUTPUT (w2v2_layernorm_bwd_from_output) instead of re-reading the two inputs. */
+int w2v2_layernorm_ex2(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
+                       const float* beta, float eps, float* y32, void* y16, float* rstd_out, int64_t rows, int H,
+                       float drop_p, uint64_t drop_seed, void* stream);
+
 /* ---- positional conv embedding --------------------------------------------------------------- */
 /* Number of taps U that share one tensor-core A tile for sequences of T frames (0 = T too long
  * for the single-slab kernel).  The folded weight layout depends on it. */
@@ -155,6 +161,14 @@ int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, 
                           const float* residual, const float* gamma, float eps, float* dx32, void* dx16, float* dgamma,
                           float* dbeta, float* dbias, int64_t rows, int H, float drop_p, uint64_t drop_seed,
                           void* stream);
+/* LayerNorm backward from the OUTPUT y = LN(drop(xa + bias) + residual): xhat = (y - beta) / gamma and the row's
+ * rstd (saved by w2v2_layernorm_ex2) replace the recomputation from xa / residual -- one [rows, H] fp32 stream
+ * less and no statistics.  Outputs and the dropout of the branch gradient as in w2v2_layernorm_bwd_ex.
+ * H in {512, 768, 1024}. */
+int w2v2_layernorm_bwd_from_output(const float* dy_a, const float* dy_b, const float* y32, const float* rstd,
+                                   const float* gamma, const float* beta, float* dx32, void* dx16, float* dgamma,
+                                   float* dbeta, float* dbias, int64_t rows, int H, float drop_p, uint64_t drop_seed,
+                                   void* stream);
 /* dz = dg * gelu'(z), all f16, n % 8 == 0. */
 int w2v2_gelu_bwd(const void* dg16, const void* z16, void* dz16, int64_t n, void* stream);
 /* Same over [rows, cols], plus dbias[c] += sum_r dz[r, c] (gradient of the bias that was added to form z). */
@@ -304,6 +318,8 @@ typedef struct {
   float* f2_32;
   float* h2_32;        /* layer output */
   void* h2_16;
+  float* rstd1;        /* f32 [B*T] 1/sigma of LayerNorm 1 / 2 (training; NULL in inference) */
+  float* rstd2;
 } w2v2_layer_fwd_args;
 int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* args, void* stream);
 
@@ -359,6 +375,11 @@ typedef struct {
   void* dqkv16;       /* scratch f16 [B*T, 3H] */
   float* dx1_32;      /* out: residual-path term of the input gradient */
   float* dh_in32;     /* out: term through the q/k/v projections */
+  const float* h2_32; /* the layer's output (LayerNorm 2 output) and the saved rstd of both LayerNorms: */
+  const float* rstd1; /* the LayerNorm backward works from the outputs (h1_32, h2_32) */
+  const float* rstd2;
+  const float* ln1_b;
+  const float* ln2_b;
 } w2v2_layer_bwd_args;
 int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* args, void* stream);
 
@@ -401,6 +422,11 @@ int w2v2_groupnorm_bwd(const void* dy16, const void* y16, const float* gamma, co
  * given (the evaluator's centring), identity otherwise; torch.nn.CosineSimilarity semantics (eps 1e-8). */
 int w2v2_cosine_pairs(const float* emb, const float* mean, const float* stdv, const int32_t* idx_a, const int32_t* idx_b,
                       float* scores, int64_t P, int E, void* stream);
+
+/* ---- in front of the path: waveform standardisation (R:src/data/preprocess/input_normalisation.py:53-67) ----
+ * out[b, :] = (x[b, :] - mean_b) / (std_b + 1e-5), std unbiased; x = in (float32, in_dtype 1) or in / 32768
+ * (int16 PCM, in_dtype 0).  mean / std (f32 [B]) may be NULL. */
+int w2v2_normalize_wav(const void* in, int in_dtype, float* out, float* mean, float* stdv, int B, int N, void* stream);
 
 /* ---- utility ---------------------------------------------------------------------------------- */
 /* f32 -> f16 (RNE) with optional scale: y = half(x * scale). */

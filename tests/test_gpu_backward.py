@@ -162,6 +162,30 @@ def test_attention_bwd_scaled_dq_and_bias_gradients(ops, B, T, H, heads):
     assert dbias[H:2 * H].double().norm() < 1e-2 * ref_b[2 * H:].norm()
 
 
+@pytest.mark.parametrize("rows,H,p", [(9536, 768, 0.1), (1000, 1024, 0.0), (333, 512, 0.25)])
+def test_layernorm_bwd_from_output_equals_bwd_from_inputs(ops, rows, H, p):
+    """The training layers run the LayerNorm backward from the LayerNorm OUTPUT + saved rstd (one fp32 stream less):
+    it must agree with the backward that recomputes the statistics from the inputs."""
+    x = _rand((rows, H), 60); res = _rand((rows, H), 61); bias = _rand((H,), 62)
+    gamma = 1 + 0.2 * _rand((H,), 63); beta = 0.3 * _rand((H,), 64)
+    dy_a = _rand((rows, H), 65); dy_b = _rand((rows, H), 66)
+    seed = 987654321
+    y32, y16, rstd = ops.layernorm_with_rstd(x, gamma, beta, 1e-5, bias=bias, residual=res, drop_p=p, drop_seed=seed)
+    r32, r16 = ops.layernorm(x, gamma, beta, 1e-5, bias=bias, residual=res, drop_p=p, drop_seed=seed)
+    assert torch.equal(y32, r32) and torch.equal(y16, r16)
+    g1, b1, d1 = (torch.zeros(H, device="cuda") for _ in range(3))
+    g2, b2, d2 = (torch.zeros(H, device="cuda") for _ in range(3))
+    a32, a16 = ops.layernorm_bwd(dy_a, x, gamma, 1e-5, dy_b=dy_b, bias=bias, residual=res, dgamma=g1, dbeta=b1, dbias=d1,
+                                 drop_p=p, drop_seed=seed)
+    o32, o16 = ops.layernorm_bwd_from_output(dy_a, y32, rstd, gamma, beta, dy_b=dy_b, dgamma=g2, dbeta=b2, dbias=d2,
+                                             drop_p=p, drop_seed=seed)
+    torch.cuda.synchronize()
+    assert rel(o32, a32) < 2e-5
+    assert rel(o16.float(), a16.float()) < 1e-3
+    assert torch.equal(o16 != 0, a16 != 0) or ((o16 != 0) ^ (a16 != 0)).float().mean().item() < 1e-3
+    assert rel(g2, g1) < 2e-5 and rel(b2, b1) < 1e-6 and rel(d2, d1) < 2e-5
+
+
 def test_adam_matches_torch(ops):
     n = 100003
     p0 = _rand((n,), 22)

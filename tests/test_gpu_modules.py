@@ -160,3 +160,25 @@ def test_cosine_evaluator_matches_reference_formulation(center):
     assert 0.0 < res["eer"] < 0.5
     missing = ev.evaluate([EvaluationPair(True, "nope", ids[0])], samples)
     assert missing == {"eer": -1, "eer_threshold": -1, "mdc": -1, "mdc_threshold": -1}
+
+
+
+def test_input_normaliser_on_device():
+    """InputNormalizer2D.normalize(channel_wise=False) per utterance on the GPU, from float32 and from
+    16-bit PCM, against the reference's tensor expression."""
+    _need_cuda()
+    from w2v2_speaker_b200.data.preprocess import InputNormalizer2D
+    g = torch.Generator().manual_seed(12)
+    x = (torch.randn(5, 48000, generator=g) * 0.05 + 0.01).clamp(-1, 1)
+    std, mean = torch.std_mean(x, dim=1, keepdim=True)
+    ref = (x - mean) / (std + 1e-5)
+    got = InputNormalizer2D.normalize_batch(x.cuda())
+    assert rel_rows(got, ref) < 1e-5
+    pcm = (x * 32768).round().clamp(-32768, 32767).to(torch.int16)
+    xq = pcm.float() / 32768
+    std, mean = torch.std_mean(xq, dim=1, keepdim=True)
+    got16 = InputNormalizer2D.normalize_batch(pcm.cuda())
+    assert rel_rows(got16, (xq - mean) / (std + 1e-5)) < 1e-5
+    one, m1, s1 = InputNormalizer2D.normalize(x[:1].cuda(), channel_wise=False)
+    r1, rm, rs = InputNormalizer2D.normalize(x[:1], channel_wise=False)          # CPU tensors: the reference expression
+    assert rel_rows(one, r1) < 1e-5 and abs(m1.item() - rm.item()) < 1e-7 and abs(s1.item() - rs.item()) < 1e-6

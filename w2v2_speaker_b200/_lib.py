@@ -17,6 +17,11 @@ LIB_PATH = os.path.join(_HERE, "libw2v2_b200.so")
 # name -> (restype, argtypes); must list every symbol declared in include/w2v2_b200.h
 SIGNATURES = {
     "w2v2_last_error": (c_char_p, []),
+    "w2v2_layernorm_ex2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_int64, c_int, c_float, c_uint64, c_void_p]),
+    "w2v2_layernorm_bwd_from_output": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_uint64, c_void_p]),
+    "w2v2_normalize_wav": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "w2v2_cosine_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "w2v2_gemm_f16_dual_gelu": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p]),

@@ -41,8 +41,13 @@ __global__ void cast_f16_transpose_kernel(const float* __restrict__ w, __half* _
 // EXACT: H == 128 * MAXV, the per-slot bounds checks (and the branches that would serialise the loads) vanish.
 // The per-warp dgamma / dbeta partial sums live in shared memory (registers are what limits the number of
 // rows in flight per SM), one private strip per warp, reduced over the block's warps at the end.
+// FROM_Y: the normalised activation is recovered from the LayerNorm OUTPUT, xhat = (y - beta) / gamma, with the
+// row's rstd saved by the forward (w2v2_layernorm_ex2): one [rows, H] fp32 stream (y) instead of two (xa and the
+// residual) and no mean / variance reductions.  `xa_` then carries y, `bias` carries beta, `residual` carries the
+// saved rstd [rows].
 constexpr int LNB_WARPS = 4;
-template <bool XA_F32, int MAXV, bool EXACT>
+__device__ __forceinline__ float ln_safe_inv(float g) { return fabsf(g) > 1e-30f ? 1.0f / g : 0.f; }
+template <bool XA_F32, int MAXV, bool EXACT, bool FROM_Y = false>
 __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_bwd_kernel(const float* __restrict__ dy_a, const float* __restrict__ dy_b,
                                                             const void* __restrict__ xa_, const float* __restrict__ bias,
                                                             const float* __restrict__ residual,
@@ -92,30 +97,42 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
           g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
         }
         d[i] = g;
-        if (bias != nullptr) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-        }
-        if (thr != 0) dropout4(a, dkeys, row * H + c, thr, inv_keep);
-        if (residual != nullptr) {
-          const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
-          a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        if constexpr (FROM_Y) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));          // beta
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+          a.x = (a.x - bb.x) * ln_safe_inv(gm.x); a.y = (a.y - bb.y) * ln_safe_inv(gm.y);
+          a.z = (a.z - bb.z) * ln_safe_inv(gm.z); a.w = (a.w - bb.w) * ln_safe_inv(gm.w);
+        } else {
+          if (bias != nullptr) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+            a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+          }
+          if (thr != 0) dropout4(a, dkeys, row * H + c, thr, inv_keep);
+          if (residual != nullptr) {
+            const float4 r = *reinterpret_cast<const float4*>(residual + row * H + c);
+            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+          }
         }
         x[i] = a;
         sum += (a.x + a.y) + (a.z + a.w);
       }
     }
-    const float mean = warp_sum(sum) / float(H);
-    float sq = 0.f;
+    float rstd;
+    if constexpr (FROM_Y) {
+      rstd = __ldg(residual + row);                   // saved by the forward
+    } else {
+      const float mean = warp_sum(sum) / float(H);
+      float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (EXACT || c < H) {
-        x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
-        sq += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (EXACT || c < H) {
+          x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+          sq += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+        }
       }
+      rstd = rsqrtf(warp_sum(sq) / float(H) + eps);
     }
-    const float rstd = rsqrtf(warp_sum(sq) / float(H) + eps);
     // xhat = x * rstd ; g = dy * gamma ; dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -123,7 +140,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
       const int c = (i * 32 + lane) * 4;
       if (EXACT || c < H) {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        x[i].x *= rstd; x[i].y *= rstd; x[i].z *= rstd; x[i].w *= rstd;
+        if constexpr (!FROM_Y) { x[i].x *= rstd; x[i].y *= rstd; x[i].z *= rstd; x[i].w *= rstd; }
         float4 ag = sg[i * 32 + lane], ab = sb[i * 32 + lane];
         ag.x += d[i].x * x[i].x; ag.y += d[i].y * x[i].y; ag.z += d[i].z * x[i].z; ag.w += d[i].w * x[i].w;
         ab.x += d[i].x; ab.y += d[i].y; ab.z += d[i].z; ab.w += d[i].w;
@@ -412,6 +429,29 @@ int w2v2_layernorm_bwd(const float* dy_a, const float* dy_b, const void* xa, int
                        float* dbeta, int64_t rows, int H, void* stream) {
   return w2v2_layernorm_bwd_ex(dy_a, dy_b, xa, xa_dtype, bias, residual, gamma, eps, dx32, dx16, dgamma, dbeta, nullptr,
                                rows, H, 0.f, 0, stream);
+}
+
+int w2v2_layernorm_bwd_from_output(const float* dy_a, const float* dy_b, const float* y32, const float* rstd,
+                                   const float* gamma, const float* beta, float* dx32, void* dx16, float* dgamma,
+                                   float* dbeta, float* dbias, int64_t rows, int H, float drop_p, uint64_t drop_seed,
+                                   void* stream) {
+  W2V2_REQUIRE(H == 512 || H == 768 || H == 1024, "w2v2_layernorm_bwd_from_output: H=%d not in {512, 768, 1024}", H);
+  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_layernorm_bwd_from_output: drop_p=%f out of [0,1)", drop_p);
+  W2V2_REQUIRE(y32 != nullptr && rstd != nullptr && beta != nullptr, "w2v2_layernorm_bwd_from_output: y, rstd, beta are required");
+  if (rows == 0) return 0;
+  const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
+  const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
+  const int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS, slots = int64_t(device_sm_count()) * (H <= 768 ? 4 : 3);
+  const int64_t per_warp = (want + slots - 1) / slots;
+  const int grid = int((want + per_warp - 1) / per_warp);
+  cudaStream_t st = (cudaStream_t)stream;
+#define W2V2_LNY(NV) \
+  launch_k(layernorm_bwd_kernel<true, NV, true, true>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, 1, dy_a, dy_b, (const void*)y32, beta, rstd, gamma, 0.f, dx32, (__half*)dx16, dgamma, dbeta, dbias, rows, H, thr, inv_keep, drop_seed)
+  if (H == 512) W2V2_LNY(4); else if (H == 768) W2V2_LNY(6); else W2V2_LNY(8);
+#undef W2V2_LNY
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int w2v2_layernorm_bwd_ex(const float* dy_a, const float* dy_b, const void* xa, int xa_dtype, const float* bias,

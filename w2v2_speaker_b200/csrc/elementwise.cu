@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
                                                         const float* __restrict__ residual,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float* __restrict__ y32, __half* __restrict__ y16,
-                                                        int64_t rows, int H, uint32_t thr, float inv_keep, uint64_t seed) {
+                                                        int64_t rows, int H, uint32_t thr, float inv_keep, uint64_t seed,
+                                                        float* __restrict__ rstd_out) {
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / float(H) + eps);
+  if (rstd_out != nullptr && lane == 0) rstd_out[row] = rstd;       // kept for w2v2_layernorm_bwd_from_output
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 32 + lane) * 4;
@@ -742,6 +744,12 @@ int w2v2_layernorm(const void* x, int x_dtype, const float* bias, const float* r
 int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
                       const float* beta, float eps, float* y32, void* y16, int64_t rows, int H, float drop_p,
                       uint64_t drop_seed, void* stream) {
+  return w2v2_layernorm_ex2(x, x_dtype, bias, residual, gamma, beta, eps, y32, y16, nullptr, rows, H, drop_p, drop_seed, stream);
+}
+
+int w2v2_layernorm_ex2(const void* x, int x_dtype, const float* bias, const float* residual, const float* gamma,
+                       const float* beta, float eps, float* y32, void* y16, float* rstd_out, int64_t rows, int H,
+                       float drop_p, uint64_t drop_seed, void* stream) {
   W2V2_REQUIRE(H % 4 == 0 && H <= 1024, "w2v2_layernorm: H=%d must be a multiple of 4 and <= 1024", H);
   W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_layernorm: drop_p=%f out of [0,1)", drop_p);
   if (rows == 0) return 0;
@@ -749,7 +757,7 @@ int w2v2_layernorm_ex(const void* x, int x_dtype, const float* bias, const float
   const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
   const int grid = int((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define W2V2_LN(F32, NV, EX) launch_k(layernorm_kernel<F32, NV, EX>, dim3(grid), dim3(256), 0, st, 1, x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed)
+#define W2V2_LN(F32, NV, EX) launch_k(layernorm_kernel<F32, NV, EX>, dim3(grid), dim3(256), 0, st, 1, x, bias, residual, gamma, beta, eps, y32, (__half*)y16, rows, H, thr, inv_keep, drop_seed, rstd_out)
   if (x_dtype == 1) {
     if (H == 512) W2V2_LN(true, 4, true); else if (H == 768) W2V2_LN(true, 6, true);
     else if (H == 1024) W2V2_LN(true, 8, true); else W2V2_LN(true, 8, false);

@@ -28,8 +28,8 @@ extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream
   W2V2_TRY(w2v2_gemm_f16(a->h_in16, M, H, 0, 1, 1, 0, H, a->wqkv, H, 3 * H, a->bqkv, 0, a->qkv16, 0, 3 * H, 0, stream));
   W2V2_TRY(w2v2_attention_ex(a->qkv16, a->att16, a->lse, a->B, a->T, H, a->heads, a->p_attn, seed + 100 + l, stream));
   W2V2_TRY(w2v2_gemm_f16(a->att16, M, H, 0, 1, 1, 0, H, a->wo, H, H, nullptr, 0, a->o32, 1, H, 0, stream));
-  W2V2_TRY(w2v2_layernorm_ex(a->o32, 1, a->bo, a->h_in32, a->ln1_g, a->ln1_b, a->eps, a->h1_32, a->h1_16, M, H, a->p_hidden,
-                             seed + 200 + l, stream));
+  W2V2_TRY(w2v2_layernorm_ex2(a->o32, 1, a->bo, a->h_in32, a->ln1_g, a->ln1_b, a->eps, a->h1_32, a->h1_16, a->rstd1, M, H,
+                              a->p_hidden, seed + 200 + l, stream));
   // feed-forward block
   if (a->z16 != nullptr) {      // training: keep the pre-activation, GELU as its own pass
     // one GEMM, two outputs: z (kept for the backward) and g = gelu(z)
@@ -40,8 +40,8 @@ extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream
     W2V2_TRY(w2v2_gemm_f16(a->h1_16, M, H, 0, 1, 1, 0, H, a->w1, H, FF, a->b1, 1, a->g16, 0, FF, 0, stream));
   }
   W2V2_TRY(w2v2_gemm_f16(a->g16, M, FF, 0, 1, 1, 0, FF, a->w2, FF, H, nullptr, 0, a->f2_32, 1, H, 0, stream));
-  W2V2_TRY(w2v2_layernorm_ex(a->f2_32, 1, a->b2, a->h1_32, a->ln2_g, a->ln2_b, a->eps, a->h2_32, a->h2_16, M, H, a->p_hidden,
-                             seed + 300 + l, stream));
+  W2V2_TRY(w2v2_layernorm_ex2(a->f2_32, 1, a->b2, a->h1_32, a->ln2_g, a->ln2_b, a->eps, a->h2_32, a->h2_16, a->rstd2, M, H,
+                              a->p_hidden, seed + 300 + l, stream));
   return 0;
 }
 
@@ -52,8 +52,9 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
   const uint64_t seed = a->seed;
   const int l = a->layer;
   // LN2:  h2 = LN(drop(f2 + b2) + h1); dx2_16 is the gradient of the dropped branch, the residual keeps dx2_32
-  W2V2_TRY(w2v2_layernorm_bwd_ex(a->dy_a, a->dy_b, a->f2_32, 1, a->b2, a->h1_32, a->ln2_g, a->eps, a->dx2_32, a->dx2_16,
-                                 a->d_ln2_g, a->d_ln2_b, a->d_b2, M, H, a->p_hidden, seed + 300 + l, stream));
+  // (the LayerNorm backward works from the LayerNorm OUTPUT + the saved rstd: one fp32 stream less than from its inputs)
+  W2V2_TRY(w2v2_layernorm_bwd_from_output(a->dy_a, a->dy_b, a->h2_32, a->rstd2, a->ln2_g, a->ln2_b, a->dx2_32, a->dx2_16,
+                                          a->d_ln2_g, a->d_ln2_b, a->d_b2, M, H, a->p_hidden, seed + 300 + l, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx2_16, H, a->g16, FF, M, H, FF, a->d_w2, FF, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dx2_16, M, H, 0, 1, 1, 0, H, a->w2T, H, FF, nullptr, 0, a->dg16, 0, FF, 0, stream));
   if (a->p_act > 0.f)
@@ -62,8 +63,8 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dz16, FF, a->h1_16, H, M, FF, H, a->d_w1, H, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dz16, M, FF, 0, 1, 1, 0, FF, a->w1T, FF, H, nullptr, 0, a->dh1_32, 1, H, 0, stream));
   // LN1:  h1 = LN(drop(o + bo) + h_in)
-  W2V2_TRY(w2v2_layernorm_bwd_ex(a->dh1_32, a->dx2_32, a->o32, 1, a->bo, a->h_in32, a->ln1_g, a->eps, a->dx1_32, a->dx1_16,
-                                 a->d_ln1_g, a->d_ln1_b, a->d_bo, M, H, a->p_hidden, seed + 200 + l, stream));
+  W2V2_TRY(w2v2_layernorm_bwd_from_output(a->dh1_32, a->dx2_32, a->h1_32, a->rstd1, a->ln1_g, a->ln1_b, a->dx1_32, a->dx1_16,
+                                          a->d_ln1_g, a->d_ln1_b, a->d_bo, M, H, a->p_hidden, seed + 200 + l, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx1_16, H, a->att16, H, M, H, H, a->d_wo, H, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dx1_16, M, H, 0, 1, 1, 0, H, a->woT, H, H, nullptr, 0, a->datt16, 0, H, 0, stream));
   // The q projection was used pre-scaled by d^-0.5: the attention backward multiplies dq by the same factor (chain

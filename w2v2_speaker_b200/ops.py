@@ -111,6 +111,31 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return y32, y16
 
 
+def layernorm_with_rstd(x, gamma, beta, eps=1e-5, bias=None, residual=None, drop_p: float = 0.0, drop_seed: int = 0):
+    """LayerNorm(dropout(x + bias) + residual) -> (y32, y16, rstd [rows]): the forward of the training layers."""
+    assert x.is_contiguous()
+    H = x.shape[-1]
+    rows = x.numel() // H
+    y32 = torch.empty(x.shape, dtype=F32, device=x.device)
+    y16 = torch.empty(x.shape, dtype=F16, device=x.device)
+    rstd = torch.empty(rows, dtype=F32, device=x.device)
+    call("w2v2_layernorm_ex2", ptr(x), 1 if x.dtype == F32 else 0, ptr(bias), ptr(residual), ptr(gamma), ptr(beta), eps,
+         ptr(y32), ptr(y16), ptr(rstd), rows, H, float(drop_p), int(drop_seed), stream_ptr())
+    return y32, y16, rstd
+
+
+def layernorm_bwd_from_output(dy_a, y32, rstd, gamma, beta, dy_b=None, dgamma=None, dbeta=None, dbias=None,
+                              drop_p: float = 0.0, drop_seed: int = 0):
+    """LayerNorm backward from the LayerNorm output y32 and the saved rstd -> (dx32, dx16)."""
+    H = y32.shape[-1]
+    rows = y32.numel() // H
+    dx32 = torch.empty(rows, H, dtype=F32, device=y32.device)
+    dx16 = torch.empty(rows, H, dtype=F16, device=y32.device)
+    call("w2v2_layernorm_bwd_from_output", ptr(dy_a), ptr(dy_b), ptr(y32), ptr(rstd), ptr(gamma), ptr(beta), ptr(dx32),
+         ptr(dx16), ptr(dgamma), ptr(dbeta), ptr(dbias), rows, H, float(drop_p), int(drop_seed), stream_ptr())
+    return dx32, dx16
+
+
 def posconv_taps_per_mma(T: int, H: int, groups: int) -> int:
     u = _lib.load().w2v2_posconv_taps_per_mma(T, H, groups)
     if u < 1:
@@ -562,3 +587,19 @@ def cosine_pairs(emb: torch.Tensor, idx_a: torch.Tensor, idx_b: torch.Tensor, me
     call("w2v2_cosine_pairs", ptr(emb.contiguous()), ptr(mean), ptr(std), ptr(idx_a.contiguous()), ptr(idx_b.contiguous()),
          ptr(scores), P, emb.shape[1], stream_ptr())
     return scores
+
+
+def normalize_wav(wav: torch.Tensor):
+    """Per-utterance standardisation of a [B, N] batch (float32 or int16 PCM) -> (f32 [B, N], mean [B], std [B])."""
+    if not wav.is_cuda:
+        raise _lib.W2V2Error("normalize_wav: expected a CUDA tensor (no CPU fallback exists)")
+    if wav.dtype not in (torch.float32, torch.int16):
+        raise _lib.W2V2Error(f"normalize_wav: expected float32 or int16, got {wav.dtype}")
+    B, N = wav.shape
+    wav = wav.contiguous()
+    out = torch.empty(B, N, dtype=F32, device=wav.device)
+    mean = torch.empty(B, dtype=F32, device=wav.device)
+    std = torch.empty(B, dtype=F32, device=wav.device)
+    call("w2v2_normalize_wav", ptr(wav), 1 if wav.dtype == torch.float32 else 0, ptr(out), ptr(mean), ptr(std), B, N,
+         stream_ptr())
+    return out, mean, std

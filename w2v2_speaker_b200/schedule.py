@@ -24,7 +24,7 @@ class LayerFwdArgs(ctypes.Structure):
                 [("seed", c_uint64)] +
                 [(n, c_void_p) for n in ("wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g", "ln2_b",
                                          "h_in32", "h_in16", "qkv16", "att16", "lse", "o32", "h1_32", "h1_16", "z16", "g16",
-                                         "f2_32", "h2_32", "h2_16")])
+                                         "f2_32", "h2_32", "h2_16", "rstd1", "rstd2")])
 
 
 class LayerBwdArgs(ctypes.Structure):
@@ -38,7 +38,7 @@ class LayerBwdArgs(ctypes.Structure):
                                          "d_wqkv", "d_bqkv", "d_wo", "d_bo", "d_ln1_g", "d_ln1_b", "d_w1", "d_b1", "d_w2", "d_b2",
                                          "d_ln2_g", "d_ln2_b",
                                          "dx2_32", "dx2_16", "dg16", "dz16", "dh1_32", "dx1_16", "datt16", "dqkv16",
-                                         "dx1_32", "dh_in32")])
+                                         "dx1_32", "dh_in32", "h2_32", "rstd1", "rstd2", "ln1_b", "ln2_b")])
 
 
 class Arena:
@@ -69,6 +69,8 @@ def layer_buffer_sizes(B: int, T: int, H: int, heads: int, FF: int, train: bool)
     if train:
         s["lse"] = B * heads * T * 4
         s["z16"] = M * FF * 2
+        s["rstd1"] = M * 4
+        s["rstd2"] = M * 4
     return s
 
 
@@ -114,6 +116,8 @@ def fwd_args(arch, B: int, T: int, layer: int, lw: dict, h_in32: int, h_in16: in
         setattr(a, k, arena.ptr(k))
     a.lse = arena.ptr("lse") if train else None
     a.z16 = arena.ptr("z16") if train else None
+    a.rstd1 = arena.ptr("rstd1") if train else None
+    a.rstd2 = arena.ptr("rstd2") if train else None
     a.h2_32 = out32 if out32 is not None else arena.ptr("h2_32")
     a.h2_16 = out16 if out16 is not None else arena.ptr("h2_16")
     return a

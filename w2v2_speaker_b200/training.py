@@ -332,8 +332,9 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
         b.wqkvT, b.woT, b.w1T, b.w2T = (tl[k].data_ptr() for k in ("wqkvT", "woT", "w1T", "w2T"))
         b.bo, b.b2, b.ln1_g, b.ln2_g = (lw[k].data_ptr() for k in ("bo", "b2", "ln1_g", "ln2_g"))
         b.h_in32, b.h_in16 = L["h_in32"], L["h_in16"]
-        for k in ("qkv16", "att16", "lse", "o32", "h1_32", "h1_16", "z16", "g16", "f2_32"):
+        for k in ("qkv16", "att16", "lse", "o32", "h1_32", "h1_16", "z16", "g16", "f2_32", "h2_32", "rstd1", "rstd2"):
             setattr(b, k, ar.ptr(k))
+        b.ln1_b, b.ln2_b = lw["ln1_b"].data_ptr(), lw["ln2_b"].data_ptr()
         b.dy_a, b.dy_b = pa, pb
         b.d_wqkv, b.d_bqkv = g("attention.q_proj.weight"), g("attention.q_proj.bias")
         b.d_wo, b.d_bo = g("attention.out_proj.weight"), g("attention.out_proj.bias")
