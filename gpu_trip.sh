@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
 T0=$(date +%s)
-timeout -k 5 900 python -m pytest tests -m gpu -x -q > gpurun_out/t49_tests.log 2>&1; tail -6 gpurun_out/t49_tests.log
-echo "tests done $(( $(date +%s) - T0 )) s"
-timeout -k 5 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/t49_train1.log 2>&1; tail -1 gpurun_out/t49_train1.log | cut -c1-200
+timeout -k 5 900 python -m pytest tests -m gpu -x -q > gpurun_out/t50_tests.log 2>&1; tail -3 gpurun_out/t50_tests.log
+timeout -k 5 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/t50_smoke.log 2>&1; tail -1 gpurun_out/t50_smoke.log
+echo "tests+smoke done $(( $(date +%s) - T0 )) s"
+timeout -k 5 600 python bench.py > gpurun_out/t50_bench_default.log 2>&1; tail -1 gpurun_out/t50_bench_default.log | cut -c1-260
+timeout -k 5 300 python bench.py --mode forward --no-cpu-baseline > gpurun_out/t50_bench_fwd.log 2>&1; tail -1 gpurun_out/t50_bench_fwd.log | cut -c1-260
 echo "all done $(( $(date +%s) - T0 )) s"
