@@ -245,6 +245,9 @@ int w2v2_add2_cast(const float* a, const float* b, float* out32, void* out16, in
 int w2v2_cast_f16_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int64_t rows, int cols, float scale,
                        void* stream);
 int w2v2_scale_f32(float* x, int64_t n, float s, void* stream);
+/* y = x * s, out of place (the loss scale entering / leaving an autograd Function: gradients that cross a Function
+ * boundary are plain unscaled fp32 and belong to autograd). */
+int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stream);
 int w2v2_softmax_ce_bwd_f32(const float* prob, const int64_t* labels, const float* dloss, float coef, float* dlogits,
                             int B, int S, void* stream);
 /* torch.optim.Adam step (weight_decay 0) over flat fp32 buffers; `g` is multiplied by grad_scale first
@@ -408,6 +411,11 @@ int w2v2_conv0_workspace_offsets(int B, int N, int C, int64_t* scale_off, int64_
  * the training forward keeps the pre-activation for the backward. */
 int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
                             const float* bias, void* out_act16, void* out_pre16, int64_t ldo, void* stream);
+/* dz = (A W^T) * gelu'(z) (f16 [M, N], row pitch ldo) and dbias[n] += sum_r dz[r, n] from ONE GEMM: the FFN2 data
+ * gradient of the training backward (HF:560-573 reversed) with the GELU backward and the FFN1 bias gradient in its
+ * epilogue.  z: the pre-activation w2v2_gemm_f16_dual_gelu kept, f16 [M, ldz]. */
+int w2v2_gemm_f16_gelu_bwd(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                           const void* z16, int64_t ldz, void* dz16, int64_t ldo, float* dbias, void* stream);
 int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
                        int64_t a_batch_stride, int batch, int ntaps, int cin, const void* W, int64_t ldw, int N, void* out,
                        int out_dtype, int64_t ldo, int64_t out_batch_stride, void* stream);

@@ -1,0 +1,119 @@
+"""CPU tier: the host side of the training / evaluation path with the kernels stubbed out (tests/dryrun.py).
+What is checked here is what a GPU is not needed for: that every module variant drives the launch schedules end to end
+(forward, loss, ``loss.backward()``), that each C entry point is called with an argument list its ctypes signature
+accepts, how many per-layer schedule calls a step makes, and which parameters end up with a gradient."""
+import collections
+
+import pytest
+import torch
+
+from dryrun import dry_library
+
+S = 64
+
+
+def _fc_module(pooling, loss, **cfg_kw):
+    from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type=pooling, test_stat_pooling_type=pooling, mask_time_prob=0.0, **cfg_kw)
+    ctor = CrossEntropyLoss if loss == "ce" else (
+        lambda: AngularAdditiveMarginSoftMaxLoss(input_features=1, output_features=1, margin=0.2, scale=30))
+    return Wav2vec2FCModule(cfg, S, ctor)
+
+
+@pytest.mark.parametrize("pooling,loss,freeze_cnn", [("mean", "ce", True), ("mean+std", "aam", True), ("attentive", "aam", True),
+                                                     ("first+cls", "ce", True), ("mean", "ce", False), ("first+cls", "ce", False)])
+def test_training_step_control_flow(pooling, loss, freeze_cnn):
+    with dry_library() as lib:
+        m = _fc_module(pooling, loss, layerdrop=0.0, completely_freeze_feature_extractor=freeze_cnn).train()
+        m.wav2vec.model.feature_extractor.requires_grad_(not freeze_cnn)
+        emb, pred = m(torch.randn(3, 1, 16000))
+        out, prob = m.loss_fn(pred, torch.tensor([1, 2, 3]))
+        assert emb.shape == (3, 768 if pooling in ("mean", "first+cls") else 1536) and prob.shape == (3, S)
+        out.backward()
+        calls = collections.Counter(lib.calls)
+    assert calls["w2v2_encoder_layer_fwd"] == 12 and calls["w2v2_encoder_layer_bwd"] == 12
+    # the loss scale enters the encoder backward exactly once per step, out of place (autograd owns the incoming gradient)
+    assert calls["w2v2_scale_copy_f32"] >= 1
+    for n, q in m.wav2vec.model.named_parameters():
+        if n == "masked_spec_embed":
+            continue
+        frozen = n.startswith("feature_extractor.") and freeze_cnn
+        assert (q.grad is None) == frozen, n
+    for n, q in m.named_parameters():
+        if not n.startswith("wav2vec.") and q.requires_grad:
+            assert q.grad is not None, n
+
+
+def test_layerdrop_of_every_layer_is_the_identity_stack():
+    with dry_library() as lib:
+        m = _fc_module("mean", "ce", layerdrop=1.0).train()
+        m.wav2vec.model.feature_extractor.requires_grad_(False)
+        emb, pred = m(torch.randn(2, 1, 8000))
+        m.loss_fn(pred, torch.tensor([0, 1]))[0].backward()
+        calls = collections.Counter(lib.calls)
+    assert calls["w2v2_encoder_layer_fwd"] == 0 and calls["w2v2_encoder_layer_bwd"] == 0
+    named = dict(m.wav2vec.model.named_parameters())
+    assert named["feature_projection.projection.weight"].grad is not None
+
+
+def test_paired_input_step_control_flow():
+    from w2v2_speaker_b200.optim.loss import BinaryCrossEntropyLoss
+    from w2v2_speaker_b200.paired_speaker_module import Wav2vec2PairedSpeakerModule, Wav2vec2PairedSpeakerModuleConfig
+    with dry_library() as lib:
+        m = Wav2vec2PairedSpeakerModule(Wav2vec2PairedSpeakerModuleConfig(layerdrop=0.0), BinaryCrossEntropyLoss).train()
+        m.on_train_start()
+        scores = m(torch.randn(2, 16000), torch.randn(2, 12000))
+        assert scores.shape == (2, 1)
+        loss, prediction = m.loss_fn(scores, torch.tensor([1, 0]))
+        loss.backward()
+        m.on_after_backward()
+        calls = collections.Counter(lib.calls)
+    assert prediction.shape == (2,) and m.steps == 1
+    assert calls["w2v2_encoder_layer_fwd"] == 12 and calls["w2v2_encoder_layer_bwd"] == 12
+    named = dict(m.wav2vec.model.named_parameters())
+    assert named["feature_extractor.conv_layers.3.conv.weight"].grad is None         # completely_freeze_feature_extractor
+    assert named["feature_projection.projection.weight"].grad is not None           # two calls, gradients summed by autograd
+    assert named["encoder.layers.11.final_layer_norm.bias"].grad is not None
+    assert m.linear.weight.grad is not None
+
+
+def test_paired_input_freeze_protocol():
+    from w2v2_speaker_b200.optim.loss import BinaryCrossEntropyLoss
+    from w2v2_speaker_b200.paired_speaker_module import Wav2vec2PairedSpeakerModule, Wav2vec2PairedSpeakerModuleConfig
+    cfg = Wav2vec2PairedSpeakerModuleConfig(wav2vec_initially_frozen=True, num_frozen_steps=2,
+                                            completely_freeze_feature_projector=True)
+    m = Wav2vec2PairedSpeakerModule(cfg, BinaryCrossEntropyLoss)
+    m.on_train_start()
+    assert not any(q.requires_grad for q in m.wav2vec.parameters()) and m.linear.weight.requires_grad
+    m.on_after_backward()
+    assert not any(q.requires_grad for q in m.wav2vec.parameters())
+    m.on_after_backward()                                                           # step 2: unfreeze, keep the permanent ones
+    named = dict(m.wav2vec.model.named_parameters())
+    assert named["encoder.layers.0.attention.q_proj.weight"].requires_grad
+    assert not named["feature_extractor.conv_layers.0.conv.weight"].requires_grad
+    assert not named["feature_projection.projection.weight"].requires_grad
+
+
+@pytest.mark.parametrize("seconds", [1, 6])
+def test_evaluation_forward_control_flow(seconds):
+    """Eval forward of a short and of a 6 s utterance (299 frames > 256: key-tiled attention, chunked positional conv)."""
+    with dry_library() as lib:
+        m = _fc_module("mean+std", "aam").eval()
+        with torch.no_grad():
+            emb, pred = m(torch.randn(2, 1, 16000 * seconds))
+        calls = collections.Counter(lib.calls)
+    assert emb.shape == (2, 1536)
+    assert calls["w2v2_encoder_layer_fwd"] == 12 and calls["w2v2_encoder_layer_bwd"] == 0
+
+
+def test_bce_loss_matches_torch():
+    from w2v2_speaker_b200.optim.loss import BinaryCrossEntropyLoss
+    logits = torch.tensor([[0.3], [-1.2], [2.0]], requires_grad=True)
+    labels = torch.tensor([1, 0, 0])
+    loss, prediction = BinaryCrossEntropyLoss()(logits, labels)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(logits.detach().squeeze(), labels.float())
+    assert torch.allclose(loss, ref) and torch.allclose(prediction, torch.sigmoid(logits.detach().squeeze()))
+    assert not prediction.requires_grad
+    loss.backward()
+    assert logits.grad is not None

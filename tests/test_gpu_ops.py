@@ -109,6 +109,31 @@ def test_gemm_dual_output_gelu(ops, M, N, K):
     assert rel(act.float(), g.float()) < 6e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(9536, 3072, 768), (1000, 4096, 1024), (300, 384, 64), (77, 160, 128)])
+def test_gemm_gelu_backward_epilogue(ops, M, N, K):
+    """FFN2 data gradient of the training backward: dz = (a W^T) * gelu'(z) and the column sums of dz from one GEMM,
+    against autograd through F.gelu in fp32 and against the two-pass form (GEMM, then w2v2_gelu_bwd_colsum)."""
+    a = _rand((M, K), 61).half()
+    w = _rand((N, K), 62, 1.0 / math.sqrt(K)).half()
+    z = _rand((M, N), 63, 1.5).half()
+    dbias = torch.full((N,), 0.25, device="cuda")          # accumulated into, not overwritten
+    for _ in range(2):                                    # twice: the shared-memory accumulators re-arm themselves
+        dz = ops.gemm_f16_gelu_bwd(a, w, z, dbias)
+    torch.cuda.synchronize()
+    zf = z.float().requires_grad_(True)
+    dg = a.float() @ w.float().t()
+    F.gelu(zf).backward(dg)
+    assert rel(dz.float(), zf.grad) < 6e-4
+    ref_sum = 0.25 + 2 * dz.double().sum(0)                # the sums of the fp16 values the wgrad GEMM reads
+    scale = dz.double().abs().sum(0) + 1.0
+    assert ((dbias.double() - ref_sum).abs() / scale).max().item() < 2e-6
+    dg16 = ops.gemm_f16(a, w, None, 0, torch.float16)
+    db2 = torch.zeros(N, device="cuda")
+    dz2 = ops.gelu_bwd(dg16, z, db2)
+    assert rel(dz.float(), dz2.float()) < 8e-4           # two-pass rounds dg to fp16 before the multiply
+    assert ((2 * db2.double() + 0.25 - dbias.double()).abs() / scale).max().item() < 1e-3
+
+
 def test_gemm_rejects_bad_k(ops):
     from w2v2_speaker_b200._lib import W2V2Error
     a = torch.zeros(8, 40, dtype=torch.float16, device="cuda")

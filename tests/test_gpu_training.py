@@ -185,7 +185,6 @@ def test_attentive_pooling_backward_matches_oracle_autograd(train_bn):
     from oracle import w2v2_oracle as O
     from oracle.params import make_asp_params
     from w2v2_speaker_b200.layers.pooling import AttentiveStatPool1D
-    from w2v2_speaker_b200.training import LOSS_SCALE
     B, T, C = 5, 149, 768
     g = torch.Generator().manual_seed(21)
     x = torch.randn(B, T, C, generator=g)
@@ -197,7 +196,7 @@ def test_attentive_pooling_backward_matches_oracle_autograd(train_bn):
     layer = layer.cuda().train(train_bn)
     xg = x.cuda().requires_grad_(True)
     out = layer(xg)
-    out.backward(dout.cuda() * LOSS_SCALE)                 # activation gradients travel loss-scaled on this path
+    out.backward(dout.cuda())                 # Function boundaries carry plain unscaled gradients
     torch.cuda.synchronize()
 
     ref_p = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in asp.items()}
@@ -210,7 +209,7 @@ def test_attentive_pooling_backward_matches_oracle_autograd(train_bn):
         return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
     got = dict(layer.pooling_layer.named_parameters())
-    errs = {"out": rel(out, ref), "dx": rel(xg.grad / LOSS_SCALE, xr.grad)}
+    errs = {"out": rel(out, ref), "dx": rel(xg.grad, xr.grad)}
     for k, v in ref_p.items():
         if v.grad is not None:
             errs[k] = rel(got[k].grad.reshape(v.shape), v.grad)
@@ -291,18 +290,20 @@ def test_training_step_attentive_aam_matches_oracle_autograd(base_params):
     assert ((g - r).norm() / r.norm()).item() < 1e-2
 
 
-def test_flat_adam_trainer_matches_torch_adam(base_params):
+@pytest.mark.parametrize("pooling", ["mean", "first+cls"])
+def test_flat_adam_trainer_matches_torch_adam(base_params, pooling):
     """trainer.FlatAdamTrainer (gradient sink, fused Adam, optimizer stream overlapped with the next step's CNN
     forward, in-place refresh of the fp16 operand copies) against loss.backward() + torch.optim.Adam on an
-    identical module: same losses step by step, same parameter updates."""
+    identical module: same losses step by step, same parameter updates.  "first+cls" drives the split call path
+    (CLS token in front of the sequence), whose Functions write into the same sink."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     from oracle.params import make_inputs
     from w2v2_speaker_b200.trainer import FlatAdamTrainer
     wav, labels = make_inputs(4, 16000, S, seed=5)
     x, y = wav[:, None, :].cuda(), labels.cuda()
-    ma, _ = _module(base_params)
-    mb, _ = _module(base_params)
+    ma, _ = _module(base_params, pooling)
+    mb, _ = _module(base_params, pooling)
     start = {k: v.detach().clone() for k, v in mb.named_parameters()}
     tr = FlatAdamTrainer(ma, lr=1e-4)
     opt = torch.optim.Adam([q for q in mb.parameters() if q.requires_grad], lr=1e-4)
@@ -338,9 +339,12 @@ def test_flat_adam_trainer_matches_torch_adam(base_params):
     # gradient is at rounding level move differently in the two runs (the wgrad reduce-adds are not ordered); the
     # bulk of every tensor must agree, and the large matrices closely
     vals = sorted(errs.values())
-    assert vals[len(vals) // 2] < 0.05, worst
-    assert errs["wav2vec.model.encoder.layers.5.feed_forward.intermediate_dense.weight"] < 0.1, worst
-    assert max(vals) < 0.8, worst
+    if pooling == "mean":
+        assert vals[len(vals) // 2] < 0.05, worst
+        assert errs["wav2vec.model.encoder.layers.5.feed_forward.intermediate_dense.weight"] < 0.1, worst
+        assert max(vals) < 0.8, worst
+    else:      # one token carries the whole gradient: more elements sit at rounding level, the bulk must still agree
+        assert vals[len(vals) // 2] < 0.1, worst
 
 
 def test_inplace_weight_refresh_equals_rebuild(base_params):

@@ -25,6 +25,9 @@ SIGNATURES = {
     "w2v2_cosine_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "w2v2_gemm_f16_dual_gelu": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p]),
+    "w2v2_scale_copy_f32": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "w2v2_gemm_f16_gelu_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                       c_void_p, c_int64, c_void_p, c_void_p]),
     "w2v2_attention_bwd_ex2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                        c_uint64, c_float, c_void_p, c_void_p]),
     "w2v2_adam_step_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int,

@@ -49,6 +49,20 @@ __global__ void scale_f32_kernel(float* __restrict__ x, int64_t n, float s) {
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) x[i] *= s;
 }
 
+// y = x * s (out of place: autograd's gradient tensors are not ours to overwrite); 16-byte vectors + scalar tail
+__global__ void scale_copy_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float s, int vec) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t i = tid; i < n4; i += nth) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += nth) y[i] = x[i] * s;
+}
+
 // dlogits (f32) = (prob - onehot) * coef
 __global__ void softmax_ce_bwd_f32_kernel(const float* __restrict__ prob, const int64_t* __restrict__ labels,
                                           const float* __restrict__ coef_ptr, float coef, float* __restrict__ dl, int S) {
@@ -87,6 +101,16 @@ int w2v2_cast_f16_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int6
 int w2v2_scale_f32(float* x, int64_t n, float s, void* stream) {
   if (n == 0) return 0;
   W2V2_CHECK_CUDA(launch_k(scale_f32_kernel, dim3(mgrid(n, 256, 8)), dim3(256), 0, (cudaStream_t)stream, 1, x, n, s));
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stream) {
+  if (n == 0) return 0;
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  W2V2_CHECK_CUDA(launch_k(scale_copy_f32_kernel, dim3(mgrid((n + 3) / 4, 256, 8)), dim3(256), 0, (cudaStream_t)stream, 1, x, y,
+                           n, s, vec));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

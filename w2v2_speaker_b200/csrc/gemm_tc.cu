@@ -51,6 +51,9 @@ struct alignas(64) GemmParams {
   int N;
   long long rows;                // valid rows per batch element
   unsigned int* sk_flags;        // stream-K: per-tile hand-shake counters (nullptr = whole tiles per CTA)
+  const __half* aux;             // ACT 2: z [rows, ld_aux] f16, the pre-activation whose gelu' multiplies the output
+  long long ld_aux;
+  float* colsum;                 // ACT 2: colsum[n] += sum over rows of the (fp16-rounded) output
 };
 
 // Stream-K (fp32 output, no activation): the (tile, k-block) iteration space is cut into gridDim.x equal
@@ -114,10 +117,14 @@ struct GemmCfg {
 };
 
 // EPI: 0 = none, 1 = + bias[n], 2 = * scale[b, n] + shift[b, n]  (GroupNorm affine of conv layer 0)
+// ACT: 0 = none, 1 = GELU, 2 = multiply by gelu'(aux[r, n]) and accumulate the column sums of the result: the data
+//      gradient of FFN2 fused with the GELU backward and the FFN1 bias gradient (f16 output, EPI 0, one batch)
 template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, bool DUAL = false>
 __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
   static_assert(!DUAL || (!OUT_F32 && ACT == 1), "the dual-output epilogue is the fp16 pre-activation + GELU pair");
+  static_assert(ACT != 2 || (!OUT_F32 && EPI == 0 && !DUAL), "the gelu'-multiply epilogue writes f16 and takes no bias");
+  constexpr bool GRAD = (ACT == 2);
   constexpr int STAGES = Cfg::STAGES;
   // the 128B-swizzled tiles need a 1024-byte aligned base; the kernel has no static shared memory, so
   // the dynamic window starts at the CTA's (1024-aligned) shared base -- verified, not assumed
@@ -291,11 +298,34 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
     uint32_t tcount = 0;
 
     int prev_b = -1, prev_nt = -1;
+    if constexpr (GRAD) {       // sbias holds the column-sum accumulators of two tiles in flight
+      for (int i = epi_tid; i < 2 * BN; i += EPI_WARPS * 32) sbias[i] = 0.f;
+      named_bar_sync(1, EPI_WARPS * 32);
+    }
     WorkIter work = work0;
     int tile, k_begin, k_end;
     for (; work.next(tile, k_begin, k_end); ++tcount) {
       int nt, mt, b;
       decode(tile, nt, mt, b);
+      const int col0 = nt * BN + half * HALF_COLS;      // first output column of this warp
+      const int row0 = (mt * CL + cta_rank) * BM + quarter * 32;      // first output row of this warp
+      // GRAD: this thread's 32-column slices of the aux row, fetched one chunk pair ahead of their use
+      uint4 za[4], zb[4];
+      const bool zrow_ok = GRAD && (row0 + lane) < p.rows;
+      const __half* zrow = GRAD ? p.aux + (long long)(row0 + lane) * p.ld_aux + col0 : nullptr;
+      auto load_z = [&](uint4 (&zz)[4], int c) {
+        if (zrow_ok && col0 + c * 32 < p.N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) zz[q] = __ldg(reinterpret_cast<const uint4*>(zrow + c * 32 + q * 8));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) zz[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if constexpr (GRAD) {
+        load_z(za, 0);
+        load_z(zb, 1);
+      }
       // stream-K roles of this segment: `lead` holds the tile's first k-blocks (plain store, adds the bias,
       // then signals), `trail` the rest (waits for the signal, reduce-adds, no bias)
       const bool sk_lead = SK_OK && k_begin == 0 && k_end < k_iters;
@@ -327,8 +357,6 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
       __syncwarp();
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * HALF_COLS;
-      const int col0 = nt * BN + half * HALF_COLS;      // first output column of this warp
-      const int row0 = (mt * CL + cta_rank) * BM + quarter * 32;      // first output row of this warp
 
       if (SK_OK && sk_trail) {
         // the lead CTA's plain stores of this tile must have landed before anything is added to them
@@ -345,7 +373,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
       uint32_t ra[32], rb[32];
       tmem_ld_32x32b_x32(t_addr, ra);
 
-      auto process = [&](uint32_t (&r)[32], int c) {
+      auto process = [&](uint32_t (&r)[32], int c, const uint4 (&zz)[4]) {
         // c: chunk index within this warp's half; 32 consecutive columns of one row per thread
         const float* bsrc = bias_tile + half * HALF_COLS + c * 32;
         float v[32];
@@ -391,6 +419,17 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
         }
+        if constexpr (GRAD) {
+          const __half2* zh = reinterpret_cast<const __half2*>(&zz[0]);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 zf = __half22float2(zh[j >> 1]);
+            float d0, d1;
+            gelu_grad2(zf.x, zf.y, d0, d1);
+            v[j] *= d0;
+            v[j + 1] *= d1;
+          }
+        }
         if constexpr (OUT_F32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {                  // 8 chunks of 16 B (4 floats)
@@ -419,6 +458,21 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
             if constexpr (DUAL) tma_store_3d(&p.tmOut2, mystage + WSTAGE_BYTES, scol, row0, b);
             tma_store_commit();
           }
+          if constexpr (GRAD) {
+            // column sums of the 32 x 64 block just staged (what the weight-gradient GEMM will read: the fp16
+            // values): lane owns two adjacent columns, walks the rows through the swizzle, conflict-free
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const int pc = (lane >> 2) ^ (rr & 7);
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(mystage + rr * 128 + pc * 16 + (lane & 3) * 4));
+              s0 += f.x;
+              s1 += f.y;
+            }
+            float* dst = sbias + (tcount & 1) * BN + half * HALF_COLS + (c - sub) * 32 + lane * 2;
+            atomicAdd(dst, s0);
+            atomicAdd(dst + 1, s1);
+          }
         }
       };
 
@@ -426,7 +480,10 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
       for (int c = 0; c < NCHUNK; c += 2) {
         tmem_ld_wait();
         tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);
-        process(ra, c);
+        process(ra, c, za);
+        if constexpr (GRAD) {
+          if (c + 2 < NCHUNK) load_z(za, c + 2);
+        }
         tmem_ld_wait();
         if (c + 2 < NCHUNK) {
           tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, ra);
@@ -439,7 +496,22 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
             else mbar_arrive(&tmem_empty[acc]);
           }
         }
-        process(rb, c + 1);
+        process(rb, c + 1, zb);
+        if constexpr (GRAD) {
+          if (c + 3 < NCHUNK) load_z(zb, c + 3);
+        }
+      }
+      if constexpr (GRAD) {
+        // all eight warps have added this tile's partial sums: one global atomic per column, accumulator re-armed
+        // (the other buffer serves the next tile, so nobody adds to this one before the next barrier)
+        named_bar_sync(1, EPI_WARPS * 32);
+        if (epi_tid < BN) {
+          float* sacc = sbias + (tcount & 1) * BN + epi_tid;
+          const float t = *sacc;
+          *sacc = 0.f;
+          const int n = nt * BN + epi_tid;
+          if (n < p.N) atomicAdd(p.colsum + n, t);
+        }
       }
       if (SK_OK && (sk_lead || sk_trail) && lane == 0) {
         if (sk_lead) {
@@ -741,6 +813,40 @@ extern "C" int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, in
   p.rows = M;
   const int slot = gemm_prof_begin(2.0 * double(M) * K * N, stream);
   rc = CL == 2 ? launch_gemm<256, false, 1, 1, 2, 1, true>(p, stream) : launch_gemm<256, false, 1, 1, 1, 1, true>(p, stream);
+  gemm_prof_end(slot, stream);
+  return rc;
+}
+
+// dz = (A W^T) * gelu'(z) (f16 [M, N]) and dbias[n] += sum_r dz[r, n]: the FFN2 data-gradient GEMM of the training
+// backward with the GELU backward and the FFN1 bias gradient done in its epilogue (saves writing and re-reading the
+// [M, FF] gradient of the activation).
+extern "C" int w2v2_gemm_f16_gelu_bwd(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                      const void* z16, int64_t ldz, void* dz16, int64_t ldo, float* dbias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  W2V2_REQUIRE(K % BK == 0 && N > 128 && N % 32 == 0 && M > 0, "w2v2_gemm_f16_gelu_bwd: needs K %% 64 == 0, N > 128, N %% 32 == 0");
+  W2V2_REQUIRE(z16 != nullptr && dbias != nullptr && ldz % 8 == 0 && (reinterpret_cast<uintptr_t>(z16) & 15) == 0,
+               "w2v2_gemm_f16_gelu_bwd: z must be 16-byte aligned with ldz %% 8 == 0, dbias is required");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int CL = pair_enabled() ? 2 : 1;
+  int rc = make_tmap_3d(&p.tmA[0], A, 2, K, M, 1, uint64_t(lda) * 2, uint64_t(M) * lda * 2, BK, BM, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmB, W, 2, K, N, 1, uint64_t(ldw) * 2, uint64_t(N) * ldw * 2, BK, 256 / CL, 1, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&p.tmOut, dz16, 2, N, M, 1, uint64_t(ldo) * 2, uint64_t(M) * ldo * 2, 64, 32, 1, 128);
+  if (rc) return rc;
+  p.aux = static_cast<const __half*>(z16);
+  p.ld_aux = ldz;
+  p.colsum = dbias;
+  p.ntaps = 1;
+  p.kblocks_per_tap = K / BK;
+  p.m_tiles = int((M + BM * CL - 1) / (BM * CL));
+  p.n_tiles = (N + 255) / 256;
+  p.batch = 1;
+  p.N = N;
+  p.rows = M;
+  const int slot = gemm_prof_begin(2.0 * double(M) * K * N, stream);
+  rc = CL == 2 ? launch_gemm<256, false, 2, 0, 2>(p, stream) : launch_gemm<256, false, 2, 0, 1>(p, stream);
   gemm_prof_end(slot, stream);
   return rc;
 }

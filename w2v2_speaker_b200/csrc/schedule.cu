@@ -7,6 +7,7 @@
 //   forward :  qkv = h Wqkv^T + b ; att = softmax(q k^T) v ; o = att Wo^T ; h1 = LN1(drop(o + bo) + h)
 //              z = h1 W1^T + b1 ; g = gelu(z) ; f2 = g W2^T ; h2 = LN2(drop(f2 + b2) + h1)
 //   backward:  the reverse, with the weight gradients accumulated into the caller's flat fp32 buffer.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -17,6 +18,12 @@
     const int _rc = (expr); \
     if (_rc != 0) return _rc; \
   } while (0)
+
+// W2V2_FUSE_GELU_BWD=1: the FFN2 data-gradient GEMM applies the GELU backward in its epilogue (A/B switch)
+static bool fuse_gelu_bwd() {
+  static const bool on = []() { const char* e = getenv("W2V2_FUSE_GELU_BWD"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
 
 extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream) {
   W2V2_REQUIRE(a != nullptr, "w2v2_encoder_layer_fwd: null argument block");
@@ -56,10 +63,15 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
   W2V2_TRY(w2v2_layernorm_bwd_from_output(a->dy_a, a->dy_b, a->h2_32, a->rstd2, a->ln2_g, a->ln2_b, a->dx2_32, a->dx2_16,
                                           a->d_ln2_g, a->d_ln2_b, a->d_b2, M, H, a->p_hidden, seed + 300 + l, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx2_16, H, a->g16, FF, M, H, FF, a->d_w2, FF, stream));
-  W2V2_TRY(w2v2_gemm_f16(a->dx2_16, M, H, 0, 1, 1, 0, H, a->w2T, H, FF, nullptr, 0, a->dg16, 0, FF, 0, stream));
-  if (a->p_act > 0.f)
-    W2V2_TRY(w2v2_dropout(a->dg16, 0, nullptr, FF, a->dg16, nullptr, M * FF, a->p_act, seed + 400 + l, stream));
-  W2V2_TRY(w2v2_gelu_bwd_colsum(a->dg16, a->z16, a->dz16, M, FF, a->d_b1, stream));
+  if (a->p_act > 0.f || !fuse_gelu_bwd()) {
+    W2V2_TRY(w2v2_gemm_f16(a->dx2_16, M, H, 0, 1, 1, 0, H, a->w2T, H, FF, nullptr, 0, a->dg16, 0, FF, 0, stream));
+    if (a->p_act > 0.f)
+      W2V2_TRY(w2v2_dropout(a->dg16, 0, nullptr, FF, a->dg16, nullptr, M * FF, a->p_act, seed + 400 + l, stream));
+    W2V2_TRY(w2v2_gelu_bwd_colsum(a->dg16, a->z16, a->dz16, M, FF, a->d_b1, stream));
+  } else {
+    // no activation dropout (the reference's default): dz = (dx2 W2) * gelu'(z) and d_b1 straight from the GEMM epilogue
+    W2V2_TRY(w2v2_gemm_f16_gelu_bwd(a->dx2_16, M, H, H, a->w2T, H, FF, a->z16, FF, a->dz16, FF, a->d_b1, stream));
+  }
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dz16, FF, a->h1_16, H, M, FF, H, a->d_w1, H, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dz16, M, FF, 0, 1, 1, 0, FF, a->w1T, FF, H, nullptr, 0, a->dh1_32, 1, H, 0, stream));
   // LN1:  h1 = LN(drop(o + bo) + h_in)

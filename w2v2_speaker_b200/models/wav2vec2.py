@@ -85,23 +85,42 @@ class _FeatureExtractor(_Holder):
     """``model.feature_extractor``: [B,N] -> [B,512,T] (HF:409-419)."""
 
     def forward(self, input_values: torch.Tensor) -> torch.Tensor:
-        return self._owner()._engine().feature_extractor(input_values).transpose(1, 2)
+        model = self._owner()
+        cnn = model._items()[3]
+        if torch.is_grad_enabled() and any(q.requires_grad for q in cnn):
+            from ..training import FeatureExtractorFn
+            names = [n for n in model._items()[0] if n.startswith("feature_extractor.")]
+            return FeatureExtractorFn.apply(input_values.float(), model, names, *cnn).transpose(1, 2)
+        return model._engine().feature_extractor(input_values).transpose(1, 2)
 
 
 class _FeatureProjection(_Holder):
     """``model.feature_projection``: [B,T,512] -> (hidden [B,T,H], normed input) (HF:429-434)."""
 
     def forward(self, hidden_states: torch.Tensor):
-        h = self._owner()._engine().feature_projection(hidden_states.contiguous())
-        return h, None
+        model = self._owner()
+        model._check_mode()
+        names, params = model._split_params("feature_projection.")
+        if torch.is_grad_enabled() and (hidden_states.requires_grad or any(q.requires_grad for q in params)):
+            from ..training import FeatureProjectionFn
+            return FeatureProjectionFn.apply(hidden_states, model, names, *params), None
+        return model._engine().feature_projection(hidden_states.contiguous()), None
 
 
 class _Encoder(_Holder):
     """``model.encoder``: [B,T',H] -> object with ``last_hidden_state`` (HF:668-727)."""
 
     def forward(self, hidden_states: torch.Tensor, output_hidden_states: bool = False, **_):
+        model = self._owner()
+        model._check_mode()
+        names, params = model._split_params("encoder.")
+        if torch.is_grad_enabled() and (hidden_states.requires_grad or any(q.requires_grad for q in params)):
+            if output_hidden_states:
+                raise NotImplementedError("output_hidden_states is only available without gradients")
+            from ..training import EncoderStackFn
+            return _EncoderOutput(EncoderStackFn.apply(hidden_states, model, names, *params), None)
         hs = [] if output_hidden_states else None
-        out = self._owner()._engine().encoder(hidden_states.float(), hs)
+        out = model._engine().encoder(hidden_states.float(), hs)
         return _EncoderOutput(out, tuple(hs) if hs is not None else None)
 
 
@@ -185,6 +204,8 @@ class Wav2Vec2ModelB200(nn.Module):
         if getattr(self, "_rng", None) is None:
             self._rng = np.random.default_rng(torch.initial_seed() % (1 << 63))
         T = self.arch.conv_lengths(wav.shape[1])[-1]
+        if self.reg_cfg.mask_time_prob <= 0:
+            return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device)
         # ring of pinned staging buffers for the SpecAugment mask (the host may run a few steps ahead of the device)
         ring = self.__dict__.setdefault("_mask_ring", {})
         key = (wav.shape[0], T)
@@ -193,6 +214,28 @@ class Wav2Vec2ModelB200(nn.Module):
         bufs, i = ring[key]
         ring[key][1] = (i + 1) % len(bufs)
         return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device, bufs[i])
+
+    def _split_params(self, prefix: str):
+        """(names, parameters) of one part of the model, in registration order (cached)."""
+        c = self.__dict__.setdefault("_split_cache", {})
+        if prefix not in c:
+            names, params = self._items()[:2]
+            keep = [i for i, n in enumerate(names) if n.startswith(prefix)]
+            c[prefix] = ([names[i] for i in keep], [params[i] for i in keep])
+        return c[prefix]
+
+    def _draw_split_plan(self, B: int, T: int, device):
+        """Regularisation draw for one call of the split path (model.feature_projection / model.encoder called on
+        their own): dropouts and LayerDrop as usual, no SpecAugment -- HF applies the time mask in
+        ``Wav2Vec2Model.forward`` only, which that path bypasses."""
+        if not self.training or not self._stochastic():
+            return None
+        import dataclasses
+        import numpy as np
+        from ..training import RegPlan
+        if getattr(self, "_rng", None) is None:
+            self._rng = np.random.default_rng(torch.initial_seed() % (1 << 63))
+        return RegPlan(dataclasses.replace(self.reg_cfg, mask_time_prob=0.0), self.arch.layers, B, T, self._rng, device)
 
     def _check_mode(self):
         if self.reg_cfg.mask_feature_prob > 0 and self.training:

@@ -51,6 +51,18 @@ def gemm_f16_dual_gelu(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
     return act, pre
 
 
+def gemm_f16_gelu_bwd(a: torch.Tensor, w: torch.Tensor, z: torch.Tensor, dbias: torch.Tensor) -> torch.Tensor:
+    """-> dz = (a @ w^T) * gelu'(z), f16 [M, N]; dbias[n] += sum_r dz[r, n] (fp32, accumulated in place)."""
+    _chk(a, F16, "a"); _chk(w, F16, "w"); _chk(z, F16, "z"); _chk(dbias, F32, "dbias")
+    M, K = a.shape
+    N = w.shape[0]
+    assert z.shape == (M, N) and dbias.numel() == N
+    dz = torch.empty(M, N, dtype=F16, device=a.device)
+    call("w2v2_gemm_f16_gelu_bwd", ptr(a), M, a.stride(0), K, ptr(w), w.stride(0), N, ptr(z), z.stride(0), ptr(dz), N,
+         ptr(dbias), stream_ptr())
+    return dz
+
+
 def conv1d_cl_f16(x: torch.Tensor, w_tap: torch.Tensor, ksize: int, stride: int, act: int = 1,
                   out_dtype=F16) -> torch.Tensor:
     """Strided Conv1d (no bias) + activation over a channels-last fp16 activation x[B,L,C] with the
@@ -404,6 +416,15 @@ def cast_f16_rows(x: torch.Tensor, ldy: int, scale: float = 1.0) -> torch.Tensor
 def scale_f32_(x: torch.Tensor, s: float):
     call("w2v2_scale_f32", ptr(x), x.numel(), float(s), stream_ptr())
     return x
+
+
+def scaled_copy_f32(x: torch.Tensor, s: float) -> torch.Tensor:
+    """x * s into a fresh tensor (x: f32, any shape, contiguous)."""
+    _chk(x, F32, "x")
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    call("w2v2_scale_copy_f32", ptr(x), ptr(y), x.numel(), float(s), stream_ptr())
+    return y
 
 
 def softmax_ce_bwd_f32(prob, labels, dloss, coef: float):

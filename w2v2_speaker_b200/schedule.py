@@ -50,9 +50,11 @@ class Arena:
         for name, nbytes in sizes.items():
             self.offsets[name] = (off, nbytes)
             off += (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
-        self.buf = torch.empty(max(off, _ALIGN), dtype=torch.uint8, device=device)
+        total = max(off, _ALIGN)
+        raw = torch.empty(total + _ALIGN, dtype=torch.uint8, device=device)
+        pad = -raw.data_ptr() % _ALIGN            # 0 with torch's CUDA allocator (512-byte blocks)
+        self.buf = raw[pad:pad + total]
         self.base = self.buf.data_ptr()
-        assert self.base % _ALIGN == 0
 
     def ptr(self, name: str) -> int:
         return self.base + self.offsets[name][0]

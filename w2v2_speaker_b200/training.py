@@ -8,9 +8,12 @@ Scope: wav2vec2-base/large encoder with the CNN feature extractor frozen (the re
 reference's train-mode regularisation (dropout / LayerDrop / SpecAugment), mean / mean+std / attentive
 pooling, CE and AAM-softmax heads.
 
-Gradient convention between the Functions of this module: activation gradients carry ``LOSS_SCALE``
-(their fp16 copies feed the tensor cores), parameter gradients are unscaled before they are returned
-to autograd.
+Gradient convention: every gradient that crosses a Function boundary -- in or out, activation or parameter -- is a
+plain UNSCALED fp32 tensor, so these Functions compose with any torch op, head or loss around them (the paired-input
+model scores its CLS token with an ``nn.Linear`` and torch's BCE).  INSIDE a backward the activation gradients are
+multiplied by ``LOSS_SCALE`` before they are rounded to the fp16 operands of the dgrad / wgrad GEMMs and the results
+are divided by it again (one extra pass over [B, T, H] per step, ~10 us).  The one exception is the trainer's gradient
+sink (``model._grad_sink``): what is accumulated there stays loss-scaled and Adam's gradient scale undoes it.
 """
 from __future__ import annotations
 
@@ -195,10 +198,7 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
                           mask_embed: Optional[torch.Tensor] = None, train_cnn: bool = False, pre_encoder_hook=None):
     """Same arithmetic as EncoderEngine.forward (the GELUs run as separate passes so the pre-activations
     can be kept) plus the train-mode regularisation of `plan`; returns (last_hidden_state f32 [B,T,H], saved)."""
-    a, w = eng.arch, eng.w
     S = {"plan": plan}
-    ph = plan.p_hidden if plan is not None else 0.0
-    seed = plan.seed if plan is not None else 0
     if train_cnn:
         feat, S["cnn"] = cnn_forward_train(eng, wav)          # unfrozen CNN: pre-activations kept
     else:
@@ -206,21 +206,40 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
     if pre_encoder_hook is not None:
         pre_encoder_hook()                                    # e.g. join the optimizer stream (trainer.py)
     B, T, C = feat.shape
-    H, M = a.hidden, B * T
-    feat2 = feat.contiguous().view(M, C)
+    feat2 = feat.contiguous().view(B * T, C)
+    h0, n16 = projection_forward_train(eng, feat2, plan)
+    if plan is not None and plan.mask is not None:
+        ops.time_mask_apply_(h0, plan.mask, mask_embed)                  # HF:1301-1310
+    S.update(feat=feat2, n16=n16)
+    return stack_forward_train(eng, h0, B, T, plan, S), S
+
+
+def projection_forward_train(eng: EncoderEngine, feat2: torch.Tensor, plan: Optional[RegPlan]):
+    """Feature projection (HF:429-434): LayerNorm(C) -> Linear C -> H -> dropout.  feat2: f32 [M, C].
+    -> (h0 f32 [M, H] (a fresh tensor), the fp16 LayerNorm output the weight gradient needs)."""
+    a, w = eng.arch, eng.w
     _, n16 = ops.layernorm(feat2, w.fp_ln_g, w.fp_ln_b, a.eps, want32=False)
     h0 = ops.gemm_f16(n16, w.fp_w, w.fp_b, 0, F32).contiguous()          # [M,H]
     if plan is not None and plan.p_feat > 0:
-        ops.dropout_(h0, plan.p_feat, seed + 1)                          # HF:433
-    if plan is not None and plan.mask is not None:
-        ops.time_mask_apply_(h0, plan.mask, mask_embed)                  # HF:1301-1310
+        ops.dropout_(h0, plan.p_feat, plan.seed + 1)                     # HF:433
+    return h0, n16
+
+
+def stack_forward_train(eng: EncoderEngine, h0: torch.Tensor, B: int, T: int, plan: Optional[RegPlan], S: dict):
+    """The transformer stack (HF:668-727) on an arbitrary sequence h0 (f32 [B*T, H], contiguous, left untouched):
+    positional conv + GELU, LayerNorm, dropout, the encoder layers.  Fills `S` with what stack_backward needs;
+    -> last_hidden_state f32 [B, T, H]."""
+    a, w = eng.arch, eng.w
+    H, M = a.hidden, B * T
+    ph = plan.p_hidden if plan is not None else 0.0
+    seed = plan.seed if plan is not None else 0
     x16 = ops.cast_f16(h0)
     zpos = ops.posconv_ex(x16.view(B, T, H), w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel, 0, 0)
     pos, zpos16 = ops.gelu_fwd(zpos.view(M, H), F32, want_x16=True)
     h32, h16 = ops.layernorm(pos, w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0)
     if ph > 0:
         h32, h16 = ops.dropout_(h32, ph, seed + 2, want16=True)          # HF:693
-    S.update(B=B, T=T, feat=feat2, n16=n16, h0=h0, x16=x16, pos=pos, zpos16=zpos16, layers=[], top=(h32, h16))
+    S.update(B=B, T=T, h0=h0, x16=x16, pos=pos, zpos16=zpos16, layers=[], top=(h32, h16))
     # transformer layers: one native schedule call per layer (csrc/schedule.cu), buffers from one arena each
     sizes = sched.layer_buffer_sizes(B, T, H, a.heads, a.ffn, True)
     p32, p16 = h32.data_ptr(), h16.data_ptr()
@@ -236,8 +255,7 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
         S["layers"].append(dict(arena=ar, h_in32=p32, h_in16=p16))
         p32, p16 = ar.ptr("h2_32"), ar.ptr("h2_16")
         last = ar
-    out = last.tensor("h2_32", F32, (B, T, H)) if last is not None else h32.view(B, T, H)
-    return out, S
+    return last.tensor("h2_32", F32, (B, T, H)) if last is not None else h32.view(B, T, H)
 
 
 class GradBook:
@@ -266,10 +284,17 @@ class GradBook:
         return self.flat[o:o + rows * cols].view(rows, cols)
 
 
+PROJECTION_GRAD_ORDER = ["feature_projection.layer_norm.weight", "feature_projection.layer_norm.bias",
+                         "feature_projection.projection.weight", "feature_projection.projection.bias"]
+
+
 def encoder_grad_order(arch: ArchConfig) -> List[str]:
-    order = ["masked_spec_embed", "feature_projection.layer_norm.weight", "feature_projection.layer_norm.bias",
-             "feature_projection.projection.weight", "feature_projection.projection.bias",
-             "encoder.pos_conv_embed.conv.bias", "encoder.pos_conv_embed.conv.parametrizations.weight.original0",
+    """Layout of the flat gradient of everything behind the CNN (the trainer's buffer follows it)."""
+    return ["masked_spec_embed"] + PROJECTION_GRAD_ORDER + stack_grad_order(arch)
+
+
+def stack_grad_order(arch: ArchConfig) -> List[str]:
+    order = ["encoder.pos_conv_embed.conv.bias", "encoder.pos_conv_embed.conv.parametrizations.weight.original0",
              "encoder.pos_conv_embed.conv.parametrizations.weight.original1",
              "encoder.layer_norm.weight", "encoder.layer_norm.bias"]
     for l in range(arch.layers):
@@ -286,10 +311,45 @@ def encoder_grad_order(arch: ArchConfig) -> List[str]:
 
 def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, torch.Tensor], S: dict,
                      dh: torch.Tensor, sink: Optional[GradBook] = None, on_layer_done=None) -> GradBook:
-    """dh: f32 [B,T,H] gradient of last_hidden_state, carrying LOSS_SCALE.  Returns the (still scaled)
+    """dh: f32 [B,T,H] gradient of last_hidden_state, already multiplied by LOSS_SCALE.  Returns the (still scaled)
     parameter gradients of everything behind the frozen CNN.  `on_layer_done(lo, hi)` is called (in
     reverse layer order, also for LayerDrop-skipped layers) once flat[lo:hi] -- all gradients of one
     transformer layer -- has been enqueued: the trainer overlaps that span's all-reduce with the rest."""
+    plan = S.get("plan")
+    order = encoder_grad_order(eng.arch)
+    G = sink if sink is not None else GradBook({k: params[k].shape for k in order}, order, dh.device)
+    dxe32, dx_pos = stack_backward(eng, tw, S, dh, G, on_layer_done)
+    # feature projection:  h0 = timemask(drop(LN512(feat) Wp^T + bp))
+    dh0_32, dh0_16 = ops.add2_cast(dxe32, dx_pos, want32=True, want16=True)
+    if plan is not None and (plan.mask is not None or plan.p_feat > 0):
+        if plan.mask is not None:
+            ops.time_mask_bwd_(dh0_32, plan.mask, G.view("masked_spec_embed"))
+        if plan.p_feat > 0:
+            ops.dropout_(dh0_32, plan.p_feat, plan.seed + 1)
+        dh0_16 = ops.cast_f16(dh0_32)
+    dfeat = projection_backward(eng, tw, S, dh0_16, G, want_dfeat="cnn" in S)
+    if "cnn" in S:                                     # unfrozen feature extractor: its gradients are returned unscaled
+        G.cnn_grads = cnn_backward(eng, params, S["cnn"], dfeat.view(S["B"], S["T"], -1))
+    return G
+
+
+def projection_backward(eng: EncoderEngine, tw: TrainWeights, S: dict, dh0_16: torch.Tensor, G: GradBook,
+                        want_dfeat: bool):
+    """dh0_16: f16 [M, H] gradient of the projection output BEFORE its dropout (mask already applied), loss-scaled.
+    Accumulates the four projection gradients into G; -> d feat f32 [M, C] (loss-scaled) or None."""
+    a, w = eng.arch, eng.w
+    ops.colsum(dh0_16, G.view("feature_projection.projection.bias"))
+    ops.gemm_wgrad_f16(dh0_16, S["n16"], G.view("feature_projection.projection.weight"))
+    dn32 = ops.gemm_f16(dh0_16, tw.fp_wT, None, 0, F32)                           # [M, 512]
+    dfeat, _ = ops.layernorm_bwd(dn32, S["feat"], w.fp_ln_g, a.eps, dgamma=G.view("feature_projection.layer_norm.weight"),
+                                 dbeta=G.view("feature_projection.layer_norm.bias"), want32=want_dfeat, want16=False)
+    return dfeat
+
+
+def stack_backward(eng: EncoderEngine, tw: TrainWeights, S: dict, dh: torch.Tensor, G: GradBook, on_layer_done=None):
+    """Backward of stack_forward_train.  dh: f32 [B,T,H], loss-scaled.  Accumulates the gradients of the positional
+    conv, the encoder LayerNorm and every layer into G; -> the two (loss-scaled, f32 [M, H]) terms of d h0:
+    through the LayerNorm residual and through the positional conv."""
     a, w = eng.arch, eng.w
     B, T = S["B"], S["T"]
     H, M, FF = a.hidden, B * T, a.ffn
@@ -297,8 +357,6 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
     plan = S.get("plan")
     ph = plan.p_hidden if plan is not None else 0.0
     seed = plan.seed if plan is not None else 0
-    order = encoder_grad_order(a)
-    G = sink if sink is not None else GradBook({k: params[k].shape for k in order}, order, dev)
     d = H // a.heads
     qscale = float(d) ** -0.5
     dy_a, dy_b = dh.contiguous().view(M, H), None
@@ -370,22 +428,7 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
     ops.weight_norm_bwd(dw_hki, w._pos_v, w._pos_g, 1.0,
                         G.view("encoder.pos_conv_embed.conv.parametrizations.weight.original1"),
                         G.view("encoder.pos_conv_embed.conv.parametrizations.weight.original0").view(-1))
-    # feature projection:  h0 = timemask(drop(LN512(feat) Wp^T + bp))
-    dh0_32, dh0_16 = ops.add2_cast(dxe32, dx_pos.view(M, H), want32=True, want16=True)
-    if plan is not None and (plan.mask is not None or plan.p_feat > 0):
-        if plan.mask is not None:
-            ops.time_mask_bwd_(dh0_32, plan.mask, G.view("masked_spec_embed"))
-        if plan.p_feat > 0:
-            ops.dropout_(dh0_32, plan.p_feat, seed + 1)
-        dh0_16 = ops.cast_f16(dh0_32)
-    ops.colsum(dh0_16, G.view("feature_projection.projection.bias"))
-    ops.gemm_wgrad_f16(dh0_16, S["n16"], G.view("feature_projection.projection.weight"))
-    dn32 = ops.gemm_f16(dh0_16, tw.fp_wT, None, 0, F32)                           # [M, 512]
-    dfeat, _ = ops.layernorm_bwd(dn32, S["feat"], w.fp_ln_g, a.eps, dgamma=G.view("feature_projection.layer_norm.weight"),
-                                 dbeta=G.view("feature_projection.layer_norm.bias"), want32="cnn" in S, want16=False)
-    if "cnn" in S:                                     # unfrozen feature extractor: its gradients are returned unscaled
-        G.cnn_grads = cnn_backward(eng, params, S["cnn"], dfeat.view(B, T, -1))
-    return G
+    return dxe32, dx_pos.view(M, H)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -411,7 +454,7 @@ class EncoderFn(torch.autograd.Function):
         pd = model._items()[2]
         tw = model._train_weights(eng)
         sink = getattr(model, "_grad_sink", None)
-        G = encoder_backward(eng, tw, pd, ctx.saved, dh.float(), sink,
+        G = encoder_backward(eng, tw, pd, ctx.saved, ops.scaled_copy_f32(dh.float().contiguous(), LOSS_SCALE), sink,
                              getattr(model, "_grad_ready_hook", None) if sink is not None else None)
         ctx.saved = None
         cnn = getattr(G, "cnn_grads", None) or {}
@@ -430,6 +473,115 @@ class EncoderFn(torch.autograd.Function):
             else:
                 grads.append(cnn.get(n))
         return (None, None, None, *grads)
+
+
+# ---- the split call path: model.feature_extractor / model.feature_projection / model.encoder ---------------------
+# The reference's CLS-token wrapper (R:src/models/wav2vec2.py:128-140) and its paired-input model
+# (R:src/lightning_modules/speaker/wav2vec2_paired_input.py:162-207) call the three parts of the HF model one by one
+# and build the encoder's input sequence themselves; each part is its own autograd node here, on the same kernels.
+
+
+def _own_book(model, order: List[str], device):
+    """(gradient book, owned): the trainer's flat buffer when one is installed, else a fresh one for `order`."""
+    sink = getattr(model, "_grad_sink", None)
+    if sink is not None:
+        return sink, False
+    pd = model._items()[2]
+    return GradBook({k: pd[k].shape for k in order}, order, device), True
+
+
+def _book_grads(model, G: GradBook, owned: bool, names: List[str]):
+    """Gradients to hand back to autograd for `names`: views of an owned book (unscaled here), None when the
+    trainer's sink holds them (it stays loss-scaled, Adam undoes the scale)."""
+    if not owned:
+        return [None] * len(names)
+    ops.scale_f32_(G.flat, 1.0 / LOSS_SCALE)
+    pd = model._items()[2]
+    return [G.view(n) if pd[n].requires_grad else None for n in names]
+
+
+class FeatureExtractorFn(torch.autograd.Function):
+    """features f32 [B, T, C] = CNN(wav), with the CNN trained (a frozen one needs no autograd node)."""
+
+    @staticmethod
+    def forward(ctx, wav, model, names, *params):
+        eng = model._engine()
+        feat, saved = cnn_forward_train(eng, wav.float())
+        ctx.model, ctx.names, ctx.saved, ctx.eng = model, names, saved, eng
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        model, names = ctx.model, ctx.names
+        pd = model._items()[2]
+        d = ops.scaled_copy_f32(dfeat.float().contiguous(), LOSS_SCALE)
+        grads = cnn_backward(ctx.eng, pd, ctx.saved, d)
+        ctx.saved = None
+        return (None, None, None, *[grads.get(n) if pd[n].requires_grad else None for n in names])
+
+
+class FeatureProjectionFn(torch.autograd.Function):
+    """hidden f32 [B, T, H] = dropout(Linear(LayerNorm(features))) (HF:429-434)."""
+
+    @staticmethod
+    def forward(ctx, feat, model, names, *params):
+        eng = model._engine()
+        hook = getattr(model, "_pre_encoder_hook", None)
+        if hook is not None:
+            hook()
+        B, T, C = feat.shape
+        plan = model._draw_split_plan(B, T, feat.device)
+        feat2 = feat.detach().float().contiguous().view(B * T, C)
+        h0, n16 = projection_forward_train(eng, feat2, plan)
+        ctx.model, ctx.names, ctx.eng, ctx.plan = model, names, eng, plan
+        ctx.saved = dict(feat=feat2, n16=n16, B=B, T=T)
+        return h0.view(B, T, -1)
+
+    @staticmethod
+    def backward(ctx, dh):
+        model, eng, plan, S = ctx.model, ctx.eng, ctx.plan, ctx.saved
+        M = S["B"] * S["T"]
+        d32 = ops.scaled_copy_f32(dh.float().contiguous(), LOSS_SCALE).view(M, -1)
+        if plan is not None and plan.p_feat > 0:
+            ops.dropout_(d32, plan.p_feat, plan.seed + 1)
+        G, owned = _own_book(model, PROJECTION_GRAD_ORDER, dh.device)
+        dfeat = projection_backward(eng, model._train_weights(eng), S, ops.cast_f16(d32), G, ctx.needs_input_grad[0])
+        ctx.saved = None
+        if dfeat is not None:
+            dfeat = ops.scale_f32_(dfeat, 1.0 / LOSS_SCALE).view(S["B"], S["T"], -1)
+        return (dfeat, None, None, *_book_grads(model, G, owned, ctx.names))
+
+
+class EncoderStackFn(torch.autograd.Function):
+    """last_hidden_state f32 [B, T', H] = transformer stack(sequence) (HF:668-727) for a caller-built sequence."""
+
+    @staticmethod
+    def forward(ctx, seq, model, names, *params):
+        eng = model._engine()
+        hook = getattr(model, "_pre_encoder_hook", None)
+        if hook is not None:
+            hook()
+        B, T, H = seq.shape
+        plan = model._draw_split_plan(B, T, seq.device)
+        h0 = seq.detach().float().contiguous().view(B * T, H)
+        S = {"plan": plan}
+        out = stack_forward_train(eng, h0, B, T, plan, S)
+        ctx.model, ctx.names, ctx.eng, ctx.saved = model, names, eng, S
+        return out
+
+    @staticmethod
+    def backward(ctx, dh):
+        model, eng, S = ctx.model, ctx.eng, ctx.saved
+        G, owned = _own_book(model, stack_grad_order(eng.arch), dh.device)
+        hook = getattr(model, "_grad_ready_hook", None) if not owned else None
+        dxe32, dx_pos = stack_backward(eng, model._train_weights(eng), S, ops.scaled_copy_f32(dh.float().contiguous(), LOSS_SCALE),
+                                       G, hook)
+        ctx.saved = None
+        dseq = None
+        if ctx.needs_input_grad[0]:
+            dseq, _ = ops.add2_cast(dxe32, dx_pos, want32=True, want16=False)
+            dseq = ops.scale_f32_(dseq, 1.0 / LOSS_SCALE).view(S["B"], S["T"], -1)
+        return (dseq, None, None, *_book_grads(model, G, owned, ctx.names))
 
 
 class MeanPoolFn(torch.autograd.Function):
@@ -460,7 +612,7 @@ class SpeakerLinearFn(torch.autograd.Function):
         Bn, S = dlogits.shape
         E = W.shape[1]
         ld = (S + 63) // 64 * 64
-        dl16 = ops.cast_f16_rows(dlogits.float(), ld)                          # already carries LOSS_SCALE
+        dl16 = ops.cast_f16_rows(dlogits.float(), ld, LOSS_SCALE)
         x16 = ops.cast_f16(x.float().contiguous())
         dW = torch.zeros(S, E, dtype=F32, device=W.device)
         ops.gemm_wgrad_f16(dl16[:, :S], x16, dW)
@@ -470,12 +622,12 @@ class SpeakerLinearFn(torch.autograd.Function):
             db = torch.zeros(S, dtype=F32, device=W.device)
             ops.colsum(dl16[:, :S], db, 1.0 / LOSS_SCALE)
         wT = ops.cast_f16_transpose(W.float(), ld)                              # [E, ld]
-        dx = ops.gemm_f16(dl16, wT, None, 0, F32)                               # scaled, flows on
+        dx = ops.scaled_copy_f32(ops.gemm_f16(dl16, wT, None, 0, F32).contiguous(), 1.0 / LOSS_SCALE)
         return dx, dW, db, None
 
 
 class CrossEntropyFn(torch.autograd.Function):
-    """(loss, softmax) = CE(logits, labels); the gradient that leaves this node carries LOSS_SCALE."""
+    """(loss, softmax) = CE(logits, labels) (mean over the batch)."""
 
     @staticmethod
     def forward(ctx, logits, labels):
@@ -490,7 +642,7 @@ class CrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _dprob):
         prob, labels = ctx.saved_tensors
-        dl = ops.softmax_ce_bwd_f32(prob, labels, dloss.float().contiguous().view(1), LOSS_SCALE / prob.shape[0])
+        dl = ops.softmax_ce_bwd_f32(prob, labels, dloss.float().contiguous().view(1), 1.0 / prob.shape[0])
         return dl, None
 
 
@@ -510,8 +662,7 @@ class MeanStdPoolFn(torch.autograd.Function):
 
 
 class AamSoftmaxFn(torch.autograd.Function):
-    """(loss, softmax) of AAM-softmax (R:src/optim/loss/aam_softmax.py:50-74); the gradient that leaves this
-    node towards the embedding carries LOSS_SCALE, the classifier gradient is unscaled."""
+    """(loss, softmax) of AAM-softmax (R:src/optim/loss/aam_softmax.py:50-74)."""
 
     @staticmethod
     def forward(ctx, x, fc_weights, labels, margin, scale, easy_margin, w_split):
@@ -537,7 +688,7 @@ class AamSoftmaxFn(torch.autograd.Function):
         inv_w = ops.row_inv_norm(Wf)
         whT = ops.cast_f16_transpose(Wf, ld, inv_w)                               # normalised W, transposed [E, ld]
         dxh = ops.gemm_f16(dc16, whT, None, 0, F32)                               # d(x_hat) [B, E]
-        dx = ops.l2norm_rows_bwd(x, dxh, 1.0)                                     # stays loss-scaled
+        dx = ops.l2norm_rows_bwd(x, dxh, 1.0 / LOSS_SCALE)
         xh16 = ops.l2norm_rows_f16(x)
         dwh = torch.zeros(S, E, dtype=F32, device=W.device)
         ops.gemm_wgrad_f16(dc16[:, :S], xh16, dwh)                                # d(W_hat) [S, E]
@@ -548,8 +699,7 @@ class AamSoftmaxFn(torch.autograd.Function):
 class AspPoolFn(torch.autograd.Function):
     """[mean || std] of attentive-statistics pooling (R:src/layers/pooling.py:87-106) with its backward.
     `layer` is the parameter holder (layers.pooling._AttentiveStatisticsPooling): training-mode BatchNorm
-    uses (and updates) batch statistics exactly like torch's BatchNorm1d.  The incoming gradient carries
-    LOSS_SCALE and so does the returned d x; parameter gradients are unscaled."""
+    uses (and updates) batch statistics exactly like torch's BatchNorm1d."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, gamma, beta, w2, b2, layer):
@@ -593,7 +743,7 @@ class AspPoolFn(torch.autograd.Function):
         A = z.shape[1]
         dev = x.device
         inv_ls = 1.0 / LOSS_SCALE
-        dlg16, dx = ops.asp_pool_bwd(x, logits.view(B, T, C), out, dout.float())
+        dlg16, dx = ops.asp_pool_bwd(x, logits.view(B, T, C), out, ops.scaled_copy_f32(dout.float().contiguous(), LOSS_SCALE))
         dW2 = torch.zeros(C, A, dtype=F32, device=dev)
         ops.gemm_wgrad_f16(dlg16, y16, dW2)
         db2 = torch.zeros(C, dtype=F32, device=dev)
@@ -608,6 +758,7 @@ class AspPoolFn(torch.autograd.Function):
         ops.colsum(dz16, db1, inv_ls)
         dcat = ops.gemm_f16(dz16, ops.cast_f16_transpose(w1f, A), None, 0, F32)                    # [B*T, 3C]
         ops.asp_front_bwd_(x, dcat, dx)
+        ops.scale_f32_(dx, inv_ls)
         ops.scale_f32_(dW1, inv_ls)
         ops.scale_f32_(dW2, inv_ls)
         s1, s2 = ctx.shapes
