@@ -19,9 +19,10 @@
     if (_rc != 0) return _rc; \
   } while (0)
 
-// W2V2_FUSE_GELU_BWD=1: the FFN2 data-gradient GEMM applies the GELU backward in its epilogue (A/B switch)
+// The FFN2 data-gradient GEMM applies the GELU backward in its epilogue; W2V2_FUSE_GELU_BWD=0 restores the two-pass
+// form (A/B measurements: 11.35 -> 11.22 ms per train step)
 static bool fuse_gelu_bwd() {
-  static const bool on = []() { const char* e = getenv("W2V2_FUSE_GELU_BWD"); return e != nullptr && e[0] == '1'; }();
+  static const bool on = []() { const char* e = getenv("W2V2_FUSE_GELU_BWD"); return !(e != nullptr && e[0] == '0'); }();
   return on;
 }
 
