@@ -416,6 +416,14 @@ int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const 
  * epilogue.  z: the pre-activation w2v2_gemm_f16_dual_gelu kept, f16 [M, ldz]. */
 int w2v2_gemm_f16_gelu_bwd(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
                            const void* z16, int64_t ldz, void* dz16, int64_t ldo, float* dbias, void* stream);
+/* EXPERIMENTAL (compiled, not yet measured on a GPU; off unless W2V2_SAVE_GELU_GRAD=1, see csrc/schedule.cu): the same
+ * pair of GEMMs with gelu'(z) kept instead of z, so that the backward epilogue is a plain multiply.
+ * w2v2_gemm_f16_dual_gelu_grad: out_act = gelu(A W^T + bias), out_grad = gelu'(A W^T + bias).
+ * w2v2_gemm_f16_mul_colsum:     out = (A W^T) * mul, colsum[n] += sum_r out[r, n]. */
+int w2v2_gemm_f16_dual_gelu_grad(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                 const float* bias, void* out_act16, void* out_grad16, int64_t ldo, void* stream);
+int w2v2_gemm_f16_mul_colsum(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                             const void* mul16, int64_t ldm, void* out16, int64_t ldo, float* colsum, void* stream);
 int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
                        int64_t a_batch_stride, int batch, int ntaps, int cin, const void* W, int64_t ldw, int N, void* out,
                        int out_dtype, int64_t ldo, int64_t out_batch_stride, void* stream);

@@ -26,6 +26,10 @@ SIGNATURES = {
     "w2v2_gemm_f16_dual_gelu": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p]),
     "w2v2_scale_copy_f32": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "w2v2_gemm_f16_dual_gelu_grad": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_int64, c_void_p]),
+    "w2v2_gemm_f16_mul_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                         c_void_p, c_int64, c_void_p, c_void_p]),
     "w2v2_gemm_f16_gelu_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,
                                        c_void_p, c_int64, c_void_p, c_void_p]),
     "w2v2_attention_bwd_ex2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,

@@ -393,6 +393,30 @@ __device__ __forceinline__ void gelu_grad2(float z0, float z1, float& d0, float&
   d1 = fmaf(z1, p1, c1);
 }
 
+// GELU and its derivative from ONE evaluation of the tail polynomial (the training forward of FFN1 can keep
+// gelu'(z) instead of z: the backward epilogue then only multiplies).  x0/x1: in = z, out = gelu(z).
+__device__ __forceinline__ void gelu_and_grad2(float& x0, float& x1, float& d0, float& d1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const f32x2 u = fma2(pack2(fminf(a0, W2V2_GELU_A), fminf(a1, W2V2_GELU_A)), splat2(2.0f / W2V2_GELU_A), splat2(-1.0f));
+  f32x2 q = fma2(splat2(W2V2_GELU_C8), u, splat2(W2V2_GELU_C7));
+  q = fma2(q, u, splat2(W2V2_GELU_C6));
+  q = fma2(q, u, splat2(W2V2_GELU_C5));
+  q = fma2(q, u, splat2(W2V2_GELU_C4));
+  q = fma2(q, u, splat2(W2V2_GELU_C3));
+  q = fma2(q, u, splat2(W2V2_GELU_C2));
+  q = fma2(q, u, splat2(W2V2_GELU_C1));
+  q = fma2(q, u, splat2(W2V2_GELU_C0));
+  float q0, q1;
+  unpack2(q, q0, q1);
+  const float t0 = fast_ex2(q0), t1 = fast_ex2(q1);                  // Phi(-|z|)
+  const float p0 = 0.3989422804014327f * fast_ex2(x0 * x0 * -0.72134752044448170f);
+  const float p1 = 0.3989422804014327f * fast_ex2(x1 * x1 * -0.72134752044448170f);
+  d0 = fmaf(x0, p0, x0 >= 0.f ? 1.0f - t0 : t0);
+  d1 = fmaf(x1, p1, x1 >= 0.f ? 1.0f - t1 : t1);
+  x0 = fmaf(-a0, t0, fmaxf(x0, 0.f));
+  x1 = fmaf(-a1, t1, fmaxf(x1, 0.f));
+}
+
 // counter-based random bits for dropout: a 32-bit multiply / xor-shift mix (murmur3 finaliser) of the pair
 // index with both seed halves folded in; low / high 16 bits decide the two elements of the pair.
 // (32-bit on purpose: a 64-bit mix costs ~3x the instructions, and the attention kernels run it on a

@@ -101,9 +101,10 @@ struct WorkIter {
 // each CTA stages its 128 rows of A and BN/2 columns of B)
 // MINB = CTAs per SM the kernel is built for: 2 only for the epilogue-bound conv0 GEMM (K = 64: one k-block per
 // tile, so two pipeline stages are plenty and two CTAs -- 16 epilogue warps -- share an SM)
-// DUAL: the epilogue stores the pre-activation next to the activated output (training keeps both): twice the
+// DUAL: 1 = the epilogue stores the pre-activation next to the activated output (training keeps both), 2 = it stores
+// gelu'(pre-activation) instead (all the backward needs of it; experimental, see schedule.cu): twice the
 // staging, one pipeline stage less
-template <int BN, int CL = 1, int MINB = 1, bool DUAL = false>
+template <int BN, int CL = 1, int MINB = 1, int DUAL = 0>
 struct GemmCfg {
   static constexpr int B_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -119,12 +120,12 @@ struct GemmCfg {
 // EPI: 0 = none, 1 = + bias[n], 2 = * scale[b, n] + shift[b, n]  (GroupNorm affine of conv layer 0)
 // ACT: 0 = none, 1 = GELU, 2 = multiply by gelu'(aux[r, n]) and accumulate the column sums of the result: the data
 //      gradient of FFN2 fused with the GELU backward and the FFN1 bias gradient (f16 output, EPI 0, one batch)
-template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, bool DUAL = false>
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, int DUAL = 0>
 __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
   static_assert(!DUAL || (!OUT_F32 && ACT == 1), "the dual-output epilogue is the fp16 pre-activation + GELU pair");
-  static_assert(ACT != 2 || (!OUT_F32 && EPI == 0 && !DUAL), "the gelu'-multiply epilogue writes f16 and takes no bias");
-  constexpr bool GRAD = (ACT == 2);
+  static_assert(ACT < 2 || (!OUT_F32 && EPI == 0 && !DUAL), "the gelu'-multiply epilogue writes f16 and takes no bias");
+  constexpr bool GRAD = (ACT == 2 || ACT == 3);      // 3: aux already holds gelu'(z), the epilogue only multiplies
   constexpr int STAGES = Cfg::STAGES;
   // the 128B-swizzled tiles need a 1024-byte aligned base; the kernel has no static shared memory, so
   // the dynamic window starts at the CTA's (1024-aligned) shared base -- verified, not assumed
@@ -403,7 +404,21 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
         }
-        if constexpr (DUAL) {                            // the pre-activation goes to the second staging buffer
+        if constexpr (DUAL == 2) {                       // gelu'(pre-activation) goes to the second staging buffer
+          float dv[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) gelu_and_grad2(v[j], v[j + 1], dv[j], dv[j + 1]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int pc = (sub * 4 + q) ^ (lane & 7);
+            uint4 w;
+            w.x = pack_half2(dv[8 * q], dv[8 * q + 1]);
+            w.y = pack_half2(dv[8 * q + 2], dv[8 * q + 3]);
+            w.z = pack_half2(dv[8 * q + 4], dv[8 * q + 5]);
+            w.w = pack_half2(dv[8 * q + 6], dv[8 * q + 7]);
+            *reinterpret_cast<uint4*>(crow + WSTAGE_BYTES + pc * 16) = w;
+          }
+        } else if constexpr (DUAL == 1) {                // the pre-activation goes to the second staging buffer
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int pc = (sub * 4 + q) ^ (lane & 7);
@@ -415,7 +430,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
             *reinterpret_cast<uint4*>(crow + WSTAGE_BYTES + pc * 16) = w;
           }
         }
-        if constexpr (ACT == 1) {
+        if constexpr (ACT == 1 && DUAL != 2) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
         }
@@ -424,10 +439,15 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const float2 zf = __half22float2(zh[j >> 1]);
-            float d0, d1;
-            gelu_grad2(zf.x, zf.y, d0, d1);
-            v[j] *= d0;
-            v[j + 1] *= d1;
+            if constexpr (ACT == 2) {
+              float d0, d1;
+              gelu_grad2(zf.x, zf.y, d0, d1);
+              v[j] *= d0;
+              v[j + 1] *= d1;
+            } else {
+              v[j] *= zf.x;
+              v[j + 1] *= zf.y;
+            }
           }
         }
         if constexpr (OUT_F32) {
@@ -623,7 +643,7 @@ static bool pair_enabled() {
   return v == 1;
 }
 
-template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, bool DUAL = false>
+template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, int DUAL = 0>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
   static bool configured = false;
@@ -788,8 +808,8 @@ extern "C" int w2v2_gemm_profile_stop(double* total_ms, double* total_flops, int
 
 // out_act = gelu(A W^T + bias) and out_pre = A W^T + bias, both f16 [M, N]: the FFN1 GEMM of the training forward,
 // which has to keep the pre-activation for the backward (saves the separate GELU pass over [M, FF]).
-extern "C" int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
-                                       const float* bias, void* out_act16, void* out_pre16, int64_t ldo, void* stream_) {
+static int gemm_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N, const float* bias,
+                          void* out_act16, void* out_pre16, int64_t ldo, bool store_grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(K % BK == 0 && N > 128 && bias != nullptr && M > 0, "w2v2_gemm_f16_dual_gelu: needs K %% 64 == 0, N > 128, a bias");
   GemmParams p;
@@ -812,16 +832,31 @@ extern "C" int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, in
   p.N = N;
   p.rows = M;
   const int slot = gemm_prof_begin(2.0 * double(M) * K * N, stream);
-  rc = CL == 2 ? launch_gemm<256, false, 1, 1, 2, 1, true>(p, stream) : launch_gemm<256, false, 1, 1, 1, 1, true>(p, stream);
+  if (store_grad)
+    rc = CL == 2 ? launch_gemm<256, false, 1, 1, 2, 1, 2>(p, stream) : launch_gemm<256, false, 1, 1, 1, 1, 2>(p, stream);
+  else
+    rc = CL == 2 ? launch_gemm<256, false, 1, 1, 2, 1, 1>(p, stream) : launch_gemm<256, false, 1, 1, 1, 1, 1>(p, stream);
   gemm_prof_end(slot, stream);
   return rc;
+}
+
+extern "C" int w2v2_gemm_f16_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                       const float* bias, void* out_act16, void* out_pre16, int64_t ldo, void* stream) {
+  return gemm_dual_gelu(A, M, lda, K, W, ldw, N, bias, out_act16, out_pre16, ldo, false, stream);
+}
+
+// Same GEMM, second output = gelu'(A W^T + bias) instead of the pre-activation itself (the only thing the backward
+// computes from it): pairs with w2v2_gemm_f16_mul_colsum, whose epilogue then only multiplies.
+extern "C" int w2v2_gemm_f16_dual_gelu_grad(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                            const float* bias, void* out_act16, void* out_grad16, int64_t ldo, void* stream) {
+  return gemm_dual_gelu(A, M, lda, K, W, ldw, N, bias, out_act16, out_grad16, ldo, true, stream);
 }
 
 // dz = (A W^T) * gelu'(z) (f16 [M, N]) and dbias[n] += sum_r dz[r, n]: the FFN2 data-gradient GEMM of the training
 // backward with the GELU backward and the FFN1 bias gradient done in its epilogue (saves writing and re-reading the
 // [M, FF] gradient of the activation).
-extern "C" int w2v2_gemm_f16_gelu_bwd(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
-                                      const void* z16, int64_t ldz, void* dz16, int64_t ldo, float* dbias, void* stream_) {
+static int gemm_mul_epilogue(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N, const void* z16,
+                             int64_t ldz, void* dz16, int64_t ldo, float* dbias, bool z_is_grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(K % BK == 0 && N > 128 && N % 32 == 0 && M > 0, "w2v2_gemm_f16_gelu_bwd: needs K %% 64 == 0, N > 128, N %% 32 == 0");
   W2V2_REQUIRE(z16 != nullptr && dbias != nullptr && ldz % 8 == 0 && (reinterpret_cast<uintptr_t>(z16) & 15) == 0,
@@ -846,9 +881,22 @@ extern "C" int w2v2_gemm_f16_gelu_bwd(const void* A, int64_t M, int64_t lda, int
   p.N = N;
   p.rows = M;
   const int slot = gemm_prof_begin(2.0 * double(M) * K * N, stream);
-  rc = CL == 2 ? launch_gemm<256, false, 2, 0, 2>(p, stream) : launch_gemm<256, false, 2, 0, 1>(p, stream);
+  if (z_is_grad) rc = CL == 2 ? launch_gemm<256, false, 3, 0, 2>(p, stream) : launch_gemm<256, false, 3, 0, 1>(p, stream);
+  else rc = CL == 2 ? launch_gemm<256, false, 2, 0, 2>(p, stream) : launch_gemm<256, false, 2, 0, 1>(p, stream);
   gemm_prof_end(slot, stream);
   return rc;
+}
+
+extern "C" int w2v2_gemm_f16_gelu_bwd(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                      const void* z16, int64_t ldz, void* dz16, int64_t ldo, float* dbias, void* stream) {
+  return gemm_mul_epilogue(A, M, lda, K, W, ldw, N, z16, ldz, dz16, ldo, dbias, false, stream);
+}
+
+// out = (A W^T) * mul (f16 [M, N]) and colsum[n] += sum_r out[r, n]: the gelu'-multiply epilogue when the forward
+// kept gelu'(z) itself (w2v2_gemm_f16_dual_gelu_grad).
+extern "C" int w2v2_gemm_f16_mul_colsum(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                        const void* mul16, int64_t ldm, void* out16, int64_t ldo, float* colsum, void* stream) {
+  return gemm_mul_epilogue(A, M, lda, K, W, ldw, N, mul16, ldm, out16, ldo, colsum, true, stream);
 }
 
 extern "C" int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,

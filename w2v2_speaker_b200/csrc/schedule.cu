@@ -26,6 +26,15 @@ static bool fuse_gelu_bwd() {
   return on;
 }
 
+// EXPERIMENTAL, W2V2_SAVE_GELU_GRAD=1 (off by default: compiled but not yet measured on a GPU): the training forward keeps
+// gelu'(z) in the z buffer instead of z, and the FFN2 data-gradient epilogue only multiplies by it.  Needs the fused
+// backward epilogue and no activation dropout (the two-pass fallback reads z itself); both directions take the same
+// decision from the same inputs.
+static bool save_gelu_grad(float p_act) {
+  static const bool on = []() { const char* e = getenv("W2V2_SAVE_GELU_GRAD"); return e != nullptr && e[0] == '1'; }();
+  return on && fuse_gelu_bwd() && !(p_act > 0.f);
+}
+
 extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream) {
   W2V2_REQUIRE(a != nullptr, "w2v2_encoder_layer_fwd: null argument block");
   const int64_t M = int64_t(a->B) * a->T;
@@ -41,7 +50,10 @@ extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream
   // feed-forward block
   if (a->z16 != nullptr) {      // training: keep the pre-activation, GELU as its own pass
     // one GEMM, two outputs: z (kept for the backward) and g = gelu(z)
-    W2V2_TRY(w2v2_gemm_f16_dual_gelu(a->h1_16, M, H, H, a->w1, H, FF, a->b1, a->g16, a->z16, FF, stream));
+    if (save_gelu_grad(a->p_act))
+      W2V2_TRY(w2v2_gemm_f16_dual_gelu_grad(a->h1_16, M, H, H, a->w1, H, FF, a->b1, a->g16, a->z16, FF, stream));
+    else
+      W2V2_TRY(w2v2_gemm_f16_dual_gelu(a->h1_16, M, H, H, a->w1, H, FF, a->b1, a->g16, a->z16, FF, stream));
     if (a->p_act > 0.f)
       W2V2_TRY(w2v2_dropout(a->g16, 0, nullptr, FF, a->g16, nullptr, M * FF, a->p_act, seed + 400 + l, stream));
   } else {                      // inference: GELU in the GEMM epilogue
@@ -71,7 +83,10 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
     W2V2_TRY(w2v2_gelu_bwd_colsum(a->dg16, a->z16, a->dz16, M, FF, a->d_b1, stream));
   } else {
     // no activation dropout (the reference's default): dz = (dx2 W2) * gelu'(z) and d_b1 straight from the GEMM epilogue
-    W2V2_TRY(w2v2_gemm_f16_gelu_bwd(a->dx2_16, M, H, H, a->w2T, H, FF, a->z16, FF, a->dz16, FF, a->d_b1, stream));
+    if (save_gelu_grad(a->p_act))
+      W2V2_TRY(w2v2_gemm_f16_mul_colsum(a->dx2_16, M, H, H, a->w2T, H, FF, a->z16, FF, a->dz16, FF, a->d_b1, stream));
+    else
+      W2V2_TRY(w2v2_gemm_f16_gelu_bwd(a->dx2_16, M, H, H, a->w2T, H, FF, a->z16, FF, a->dz16, FF, a->d_b1, stream));
   }
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dz16, FF, a->h1_16, H, M, FF, H, a->d_w1, H, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dz16, M, FF, 0, 1, 1, 0, FF, a->w1T, FF, H, nullptr, 0, a->dh1_32, 1, H, 0, stream));

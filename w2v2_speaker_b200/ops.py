@@ -51,6 +51,30 @@ def gemm_f16_dual_gelu(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
     return act, pre
 
 
+def gemm_f16_dual_gelu_grad(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor):
+    """EXPERIMENTAL -> (gelu(a @ w^T + bias), gelu'(a @ w^T + bias)), both f16 [M, N], from one GEMM."""
+    _chk(a, F16, "a"); _chk(w, F16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    act = torch.empty(M, N, dtype=F16, device=a.device)
+    grad = torch.empty(M, N, dtype=F16, device=a.device)
+    call("w2v2_gemm_f16_dual_gelu_grad", ptr(a), M, a.stride(0), K, ptr(w), w.stride(0), N, ptr(bias), ptr(act), ptr(grad), N,
+         stream_ptr())
+    return act, grad
+
+
+def gemm_f16_mul_colsum(a: torch.Tensor, w: torch.Tensor, mul: torch.Tensor, colsum: torch.Tensor) -> torch.Tensor:
+    """EXPERIMENTAL -> out = (a @ w^T) * mul, f16 [M, N]; colsum[n] += sum_r out[r, n] (fp32, in place)."""
+    _chk(a, F16, "a"); _chk(w, F16, "w"); _chk(mul, F16, "mul"); _chk(colsum, F32, "colsum")
+    M, K = a.shape
+    N = w.shape[0]
+    assert mul.shape == (M, N) and colsum.numel() == N
+    out = torch.empty(M, N, dtype=F16, device=a.device)
+    call("w2v2_gemm_f16_mul_colsum", ptr(a), M, a.stride(0), K, ptr(w), w.stride(0), N, ptr(mul), mul.stride(0), ptr(out), N,
+         ptr(colsum), stream_ptr())
+    return out
+
+
 def gemm_f16_gelu_bwd(a: torch.Tensor, w: torch.Tensor, z: torch.Tensor, dbias: torch.Tensor) -> torch.Tensor:
     """-> dz = (a @ w^T) * gelu'(z), f16 [M, N]; dbias[n] += sum_r dz[r, n] (fp32, accumulated in place)."""
     _chk(a, F16, "a"); _chk(w, F16, "w"); _chk(z, F16, "z"); _chk(dbias, F32, "dbias")
