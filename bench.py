@@ -452,7 +452,10 @@ def main():
                     # ncu --set full capture in profiles/r01_e_gemm_pair_full.txt
                     "traffic": 76.79e6 if WL is WORKLOADS["cfg1"] else None,
                     "traffic_note": "bytes per launch of the FFN2 GEMM instance (profiles/r01_e_gemm_pair_full.txt)",
-                    "peak_source": peak_src, "launches": t["gemm_launches"], "ms_per_step": g_ms, "tflop_per_step": fl / 1e12}
+                    "peak_source": peak_src, "launches": t["gemm_launches"], "ms_per_step": g_ms, "tflop_per_step": fl / 1e12,
+                    # train mode: the FFN2 data-gradient launches carry the GELU backward and the bias-gradient sums in
+                    # their epilogue (counted in the time, not in the FLOPs); per-role rates: profiles/r01_g_kernel_roofline_table.txt
+                    "note": "GEMM FLOPs only; epilogue work (GELU / GELU-backward / bias sums) is inside the timed launches"}
         roof_hbm = None
         if t["conv0"]:
             c0_bytes = B * (WL["samples"] * 4 * 2 + ((WL["samples"] - 10) // 5 + 1) * 512 * 2)
