@@ -175,3 +175,23 @@ def test_reference_era_checkpoints_load(wrapper):
     k = "wav2vec.model.encoder.pos_conv_embed.conv.parametrizations.weight.original1"
     assert torch.equal(m.state_dict()[k], ckpt["state_dict"][k.replace("parametrizations.weight.original1", "weight_v")])
     assert torch.equal(m.state_dict()["fc_list.0.0.weight"], ckpt["state_dict"]["fc_list.0.0.weight"])
+
+
+def test_profile_tools_reproduce_the_committed_tables():
+    """tools/launch_summary.py and tools/roofline_table.py on the committed end-of-round launch list: the step they cut
+    out, the launch count and the headline rows are the ones profiles/ holds."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "r01_g_train_launches.csv")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "roofline_table.py"), csv_path], check=True,
+                         capture_output=True, text=True).stdout
+    assert out == open(os.path.join(root, "profiles", "r01_g_kernel_roofline_table.txt")).read()
+    lines = out.splitlines()
+    assert "270 launches" in lines[1]
+    shares = [float(l.split("%")[0].split()[-1]) for l in lines[3:]]
+    assert abs(sum(shares) - 100.0) < 1.0
+    summ = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), csv_path, "--step"], check=True,
+                          capture_output=True, text=True).stdout
+    assert summ.splitlines()[0].startswith("# 270 launches")
