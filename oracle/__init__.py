@@ -15,5 +15,12 @@ against those fixtures, and against the HuggingFace ``Wav2Vec2Model`` (the
 third-party dependency that holds the encoder arithmetic) when it is importable.
 The speechbrain attentive-statistics pooling source is absent offline; its
 restatement (``w2v2_oracle.attentive_stat_pool``) follows the published
-speechbrain 0.5.x algorithm and is therefore "parity unpinned" for that one layer.
+speechbrain 0.5.x algorithm.  It is checked (tests/test_oracle_golden.py) against an
+independent port of the same speechbrain layer that IS in the image --
+``transformers.models.qwen2_5_omni.modeling_qwen2_5_omni.AttentiveStatisticsPooling``
+(ECAPA-TDNN of the Qwen2.5-Omni token2wav speaker encoder): statistics with the
+1e-12 clamp, the [x | mean | std] context, tanh, the 1x1 convs, softmax over time and
+the [mean | std] output agree exactly.  That port's TDNN block has no BatchNorm, so
+the one thing still "parity unpinned" is the position of speechbrain's BatchNorm1d
+(conv -> ReLU -> BatchNorm, speechbrain ``TDNNBlock``), which the check neutralises.
 """

@@ -198,7 +198,8 @@ def attentive_stat_pool(x_btc: torch.Tensor, asp: P, training: bool = False,
         attn = conv(tanh(tdnn(attn)));  tdnn = Conv1d(3C,128,1) -> ReLU -> BatchNorm1d(128)
         attn = softmax(attn, dim=L);  mean, std = stats(x, attn);  out = cat[mean, std]  -> [N, 2C]
 
-    Source unavailable offline => this layer is "parity unpinned" (oracle/__init__.py)."""
+    Source unavailable offline; pinned against transformers' port of the same layer except for the BatchNorm position,
+    which stays "parity unpinned" (oracle/__init__.py, tests/test_oracle_golden.py)."""
     x = x_btc.transpose(1, 2)                                   # [N, C, L]
     L = x.shape[-1]
 

@@ -88,3 +88,29 @@ def test_pos_conv_weight_norm_formula(base_params):
     g = base_params["encoder.pos_conv_embed.conv.parametrizations.weight.original0"]
     ref = torch._weight_norm(v, g, 2)
     assert rel(w, ref) < 1e-6
+
+
+def test_attentive_pooling_restatement_matches_an_independent_port():
+    """speechbrain's source is absent offline; transformers ships a port of the same ECAPA-TDNN layer (Qwen2.5-Omni's
+    speaker encoder).  With the BatchNorm of speechbrain's TDNN block neutralised (the port has none) the oracle's
+    restatement and the port agree exactly: statistics + clamp, [x | mean | std] context, tanh, 1x1 convs, softmax over
+    time, [mean | std] output."""
+    mod = pytest.importorskip("transformers.models.qwen2_5_omni.modeling_qwen2_5_omni")
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_asp_params
+    C = 96
+    asp = make_asp_params(C, seed=2)
+    asp["tdnn.norm.norm.running_mean"].zero_()
+    asp["tdnn.norm.norm.running_var"].fill_(1.0 - 1e-5)          # + eps = 1: the eval-mode BatchNorm is the identity
+    asp["tdnn.norm.norm.weight"].fill_(1.0)
+    asp["tdnn.norm.norm.bias"].zero_()
+    port = mod.AttentiveStatisticsPooling(C, attention_channels=asp["tdnn.conv.conv.weight"].shape[0]).eval()
+    with torch.no_grad():
+        port.tdnn.conv.weight.copy_(asp["tdnn.conv.conv.weight"]); port.tdnn.conv.bias.copy_(asp["tdnn.conv.conv.bias"])
+        port.conv.weight.copy_(asp["conv.conv.weight"]); port.conv.bias.copy_(asp["conv.conv.bias"])
+        for T in (37, 149):
+            x = torch.randn(3, T, C, generator=torch.Generator().manual_seed(T))
+            ours = O.attentive_stat_pool(x, asp, training=False)
+            theirs = port(x.transpose(1, 2)).squeeze(2)
+            assert ours.shape == theirs.shape == (3, 2 * C)
+            assert (ours - theirs).abs().max().item() <= 1e-6 * theirs.abs().max().item()
