@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz by running THE REFERENCE ITSELF (build container only).
 
-TEST INFRASTRUCTURE -- see oracle/__init__.py.  Run:  python -m oracle.make_golden
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  Run:  python -m oracle.make_golden          (ref_cfg0_*, ref_b3_*)
+                                                     python -m oracle.make_golden paired   (ref_paired_b3)
 
 The reference (/root/reference, read-only, python) is imported unmodified under import
 shims for the packages missing from this image (pytorch_lightning, omegaconf, torchmetrics,
@@ -191,14 +192,14 @@ def build_reference_module(pooling: str, loss: str, num_speakers: int = 5994):
     return m
 
 
-def summarise(name: str, t: torch.Tensor, out: dict):
+def summarise(name: str, t: torch.Tensor, out: dict, n: int = 4096):
     t = t.detach().float()
     out[name + ".shape"] = np.array(t.shape, dtype=np.int64)
     out[name + ".norm"] = np.array(t.double().norm().item())
     out[name + ".mean"] = np.array(t.double().mean().item())
     flat = t.reshape(-1)
-    step = max(1, flat.numel() // 4096)
-    out[name + ".sample"] = flat[::step][:4096].numpy().copy()
+    step = max(1, flat.numel() // n)
+    out[name + ".sample"] = flat[::step][:n].numpy().copy()
 
 
 def main():
@@ -258,5 +259,68 @@ def main():
         print("wrote", tag, sum(v.nbytes for v in out.values()) / 1e6, "MB")
 
 
+def paired_main():
+    """tests/golden/ref_paired_b3.npz: the reference's sibling heads on the same encoder, run by the reference's own
+    classes -- ``Wav2vec2PairedSpeakerModule.compute_speaker_equality`` + ``BinaryCrossEntropyLoss``
+    (R:src/lightning_modules/speaker/wav2vec2_paired_input.py:162-207, R:src/optim/loss/binary_cross_entropy.py) for one
+    training step (scores, loss, and the gradients torch autograd gives the reference), and the CLS-token path of
+    ``Wav2Vec2WrapperModule`` (R:src/models/wav2vec2.py:128-140)."""
+    install_shims()
+    from oracle.params import BASE, make_inputs, make_params
+    from src.lightning_modules.speaker.wav2vec2_paired_input import (Wav2vec2PairedSpeakerModule,
+                                                                      Wav2vec2PairedSpeakerModuleConfig)
+    from src.models.wav2vec2 import Wav2Vec2RegularisationConfig, Wav2Vec2WrapperModule
+    from src.optim.loss.binary_cross_entropy import BinaryCrossEntropyLoss
+    torch.set_num_threads(8)
+    params = make_params(BASE, seed=0)
+    B = 3
+    wav_a, _ = make_inputs(B, 16000, seed=31)
+    wav_b, _ = make_inputs(B, 11283, seed=32)
+    labels = torch.tensor([1, 0, 1])
+    zero = dict(activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
+                mask_feature_length=10, mask_feature_prob=0.0, mask_time_length=10, mask_time_prob=0.0)
+    cfg = Wav2vec2PairedSpeakerModuleConfig(
+        wav2vec_hunggingface_id="facebook/wav2vec2-base", reset_weights=False, wav2vec_initially_frozen=False,
+        num_frozen_steps=None, completely_freeze_feature_extractor=True, completely_freeze_feature_projector=False,
+        final_channel_mask_prob=0.0, final_channel_mask_width=5, **zero)
+    torch.manual_seed(3)
+    m = Wav2vec2PairedSpeakerModule(hyperparameters_to_save={}, cfg=cfg, loss_fn_constructor=BinaryCrossEntropyLoss)
+    res = m.wav2vec.model.load_state_dict(params, strict=False)
+    assert not res.missing_keys and set(res.unexpected_keys) <= {"masked_spec_embed"}, res
+    out = {"labels": labels.numpy(), "linear.weight": m.linear.weight.detach().numpy().copy(),
+           "linear.bias": m.linear.bias.detach().numpy().copy()}
+    m.eval()
+    with torch.no_grad():
+        out["scores.eval"] = m.compute_speaker_equality(wav_a, wav_b).numpy()
+    m.train()
+    m.on_train_start()
+    scores = m.compute_speaker_equality(wav_a, wav_b)
+    loss, prediction = m.loss_fn(scores, labels)
+    loss.backward()
+    out["scores.train"] = scores.detach().numpy()
+    out["loss"] = np.array(loss.item())
+    out["prediction"] = prediction.numpy()
+    out["grad.linear.weight"] = m.linear.weight.grad.numpy().copy()
+    out["grad.linear.bias"] = m.linear.bias.grad.numpy().copy()
+    for k, q in m.wav2vec.model.named_parameters():
+        if q.grad is not None:
+            summarise("grad." + k, q.grad, out, n=256)
+        else:
+            assert k.startswith("feature_extractor."), k
+    print("paired: scores", out["scores.train"].ravel(), "loss", float(loss))
+    # CLS-token wrapper path (eval)
+    w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False, reg_cfg=Wav2Vec2RegularisationConfig(**zero),
+                              insert_clc_token=True)
+    res = w.model.load_state_dict(params, strict=False)
+    assert not res.missing_keys and set(res.unexpected_keys) <= {"masked_spec_embed"}, res
+    w.eval()
+    with torch.no_grad():
+        cls_out = w(wav_b)                                       # [B, 768, 35 + 1]
+    out["cls.first_token"] = cls_out[:, :, 0].numpy()
+    summarise("cls.output", cls_out, out)
+    np.savez_compressed(os.path.join(OUT, "ref_paired_b3.npz"), **out)
+    print("wrote ref_paired_b3.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB")
+
+
 if __name__ == "__main__":
-    main()
+    paired_main() if sys.argv[1:] == ["paired"] else main()

@@ -226,6 +226,22 @@ def attentive_stat_pool(x_btc: torch.Tensor, asp: P, training: bool = False,
     return torch.cat([mean, std], dim=1)                        # [N, 2C]
 
 
+def split_path_forward(wavs, p: P, tokens, arch: ArchConfig = BASE) -> torch.Tensor:
+    """The encoder on a caller-built sequence, as the reference's CLS-token wrapper (R:src/models/wav2vec2.py:128-140,
+    one utterance, tokens = [cls]) and its paired-input model (R:src/lightning_modules/speaker/wav2vec2_paired_input.py:
+    162-207, two utterances, tokens = [cls, sep, sep]) run it: every utterance goes through the CNN and the feature
+    projection on its own, a constant-valued token row precedes each of them, the remaining tokens close the
+    sequence, and the transformer stack runs on the concatenation.  -> last_hidden_state [B, T', H]."""
+    B = wavs[0].shape[0]
+    parts = []
+    for i, wav in enumerate(wavs):
+        parts.append(torch.ones(B, 1, arch.hidden) * tokens[i])
+        parts.append(feature_projection(feature_extractor(wav, p, arch).transpose(1, 2), p, arch))
+    for t in tokens[len(wavs):]:
+        parts.append(torch.ones(B, 1, arch.hidden) * t)
+    return encoder(torch.cat(parts, dim=1), p, arch)
+
+
 # --------------------------------------------------------------------------------------
 # heads / losses
 

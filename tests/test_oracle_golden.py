@@ -114,3 +114,51 @@ def test_attentive_pooling_restatement_matches_an_independent_port():
             theirs = port(x.transpose(1, 2)).squeeze(2)
             assert ours.shape == theirs.shape == (3, 2 * C)
             assert (ours - theirs).abs().max().item() <= 1e-6 * theirs.abs().max().item()
+
+
+def test_split_path_restatement_matches_the_reference_paired_model(base_params):
+    """tests/golden/ref_paired_b3.npz was produced by the reference's own Wav2vec2PairedSpeakerModule +
+    BinaryCrossEntropyLoss (one training step, regularisation off) and by the CLS-token path of its
+    Wav2Vec2WrapperModule (oracle/make_golden.py paired).  The oracle's composition -- split_path_forward, a Linear on the
+    CLS position, BCE, torch autograd -- reproduces scores, loss and every gradient."""
+    import torch.nn.functional as F
+    g = golden("ref_paired_b3.npz")
+    torch.set_num_threads(8)
+    p = {k: v.clone().requires_grad_(not k.startswith("feature_extractor")) for k, v in base_params.items()}
+    wav_a, _ = make_inputs(3, 16000, seed=31)
+    wav_b, _ = make_inputs(3, 11283, seed=32)
+    labels = torch.from_numpy(g["labels"])
+    lw = torch.from_numpy(g["linear.weight"]).clone().requires_grad_(True)
+    lb = torch.from_numpy(g["linear.bias"]).clone().requires_grad_(True)
+    tokens = O.split_path_forward([wav_a, wav_b], p, [1.0, -1.0, -1.0])
+    scores = F.linear(tokens[:, 0, :], lw, lb)
+    loss = F.binary_cross_entropy_with_logits(scores.squeeze(), labels.float())
+    loss.backward()
+    assert np.abs(scores.detach().numpy() - g["scores.train"]).max() < 2e-5
+    assert np.abs(scores.detach().numpy() - g["scores.eval"]).max() < 2e-5          # regularisation off: train == eval
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    assert np.abs(torch.sigmoid(scores.detach().squeeze()).numpy() - g["prediction"]).max() < 1e-5
+
+    def close(a, b, tol=2e-4):
+        a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+        return np.linalg.norm(a - b) <= tol * max(np.linalg.norm(b), 1e-12)
+
+    assert close(lw.grad.numpy(), g["grad.linear.weight"]) and close(lb.grad.numpy(), g["grad.linear.bias"])
+    checked = 0
+    for k, v in p.items():
+        if v.grad is None:
+            assert k.startswith("feature_extractor.") or k == "masked_spec_embed", k
+            continue
+        if k.endswith("k_proj.bias"):                 # exactly 0 in exact arithmetic: both sides are rounding noise
+            continue
+        flat = v.grad.reshape(-1)
+        step = max(1, flat.numel() // 256)
+        assert tuple(g[f"grad.{k}.shape"]) == tuple(v.grad.shape), k
+        assert abs(v.grad.double().norm().item() - float(g[f"grad.{k}.norm"])) <= 2e-4 * float(g[f"grad.{k}.norm"]), k
+        assert close(flat[::step][:256].numpy(), g[f"grad.{k}.sample"], 1e-3), k
+        checked += 1
+    assert checked > 150
+    with torch.no_grad():
+        cls = O.split_path_forward([wav_b], {k: v.detach() for k, v in p.items()}, [1.0])
+    assert cls.shape[1] == 36
+    assert close(cls[:, 0, :].numpy(), g["cls.first_token"], 2e-5)
