@@ -2,6 +2,7 @@
 
 TEST INFRASTRUCTURE -- see oracle/__init__.py.  Run:  python -m oracle.make_golden          (ref_cfg0_*, ref_b3_*)
                                                      python -m oracle.make_golden paired   (ref_paired_b3)
+                                                     python -m oracle.make_golden train    (ref_train_b2_1s)
 
 The reference (/root/reference, read-only, python) is imported unmodified under import
 shims for the packages missing from this image (pytorch_lightning, omegaconf, torchmetrics,
@@ -322,5 +323,55 @@ def paired_main():
     print("wrote ref_paired_b3.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB")
 
 
+def train_main():
+    """tests/golden/ref_train_b2_1s.npz: one TRAINING step of the reference's own Wav2vec2FCModule (regularisation off,
+    CNN frozen as R:config/network/wav2vec2_fc.yaml:16 has it) for the three pooling / loss pairs of the forward fixtures:
+    loss and every parameter gradient torch autograd gives the reference (norm + strided sample each)."""
+    install_shims()
+    from oracle.params import BASE, make_asp_params, make_head_params, make_inputs, make_params
+    torch.set_num_threads(8)
+    S = 5994
+    params = make_params(BASE, seed=0)
+    wav, labels = make_inputs(2, 16000, S, seed=1234)
+    out = {"labels": labels.numpy()}
+    for pooling, loss in (("mean", "ce"), ("mean+std", "aam"), ("attentive", "aam")):
+        E = 768 if pooling == "mean" else 1536
+        m = build_reference_module(pooling, loss, S)
+        res = m.wav2vec.model.load_state_dict(params, strict=False)
+        assert not res.missing_keys and set(res.unexpected_keys) <= {"masked_spec_embed"}, res
+        head = make_head_params(E, S, seed=1)
+        if loss == "ce":
+            m.fc_list[-1][0].weight.data.copy_(head["fc.weight"])
+            m.fc_list[-1][0].bias.data.copy_(head["fc.bias"])
+        else:
+            m.loss_fn.fc_weights.data.copy_(head["aam.fc_weights"])
+        if pooling == "attentive":
+            m.stat_pooling.pooling_layer.load_state_dict(make_asp_params(768, seed=2), strict=False)
+        m.train()
+        m.on_train_start()                                         # freezes the feature extractor
+        emb = m.compute_speaker_embedding(wav[:, None, :])
+        pred = m.compute_speaker_prediction(emb)
+        loss_v, _ = m.loss_fn(pred, labels)
+        loss_v.backward()
+        key = f"{pooling}.{loss}"
+        out[key + ".loss"] = np.array(loss_v.item())
+        # packed (one zip entry per array costs more than a small gradient summary): names, norms, strided samples
+        names, norms, samples = [], [], []
+        for k, q in m.named_parameters():
+            if q.grad is not None:
+                flat = q.grad.detach().float().reshape(-1)
+                step = max(1, flat.numel() // 128)
+                smp = np.zeros(128, dtype=np.float32)
+                got = flat[::step][:128].numpy()
+                smp[:got.size] = got
+                names.append(k); norms.append(q.grad.double().norm().item()); samples.append(smp)
+        out[key + ".grad.names"] = np.array(names)
+        out[key + ".grad.norms"] = np.array(norms)
+        out[key + ".grad.samples"] = np.stack(samples)
+        print(key, "loss", float(loss_v.item()), "gradients", len(names))
+    np.savez_compressed(os.path.join(OUT, "ref_train_b2_1s.npz"), **out)
+    print("wrote ref_train_b2_1s.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB")
+
+
 if __name__ == "__main__":
-    paired_main() if sys.argv[1:] == ["paired"] else main()
+    {"paired": paired_main, "train": train_main}.get((sys.argv[1:] or [""])[0], main)()

@@ -162,3 +162,54 @@ def test_split_path_restatement_matches_the_reference_paired_model(base_params):
         cls = O.split_path_forward([wav_b], {k: v.detach() for k, v in p.items()}, [1.0])
     assert cls.shape[1] == 36
     assert close(cls[:, 0, :].numpy(), g["cls.first_token"], 2e-5)
+
+
+@pytest.mark.parametrize("pooling,loss", [("mean", "ce"), ("mean+std", "aam"), ("attentive", "aam")])
+def test_oracle_autograd_matches_the_reference_training_step(base_params, pooling, loss):
+    """tests/golden/ref_train_b2_1s.npz: loss and every parameter gradient of ONE training step of the reference's own
+    Wav2vec2FCModule (oracle/make_golden.py train; regularisation off, CNN frozen, BatchNorm of the attentive pooling on
+    batch statistics).  The GPU training tests compare the CUDA backward with autograd of the oracle; this pins that
+    autograd to the reference's."""
+    g = golden("ref_train_b2_1s.npz")
+    torch.set_num_threads(8)
+    S = 5994
+    wav, labels = make_inputs(2, 16000, S, seed=1234)
+    assert np.array_equal(labels.numpy(), g["labels"])
+    p = {k: v.clone().requires_grad_(not k.startswith("feature_extractor")) for k, v in base_params.items()}
+    E = 768 if pooling == "mean" else 1536
+    head = {k: v.clone().requires_grad_(True) for k, v in make_head_params(E, S, seed=1).items()}
+    asp = None
+    h = O.wav2vec2_forward(wav, p, BASE)
+    if pooling == "attentive":
+        asp = {k: (v.clone().requires_grad_(True) if "running" not in k else v.clone())
+               for k, v in make_asp_params(768, seed=2).items()}
+        emb = O.attentive_stat_pool(h, asp, training=True)
+    else:
+        emb = O.mean_pool(h) if pooling == "mean" else O.mean_std_pool(h)
+    if loss == "ce":
+        _, loss_v, _ = O.cross_entropy_head(emb, head["fc.weight"], head["fc.bias"], labels)
+    else:
+        _, loss_v, _ = O.aam_softmax(emb, head["aam.fc_weights"], labels, 0.2, 30.0)
+    loss_v.backward()
+    key = f"{pooling}.{loss}"
+    assert abs(loss_v.item() - float(g[key + ".loss"])) < 2e-5 * float(g[key + ".loss"])
+    ours = {"wav2vec.model." + k: v for k, v in p.items()}
+    ours.update({"fc_list.0.0.weight": head.get("fc.weight"), "fc_list.0.0.bias": head.get("fc.bias"),
+                 "loss_fn.fc_weights": head.get("aam.fc_weights")})
+    if asp is not None:
+        ours.update({"stat_pooling.pooling_layer." + k: v for k, v in asp.items()})
+    names, norms, samples = g[key + ".grad.names"], g[key + ".grad.norms"], g[key + ".grad.samples"]
+    assert len(names) > 200
+    for name, norm, smp in zip(names, norms, samples):
+        t = ours[str(name)]
+        assert t is not None and t.grad is not None, name
+        if str(name).endswith("k_proj.bias") or str(name).endswith("pooling_layer.conv.conv.bias"):
+            continue                                   # exactly 0 in exact arithmetic (softmax shift invariance): noise
+        flat = t.grad.reshape(-1)
+        step = max(1, flat.numel() // 128)
+        got = flat[::step][:128].double().numpy()
+        ref = smp[:got.size].astype(np.float64)
+        assert abs(t.grad.double().norm().item() - norm) <= 5e-4 * norm, name
+        assert np.linalg.norm(got - ref) <= 2e-3 * max(np.linalg.norm(ref), 1e-12), name
+    frozen = [k for k, v in p.items() if v.grad is None]
+    assert all(k.startswith("feature_extractor.") or k == "masked_spec_embed" for k in frozen)
