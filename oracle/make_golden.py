@@ -3,6 +3,7 @@
 TEST INFRASTRUCTURE -- see oracle/__init__.py.  Run:  python -m oracle.make_golden          (ref_cfg0_*, ref_b3_*)
                                                      python -m oracle.make_golden paired   (ref_paired_b3)
                                                      python -m oracle.make_golden train    (ref_train_b2_1s)
+                                                     python -m oracle.make_golden eval     (ref_eval)
 
 The reference (/root/reference, read-only, python) is imported unmodified under import
 shims for the packages missing from this image (pytorch_lightning, omegaconf, torchmetrics,
@@ -373,5 +374,53 @@ def train_main():
     print("wrote ref_train_b2_1s.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB")
 
 
+def eval_main():
+    """tests/golden/ref_eval.npz: the reference's own CosineDistanceEvaluator.evaluate (with and without centring) and
+    calculate_eer / calculate_mdc (R:src/evaluation/speaker/cosine_distance.py, R:src/eval_metrics.py) on seeded
+    embeddings and trial lists."""
+    install_shims()
+    import contextlib
+    import io
+    from src.eval_metrics import calculate_eer, calculate_mdc
+    from src.evaluation.speaker.cosine_distance import CosineDistanceEvaluator
+    from src.evaluation.speaker.speaker_recognition_evaluator import EmbeddingSample, EvaluationPair
+    g = torch.Generator().manual_seed(9)
+    n_spk, per, E = 30, 5, 96
+    centers = torch.randn(n_spk, E, generator=g)
+    emb = (centers[:, None, :] + 4.0 * torch.randn(n_spk, per, E, generator=g) + 0.5).reshape(-1, E)
+    ids = [f"spk{s}/utt{u}" for s in range(n_spk) for u in range(per)]
+    rng = np.random.default_rng(4)
+    left, right = [], []
+    while len(left) < 2000:
+        a, b = rng.integers(0, len(ids), 2)
+        if a != b:
+            left.append(int(a)); right.append(int(b))
+    pairs = [EvaluationPair(ids[a].split("/")[0] == ids[b].split("/")[0], ids[a], ids[b]) for a, b in zip(left, right)]
+    samples = [EmbeddingSample(i, e) for i, e in zip(ids, emb)]
+    out = {"embeddings": emb.numpy(), "left": np.array(left), "right": np.array(right),
+           "same": np.array([p.same_speaker for p in pairs]), "fit_stride": np.array(3)}
+    for center in (False, True):
+        ev = CosineDistanceEvaluator(center_before_scoring=center, length_norm_before_scoring=True,
+                                     max_num_training_samples=0)
+        ev.fit_parameters(list(emb[::3]), [])
+        with contextlib.redirect_stdout(io.StringIO()):           # the reference prints the centring statistics
+            res = ev.evaluate(pairs, samples)
+        key = "center" if center else "plain"
+        for k, v in res.items():
+            out[f"{key}.{k}"] = np.array(float(v))
+        print(key, {k: float(v) for k, v in res.items()})
+    # the metric functions on their own, on scores with ties and an awkward operating point
+    gt = rng.integers(0, 2, 1500).tolist()
+    pred = np.round(np.clip(rng.normal(0.45, 0.2, 1500) + 0.15 * np.array(gt), 0, 1), 3).tolist()
+    out["metric.gt"], out["metric.pred"] = np.array(gt), np.array(pred)
+    e, et = calculate_eer(gt, pred)
+    m, mt = calculate_mdc(gt, pred)
+    out["metric.eer"], out["metric.eer_threshold"] = np.array(float(e)), np.array(float(et))
+    out["metric.mdc"], out["metric.mdc_threshold"] = np.array(float(m)), np.array(float(mt))
+    print("metrics", float(e), float(et), float(m), float(mt))
+    np.savez_compressed(os.path.join(OUT, "ref_eval.npz"), **out)
+    print("wrote ref_eval.npz", sum(v.nbytes for v in out.values()) / 1e6, "MB")
+
+
 if __name__ == "__main__":
-    {"paired": paired_main, "train": train_main}.get((sys.argv[1:] or [""])[0], main)()
+    {"paired": paired_main, "train": train_main, "eval": eval_main}.get((sys.argv[1:] or [""])[0], main)()

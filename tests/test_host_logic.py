@@ -195,3 +195,37 @@ def test_profile_tools_reproduce_the_committed_tables():
     summ = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), csv_path, "--step"], check=True,
                           capture_output=True, text=True).stdout
     assert summ.splitlines()[0].startswith("# 270 launches")
+
+
+def test_eval_metrics_match_the_reference_functions():
+    """tests/golden/ref_eval.npz holds outputs of the reference's OWN calculate_eer / calculate_mdc and
+    CosineDistanceEvaluator.evaluate (oracle/make_golden.py eval).  The product's host-side metric code
+    (w2v2_speaker_b200/eval_metrics.py) reproduces them; so does the restatement the GPU evaluator test uses
+    (oracle/eval_oracle.py), fed with CPU cosine scores."""
+    import numpy as np
+    from conftest import golden
+    from oracle import eval_oracle as EO
+    from w2v2_speaker_b200.eval_metrics import calculate_eer, calculate_mdc
+    g = golden("ref_eval.npz")
+    gt, pred = g["metric.gt"].tolist(), g["metric.pred"].tolist()
+    e, et = calculate_eer(gt, pred)
+    m, mt = calculate_mdc(gt, pred)
+    assert abs(e - float(g["metric.eer"])) < 1e-9 and abs(et - float(g["metric.eer_threshold"])) < 1e-9
+    assert abs(m - float(g["metric.mdc"])) < 1e-9 and abs(mt - float(g["metric.mdc_threshold"])) < 1e-9
+    oe, oet = EO.eer(gt, pred)
+    om, omt = EO.mdc(gt, pred)
+    assert abs(oe - e) < 1e-12 and abs(oet - et) < 1e-12 and abs(om - m) < 1e-12 and abs(omt - mt) < 1e-12
+    emb = torch.from_numpy(g["embeddings"])
+    left, right = emb[g["left"]], emb[g["right"]]
+    same = g["same"].astype(int).tolist()
+    for key, center in (("plain", False), ("center", True)):
+        mean = std = None
+        if center:
+            std, mean = torch.std_mean(emb[::int(g["fit_stride"])], dim=0)
+        scores = EO.cosine_scores(left, right, mean, std).numpy().astype(np.float64)
+        pred = np.clip((scores + 1) / 2, 0, 1).tolist()
+        e, et = calculate_eer(same, pred)
+        m, mt = calculate_mdc(same, pred)
+        assert abs(e - float(g[key + ".eer"])) < 1e-6, key
+        assert abs(et - float(g[key + ".eer_threshold"])) < 1e-5, key
+        assert abs(m - float(g[key + ".mdc"])) < 1e-6 and abs(mt - float(g[key + ".mdc_threshold"])) < 1e-5, key
