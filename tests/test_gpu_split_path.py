@@ -181,59 +181,3 @@ def test_paired_model_trains_with_default_regularisation(base_params):
     assert named["feature_extractor.conv_layers.1.conv.weight"].grad is None
     after = eval_loss()
     assert after < before, (before, after)
-
-
-def test_paired_input_model_matches_the_reference_fixture(base_params):
-    """The same training step against tests/golden/ref_paired_b3.npz, which the reference's OWN
-    Wav2vec2PairedSpeakerModule + BinaryCrossEntropyLoss produced (oracle/make_golden.py paired): eval scores, loss,
-    prediction, the Linear head's gradients and every encoder gradient (norm and a strided sample each)."""
-    _need_cuda()
-    import numpy as np
-    from conftest import golden
-    from oracle.params import make_inputs
-    from w2v2_speaker_b200.optim.loss import BinaryCrossEntropyLoss
-    from w2v2_speaker_b200.paired_speaker_module import Wav2vec2PairedSpeakerModule, Wav2vec2PairedSpeakerModuleConfig
-    g = golden("ref_paired_b3.npz")
-    wav_a, _ = make_inputs(3, 16000, seed=31)
-    wav_b, _ = make_inputs(3, 11283, seed=32)
-    labels = torch.from_numpy(g["labels"])
-    m = Wav2vec2PairedSpeakerModule(Wav2vec2PairedSpeakerModuleConfig(**ZERO_REG), BinaryCrossEntropyLoss)
-    m.wav2vec.model.load_state_dict(base_params)
-    with torch.no_grad():
-        m.linear.weight.copy_(torch.from_numpy(g["linear.weight"]))
-        m.linear.bias.copy_(torch.from_numpy(g["linear.bias"]))
-    m = m.cuda().eval()
-    with torch.no_grad():
-        scores = m(wav_a.cuda(), wav_b.cuda())
-    assert np.abs(scores.cpu().numpy() - g["scores.eval"]).max() < 5e-3
-    m.train()
-    m.on_train_start()
-    scores = m(wav_a.cuda(), wav_b.cuda())
-    loss, prediction = m.loss_fn(scores, labels.cuda())
-    loss.backward()
-    torch.cuda.synchronize()
-    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 5e-3
-    assert np.abs(prediction.cpu().numpy() - g["prediction"]).max() < 2e-3
-
-    def rel(a, b):
-        a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-        return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
-
-    assert rel(m.linear.weight.grad.cpu().numpy(), g["grad.linear.weight"]) < 1e-2
-    assert rel(m.linear.bias.grad.cpu().numpy(), g["grad.linear.bias"]) < 1e-2
-    worst = (0.0, None)
-    for k, q in m.wav2vec.model.named_parameters():
-        if k.startswith("feature_extractor.") or k == "masked_spec_embed":
-            assert q.grad is None or q.grad.abs().max().item() == 0.0, k
-            continue
-        if k.endswith("k_proj.bias"):                 # exactly 0 in exact arithmetic: rounding noise on both sides
-            continue
-        grad = q.grad.detach().cpu()
-        flat = grad.reshape(-1)
-        step = max(1, flat.numel() // 256)
-        norm_err = abs(grad.double().norm().item() - float(g[f"grad.{k}.norm"])) / float(g[f"grad.{k}.norm"])
-        # 256 strided elements of a tensor: a noisier statistic than the norm-wise error of the whole tensor
-        err = rel(flat[::step][:256].numpy(), g[f"grad.{k}.sample"])
-        worst = max(worst, (err, k))
-        assert norm_err < 1e-2 and err < 3e-2, (k, norm_err, err)
-    print("worst sampled gradient error against the reference fixture", worst)
