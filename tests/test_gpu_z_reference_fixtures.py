@@ -80,7 +80,7 @@ def test_paired_input_model_matches_the_reference_fixture(base_params):
 
     assert rel(m.linear.weight.grad.cpu().numpy(), g["grad.linear.weight"]) < 1e-2
     assert rel(m.linear.bias.grad.cpu().numpy(), g["grad.linear.bias"]) < 1e-2
-    worst = (0.0, None)
+    worst = (-1.0, "")
     for k, q in m.wav2vec.model.named_parameters():
         if k.startswith("feature_extractor.") or k == "masked_spec_embed":
             assert q.grad is None or q.grad.abs().max().item() == 0.0, k
@@ -139,3 +139,47 @@ def test_full_size_batch_is_consistent_with_small_batches(base_params):
         ref = O.speaker_embedding(wav[:2], base_params, "mean")                  # 2 x 3 s on the CPU: a few seconds
     # north_star: 1e-3 on fp32 embeddings
     assert rows(emb[:2], ref) < 1e-3
+
+
+def test_full_size_training_step_gradient_is_the_mean_of_half_batches(base_params):
+    """The backward at BASELINE.json's full size (64 utterances of 3 s, regularisation off): the loss is a mean over
+    utterances, so every parameter gradient of the full batch must be the average of the gradients of its two halves
+    (same kernels, other tile counts / split-K factors / atomics order; the halves' activation gradients are exactly
+    twice as large, which fp16 rounding commutes with)."""
+    _need_cuda()
+    from oracle.params import make_head_params, make_inputs
+    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    S = 5994
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type="mean", test_stat_pooling_type="mean", **ZERO_REG)
+    m = Wav2vec2FCModule(cfg, S, CrossEntropyLoss)
+    m.wav2vec.model.load_state_dict(base_params, strict=False)
+    head = make_head_params(768, S, seed=1)
+    with torch.no_grad():
+        m.fc_list[-1][0].weight.copy_(head["fc.weight"]); m.fc_list[-1][0].bias.copy_(head["fc.bias"])
+    m = m.cuda().train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    wav, labels = make_inputs(64, 48000, S, seed=6)
+    x, y = wav[:, None, :].cuda(), labels.cuda()
+
+    def grads(lo, hi):
+        m.zero_grad(set_to_none=True)
+        emb, pred = m(x[lo:hi])
+        loss, _ = m.loss_fn(pred, y[lo:hi])
+        loss.backward()
+        return loss.item(), {k: q.grad.detach().double() for k, q in m.named_parameters() if q.grad is not None}
+
+    la, ga = grads(0, 32)
+    lb, gb = grads(32, 64)
+    lf, gf = grads(0, 64)
+    assert abs(lf - 0.5 * (la + lb)) < 1e-5 * abs(lf)
+    assert set(gf) == set(ga) == set(gb) and len(gf) > 190
+    worst = (-1.0, "")
+    for k, g in gf.items():
+        if k.endswith("k_proj.bias"):                 # exactly 0 in exact arithmetic: rounding noise in all three runs
+            continue
+        want = 0.5 * (ga[k] + gb[k])
+        err = ((g - want).norm() / want.norm().clamp_min(1e-30)).item()
+        worst = max(worst, (err, k))
+        assert err < 2e-3, (k, err)
+    print("worst full-batch vs half-batch gradient difference", worst)
