@@ -117,3 +117,27 @@ def test_bce_loss_matches_torch():
     assert not prediction.requires_grad
     loss.backward()
     assert logits.grad is not None
+
+
+def test_derived_weights_follow_parameter_versions():
+    """The fp16 operand copies are rebuilt when a parameter's autograd version or storage changes, updated in place by
+    refresh(), and (documented limit) not touched by edits made through .data."""
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
+    with dry_library() as lib:
+        w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False).eval()
+        model = w.model
+        eng = model._engine()
+        assert model._engine() is eng                                   # nothing changed: cached
+        q = dict(model.named_parameters())["encoder.layers.3.attention.q_proj.weight"]
+        with torch.no_grad():
+            q.data.mul_(1.0)                                            # invisible to the version counter
+        assert model._engine() is eng
+        lib.calls.clear()
+        model.refresh()                                                 # re-derives the copies with one batched launch
+        assert model._engine() is eng and lib.calls.count("w2v2_prepare_weights") == 1
+        with torch.no_grad():
+            q.mul_(1.0)                                                 # what torch.optim does: bumps the version
+        eng2 = model._engine()
+        assert eng2 is not eng
+        model.load_state_dict(model.state_dict())                       # copies in place: versions change again
+        assert model._engine() is not eng2
