@@ -22,14 +22,17 @@ def _fc_module(pooling, loss, **cfg_kw):
 
 
 @pytest.mark.parametrize("pooling,loss,freeze_cnn", [("mean", "ce", True), ("mean+std", "aam", True), ("attentive", "aam", True),
-                                                     ("first+cls", "ce", True), ("mean", "ce", False), ("first+cls", "ce", False)])
+                                                     ("first+cls", "ce", True), ("mean", "ce", False), ("first+cls", "ce", False),
+                                                     ("max", "ce", True), ("quantile", "ce", True), ("first", "ce", True),
+                                                     ("last", "ce", True)])
 def test_training_step_control_flow(pooling, loss, freeze_cnn):
     with dry_library() as lib:
         m = _fc_module(pooling, loss, layerdrop=0.0, completely_freeze_feature_extractor=freeze_cnn).train()
         m.wav2vec.model.feature_extractor.requires_grad_(not freeze_cnn)
         emb, pred = m(torch.randn(3, 1, 16000))
         out, prob = m.loss_fn(pred, torch.tensor([1, 2, 3]))
-        assert emb.shape == (3, 768 if pooling in ("mean", "first+cls") else 1536) and prob.shape == (3, S)
+        width = {"mean+std": 1536, "attentive": 1536, "quantile": 5 * 768}.get(pooling, 768)
+        assert emb.shape == (3, width) and prob.shape == (3, S)
         out.backward()
         calls = collections.Counter(lib.calls)
     assert calls["w2v2_encoder_layer_fwd"] == 12 and calls["w2v2_encoder_layer_bwd"] == 12
@@ -141,3 +144,33 @@ def test_derived_weights_follow_parameter_versions():
         assert eng2 is not eng
         model.load_state_dict(model.state_dict())                       # copies in place: versions change again
         assert model._engine() is not eng2
+
+
+@pytest.mark.parametrize("pooling,loss", [("mean", "ce"), ("attentive", "aam")])
+def test_fc_module_freeze_protocol(pooling, loss):
+    """SURVEY 8 row a13 (R:src/lightning_modules/speaker/wav2vec2_fc.py:339-361): the encoder starts frozen, the heads
+    train on their own (their kernels must still produce gradients with a gradient-less embedding), the encoder is
+    released after num_frozen_steps while the CNN stays frozen for good."""
+    with dry_library() as lib:
+        m = _fc_module(pooling, loss, layerdrop=0.0, wav2vec_initially_frozen=True, num_frozen_steps=2).train()
+        m.on_train_start()
+        assert not any(q.requires_grad for q in m.wav2vec.parameters()) and not m.wav2vec.training
+        heads = [(n, q) for n, q in m.named_parameters() if not n.startswith("wav2vec.")]
+        assert heads and all(q.requires_grad for _, q in heads)
+        for step in (1, 2, 3):
+            m.zero_grad(set_to_none=True)
+            lib.calls.clear()
+            emb, pred = m(torch.randn(3, 1, 16000))
+            out, _ = m.loss_fn(pred, torch.tensor([1, 2, 3]))
+            out.backward()
+            calls = collections.Counter(lib.calls)
+            assert all(q.grad is not None for _, q in heads), step
+            named = dict(m.wav2vec.model.named_parameters())
+            if step <= 2:                                   # frozen phase: forward schedules only, no encoder backward
+                assert calls["w2v2_encoder_layer_bwd"] == 0 and named["encoder.layers.0.attention.q_proj.weight"].grad is None
+            else:                                           # released after the second on_after_backward
+                assert calls["w2v2_encoder_layer_bwd"] == 12 and named["encoder.layers.0.attention.q_proj.weight"].grad is not None
+                assert named["feature_extractor.conv_layers.0.conv.weight"].grad is None
+            m.on_after_backward()
+        assert m.steps == 3 and not m._is_wav2vec_frozen and m.wav2vec.training
+    assert m.generate_example_input(True, 4).shape == (4, 16000) and m.generate_example_input(False).shape == (16000,)

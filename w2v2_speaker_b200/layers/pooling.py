@@ -65,7 +65,12 @@ class MaxPool1D(nn.Module):
         self.dim_to_reduce = dim_to_reduce
 
     def forward(self, tensor: torch.Tensor):
-        return ops.stat_pool(_as_btc(tensor, self.dim_to_reduce), 2)
+        x = _as_btc(tensor, self.dim_to_reduce)
+        if torch.is_grad_enabled() and x.requires_grad:
+            # training: torch's differentiable reduction (same values; max pooling is on no measured configuration and
+            # its backward is a scatter of B*C numbers -- the kernel below has no autograd node)
+            return x.max(dim=1).values
+        return ops.stat_pool(x, 2)
 
 
 class QuantilePool1D(nn.Module):

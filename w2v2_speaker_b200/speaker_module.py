@@ -106,6 +106,32 @@ class Wav2vec2FCModule(nn.Module):
                 output_features=cfg.explicit_num_speakers if cfg.explicit_num_speakers is not None else num_speakers,
                 margin=self.loss_fn.margin, scale=self.loss_fn.scale)
 
+        self._is_wav2vec_frozen = False
+        self.steps = 0
+
+    # ---- freeze protocol (R:.../wav2vec2_fc.py:339-361): which parameters get gradients, and with
+    # them which backward kernels run (frozen encoder: the heads' only; frozen CNN: everything behind it) -----------
+    def on_train_start(self) -> None:
+        self.steps = 0
+        if self.cfg.wav2vec_initially_frozen:
+            self.wav2vec.freeze()
+            self._is_wav2vec_frozen = True
+        if self.cfg.completely_freeze_feature_extractor:
+            self.wav2vec.model.feature_extractor.requires_grad_(False)
+
+    def on_after_backward(self) -> None:
+        self.steps += 1
+        if (self._is_wav2vec_frozen and self.cfg.num_frozen_steps is not None
+                and self.steps >= self.cfg.num_frozen_steps):
+            self.wav2vec.unfreeze()
+            self._is_wav2vec_frozen = False
+            if self.cfg.completely_freeze_feature_extractor:
+                self.wav2vec.model.feature_extractor.requires_grad_(False)
+
+    def generate_example_input(self, include_batch_dimension: bool, batch_size: Optional[int] = None):
+        # R:.../wav2vec2_fc.py:321-337: one second of uniform noise
+        return torch.rand(size=[batch_size, 16000] if include_batch_dimension else [16000])
+
     # R:.../wav2vec2_fc.py:238-272
     def _determine_pooling_layer(self, stat_pooling_type: str, only_at_test_time: bool):
         if stat_pooling_type == "mean":
