@@ -39,6 +39,20 @@ class DryLib:
         return stub
 
 
+class _DryStream:
+    """torch.cuda.Stream stand-in for the dry run: ordering calls are recorded, nothing waits."""
+    log = []
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        _DryStream.log.append(("wait", id(self), id(other)))
+
+    def synchronize(self):
+        pass
+
+
 @contextlib.contextmanager
 def dry_library():
     """Patch the package so that its CUDA path 'runs' on CPU tensors; yields the DryLib (``.calls`` = the sequence of
@@ -47,11 +61,17 @@ def dry_library():
     real = _lib.load()
     dry = DryLib(real, _lib.SIGNATURES)
     saved = (_lib.load, _lib.stream_ptr, ops.stream_ptr, schedule._lib.stream_ptr, torch.Tensor.is_cuda)
+    cuda_saved = (torch.cuda.Stream, torch.cuda.current_stream, torch.cuda.stream)
     _lib.load = lambda: dry
     _lib.stream_ptr = ops.stream_ptr = lambda: None
     torch.Tensor.is_cuda = property(lambda self: True)          # the wrappers' "CUDA tensors only" guards
+    current = _DryStream()
+    torch.cuda.Stream = _DryStream                              # trainer.py: optimizer / communication streams
+    torch.cuda.current_stream = lambda *a, **k: current
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
     try:
         yield dry
     finally:
         _lib.load, _lib.stream_ptr, ops.stream_ptr = saved[0], saved[1], saved[2]
         torch.Tensor.is_cuda = saved[4]
+        torch.cuda.Stream, torch.cuda.current_stream, torch.cuda.stream = cuda_saved
