@@ -174,3 +174,17 @@ def test_fc_module_freeze_protocol(pooling, loss):
             m.on_after_backward()
         assert m.steps == 3 and not m._is_wav2vec_frozen and m.wav2vec.training
     assert m.generate_example_input(True, 4).shape == (4, 16000) and m.generate_example_input(False).shape == (16000,)
+
+
+def test_evaluation_handles_any_utterance_length():
+    """Host side of the any-length evaluation forward (frame arithmetic HF:1012-1018, single-slab / chunked positional
+    conv, single-tile / key-tiled attention): one frame up to 70 s; shorter than the receptive field raises."""
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
+    with dry_library():
+        w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False).eval()
+        with torch.no_grad():
+            for n, frames in ((400, 1), (719, 1), (720, 2), (16000, 49), (82000, 256), (82320, 257), (160400, 501),
+                              (1120000, 3499)):
+                assert w(torch.randn(1, n)).shape == (1, 768, frames), n
+            with pytest.raises(ValueError):
+                w(torch.randn(2, 399))

@@ -218,6 +218,10 @@ class EncoderEngine:
         a, w = self.arch, self.w
         if wav.dim() != 2:
             raise ValueError(f"expected wav_input of shape [BATCH_SIZE, NUM_SAMPLES], got {tuple(wav.shape)}")
+        if a.conv_lengths(wav.shape[1])[-1] < 1:
+            # HF fails inside the conv stack here ("kernel size can't be greater than actual input size")
+            raise ValueError(f"utterances of {wav.shape[1]} samples are shorter than the receptive field of the feature "
+                             f"extractor (no output frame)")
         h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps)
         if stages is not None:
             stages.append(h)
