@@ -1,0 +1,87 @@
+"""The persistent attention kernels (csrc/attention_persist.cu, csrc/attention_bwd_persist.cu; T <= 160) at shapes where
+every CTA walks several (batch, head) problems -- stage reuse, barrier phases, the rotating lane quarter of the second
+query tile -- against torch fp32 (HF:438-463), with and without attention dropout (mask replayed in numpy)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+try:                                                    # numpy replica of the counter RNG
+    from test_gpu_regularise import keep_mask          # noqa: E402
+except ImportError:
+    from tests.test_gpu_regularise import keep_mask    # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from w2v2_speaker_b200 import ops as o
+    return o
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _reference(qkv, d_o, B, T, H, heads, mask=None, inv=1.0):
+    d = H // heads
+    x = qkv.float().requires_grad_(True)
+    q, k, v = (x[:, i * H:(i + 1) * H].view(B, T, heads, d).transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(2, 3)
+    a = torch.softmax(s, -1)
+    if mask is not None:
+        a = torch.where(mask, a * inv, torch.zeros_like(a))
+    o = (a @ v).transpose(1, 2).reshape(B * T, H)
+    g = torch.autograd.grad(o, x, d_o.float())[0] if d_o is not None else None
+    return o.detach(), torch.logsumexp(s.detach(), -1), g
+
+
+@pytest.mark.parametrize("B,T,H,heads", [(64, 149, 768, 12), (40, 100, 768, 12), (33, 160, 768, 12), (31, 129, 768, 12),
+                                         (29, 145, 1024, 16), (50, 128, 768, 12), (160, 17, 768, 12)])
+def test_persistent_attention_many_problems_per_cta(ops, B, T, H, heads):
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = torch.randn(B * T, 3 * H, generator=g).cuda().half()
+    qkv[:, :H] *= 0.35
+    d_o = (torch.randn(B * T, H, generator=g) * 0.7).cuda().half()
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True)
+    dqkv = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads)
+    torch.cuda.synchronize()
+    o, lse_ref, gref = _reference(qkv, d_o, B, T, H, heads)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all()
+    # per (utterance, head) so that one wrong problem cannot hide in the norm of 768
+    eo = (out.float() - o).view(B, T, heads, -1).norm(dim=(1, 3)) / o.view(B, T, heads, -1).norm(dim=(1, 3))
+    assert eo.max().item() < 2e-3, eo.max().item()
+    assert rel(lse, lse_ref) < 1e-3
+    for i in range(3):
+        a, r = dqkv[:, i * H:(i + 1) * H].float(), gref[:, i * H:(i + 1) * H]
+        e = (a - r).view(B, T, heads, -1).norm(dim=(1, 3)) / r.view(B, T, heads, -1).norm(dim=(1, 3))
+        assert e.max().item() < 6e-3, ("qkv"[i], e.max().item())
+
+
+@pytest.mark.parametrize("B,T,H,heads", [(64, 149, 768, 12), (20, 96, 768, 12)])
+def test_persistent_attention_dropout_and_bias_gradients(ops, B, T, H, heads):
+    g = torch.Generator().manual_seed(7)
+    qkv = torch.randn(B * T, 3 * H, generator=g).cuda().half()
+    qkv[:, :H] *= 0.35
+    d_o = (torch.randn(B * T, H, generator=g) * 0.7).cuda().half()
+    p, seed = 0.1, 987654321
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True, drop_p=p, drop_seed=seed)
+    dbias = torch.zeros(3 * H, device="cuda")
+    dqkv = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads, drop_p=p, drop_seed=seed, qscale=0.125, dbias=dbias)
+    torch.cuda.synchronize()
+    TK = (T + 15) // 16 * 16
+    keep, inv = keep_mask(seed, B * heads * T * TK, p)
+    m = torch.from_numpy(keep).view(B, heads, T, TK)[..., :T].cuda()
+    o, lse_ref, gref = _reference(qkv, d_o, B, T, H, heads, m, inv)
+    gref = gref.clone()
+    gref[:, :H] *= 0.125
+    assert rel(out.float(), o) < 2e-3
+    assert rel(lse, lse_ref) < 1e-3
+    for i in range(3):
+        assert rel(dqkv[:, i * H:(i + 1) * H].float(), gref[:, i * H:(i + 1) * H]) < 6e-3, "qkv"[i]
+    # bias gradients = column sums of what was written (fp32 accumulators before the fp16 rounding of dqkv)
+    ref_b = gref.double().sum(0)
+    assert ((dbias.double() - ref_b).norm() / ref_b.norm()).item() < 5e-3
+    assert abs(float(np.mean(keep)) - (1 - p)) < 5e-3

@@ -134,14 +134,8 @@ def test_gemm_gelu_backward_epilogue(ops, M, N, K):
     assert ((2 * db2.double() + 0.25 - dbias.double()).abs() / scale).max().item() < 1e-3
 
 
-_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("W2V2_EXPERIMENTAL") != "1",
-                                   reason="kernel compiled but not yet run on a GPU (written after the round's GPU budget "
-                                          "was spent); set W2V2_EXPERIMENTAL=1 to run")
-
-
-@_EXPERIMENTAL
 @pytest.mark.parametrize("M,N,K", [(9536, 3072, 768), (300, 384, 64)])
-def test_experimental_gemm_pair_keeping_the_gelu_derivative(ops, M, N, K):
+def test_gemm_pair_keeping_the_gelu_derivative(ops, M, N, K):
     """FFN1 forward keeping gelu'(z) (w2v2_gemm_f16_dual_gelu_grad) and the multiply-only backward epilogue
     (w2v2_gemm_f16_mul_colsum) against torch fp32 and against the validated z-keeping pair."""
     a = _rand((M, K), 71).half()

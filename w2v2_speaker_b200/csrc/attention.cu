@@ -214,6 +214,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
 }
 
 int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, cudaStream_t stream);
+int attention_persist_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, uint32_t drop_thr,
+                             float drop_inv_keep, uint64_t drop_seed, cudaStream_t stream);
 
 }  // namespace w2v2
 
@@ -242,6 +244,11 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
   p.drop_inv_keep = 1.0f / (1.0f - float(p.drop_thr) / 65536.0f);
   p.drop_seed = drop_seed;
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
+  W2V2_REQUIRE(uint64_t(B) * heads * T * (TK / 2) < (1ull << 32), "w2v2_attention: dropout mask index exceeds 32 bits");
+  {     // T <= 160 (training crops): the persistent kernel (attention_persist.cu); 1 = not applicable
+    const int prc = attention_persist_launch(qkv16, out16, lse, B, T, H, heads, p.drop_thr, p.drop_inv_keep, drop_seed, stream);
+    if (prc <= 0) return prc;
+  }
   if (TK <= 192) { p.tmem_cols = 256; p.o_col = 192; } else { p.tmem_cols = 512; p.o_col = 256; }
   if (TK <= 64) { p.tmem_cols = 128; p.o_col = 64; }
   const int kvb = (TK * 128 + 1023) & ~1023;

@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
 int attention_bwd_fused_launch(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
                                int T, int H, int heads, uint32_t drop_thr, float drop_inv_keep, uint64_t drop_seed,
                                float qscale, float* dbias, cudaStream_t stream);
+int attention_bwd_persist_launch(const void* qkv16, const void* o16, const void* do16, const float* lse, void* dqkv16, int B,
+                                 int T, int H, int heads, uint32_t drop_thr, float drop_inv_keep, uint64_t drop_seed,
+                                 float qscale, float* dbias, cudaStream_t stream);
 
 }  // namespace w2v2
 
@@ -382,6 +385,10 @@ extern "C" int w2v2_attention_bwd_ex2(const void* qkv16, const void* o16, const 
   W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention_bwd: dropout p=%f out of [0,1)", drop_p);
   if (TK <= 160) {     // 3 s utterances: the short-chain kernel (attention_bwd_fused.cu)
     const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
+    // the persistent form (attention_bwd_persist.cu); 1 = switched off (W2V2_ATTN_PERSIST=0)
+    const int prc = attention_bwd_persist_launch(qkv16, o16, do16, lse, dqkv16, B, T, H, heads, thr,
+                                                 1.0f / (1.0f - float(thr) / 65536.0f), drop_seed, qscale, dbias, stream);
+    if (prc <= 0) return prc;
     return attention_bwd_fused_launch(qkv16, o16, do16, lse, dqkv16, B, T, H, heads, thr,
                                       1.0f / (1.0f - float(thr) / 65536.0f), drop_seed, qscale, dbias, stream);
   }

@@ -412,7 +412,11 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ log
   __shared__ int smi[8];
   const int b = blockIdx.x;
   float* row = logits + int64_t(b) * ldl;
-  const int label = int(labels[b]);
+  const int64_t label64 = labels[b];
+  // torch raises on a class index outside [0, S) (device-side assert); here the kernel traps instead of reading
+  // row[label] out of bounds / leaving cos_label unset for the backward
+  if (label64 < 0 || label64 >= S) __trap();
+  const int label = int(label64);
   if (aam) {
     // R:src/optim/loss/aam_softmax.py:56-69
     for (int i = threadIdx.x; i < S; i += blockDim.x) {

@@ -84,6 +84,10 @@ def calculate_mdc(groundtruth_scores: List[int], predicted_scores: List[float], 
     sc = np.asarray(predicted_scores, dtype=np.float64)
     order = np.argsort(sc, kind="mergesort")           # ascending, stable like python's sorted()
     gt, thr = gt[order], sc[order]
+    if gt.sum() == 0 or gt.sum() == gt.size:
+        # the reference divides python ints here (R:src/eval_metrics.py:130-139) and lets the ZeroDivisionError reach its
+        # evaluator, which maps it to mdc = 1, threshold = 1337 (R:src/evaluation/speaker/speaker_recognition_evaluator.py)
+        raise ZeroDivisionError("calculate_mdc needs trials of both classes (all ground-truth labels are equal)")
     fnrs = np.cumsum(gt) / gt.sum()
     fprs = 1.0 - np.cumsum(1.0 - gt) / (gt.size - gt.sum())
     c_det = c_miss * fnrs * p_target + c_fa * fprs * (1 - p_target)

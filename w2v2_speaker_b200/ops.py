@@ -373,9 +373,22 @@ def asp_pool(x: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _chk_labels(labels: torch.Tensor, B: int) -> torch.Tensor:
+    """Class indices as the kernels read them: a CUDA, contiguous int64 vector of B entries (the range check
+    0 <= label < S is done on the device: the kernel traps, like torch's device-side assert)."""
+    if not isinstance(labels, torch.Tensor) or not labels.is_cuda:
+        raise ValueError("labels must be a CUDA tensor (there is no CPU path)")
+    if labels.dtype != torch.int64:
+        raise TypeError(f"labels must be int64 class indices, got {labels.dtype}")
+    if labels.numel() != B or labels.dim() != 1:
+        raise ValueError(f"labels must have shape [{B}], got {tuple(labels.shape)}")
+    return labels if labels.is_contiguous() else labels.contiguous()
+
+
 def softmax_ce(logits: torch.Tensor, labels: torch.Tensor, want_prob: bool = True):
     """-> (prob [B,S] | None, loss_rows [B], argmax [B] int32).  logits f32 [B,S] (any row pitch)."""
     B, S = logits.shape
+    labels = _chk_labels(labels, B)
     prob = torch.empty(B, S, dtype=F32, device=logits.device) if want_prob else None
     loss = torch.empty(B, dtype=F32, device=logits.device)
     am = torch.empty(B, dtype=torch.int32, device=logits.device)
@@ -388,6 +401,7 @@ def aam_softmax_ce(cosine: torch.Tensor, labels: torch.Tensor, margin: float, sc
                    easy_margin: bool = False, want_prob: bool = True):
     """In place on `cosine` (becomes the scaled margin logits).  -> (prob, loss_rows, argmax)."""
     B, S = cosine.shape
+    labels = _chk_labels(labels, B)
     prob = torch.empty(B, S, dtype=F32, device=cosine.device) if want_prob else None
     loss = torch.empty(B, dtype=F32, device=cosine.device)
     am = torch.empty(B, dtype=torch.int32, device=cosine.device)
@@ -489,6 +503,7 @@ def meanstd_pool_bwd(x: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
 def aam_softmax_ce_train(cosine, labels, margin, scale, easy_margin=False):
     """Like aam_softmax_ce, additionally returning the pre-margin label cosines (saved for backward)."""
     B, S = cosine.shape
+    labels = _chk_labels(labels, B)
     prob = torch.empty(B, S, dtype=F32, device=cosine.device)
     loss = torch.empty(B, dtype=F32, device=cosine.device)
     am = torch.empty(B, dtype=torch.int32, device=cosine.device)

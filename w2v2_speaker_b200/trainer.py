@@ -21,6 +21,8 @@ from __future__ import annotations
 
 from typing import List
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -32,60 +34,112 @@ from .training import LOSS_SCALE, GradBook, encoder_grad_order
 
 class FlatAdamTrainer:
     def __init__(self, module: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 bucket_bytes: int = 64 << 20):
+                 bucket_bytes: int = 64 << 20, lr_schedule=None):
+        """`lr_schedule`: optional callable step (1-based) -> learning rate, evaluated once per iteration like the
+        reference steps its scheduler (`interval: step`, R:config/optim/schedule/one_cycle.yaml; `one_cycle_lr` below)."""
         self.module = module
         self.lr, self.betas, self.eps = lr, betas, eps
+        self.lr_schedule = lr_schedule
         self.model = next((m for m in module.modules() if isinstance(m, Wav2Vec2ModelB200)), None)
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self._overlapped = []
+        self._refreshable = None
+        self._pending = None
+        self.ar_layers = max(1, int(os.environ.get("W2V2_AR_LAYERS", "4")))    # transformer layers per all-reduce
+        self.params: List[torch.nn.Parameter] = []
+        self._state = {}                       # id(parameter) -> (exp_avg, exp_avg_sq) views of the previous layout
+        self._layout()
+        dev = self.params[0].device
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # optimizer stream (see module docstring); with a trainable CNN the update must finish before the next forward
+        self.opt_stream = torch.cuda.Stream(device=dev)
+        if self.world > 1:
+            self._broadcast_initial_state()
+
+    # ---- flat buffers -------------------------------------------------------------------------------------------
+    def _trainable_signature(self):
+        return tuple(p.requires_grad for p in self.module.parameters())
+
+    def _layout(self):
+        """(Re)build the flat parameter / gradient / Adam-state buffers for the CURRENT set of trainable parameters.
+        Called at construction and again whenever `requires_grad` changed between two steps -- the reference's freeze
+        protocol (R:src/lightning_modules/speaker/wav2vec2_fc.py:339-361) trains the heads alone for `num_frozen_steps`
+        and then releases the encoder; Adam state of parameters that stay trainable is carried over, newly released
+        parameters start from zero moments like a freshly added `torch.optim` param group."""
+        module = self.module
         named = dict(module.named_parameters())
         enc_named = dict(self.model.named_parameters()) if self.model is not None else {}
+        # keep the state of the previous layout (views into the old flat buffers stay alive through these references)
+        old_state = {}
+        o = 0
+        for p_ in self.params:
+            k = p_.numel()
+            old_state[id(p_)] = (self.m[o:o + k], self.v[o:o + k])
+            o += k
+        if self.model is not None:
+            self.model._grad_sink = None
+            self.model._grad_ready_hook = None
+            self.model._pre_encoder_hook = None
         # segment 0: encoder parameters in the order the backward wants (q|k|v adjacent), loss-scaled grads
         enc_order = [k for k in (encoder_grad_order(self.model.arch) if self.model is not None else [])
                      if enc_named[k].requires_grad]
         if self.model is not None and len(enc_order) != len(encoder_grad_order(self.model.arch)):
-            enc_order = []          # partially frozen encoder: fall back to autograd accumulation
+            enc_order = []          # (partially) frozen encoder: its trainable parameters go through autograd accumulation
         enc_ids = {id(enc_named[k]) for k in enc_order}
         seg0 = [enc_named[k] for k in enc_order]
         seg1 = [p for p in named.values() if p.requires_grad and id(p) not in enc_ids]
-        self.params: List[torch.nn.Parameter] = seg0 + seg1
+        self.params = seg0 + seg1
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
         self.n0 = sum(p.numel() for p in seg0)
         n = sum(p.numel() for p in self.params)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        flat_p = torch.empty(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        m = torch.zeros(n, dtype=torch.float32, device=dev)
+        v = torch.zeros(n, dtype=torch.float32, device=dev)
         o = 0
         for i, p in enumerate(self.params):
             k = p.numel()
-            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[o:o + k].view_as(p)
+            flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = flat_p[o:o + k].view_as(p)
+            if id(p) in old_state:
+                m[o:o + k].copy_(old_state[id(p)][0])
+                v[o:o + k].copy_(old_state[id(p)][1])
             if i >= len(seg0):
                 p.grad = self.flat_g[o:o + k].view_as(p)      # autograd accumulates the (unscaled) head grads here
+            else:
+                p.grad = None                                  # the backward writes straight into the flat buffer
             o += k
+        self.flat_p, self.m, self.v = flat_p, m, v
         if seg0:
             self.model._grad_sink = GradBook({k: enc_named[k].shape for k in enc_order}, enc_order, dev,
                                              flat=self.flat_g[:self.n0])
-        self.step_count = 0
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.bucket_elems = max(1, bucket_bytes // 4)
-        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
-        self._overlapped = []
-        self._refreshable = None
-        # optimizer stream (see module docstring); with a trainable CNN the update must finish before the next forward
-        self.opt_stream = torch.cuda.Stream(device=dev)
         cnn_trainable = self.model is not None and any(q.requires_grad for q in self.model._items()[3])
-        import os
         self._overlap_update = (self.model is not None and not cnn_trainable and
                                 os.environ.get("W2V2_OPT_STREAM", "1") != "0")        # =0: update in stream order (A/B)
-        if self._overlap_update:
+        # the encoder joins the optimizer stream right after its CNN; a frozen encoder never runs that hook (step() joins)
+        self._encoder_joins = self._overlap_update and bool(seg0)
+        if self._encoder_joins:
             self.model._pre_encoder_hook = self._join_update
-        import os
-        self._pending = None
-        self.ar_layers = max(1, int(os.environ.get("W2V2_AR_LAYERS", "4")))    # transformer layers per all-reduce
         if seg0 and self.world > 1:
             self.model._grad_ready_hook = self._layer_ready      # spans of flat_g[:n0] == GradBook offsets
+        self._refreshable = None
+        self._sig = self._trainable_signature()
+        if self.model is not None:
+            self.model.refresh()          # parameter storage moved: re-derive the operand copies on next use
+
+    def _broadcast_initial_state(self):
+        """What DistributedDataParallel does at construction (R:config/trainer/trainer.yaml:6-9 `accelerator: ddp`): every
+        rank starts from rank 0's parameters and buffers (BatchNorm running statistics of the attentive pooling)."""
+        for p in self.module.parameters():                 # frozen parameters included
+            dist.broadcast(p.data, src=0)
+        for b in self.module.buffers():
+            if b.is_floating_point() or b.dtype in (torch.int64, torch.int32):
+                dist.broadcast(b, src=0)
+        self._refresh_module_weights()
 
     def _refresh_module_weights(self):
         if self._refreshable is None:          # the module tree is fixed: walk it once
@@ -155,7 +209,14 @@ class FlatAdamTrainer:
     def step(self, wav: torch.Tensor, labels: torch.Tensor):
         """One optimisation step; returns (loss, softmax) like the reference's training_step uses them."""
         cur = torch.cuda.current_stream()
-        if not self._overlap_update:
+        if self._trainable_signature() != self._sig:
+            # the set of trainable parameters changed (freeze protocol released the encoder, or froze something):
+            # finish the pending update, then rebuild the flat buffers and the gradient sink for the new set
+            cur.wait_stream(self.opt_stream)
+            self._layout()
+        if not self._encoder_joins:
+            # in-order update, or an encoder without trainable parameters: its (evaluation-path) forward never calls the
+            # join hook, and the heads read weights / operand copies the optimizer stream may still be writing
             cur.wait_stream(self.opt_stream)
         emb, pred = self.module(wav)
         cur.wait_stream(self.opt_stream)          # no-op if the encoder already joined (it always does when it runs)
@@ -163,6 +224,8 @@ class FlatAdamTrainer:
         loss.backward()
         self.allreduce_grads()
         self.step_count += 1
+        if self.lr_schedule is not None:
+            self.lr = float(self.lr_schedule(self.step_count))
         b1, b2 = self.betas
         n0, n = self.n0, self.flat_p.numel()
         opt_stream = self.opt_stream if self._overlap_update else cur
@@ -176,3 +239,25 @@ class FlatAdamTrainer:
                               self.step_count, grad_scale=1.0 / self.world, zero_grad=True)
             self._refresh_module_weights()         # (the gradient buffer was cleared by the Adam pass itself)
         return loss.detach(), prob
+
+
+def one_cycle_lr(max_lr: float, total_steps: int, pct_start: float = 0.3, div_factor: float = 25.0,
+                 final_div_factor: float = 1e4):
+    """`torch.optim.lr_scheduler.OneCycleLR` (cosine annealing, two phases) as a step -> lr callable for
+    FlatAdamTrainer(lr_schedule=...): the reference's default schedule (R:config/optim/schedule/one_cycle.yaml,
+    stepped every iteration).  step is 1-based: the value returned for step s is the rate torch's scheduler holds
+    after s - 1 calls of `scheduler.step()`."""
+    import math
+    initial, min_lr = max_lr / div_factor, max_lr / div_factor / final_div_factor
+    up_end = float(pct_start * total_steps) - 1.0
+    last = float(total_steps) - 1.0
+
+    def cos(a, b, pct):
+        return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1.0)
+
+    def lr(step: int) -> float:
+        n = min(max(step - 1, 0), total_steps - 1)
+        if n <= up_end:
+            return cos(initial, max_lr, n / up_end if up_end > 0 else 1.0)
+        return cos(max_lr, min_lr, (n - up_end) / (last - up_end))
+    return lr
