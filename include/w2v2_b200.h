@@ -248,6 +248,14 @@ int w2v2_scale_f32(float* x, int64_t n, float s, void* stream);
 /* y = x * s, out of place (the loss scale entering / leaving an autograd Function: gradients that cross a Function
  * boundary are plain unscaled fp32 and belong to autograd). */
 int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stream);
+/* Gradient entry of an autograd Function with a device-chosen normalisation (an outer torch.amp.GradScaler --
+ * `precision: 16`, R:config/experiment/speaker_wav2vec2_aam.yaml:17 -- multiplies the incoming gradient by up to 2^16, which
+ * would overflow the fp16 operand copies of the backward GEMMs): y = x * s * k, where k = 1 while amax|x| * s lies in
+ * [lo, hi] (the normal case: bit-identical to w2v2_scale_copy_f32) and otherwise the power of two that brings it to `mid`;
+ * state f32[2] (device): [0] scratch, [1] = 1 / k.  No host synchronisation.  w2v2_scale_f32_dev: x *= s * dev_scale[0]. */
+int w2v2_grad_entry_scale(const float* x, float* y, int64_t n, float s, float lo, float hi, float mid, float* state,
+                          void* stream);
+int w2v2_scale_f32_dev(float* x, int64_t n, float s, const float* dev_scale, void* stream);
 int w2v2_softmax_ce_bwd_f32(const float* prob, const int64_t* labels, const float* dloss, float coef, float* dlogits,
                             int B, int S, void* stream);
 /* torch.optim.Adam step (weight_decay 0) over flat fp32 buffers; `g` is multiplied by grad_scale first

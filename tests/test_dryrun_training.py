@@ -37,7 +37,8 @@ def test_training_step_control_flow(pooling, loss, freeze_cnn):
         calls = collections.Counter(lib.calls)
     assert calls["w2v2_encoder_layer_fwd"] == 12 and calls["w2v2_encoder_layer_bwd"] == 12
     # the loss scale enters the encoder backward exactly once per step, out of place (autograd owns the incoming gradient)
-    assert calls["w2v2_scale_copy_f32"] >= 1
+    # (w2v2_grad_entry_scale: the same copy with the device-chosen normalisation that keeps an outer GradScaler harmless)
+    assert calls["w2v2_grad_entry_scale"] >= 1 and calls["w2v2_scale_f32_dev"] >= 1
     for n, q in m.wav2vec.model.named_parameters():
         if n == "masked_spec_embed":
             continue
@@ -188,3 +189,44 @@ def test_evaluation_handles_any_utterance_length():
                 assert w(torch.randn(1, n)).shape == (1, 768, frames), n
             with pytest.raises(ValueError):
                 w(torch.randn(2, 399))
+
+
+def test_frozen_encoder_in_train_mode_runs_the_stochastic_forward():
+    """`wav2vec_initially_frozen` + Lightning's `.train()` after a validation loop leaves a frozen encoder in
+    train mode; HF then runs a dropout-active forward without gradients -- so must the mirror (it used to raise)."""
+    with dry_library() as lib:
+        m = _fc_module("mean", "ce", wav2vec_initially_frozen=True, num_frozen_steps=100).train()
+        m.on_train_start()
+        m.train()                                            # what Lightning does after every validation loop
+        assert m.wav2vec.training and not any(q.requires_grad for q in m.wav2vec.parameters())
+        lib.calls.clear()
+        emb, pred = m(torch.randn(3, 1, 16000))
+        calls = collections.Counter(lib.calls)
+        assert calls["w2v2_encoder_layer_fwd"] >= 10 and calls["w2v2_dropout"] >= 1      # the regularised forward ran
+        assert not emb.requires_grad or pred.requires_grad   # heads still differentiable
+        out, _ = m.loss_fn(pred, torch.tensor([1, 2, 3]))
+        out.backward()
+        assert collections.Counter(lib.calls)["w2v2_encoder_layer_bwd"] == 0
+
+
+def test_flat_trainer_follows_the_freeze_protocol():
+    """a FlatAdamTrainer built while the encoder is frozen must pick the encoder up once
+    on_after_backward() releases it (flat buffers + gradient sink rebuilt, Adam state of the heads carried over)."""
+    from w2v2_speaker_b200.trainer import FlatAdamTrainer
+    with dry_library() as lib:
+        m = _fc_module("mean", "ce", layerdrop=0.0, wav2vec_initially_frozen=True, num_frozen_steps=1).train()
+        m.on_train_start()
+        tr = FlatAdamTrainer(m, lr=1e-3)
+        n_heads = tr.flat_p.numel()
+        assert tr.n0 == 0 and tr.model._grad_sink is None and not tr._encoder_joins
+        tr.m.fill_(0.5)                                      # stand-in for accumulated Adam state of the heads
+        tr.step(torch.randn(2, 1, 16000), torch.tensor([1, 2]))
+        m.on_after_backward()                                # releases the encoder (CNN stays frozen)
+        lib.calls.clear()
+        tr.step(torch.randn(2, 1, 16000), torch.tensor([1, 2]))
+        assert tr.n0 > 90_000_000 and tr.model._grad_sink is not None and tr._encoder_joins
+        assert tr.flat_p.numel() == tr.n0 + n_heads
+        assert collections.Counter(lib.calls)["w2v2_encoder_layer_bwd"] == 12
+        assert torch.all(tr.m[tr.n0:] == 0.5) and torch.all(tr.m[:tr.n0] == 0)          # heads kept, encoder fresh
+        q = dict(m.wav2vec.model.named_parameters())["encoder.layers.0.attention.q_proj.weight"]
+        assert q.data_ptr() >= tr.flat_p.data_ptr() and q.data_ptr() < tr.flat_p.data_ptr() + 4 * tr.flat_p.numel()

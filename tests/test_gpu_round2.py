@@ -1,0 +1,238 @@
+"""Round-2 GPU tests (VERDICT r1 "next round" items 2, 5, 8, 9):
+* an outer GradScaler (`precision: 16`) does not overflow the internal fp16 gradient operands,
+* fp16 operand RANGE under pretrained-like activation magnitudes,
+* oracle anchors at BASELINE.json's full size for 8 of the 64 utterances (cfg1) and for cfg2 (attentive + AAM),
+* a live transformers state dict renamed to 4.x keys loads through checkpoint.py and reproduces the HF forward,
+* (two GPUs) an N-rank trainer step equals the 1-rank step on the concatenated batch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+S = 5994
+ZERO_REG = dict(activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
+                mask_time_prob=0.0, mask_feature_prob=0.0)
+
+
+def _need_cuda(n=1):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} CUDA device(s)")
+
+
+def rows(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm(dim=-1) / b.norm(dim=-1)).max().item()
+
+
+def _module(pooling, loss, base_params, **cfg_over):
+    from oracle.params import make_asp_params, make_head_params
+    from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    cfg = Wav2vec2FCModuleConfig(stat_pooling_type=pooling, test_stat_pooling_type=pooling, **{**ZERO_REG, **cfg_over})
+    ctor = CrossEntropyLoss if loss == "ce" else (
+        lambda: AngularAdditiveMarginSoftMaxLoss(input_features=1, output_features=1, margin=0.2, scale=30))
+    m = Wav2vec2FCModule(cfg, S, ctor)
+    m.wav2vec.model.load_state_dict(base_params, strict=False)
+    head = make_head_params(768 if pooling == "mean" else 1536, S, seed=1)
+    with torch.no_grad():
+        if loss == "ce":
+            m.fc_list[-1][0].weight.copy_(head["fc.weight"]); m.fc_list[-1][0].bias.copy_(head["fc.bias"])
+        else:
+            m.loss_fn.fc_weights.copy_(head["aam.fc_weights"])
+        if pooling == "attentive":
+            m.stat_pooling.pooling_layer.load_state_dict(make_asp_params(768, seed=2), strict=False)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("pooling,loss", [("mean", "ce"), ("attentive", "aam")])
+def test_outer_grad_scaler_scale_is_absorbed(base_params, pooling, loss):
+    """Lightning's native AMP (`precision: 16`, R:config/experiment/speaker_wav2vec2_aam.yaml:17) multiplies the loss by the
+    GradScaler's scale, 2^16 at the start.  The backward used to carry that factor into its fp16 gradient copies (inf until
+    the scaler had backed off to ~2^10).  Now each Function normalises its incoming gradient by a device-chosen power of two:
+    the gradients of scale * loss must be finite and equal scale * (gradients of loss)."""
+    _need_cuda()
+    from oracle.params import make_inputs
+    m = _module(pooling, loss, base_params).train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    wav, labels = make_inputs(2, 16000, S, seed=1234)
+    x, y = wav[:, None, :].cuda(), labels.cuda()
+
+    def grads(scale):
+        m.zero_grad(set_to_none=True)
+        if pooling == "attentive":          # same BatchNorm running statistics for both runs
+            m.stat_pooling.pooling_layer.tdnn.norm.norm.reset_running_stats()
+        emb, pred = m(x)
+        loss_v, _ = m.loss_fn(pred, y)
+        (loss_v * scale).backward()
+        return {k: q.grad.detach().double().cpu() for k, q in m.named_parameters() if q.grad is not None}
+
+    g1 = grads(1.0)
+    for scale in (65536.0, 2.0 ** -12):
+        gs = grads(scale)
+        assert set(gs) == set(g1) and len(g1) > 190
+        for k, g in gs.items():
+            assert torch.isfinite(g).all(), (scale, k)
+            # exactly 0 in exact arithmetic (softmax shift invariance over keys / over time): rounding noise only
+            if k.endswith("k_proj.bias") or k.endswith("pooling_layer.conv.conv.bias"):
+                continue
+            err = ((g / scale - g1[k]).norm() / g1[k].norm().clamp_min(1e-30)).item()
+            assert err < 3e-3, (scale, k, err)
+
+
+def test_fp16_operand_range_with_large_activations(base_params):
+    """Random-init weights keep every activation O(1); pretrained wav2vec2 carries residual-stream / FFN activations two
+    orders of magnitude larger.  Scale the weights so that the FFN hidden activations (kept in fp16), the qkv projections
+    (fp16) and the residual stream grow ~64x and check the fp16 copies neither overflow nor lose the embedding parity."""
+    _need_cuda()
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_inputs
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
+    p = {k: v.clone() for k, v in base_params.items()}
+    for l in range(12):
+        pre = f"encoder.layers.{l}."
+        p[pre + "feed_forward.intermediate_dense.weight"] *= 24.0          # FFN hidden ~ 24 x sqrt-ish larger
+        p[pre + "feed_forward.intermediate_dense.bias"] += 2.0
+        p[pre + "feed_forward.output_dense.weight"] *= 4.0                # residual branch ~ 100 x
+        p[pre + "attention.v_proj.weight"] *= 16.0
+        p[pre + "attention.q_proj.weight"] *= 3.0
+        p[pre + "final_layer_norm.weight"] *= 8.0                          # residual stream (fp32) and its fp16 copy ~ 8 x
+        p[pre + "final_layer_norm.bias"] += 4.0
+    wav, _ = make_inputs(2, 16000, S, seed=77)
+    w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False)
+    w.model.load_state_dict(p, strict=False)
+    w = w.cuda().eval()
+    with torch.no_grad():
+        out = w.model(wav.cuda(), output_hidden_states=True)
+    hs = out.hidden_states
+    assert all(torch.isfinite(h).all() for h in hs)
+    peak = max(h.abs().max().item() for h in hs)
+    assert peak > 30.0, f"the stress did not raise the activations (peak {peak})"
+    emb = out.last_hidden_state.mean(1)
+    with torch.no_grad():
+        ref_emb = O.speaker_embedding(wav, p, "mean")
+    assert torch.isfinite(emb).all()
+    assert rows(emb, ref_emb) < 2e-3, rows(emb, ref_emb)
+
+
+@pytest.mark.parametrize("pooling,loss", [("mean", "ce"), ("attentive", "aam")])
+def test_full_size_batch_oracle_anchor_8_of_64(base_params, pooling, loss):
+    """BASELINE.json configs[1] and configs[2] at full size (64 utterances of 3 s): 8 utterances spread over the batch against
+    the CPU oracle (north_star: embeddings within 1e-3, arg-max speaker id bit-exact)."""
+    _need_cuda()
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_asp_params, make_head_params, make_inputs
+    m = _module(pooling, loss, base_params).eval()
+    wav, labels = make_inputs(64, 48000, S, seed=5)
+    with torch.no_grad():
+        emb, pred = m(wav[:, None, :].cuda())
+        loss_v, prob = m.loss_fn(pred, labels.cuda())
+    idx = [0, 9, 18, 27, 36, 45, 54, 63]
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    head = make_head_params(768 if pooling == "mean" else 1536, S, seed=1)
+    with torch.no_grad():
+        if pooling == "mean":
+            ref = O.speaker_embedding(wav[idx], base_params, "mean")
+            ref_logits, _, ref_sm = O.cross_entropy_head(ref, head["fc.weight"], head["fc.bias"], labels[idx])
+        else:
+            ref = O.speaker_embedding(wav[idx], base_params, "attentive", asp=make_asp_params(768, seed=2))
+            ref_sm = O.aam_softmax(ref, head["aam.fc_weights"], labels[idx], 0.2, 30.0)[-1]
+    assert rows(emb[idx], ref) < 1e-3, rows(emb[idx], ref)
+    assert torch.equal(prob[idx].argmax(1).cpu(), ref_sm.argmax(1))
+
+
+def test_transformers_4x_checkpoint_reproduces_the_hf_forward():
+    """SURVEY 8f-3 on the GPU: a live `transformers.Wav2Vec2Model.state_dict()`, renamed to the 4.x keys the reference's pin
+    would save (weight_g / weight_v) and wrapped like a Lightning checkpoint, loads through checkpoint.py and reproduces
+    HF's own forward (eager attention, fp32 on the same GPU) within 1e-3."""
+    _need_cuda()
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+    from w2v2_speaker_b200 import checkpoint as C
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
+    torch.manual_seed(3)
+    cfg = Wav2Vec2Config()
+    cfg._attn_implementation = "eager"
+    hf = Wav2Vec2Model(cfg).eval()
+    with torch.no_grad():                                   # make the weight-norm gain non-trivial
+        hf.encoder.pos_conv_embed.conv.parametrizations.weight.original0.mul_(1.0 + 0.1 * torch.rand(1, 1, 128))
+    sd4 = {}
+    for k, v in hf.state_dict().items():
+        k4 = k.replace("parametrizations.weight.original0", "weight_g").replace("parametrizations.weight.original1", "weight_v")
+        sd4["wav2vec2." + k4] = v.clone()
+    sd4["lm_head.weight"] = torch.zeros(32, 768)            # a Wav2Vec2ForCTC-style file
+    w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False)
+    res = w.model.load_state_dict(C.convert_hf_state_dict(sd4), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    w = w.cuda().eval()
+    wav = torch.randn(3, 24000, generator=torch.Generator().manual_seed(4))
+    wav = (wav - wav.mean(1, keepdim=True)) / wav.std(1, keepdim=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    hf = hf.cuda()
+    with torch.no_grad():
+        ref = hf(wav.cuda()).last_hidden_state              # [B, T, H]
+        got = w(wav.cuda()).transpose(1, 2)                 # wrapper returns [B, H, T]
+    assert got.shape == ref.shape
+    assert rows(got.mean(1), ref.mean(1)) < 1e-3
+    assert rows(got.reshape(3, -1), ref.reshape(3, -1)) < 3e-3
+
+
+# ---- two GPUs: data-parallel step == single-GPU step on the concatenated batch -------------------------------------------
+
+
+def _dp_worker(rank, world, port, base_params, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle.params import make_inputs
+    from w2v2_speaker_b200.trainer import FlatAdamTrainer
+    torch.manual_seed(100 + rank)                           # ranks start DIFFERENT: the trainer must broadcast rank 0's state
+    m = _module("mean", "ce", base_params).train()
+    if rank != 0:
+        with torch.no_grad():
+            for q in m.parameters():
+                q.add_(0.01)
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    tr = FlatAdamTrainer(m, lr=1e-4)
+    B = 16
+    wav, labels = make_inputs(world * B, 48000, S, seed=9)
+    x, y = wav[:, None, :].cuda(), labels.cuda()
+    lo = rank * B
+    for _ in range(2):
+        tr.step(x[lo:lo + B], y[lo:lo + B])
+    tr.synchronize()
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save({"p": tr.flat_p.cpu(), "m": tr.m.cpu()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(base_params, tmp_path):
+    """R:config/trainer/trainer.yaml:6-9 (`accelerator: ddp`) semantics on hardware: two ranks x 16 utterances, regularisation
+    off, two FlatAdamTrainer steps (gradient all-reduce over NCCL, rank 1 deliberately initialised differently) against one
+    rank on the 32-utterance batch: first Adam moments (= the averaged gradient) and parameters must agree."""
+    _need_cuda(2)
+    import torch.multiprocessing as mp
+    from oracle.params import make_inputs
+    from w2v2_speaker_b200.trainer import FlatAdamTrainer
+    out = str(tmp_path / "dp.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(2, port, base_params, out), nprocs=2, join=True)
+    got = torch.load(out)
+    m = _module("mean", "ce", base_params).train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    tr = FlatAdamTrainer(m, lr=1e-4)
+    wav, labels = make_inputs(32, 48000, S, seed=9)
+    x, y = wav[:, None, :].cuda(), labels.cuda()
+    for _ in range(2):
+        tr.step(x, y)
+    tr.synchronize()
+    torch.cuda.synchronize()
+    ref_m, ref_p = tr.m.cpu().double(), tr.flat_p.cpu().double()
+    em = ((got["m"].double() - ref_m).norm() / ref_m.norm()).item()
+    ep = ((got["p"].double() - ref_p).norm() / ref_p.norm()).item()
+    assert em < 2e-3, em            # gradients: fp16 operands see batches of 16 vs 32 (other tile counts / atomics order)
+    assert ep < 1e-6, ep

@@ -26,6 +26,8 @@ SIGNATURES = {
     "w2v2_gemm_f16_dual_gelu": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p]),
     "w2v2_scale_copy_f32": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "w2v2_grad_entry_scale": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "w2v2_scale_f32_dev": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "w2v2_gemm_f16_dual_gelu_grad": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                              c_void_p, c_int64, c_void_p]),
     "w2v2_gemm_f16_mul_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64,

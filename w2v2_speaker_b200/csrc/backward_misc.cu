@@ -73,6 +73,52 @@ __global__ void softmax_ce_bwd_f32_kernel(const float* __restrict__ prob, const 
     dl[int64_t(b) * S + i] = (prob[int64_t(b) * S + i] - (i == label ? 1.0f : 0.0f)) * c;
 }
 
+// ---- gradient entry of an autograd Function: loss-scaled working copy whose magnitude is made safe for fp16 operands ----
+// Stage 1: amax = max |x| as a bit pattern (non-negative floats order like their bits; NaN / Inf give a pattern above every
+// finite one and disable the normalisation: they must propagate so that an outer GradScaler sees them).
+__global__ void amax_f32_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ amax_bits) {
+  pdl_trigger();
+  pdl_wait();
+  unsigned int m = 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(amax_bits, m);
+}
+// The power of two k that brings a = amax * s back to `mid` when a left the window [lo, hi]; 1 inside the window (the
+// normal case: nothing changes), for an all-zero or a non-finite input.
+__device__ __forceinline__ float entry_norm_factor(unsigned int amax_bits, float s, float lo, float hi, float mid) {
+  const float a = __uint_as_float(amax_bits) * s;
+  if (!(a > 0.f) || !(a < 3.0e38f) || (a >= lo && a <= hi)) return 1.0f;
+  return exp2f(floorf(log2f(mid / a)));
+}
+// Stage 2: y = x * s * k; block 0 publishes 1 / k for the Function's outputs.
+__global__ void scale_copy_norm_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float s,
+                                           const unsigned int* __restrict__ amax_bits, float lo, float hi, float mid,
+                                           float* __restrict__ inv_out, int vec) {
+  pdl_trigger();
+  pdl_wait();
+  const float k = entry_norm_factor(*amax_bits, s, lo, hi, mid);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_out = 1.0f / k;
+  const float sk = s * k;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t i = tid; i < n4; i += nth) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= sk; v.y *= sk; v.z *= sk; v.w *= sk;
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += nth) y[i] = x[i] * sk;
+}
+// x *= s * dev[0]  (leaving a Function: undo the loss scale and the device-chosen normalisation)
+__global__ void scale_f32_dev_kernel(float* __restrict__ x, int64_t n, float s, const float* __restrict__ dev) {
+  pdl_trigger();
+  pdl_wait();
+  const float sk = s * dev[0];
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) x[i] *= sk;
+}
+
 }  // namespace w2v2
 
 using namespace w2v2;
@@ -111,6 +157,29 @@ int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stre
   const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   W2V2_CHECK_CUDA(launch_k(scale_copy_f32_kernel, dim3(mgrid((n + 3) / 4, 256, 8)), dim3(256), 0, (cudaStream_t)stream, 1, x, y,
                            n, s, vec));
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_grad_entry_scale(const float* x, float* y, int64_t n, float s, float lo, float hi, float mid, float* state,
+                          void* stream) {
+  W2V2_REQUIRE(state != nullptr && lo > 0.f && hi > lo && mid >= lo && mid <= hi, "w2v2_grad_entry_scale: bad window / state");
+  cudaStream_t st = (cudaStream_t)stream;
+  W2V2_CHECK_CUDA(cudaMemsetAsync(state, 0, sizeof(float), st));
+  if (n > 0) W2V2_CHECK_CUDA(launch_k(amax_f32_kernel, dim3(mgrid(n, 256, 4)), dim3(256), 0, st, 1, x, n, reinterpret_cast<unsigned int*>(state)));
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  W2V2_CHECK_CUDA(launch_k(scale_copy_norm_f32_kernel, dim3(mgrid((n + 3) / 4 + 1, 256, 8)), dim3(256), 0, st, 1, x, y, n, s,
+                           reinterpret_cast<const unsigned int*>(state), lo, hi, mid, state + 1, vec));
+  count_launches(2);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int w2v2_scale_f32_dev(float* x, int64_t n, float s, const float* dev_scale, void* stream) {
+  W2V2_REQUIRE(dev_scale != nullptr, "w2v2_scale_f32_dev: dev_scale is required");
+  if (n == 0) return 0;
+  W2V2_CHECK_CUDA(launch_k(scale_f32_dev_kernel, dim3(mgrid(n, 256, 8)), dim3(256), 0, (cudaStream_t)stream, 1, x, n, s, dev_scale));
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -104,6 +104,13 @@ class _FeatureProjection(_Holder):
         if torch.is_grad_enabled() and (hidden_states.requires_grad or any(q.requires_grad for q in params)):
             from ..training import FeatureProjectionFn
             return FeatureProjectionFn.apply(hidden_states, model, names, *params), None
+        if model.training and model._stochastic():          # train mode, nothing to differentiate: dropout still applies
+            from ..training import projection_forward_train
+            B, T, C = hidden_states.shape
+            with torch.no_grad():
+                h0, _ = projection_forward_train(model._engine(), hidden_states.detach().float().contiguous().view(B * T, C),
+                                                 model._draw_split_plan(B, T, hidden_states.device))
+            return h0.view(B, T, -1), None
         return model._engine().feature_projection(hidden_states.contiguous()), None
 
 
@@ -119,6 +126,14 @@ class _Encoder(_Holder):
                 raise NotImplementedError("output_hidden_states is only available without gradients")
             from ..training import EncoderStackFn
             return _EncoderOutput(EncoderStackFn.apply(hidden_states, model, names, *params), None)
+        if model.training and model._stochastic() and not output_hidden_states:
+            from ..training import stack_forward_train
+            B, T, H = hidden_states.shape
+            with torch.no_grad():
+                plan = model._draw_split_plan(B, T, hidden_states.device)
+                out = stack_forward_train(model._engine(), hidden_states.detach().float().contiguous().view(B * T, H), B, T,
+                                          plan, {"plan": plan})
+            return _EncoderOutput(out, None)
         hs = [] if output_hidden_states else None
         out = model._engine().encoder(hidden_states.float(), hs)
         return _EncoderOutput(out, tuple(hs) if hs is not None else None)
@@ -210,7 +225,8 @@ class Wav2Vec2ModelB200(nn.Module):
         ring = self.__dict__.setdefault("_mask_ring", {})
         key = (wav.shape[0], T)
         if key not in ring:
-            ring[key] = [[torch.empty(wav.shape[0] * T, dtype=torch.uint8).pin_memory() for _ in range(8)], 0]
+            pin = torch.cuda.is_available()          # (the kernel-stubbed dry run of the CPU test tier has no driver)
+            ring[key] = [[torch.empty(wav.shape[0] * T, dtype=torch.uint8, pin_memory=pin) for _ in range(8)], 0]
         bufs, i = ring[key]
         ring[key][1] = (i + 1) % len(bufs)
         return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device, bufs[i])
@@ -241,10 +257,6 @@ class Wav2Vec2ModelB200(nn.Module):
         if self.reg_cfg.mask_feature_prob > 0 and self.training:
             raise NotImplementedError("feature-axis SpecAugment (mask_feature_prob > 0) is not implemented "
                                       "(the reference configurations keep it at 0)")
-        if self.training and self._stochastic() and not self._needs_grad():
-            raise NotImplementedError(
-                "train-mode regularisation is implemented on the training path only: enable gradients, or call "
-                ".eval() for inference")
 
     def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, **_):
         """HF:1327-1383.  input_values f32 [B,N].  With gradients enabled the forward keeps what the
@@ -258,6 +270,19 @@ class Wav2Vec2ModelB200(nn.Module):
             out = EncoderFn.apply(input_values.float(), self, names, *params)
             return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         eng = self._engine()
+        if self.training and self._stochastic():
+            # train mode without gradients: the reference reaches this routinely (`wav2vec_initially_frozen`: freeze() calls
+            # eval(), Lightning calls .train() again after every validation loop while the encoder is still frozen) and HF
+            # then runs a dropout-active, gradient-less forward.  Same here: the training forward with this step's
+            # regularisation draw, its saved state discarded.
+            if output_hidden_states:
+                raise NotImplementedError("output_hidden_states is only available in eval mode")
+            from ..training import encoder_forward_train
+            with torch.no_grad():
+                out, _ = encoder_forward_train(eng, input_values.float(), self._draw_reg_plan(input_values, eng),
+                                               self.masked_spec_embed.detach(), False,
+                                               getattr(self, "_pre_encoder_hook", None))
+            return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         trace = {} if output_hidden_states else None
         out = eng.forward(input_values.float(), trace)
         hs = tuple(trace["hidden_states"]) if trace is not None else None

@@ -465,6 +465,24 @@ def scaled_copy_f32(x: torch.Tensor, s: float) -> torch.Tensor:
     return y
 
 
+def grad_entry_scale(x: torch.Tensor, s: float, lo: float = 2.0 ** -16, hi: float = 2.0 ** 8, mid: float = 1.0):
+    """-> (x * s * k as a fresh f32 tensor, inv = device scalar holding 1 / k).  k is 1 unless amax|x| * s left [lo, hi]
+    (w2v2_grad_entry_scale): the hook that keeps an outer GradScaler's 2^16 out of the fp16 gradient operands."""
+    _chk(x, F32, "x")
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    state = torch.empty(2, dtype=F32, device=x.device)
+    call("w2v2_grad_entry_scale", ptr(x), ptr(y), x.numel(), float(s), float(lo), float(hi), float(mid), ptr(state),
+         stream_ptr())
+    return y, state[1:]
+
+
+def scale_f32_dev_(x: torch.Tensor, s: float, dev_scale: torch.Tensor):
+    """x *= s * dev_scale[0] in place."""
+    call("w2v2_scale_f32_dev", ptr(x), x.numel(), float(s), ptr(dev_scale), stream_ptr())
+    return x
+
+
 def softmax_ce_bwd_f32(prob, labels, dloss, coef: float):
     B, S = prob.shape
     dl = torch.empty(B, S, dtype=F32, device=prob.device)

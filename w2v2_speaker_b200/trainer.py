@@ -47,7 +47,14 @@ class FlatAdamTrainer:
         self._overlapped = []
         self._refreshable = None
         self._pending = None
-        self.ar_layers = max(1, int(os.environ.get("W2V2_AR_LAYERS", "4")))    # transformer layers per all-reduce
+        # transformer layers per overlapped all-reduce, deepest group first.  Large groups while the rest of the backward
+        # still hides them (fewer NCCL launches competing with the GEMMs), small ones at the end: what is sent after layer 0
+        # is exposed, so the last group is a single layer (W2V2_AR_SCHEDULE="4,4,2,1,1"; W2V2_AR_LAYERS=n: uniform groups)
+        if "W2V2_AR_LAYERS" in os.environ:
+            self.ar_schedule = [max(1, int(os.environ["W2V2_AR_LAYERS"]))]
+        else:
+            self.ar_schedule = [max(1, int(x)) for x in os.environ.get("W2V2_AR_SCHEDULE", "4,4,2,1,1").split(",") if x.strip()]
+        self._ar_group = 0
         self.params: List[torch.nn.Parameter] = []
         self._state = {}                       # id(parameter) -> (exp_avg, exp_avg_sq) views of the previous layout
         self._layout()
@@ -81,6 +88,7 @@ class FlatAdamTrainer:
         if self.model is not None:
             self.model._grad_sink = None
             self.model._grad_ready_hook = None
+            self.model._backward_start_hook = None
             self.model._pre_encoder_hook = None
         # segment 0: encoder parameters in the order the backward wants (q|k|v adjacent), loss-scaled grads
         enc_order = [k for k in (encoder_grad_order(self.model.arch) if self.model is not None else [])
@@ -126,6 +134,11 @@ class FlatAdamTrainer:
             self.model._pre_encoder_hook = self._join_update
         if seg0 and self.world > 1:
             self.model._grad_ready_hook = self._layer_ready      # spans of flat_g[:n0] == GradBook offsets
+            self.model._backward_start_hook = self._heads_ready
+        for h in getattr(self, "_seg1_hooks", []):
+            h.remove()
+        self._seg1_count, self._seg1_seen = len(seg1), 0
+        self._seg1_hooks = [p.register_post_accumulate_grad_hook(self._count_seg1) for p in seg1] if self.world > 1 else []
         self._refreshable = None
         self._sig = self._trainable_signature()
         if self.model is not None:
@@ -162,8 +175,21 @@ class FlatAdamTrainer:
             self._pending[0] = min(self._pending[0], lo)
             self._pending[1] = max(self._pending[1], hi)
             self._pending[2] += 1
-        if self._pending[2] >= self.ar_layers:
+        if self._pending[2] >= self.ar_schedule[min(self._ar_group, len(self.ar_schedule) - 1)]:
+            self._ar_group += 1
             self._flush_pending()
+
+    def _count_seg1(self, _param):
+        self._seg1_seen += 1
+
+    def _heads_ready(self):
+        """Backward hook, called when the encoder's backward starts: autograd has already accumulated the gradients of
+        everything in front of it (pooling, FC head / AAM weights -- segment 1 of the flat buffer, 18-37 MB), so their
+        all-reduce goes out first and runs under the whole encoder backward instead of after it."""
+        # ... provided every one of them has been accumulated in this backward: a trainable tensor in FRONT of the encoder
+        # (none exists in the reference's modules) would get its gradient later, and the span then waits for the end
+        if self.flat_g.numel() > self.n0 and self._seg1_seen >= self._seg1_count:
+            self._reduce_span(self.n0, self.flat_g.numel())
 
     def _flush_pending(self):
         if self._pending is not None:
@@ -194,6 +220,8 @@ class FlatAdamTrainer:
         for lo, hi in remaining_spans(self._overlapped, self.flat_g.numel()):
             self._reduce_span(lo, hi)
         self._overlapped = []
+        self._ar_group = 0
+        self._seg1_seen = 0
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def _join_update(self):

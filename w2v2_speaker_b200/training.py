@@ -30,6 +30,26 @@ F16, F32 = torch.float16, torch.float32
 LOSS_SCALE = 4096.0          # static scale of the activation gradients (fp16 operands of dgrad / wgrad)
 
 
+def _entry(g: torch.Tensor, static: bool = False, hi: float = 2.0 ** 10, mid: float = 1.0):
+    """Incoming gradient of a Function -> (fp32 working copy times LOSS_SCALE [times k], inv).  k is a power of two chosen
+    ON THE DEVICE (no synchronisation) that is 1 for gradients of ordinary magnitude and brings the copy back into fp16
+    range when something outside multiplied the loss -- Lightning's native-AMP GradScaler (`precision: 16`, the paper
+    setting, R:config/experiment/speaker_wav2vec2_aam.yaml:17) starts at 2^16.  inv (device scalar 1/k, or None when
+    `static`: the trainer's flat gradient keeps the plain LOSS_SCALE that its Adam undoes) goes to `_leave_`."""
+    g = g.float().contiguous()
+    if static:
+        return ops.scaled_copy_f32(g, LOSS_SCALE), None
+    # window of amax|g| * LOSS_SCALE inside which nothing changes: everything the static scale was validated on lies in it
+    return ops.grad_entry_scale(g, LOSS_SCALE, 2.0 ** -10, hi, mid)
+
+
+def _leave_(t: torch.Tensor, inv, s: float = 1.0 / LOSS_SCALE) -> torch.Tensor:
+    """Outgoing gradient: undo the loss scale (and the entry normalisation) in place."""
+    if t is None:
+        return t
+    return ops.scale_f32_(t, s) if inv is None else ops.scale_f32_dev_(t, s, inv)
+
+
 class TrainWeights:
     """Transposed fp16 weight copies for the data-gradient GEMMs (dX = dY W == gemm(dY, W^T))."""
 
@@ -454,16 +474,23 @@ class EncoderFn(torch.autograd.Function):
         pd = model._items()[2]
         tw = model._train_weights(eng)
         sink = getattr(model, "_grad_sink", None)
-        G = encoder_backward(eng, tw, pd, ctx.saved, ops.scaled_copy_f32(dh.float().contiguous(), LOSS_SCALE), sink,
+        start_hook = getattr(model, "_backward_start_hook", None)
+        if sink is not None and start_hook is not None:
+            start_hook()                              # trainer: the heads' gradients are complete, send them now
+        d, inv = _entry(dh, static=sink is not None)
+        G = encoder_backward(eng, tw, pd, ctx.saved, d, sink,
                              getattr(model, "_grad_ready_hook", None) if sink is not None else None)
         ctx.saved = None
         cnn = getattr(G, "cnn_grads", None) or {}
         G.cnn_grads = None
+        if inv is not None:
+            for t in cnn.values():                # cnn_backward removed LOSS_SCALE itself; the entry normalisation remains
+                _leave_(t, inv, 1.0)
         if sink is not None:
             # the trainer owns the (loss-scaled) flat gradient of everything behind the CNN: only the feature
             # extractor's (unscaled) gradients go back through autograd
             return (None, None, None, *[cnn.get(n) if pd[n].requires_grad else None for n in names])
-        ops.scale_f32_(G.flat, 1.0 / LOSS_SCALE)
+        _leave_(G.flat, inv)
         grads = []
         for n in names:
             if not pd[n].requires_grad:
@@ -490,12 +517,12 @@ def _own_book(model, order: List[str], device):
     return GradBook({k: pd[k].shape for k in order}, order, device), True
 
 
-def _book_grads(model, G: GradBook, owned: bool, names: List[str]):
+def _book_grads(model, G: GradBook, owned: bool, names: List[str], inv=None):
     """Gradients to hand back to autograd for `names`: views of an owned book (unscaled here), None when the
     trainer's sink holds them (it stays loss-scaled, Adam undoes the scale)."""
     if not owned:
         return [None] * len(names)
-    ops.scale_f32_(G.flat, 1.0 / LOSS_SCALE)
+    _leave_(G.flat, inv)
     pd = model._items()[2]
     return [G.view(n) if pd[n].requires_grad else None for n in names]
 
@@ -514,9 +541,11 @@ class FeatureExtractorFn(torch.autograd.Function):
     def backward(ctx, dfeat):
         model, names = ctx.model, ctx.names
         pd = model._items()[2]
-        d = ops.scaled_copy_f32(dfeat.float().contiguous(), LOSS_SCALE)
+        d, inv = _entry(dfeat)
         grads = cnn_backward(ctx.eng, pd, ctx.saved, d)
         ctx.saved = None
+        for t in grads.values():
+            _leave_(t, inv, 1.0)
         return (None, None, None, *[grads.get(n) if pd[n].requires_grad else None for n in names])
 
 
@@ -541,15 +570,16 @@ class FeatureProjectionFn(torch.autograd.Function):
     def backward(ctx, dh):
         model, eng, plan, S = ctx.model, ctx.eng, ctx.plan, ctx.saved
         M = S["B"] * S["T"]
-        d32 = ops.scaled_copy_f32(dh.float().contiguous(), LOSS_SCALE).view(M, -1)
+        G, owned = _own_book(model, PROJECTION_GRAD_ORDER, dh.device)
+        d32, inv = _entry(dh, static=not owned)
+        d32 = d32.view(M, -1)
         if plan is not None and plan.p_feat > 0:
             ops.dropout_(d32, plan.p_feat, plan.seed + 1)
-        G, owned = _own_book(model, PROJECTION_GRAD_ORDER, dh.device)
         dfeat = projection_backward(eng, model._train_weights(eng), S, ops.cast_f16(d32), G, ctx.needs_input_grad[0])
         ctx.saved = None
         if dfeat is not None:
-            dfeat = ops.scale_f32_(dfeat, 1.0 / LOSS_SCALE).view(S["B"], S["T"], -1)
-        return (dfeat, None, None, *_book_grads(model, G, owned, ctx.names))
+            dfeat = _leave_(dfeat, inv).view(S["B"], S["T"], -1)
+        return (dfeat, None, None, *_book_grads(model, G, owned, ctx.names, inv))
 
 
 class EncoderStackFn(torch.autograd.Function):
@@ -574,14 +604,17 @@ class EncoderStackFn(torch.autograd.Function):
         model, eng, S = ctx.model, ctx.eng, ctx.saved
         G, owned = _own_book(model, stack_grad_order(eng.arch), dh.device)
         hook = getattr(model, "_grad_ready_hook", None) if not owned else None
-        dxe32, dx_pos = stack_backward(eng, model._train_weights(eng), S, ops.scaled_copy_f32(dh.float().contiguous(), LOSS_SCALE),
-                                       G, hook)
+        start_hook = getattr(model, "_backward_start_hook", None)
+        if not owned and start_hook is not None:
+            start_hook()
+        d, inv = _entry(dh, static=not owned)
+        dxe32, dx_pos = stack_backward(eng, model._train_weights(eng), S, d, G, hook)
         ctx.saved = None
         dseq = None
         if ctx.needs_input_grad[0]:
             dseq, _ = ops.add2_cast(dxe32, dx_pos, want32=True, want16=False)
-            dseq = ops.scale_f32_(dseq, 1.0 / LOSS_SCALE).view(S["B"], S["T"], -1)
-        return (dseq, None, None, *_book_grads(model, G, owned, ctx.names))
+            dseq = _leave_(dseq, inv).view(S["B"], S["T"], -1)
+        return (dseq, None, None, *_book_grads(model, G, owned, ctx.names, inv))
 
 
 class MeanPoolFn(torch.autograd.Function):
@@ -612,17 +645,20 @@ class SpeakerLinearFn(torch.autograd.Function):
         Bn, S = dlogits.shape
         E = W.shape[1]
         ld = (S + 63) // 64 * 64
-        dl16 = ops.cast_f16_rows(dlogits.float(), ld, LOSS_SCALE)
+        # logit gradients are (softmax - onehot) / B: the small ones must stay fp16-normal, hence the higher window
+        dl32, inv = _entry(dlogits, hi=2.0 ** 15, mid=2.0 ** 11)
+        dl16 = ops.cast_f16_rows(dl32, ld, 1.0)
         x16 = ops.cast_f16(x.float().contiguous())
         dW = torch.zeros(S, E, dtype=F32, device=W.device)
         ops.gemm_wgrad_f16(dl16[:, :S], x16, dW)
-        ops.scale_f32_(dW, 1.0 / LOSS_SCALE)
+        _leave_(dW, inv)
         db = None
         if ctx.has_bias:
             db = torch.zeros(S, dtype=F32, device=W.device)
-            ops.colsum(dl16[:, :S], db, 1.0 / LOSS_SCALE)
+            ops.colsum(dl16[:, :S], db, 1.0)
+            _leave_(db, inv)
         wT = ops.cast_f16_transpose(W.float(), ld)                              # [E, ld]
-        dx = ops.scaled_copy_f32(ops.gemm_f16(dl16, wT, None, 0, F32).contiguous(), 1.0 / LOSS_SCALE)
+        dx = _leave_(ops.gemm_f16(dl16, wT, None, 0, F32).contiguous(), inv)
         return dx, dW, db, None
 
 
@@ -682,17 +718,18 @@ class AamSoftmaxFn(torch.autograd.Function):
         Bn, S = prob.shape
         E = W.shape[1]
         ld = (S + 63) // 64 * 64
-        dc16 = ops.aam_bwd_dcos(prob, cos_label, labels, dloss.float().contiguous().view(1), LOSS_SCALE / Bn, margin,
-                                scale, easy, ld)                                  # [B, ld], loss-scaled
+        # dcos = (softmax - onehot) * scale * dphi * dloss / B; the entry normalisation looks at scale * dloss / B * LOSS_SCALE
+        dl, inv = ops.grad_entry_scale(dloss.float().contiguous().view(1), scale * LOSS_SCALE / Bn, 2.0 ** -8, 2.0 ** 15, 2.0 ** 12)
+        dc16 = ops.aam_bwd_dcos(prob, cos_label, labels, dl, 1.0 / scale, margin, scale, easy, ld)  # [B, ld], loss-scaled
         Wf = W.float().contiguous()
         inv_w = ops.row_inv_norm(Wf)
         whT = ops.cast_f16_transpose(Wf, ld, inv_w)                               # normalised W, transposed [E, ld]
         dxh = ops.gemm_f16(dc16, whT, None, 0, F32)                               # d(x_hat) [B, E]
-        dx = ops.l2norm_rows_bwd(x, dxh, 1.0 / LOSS_SCALE)
+        dx = _leave_(ops.l2norm_rows_bwd(x, dxh, 1.0 / LOSS_SCALE), inv, 1.0)
         xh16 = ops.l2norm_rows_f16(x)
         dwh = torch.zeros(S, E, dtype=F32, device=W.device)
         ops.gemm_wgrad_f16(dc16[:, :S], xh16, dwh)                                # d(W_hat) [S, E]
-        dW = ops.l2norm_rows_bwd(Wf, dwh, 1.0 / LOSS_SCALE)
+        dW = _leave_(ops.l2norm_rows_bwd(Wf, dwh, 1.0 / LOSS_SCALE), inv, 1.0)
         return dx, dW, None, None, None, None, None
 
 
@@ -743,7 +780,8 @@ class AspPoolFn(torch.autograd.Function):
         A = z.shape[1]
         dev = x.device
         inv_ls = 1.0 / LOSS_SCALE
-        dlg16, dx = ops.asp_pool_bwd(x, logits.view(B, T, C), out, ops.scaled_copy_f32(dout.float().contiguous(), LOSS_SCALE))
+        dscaled, inv = _entry(dout)
+        dlg16, dx = ops.asp_pool_bwd(x, logits.view(B, T, C), out, dscaled)
         dW2 = torch.zeros(C, A, dtype=F32, device=dev)
         ops.gemm_wgrad_f16(dlg16, y16, dW2)
         db2 = torch.zeros(C, dtype=F32, device=dev)
@@ -758,8 +796,10 @@ class AspPoolFn(torch.autograd.Function):
         ops.colsum(dz16, db1, inv_ls)
         dcat = ops.gemm_f16(dz16, ops.cast_f16_transpose(w1f, A), None, 0, F32)                    # [B*T, 3C]
         ops.asp_front_bwd_(x, dcat, dx)
-        ops.scale_f32_(dx, inv_ls)
-        ops.scale_f32_(dW1, inv_ls)
-        ops.scale_f32_(dW2, inv_ls)
+        _leave_(dx, inv)
+        _leave_(dW1, inv)
+        _leave_(dW2, inv)
+        for t in (db1, db2, dgamma, dbeta):           # already divided by LOSS_SCALE in their kernels
+            _leave_(t, inv, 1.0)
         s1, s2 = ctx.shapes
         return dx, dW1.view(s1), db1, dgamma, dbeta, dW2.view(s2), db2, None
