@@ -134,6 +134,12 @@ class ClockSampler:
 
 
 def cpu_reference_step_fn(batch: int, mode: str):
+    """One step of the reference path on the host CPU.  The encoder is the reference's own third-party code -- the
+    `transformers.Wav2Vec2Model` it wraps (R:src/models/wav2vec2.py:37-53; present in this image, unlike the reference
+    checkout, which cannot travel to the GPU box), in train mode with the reference's regularisation defaults (dropout,
+    LayerDrop and SpecAugment are HF's own), eager attention, fp32; pooling and loss heads are the oracle's restatement
+    of R:src/layers/pooling.py / R:src/optim/loss (a few lines of torch each); optimizer = torch.optim.Adam
+    (R:config/optim/algo/adam.yaml).  Falls back to the all-oracle port if transformers cannot build the model."""
     from oracle import w2v2_oracle as O
     from oracle import params as OP
     arch = OP.LARGE if WL["arch"] == "large" else OP.BASE
@@ -144,8 +150,27 @@ def cpu_reference_step_fn(batch: int, mode: str):
     wav, labels = OP.make_inputs(batch, WL["samples"], NUM_SPEAKERS, seed=1234)
     train = mode == "train"
 
+    hf = None
+    try:
+        from transformers import Wav2Vec2Config, Wav2Vec2Model
+        size = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096) \
+            if WL["arch"] == "large" else {}
+        cfg = Wav2Vec2Config(activation_dropout=0.0, attention_dropout=0.1, feat_proj_dropout=0.1, hidden_dropout=0.1,
+                             layerdrop=0.05, mask_time_prob=0.05, mask_time_length=10, mask_feature_prob=0.0, **size)
+        cfg._attn_implementation = "eager"
+        hf = Wav2Vec2Model(cfg)
+        res = hf.load_state_dict(p, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        hf.train(train)
+        hf.feature_extractor.requires_grad_(False)          # completely_freeze_feature_extractor: true
+    except Exception as e:                                   # pragma: no cover - depends on the installed transformers
+        print(f"[bench] transformers model unavailable ({e}); timing the oracle port", file=sys.stderr)
+        hf = None
+    cpu_reference_step_fn.kind = "HF Wav2Vec2Model (eager, the reference's encoder) + oracle heads" if hf is not None \
+        else "oracle/w2v2_oracle.py"
+
     def embed():
-        h = O.wav2vec2_forward(wav, p, arch)
+        h = hf(wav).last_hidden_state if hf is not None else O.wav2vec2_forward(wav, p, arch)
         if WL["pooling"] == "attentive":
             return O.attentive_stat_pool(h, asp, training=train)
         return O.mean_pool(h) if WL["pooling"] == "mean" else O.mean_std_pool(h)
@@ -156,8 +181,11 @@ def cpu_reference_step_fn(batch: int, mode: str):
         return O.cross_entropy_head(emb, hp["fc.weight"], hp["fc.bias"], labels)
 
     if train:
-        O.TRAIN_REG = {"feat": 0.1, "hidden": 0.1, "attn": 0.1, "layerdrop": 0.05}     # reference defaults
-        tr = [p[k] for k in p if not k.startswith("feature_extractor") and k != "masked_spec_embed"]
+        if hf is not None:
+            tr = [q for q in hf.parameters() if q.requires_grad]
+        else:
+            O.TRAIN_REG = {"feat": 0.1, "hidden": 0.1, "attn": 0.1, "layerdrop": 0.05}     # reference defaults
+            tr = [p[k] for k in p if not k.startswith("feature_extractor") and k != "masked_spec_embed"]
         tr += [hp["aam.fc_weights"]] if WL["loss"] == "aam" else [hp["fc.weight"], hp["fc.bias"]]
         if asp is not None:
             tr += [v for k, v in asp.items() if "running" not in k]
@@ -170,7 +198,7 @@ def cpu_reference_step_fn(batch: int, mode: str):
             _, loss, _ = head(embed())
             loss.backward()
             opt.step()
-            return float(loss)
+            return float(loss.detach())
         return step
 
     O.TRAIN_REG = None
@@ -216,20 +244,39 @@ def time_cpu(batch: int, steps: int, warmup: int, mode: str):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference path on the host cores, same workload / mode / step counts as the product arm.
+    The per-step batch is the configuration's own (64 at cfg1) unless W + K steps of it would take more than ~4 minutes
+    on this host, in which case the largest batch that fits is used and reported."""
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    batch = 8 if args.mode == "forward" else 4
-    steps = max(1, min(args.steps, 10))
-    uts, ms, cores = time_cpu(batch, steps, 1, args.mode)
+    cores = pick_cpu_threads()
+    torch.set_num_threads(cores)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    probe_b = 4
+    probe = cpu_reference_step_fn(probe_b, args.mode)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    per_utt = (time.perf_counter() - t0) / probe_b
+    budget = float(os.environ.get("W2V2_REF_ARM_SECONDS", "240"))
+    batch = int(max(1, min(args.batch, budget / ((steps + warmup) * per_utt))))
+    step = cpu_reference_step_fn(batch, args.mode)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    uts, ms = batch * steps / dt, dt / steps * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": uts, "unit": "utt/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.mode), "batch_per_step": batch, "device": "host CPU", "mode": args.mode},
         "cpu_baseline": {"value": uts, "unit": "utt/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {batch} utterances of 3 s (oracle/w2v2_oracle.py, torch fp32, "
-                                   f"{cores} threads, mode {args.mode})"},
+                         "sample": f"{steps} steps x {batch} utterances of {WL['samples'] / 16000:g} s ({cpu_reference_step_fn.kind}, "
+                                   f"torch fp32, {cores} threads, mode {args.mode})"},
         "e2e": {"value": uts, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -326,7 +373,7 @@ def main():
 
     from w2v2_speaker_b200 import _lib
     lib = _lib.load()
-    from oracle.params import make_inputs
+    from w2v2_speaker_b200.synthetic import synthetic_batch as make_inputs
     B = args.batch
     K, W = args.steps, max(3, args.warmup)
     train = args.mode == "train"
@@ -469,8 +516,9 @@ def main():
             cb = 4 if train else 8
             uts, ms, cores = time_cpu(cb, 2 if train else 4, 1, args.mode)
             cpu = {"value": uts, "unit": "utt/s", "cores": cores, "kind": "port",
-                   "sample": f"{2 if train else 4} steps x {cb} utterances of 3 s (oracle/w2v2_oracle.py, torch fp32 "
-                             f"{'+ autograd + torch Adam' if train else ''}, {cores} threads)"}
+                   "sample": f"{2 if train else 4} steps x {cb} utterances of {WL['samples'] / 16000:g} s "
+                             f"({cpu_reference_step_fn.kind}, torch fp32{' + autograd + torch Adam' if train else ''}, "
+                             f"{cores} threads)"}
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -253,6 +253,12 @@ int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stre
  * would overflow the fp16 operand copies of the backward GEMMs): y = x * s * k, where k = 1 while amax|x| * s lies in
  * [lo, hi] (the normal case: bit-identical to w2v2_scale_copy_f32) and otherwise the power of two that brings it to `mid`;
  * state f32[2] (device): [0] scratch, [1] = 1 / k.  No host synchronisation.  w2v2_scale_f32_dev: x *= s * dev_scale[0]. */
+/* out32[M, N] += A[M, K] (f16) W[N, K]^T (f16): the data-gradient GEMMs of the backward add straight into the gradient of
+ * the residual stream (every tile is written with TMA reduce-add, partial tiles of the stream-K schedule included), so the
+ * LayerNorm backward that follows reads ONE fp32 gradient stream instead of two (HF:596-607 residual adds, backward). */
+int w2v2_dgrad_accumulates(void);   /* 1: w2v2_encoder_layer_bwd leaves the whole input gradient in dx1_32 (dh_in32 unused) */
+int w2v2_gemm_f16_accum(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N, float* out32,
+                        int64_t ldo, void* stream);
 int w2v2_grad_entry_scale(const float* x, float* y, int64_t n, float s, float lo, float hi, float mid, float* state,
                           void* stream);
 int w2v2_scale_f32_dev(float* x, int64_t n, float s, const float* dev_scale, void* stream);

@@ -236,3 +236,77 @@ def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(base_param
     ep = ((got["p"].double() - ref_p).norm() / ref_p.norm()).item()
     assert em < 2e-3, em            # gradients: fp16 operands see batches of 16 vs 32 (other tile counts / atomics order)
     assert ep < 1e-6, ep
+
+
+def test_large_architecture_training_gradients_match_oracle_autograd():
+    """BASELINE.json configs[4] architecture (wav2vec2-large: 24 layers, H = 1024, 16 heads, FFN 4096) + mean+std pooling +
+    CE: one training step (B = 2, 1 s, regularisation off, CNN frozen) against autograd of the CPU oracle -- loss within
+    1e-3, every parameter gradient within 1.5e-2 norm-wise (24 layers of fp16-operand arithmetic)."""
+    _need_cuda()
+    from oracle import w2v2_oracle as O
+    from oracle.params import LARGE, make_head_params, make_inputs, make_params
+    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    params = make_params(LARGE, seed=3)
+    head = make_head_params(2048, S, seed=1)
+    cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id="facebook/wav2vec2-large", stat_pooling_type="mean+std",
+                                 test_stat_pooling_type="mean+std", **ZERO_REG)
+    m = Wav2vec2FCModule(cfg, S, CrossEntropyLoss)
+    res = m.wav2vec.model.load_state_dict(params, strict=False)
+    assert not res.unexpected_keys and not res.missing_keys
+    with torch.no_grad():
+        m.fc_list[-1][0].weight.copy_(head["fc.weight"]); m.fc_list[-1][0].bias.copy_(head["fc.bias"])
+    m = m.cuda().train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+    wav, labels = make_inputs(2, 16000, S, seed=1234)
+    emb, pred = m(wav[:, None, :].cuda())
+    loss, prob = m.loss_fn(pred, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    p = {k: v.clone().requires_grad_(not k.startswith("feature_extractor")) for k, v in params.items()}
+    fw, fb = head["fc.weight"].clone().requires_grad_(True), head["fc.bias"].clone().requires_grad_(True)
+    ref_emb = O.speaker_embedding(wav, p, "mean+std", arch=LARGE)
+    _, ref_loss, ref_sm = O.cross_entropy_head(ref_emb, fw, fb, labels)
+    ref_loss.backward()
+    assert rows(emb.detach(), ref_emb.detach()) < 1.5e-3
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-3
+    assert torch.equal(prob.argmax(1).cpu(), ref_sm.argmax(1))
+    got = dict(m.wav2vec.model.named_parameters())
+    worst = (0.0, None)
+    for k, v in p.items():
+        if k.startswith("feature_extractor") or k == "masked_spec_embed":
+            continue
+        g, r = got[k].grad.detach().cpu().double(), v.grad.double()
+        if k.endswith("k_proj.bias"):
+            # exactly 0 in exact arithmetic: both sides are rounding noise (fp16 operands here, fp32 there)
+            scale = p[k.replace("k_proj", "q_proj")].grad.double().norm()
+            assert g.norm() < 5e-2 * scale and r.norm() < 5e-2 * scale, k
+            continue
+        err = ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
+        worst = max(worst, (err, k))
+        assert err < 1.5e-2, (k, err)
+    lin = m.fc_list[-1][0]
+    assert ((lin.weight.grad.cpu().double() - fw.grad.double()).norm() / fw.grad.double().norm()).item() < 1e-2
+    print("worst LARGE parameter-gradient error", worst)
+
+
+def test_ensemble_embedding_matches_oracle_hidden_states(base_params):
+    """`use_transformers_as_ensembles` (R:src/lightning_modules/speaker/wav2vec2_fc.py:440-463): one pooled embedding per
+    encoder output for the last `num_ensembles` of the 13 hidden states."""
+    _need_cuda()
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_inputs
+    m = _module("mean", "ce", base_params, use_transformers_as_ensembles=True, num_ensembles=4).eval()
+    assert m.test_with_ensemble
+    wav, _ = make_inputs(2, 16000, S, seed=21)
+    with torch.no_grad():
+        got = m.compute_ensemble_embedding(wav[:, None, :].cuda())
+        trace = {}
+        O.wav2vec2_forward(wav, base_params, trace=trace)
+    ref = trace["hidden_states"]
+    assert len(got) == 4 and len(ref) == 13
+    for e, h in zip(got, ref[9:13]):
+        assert e.shape == (2, 768)
+        assert rows(e, h.mean(1)) < 1e-3

@@ -6,7 +6,7 @@ import torch
 import bench
 
 ap = argparse.ArgumentParser(); ap.add_argument("--mode", default="train"); a = ap.parse_args()
-from oracle.params import make_inputs
+from w2v2_speaker_b200.synthetic import synthetic_batch as make_inputs
 from w2v2_speaker_b200 import trainer as T
 dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
 train = a.mode == "train"

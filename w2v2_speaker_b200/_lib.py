@@ -26,6 +26,8 @@ SIGNATURES = {
     "w2v2_gemm_f16_dual_gelu": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p]),
     "w2v2_scale_copy_f32": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "w2v2_dgrad_accumulates": (c_int, []),
+    "w2v2_gemm_f16_accum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "w2v2_grad_entry_scale": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     "w2v2_scale_f32_dev": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "w2v2_gemm_f16_dual_gelu_grad": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p,
@@ -177,3 +179,27 @@ def call(name: str, *args):
     if rc != 0:
         raise W2V2Error(f"{name} failed ({rc}): {lib.w2v2_last_error().decode()}")
     return rc
+
+
+# ---- NVTX ranges (tracing) ------------------------------------------------------------------------------
+# W2V2_NVTX=1 brackets the phases of a step (forward / backward / all-reduce / optimizer, and every encoder layer) with
+# NVTX ranges, which `ncu --nvtx --nvtx-include "backward/"` and Nsight Systems pick up; off by default (two C calls
+# per range).
+_NVTX = os.environ.get("W2V2_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False

@@ -54,6 +54,7 @@ struct alignas(64) GemmParams {
   const __half* aux;             // ACT 2: z [rows, ld_aux] f16, the pre-activation whose gelu' multiplies the output
   long long ld_aux;
   float* colsum;                 // ACT 2: colsum[n] += sum over rows of the (fp16-rounded) output
+  int accumulate;                // fp32 output without activation: out += A W^T (every store is a TMA reduce-add)
 };
 
 // Stream-K (fp32 output, no activation): the (tile, k-block) iteration space is cut into gridDim.x equal
@@ -329,8 +330,12 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
       }
       // stream-K roles of this segment: `lead` holds the tile's first k-blocks (plain store, adds the bias,
       // then signals), `trail` the rest (waits for the signal, reduce-adds, no bias)
-      const bool sk_lead = SK_OK && k_begin == 0 && k_end < k_iters;
-      const bool sk_trail = SK_OK && k_begin != 0;
+      // accumulate mode (out += A W^T): every segment reduce-adds, sums commute, so no hand-shake is needed at all
+      const bool acc_out = SK_OK && p.accumulate != 0;
+      const bool sk_lead = SK_OK && !acc_out && k_begin == 0 && k_end < k_iters;
+      const bool sk_trail = SK_OK && !acc_out && k_begin != 0;
+      const bool use_red = SK_OK && (k_begin != 0 || acc_out);
+      const bool add_bias = k_begin == 0;
       const float* bias_tile = sbias + (EPI == 1 ? (tcount & 1) * BN : 0);
       if constexpr (EPI == 1) {
         // stage this tile's bias slice once (the previous user of this buffer was two tiles ago and
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
           } else {
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (EPI == 1) {
-              if (!sk_trail) bb = *reinterpret_cast<const float4*>(bsrc + j);
+              if (add_bias) bb = *reinterpret_cast<const float4*>(bsrc + j);
             }
             v[j] = __uint_as_float(r[j]) + bb.x;
             v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
           __syncwarp();
           const int scol = col0 + (c - sub) * 32;
           if (lane == 0 && row0 < p.rows && scol < p.N) {   // skip boxes that lie entirely in the M / N tail
-            if (SK_OK && sk_trail) tma_reduce_add_3d(&p.tmOut, mystage, scol, row0, b);
+            if (SK_OK && use_red) tma_reduce_add_3d(&p.tmOut, mystage, scol, row0, b);
             else tma_store_3d(&p.tmOut, mystage, scol, row0, b);
             if constexpr (DUAL) tma_store_3d(&p.tmOut2, mystage + WSTAGE_BYTES, scol, row0, b);
             tma_store_commit();
@@ -715,7 +720,7 @@ void gemm_prof_end(int slot, cudaStream_t stream) {
 int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
                    int64_t a_batch_stride, int batch, int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw,
                    int N, const float* bias, const float* shift, int act, void* out, int out_dtype, int64_t ldo,
-                   int64_t out_batch_stride, cudaStream_t stream);
+                   int64_t out_batch_stride, cudaStream_t stream, int accumulate = 0);
 
 int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch, int ntaps,
                   int64_t a_tap_stride, int cin, const void* W, int64_t ldw, int N, const float* bias,
@@ -730,7 +735,9 @@ int gemm_f16_impl(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a
 int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* tap_row, int64_t a_row_stride,
                    int64_t a_batch_stride, int batch, int ntaps, int64_t a_tap_stride, int cin, const void* W, int64_t ldw,
                    int N, const float* bias, const float* shift, int act, void* out, int out_dtype, int64_t ldo,
-                   int64_t out_batch_stride, cudaStream_t stream) {
+                   int64_t out_batch_stride, cudaStream_t stream, int accumulate) {
+  W2V2_REQUIRE(!accumulate || (out_dtype == 1 && act == 0 && shift == nullptr),
+               "w2v2_gemm_f16: accumulate needs fp32 output without activation / affine epilogue");
   W2V2_REQUIRE(ntaps >= 1 && ntaps <= 3, "w2v2_gemm_f16: ntaps=%d not in [1,3]", ntaps);
   W2V2_REQUIRE(cin % BK == 0, "w2v2_gemm_f16: cin=%d must be a multiple of %d", cin, BK);
   W2V2_REQUIRE(out_dtype == 0 || out_dtype == 1, "w2v2_gemm_f16: out_dtype must be 0 (f16) or 1 (f32)");
@@ -766,6 +773,7 @@ int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* t
   p.batch = batch;
   p.N = N;
   p.rows = a_rows;
+  p.accumulate = accumulate;
   const int slot = gemm_prof_begin(2.0 * double(a_rows) * batch * ntaps * cin * N, stream);
   if (CL == 2) rc = out_dtype == 1 ? dispatch_epilogue<256, true, 2>(p, act, stream) : dispatch_epilogue<256, false, 2>(p, act, stream);
   else if (BN == 256) rc = out_dtype == 1 ? dispatch_epilogue<256, true, 1>(p, act, stream) : dispatch_epilogue<256, false, 1>(p, act, stream);
@@ -905,6 +913,12 @@ extern "C" int w2v2_gemm_f16_taps(const void* A, int64_t out_rows, int64_t a_ext
   W2V2_REQUIRE(tap_row != nullptr, "w2v2_gemm_f16_taps: tap_row is required");
   return gemm_f16_impl2(A, out_rows, a_extent, tap_row, a_row_stride, a_batch_stride, batch, ntaps, 0, cin, W, ldw, N, nullptr,
                         nullptr, 0, out, out_dtype, ldo, out_batch_stride, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int w2v2_gemm_f16_accum(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N,
+                                   float* out32, int64_t ldo, void* stream_) {
+  return gemm_f16_impl2(A, M, M, nullptr, lda, 0, 1, 1, 0, K, W, ldw, N, nullptr, nullptr, 0, out32, 1, ldo, 0,
+                        static_cast<cudaStream_t>(stream_), 1);
 }
 
 extern "C" int w2v2_gemm_f16(const void* A, int64_t a_rows, int64_t a_row_stride, int64_t a_batch_stride, int batch,

@@ -35,6 +35,16 @@ static bool save_gelu_grad(float p_act) {
   return on && fuse_gelu_bwd() && !(p_act > 0.f);
 }
 
+// W2V2_DGRAD_ACCUM (default on; =0 restores the two-term form): the FFN1 and QKV data-gradient GEMMs add straight into the
+// residual-path gradient (w2v2_gemm_f16_accum: TMA reduce-add stores), so each LayerNorm backward reads one fp32 gradient
+// stream instead of two -- the read moves from an HBM-bound kernel into a tensor-bound one.  The layer's input gradient is
+// then dx1_32 alone (dh_in32 stays untouched); w2v2_dgrad_accumulates() tells the caller which form is active.
+static bool dgrad_accum() {
+  static const bool on = []() { const char* e = getenv("W2V2_DGRAD_ACCUM"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+extern "C" int w2v2_dgrad_accumulates(void) { return dgrad_accum() ? 1 : 0; }
+
 extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream) {
   W2V2_REQUIRE(a != nullptr, "w2v2_encoder_layer_fwd: null argument block");
   const int64_t M = int64_t(a->B) * a->T;
@@ -89,9 +99,11 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
       W2V2_TRY(w2v2_gemm_f16_gelu_bwd(a->dx2_16, M, H, H, a->w2T, H, FF, a->z16, FF, a->dz16, FF, a->d_b1, stream));
   }
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dz16, FF, a->h1_16, H, M, FF, H, a->d_w1, H, stream));
-  W2V2_TRY(w2v2_gemm_f16(a->dz16, M, FF, 0, 1, 1, 0, FF, a->w1T, FF, H, nullptr, 0, a->dh1_32, 1, H, 0, stream));
+  const bool accum = dgrad_accum();
+  if (accum) W2V2_TRY(w2v2_gemm_f16_accum(a->dz16, M, FF, FF, a->w1T, FF, H, a->dx2_32, H, stream));
+  else W2V2_TRY(w2v2_gemm_f16(a->dz16, M, FF, 0, 1, 1, 0, FF, a->w1T, FF, H, nullptr, 0, a->dh1_32, 1, H, 0, stream));
   // LN1:  h1 = LN(drop(o + bo) + h_in)
-  W2V2_TRY(w2v2_layernorm_bwd_from_output(a->dh1_32, a->dx2_32, a->h1_32, a->rstd1, a->ln1_g, a->ln1_b, a->dx1_32, a->dx1_16,
+  W2V2_TRY(w2v2_layernorm_bwd_from_output(accum ? a->dx2_32 : a->dh1_32, accum ? nullptr : a->dx2_32, a->h1_32, a->rstd1, a->ln1_g, a->ln1_b, a->dx1_32, a->dx1_16,
                                           a->d_ln1_g, a->d_ln1_b, a->d_bo, M, H, a->p_hidden, seed + 200 + l, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dx1_16, H, a->att16, H, M, H, H, a->d_wo, H, stream));
   W2V2_TRY(w2v2_gemm_f16(a->dx1_16, M, H, 0, 1, 1, 0, H, a->woT, H, H, nullptr, 0, a->datt16, 0, H, 0, stream));
@@ -101,6 +113,7 @@ extern "C" int w2v2_encoder_layer_bwd(const w2v2_layer_bwd_args* a, void* stream
   W2V2_TRY(w2v2_attention_bwd_ex2(a->qkv16, a->att16, a->datt16, a->lse, a->dqkv16, a->B, a->T, H, a->heads, a->p_attn,
                                   seed + 100 + l, a->qscale, a->d_bqkv, stream));
   W2V2_TRY(w2v2_gemm_wgrad_f16(a->dqkv16, 3 * H, a->h_in16, H, M, 3 * H, H, a->d_wqkv, H, stream));
-  W2V2_TRY(w2v2_gemm_f16(a->dqkv16, M, 3 * H, 0, 1, 1, 0, 3 * H, a->wqkvT, 3 * H, H, nullptr, 0, a->dh_in32, 1, H, 0, stream));
+  if (accum) W2V2_TRY(w2v2_gemm_f16_accum(a->dqkv16, M, 3 * H, 3 * H, a->wqkvT, 3 * H, H, a->dx1_32, H, stream));
+  else W2V2_TRY(w2v2_gemm_f16(a->dqkv16, M, 3 * H, 0, 1, 1, 0, 3 * H, a->wqkvT, 3 * H, H, nullptr, 0, a->dh_in32, 1, H, 0, stream));
   return 0;
 }

@@ -108,6 +108,7 @@ class Wav2vec2FCModule(nn.Module):
 
         self._is_wav2vec_frozen = False
         self.steps = 0
+        self.test_with_ensemble = cfg.use_transformers_as_ensembles
 
     # ---- freeze protocol (R:.../wav2vec2_fc.py:339-361): which parameters get gradients, and with
     # them which backward kernels run (frozen encoder: the heads' only; frozen CNN: everything behind it) -----------
@@ -208,6 +209,20 @@ class Wav2vec2FCModule(nn.Module):
     # R:.../wav2vec2_fc.py:433-438
     def compute_speaker_prediction(self, embedding_tensor: torch.Tensor) -> torch.Tensor:
         return self._fc_head_ops_post_spk_embedding(embedding_tensor).squeeze()
+
+    # R:.../wav2vec2_fc.py:440-463 (test-time option `use_transformers_as_ensembles`): one pooled embedding per encoder
+    # output, the last `num_ensembles` of the 13 hidden states (the engine's evaluation forward returns them all)
+    def compute_ensemble_embedding(self, input_tensor: torch.Tensor):
+        if len(input_tensor.shape) == 3 and input_tensor.shape[1] == 1:
+            input_tensor = torch.squeeze(input_tensor)
+        if len(input_tensor.shape) == 1:
+            input_tensor = torch.stack([input_tensor])
+        out = self.wav2vec.model(input_tensor, output_hidden_states=True)
+        n = self.wav2vec.model.arch.layers + 1
+        embeddings = []
+        for hidden in out.hidden_states[n - self.cfg.num_ensembles:n]:
+            embeddings.append(torch.squeeze(self.stat_pooling(hidden)))
+        return embeddings
 
     # R:src/lightning_modules/speaker/speaker_recognition_module.py:121-130
     def forward(self, input_tensor: torch.Tensor):

@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from ._lib import nvtx_range
 from .dist_utils import remaining_spans
 from .models.wav2vec2 import Wav2Vec2ModelB200
 from .training import LOSS_SCALE, GradBook, encoder_grad_order
@@ -246,11 +247,14 @@ class FlatAdamTrainer:
             # in-order update, or an encoder without trainable parameters: its (evaluation-path) forward never calls the
             # join hook, and the heads read weights / operand copies the optimizer stream may still be writing
             cur.wait_stream(self.opt_stream)
-        emb, pred = self.module(wav)
-        cur.wait_stream(self.opt_stream)          # no-op if the encoder already joined (it always does when it runs)
-        loss, prob = self.module.loss_fn(pred, labels)
-        loss.backward()
-        self.allreduce_grads()
+        with nvtx_range("forward"):
+            emb, pred = self.module(wav)
+            cur.wait_stream(self.opt_stream)      # no-op if the encoder already joined (it always does when it runs)
+            loss, prob = self.module.loss_fn(pred, labels)
+        with nvtx_range("backward"):
+            loss.backward()
+        with nvtx_range("allreduce"):
+            self.allreduce_grads()
         self.step_count += 1
         if self.lr_schedule is not None:
             self.lr = float(self.lr_schedule(self.step_count))
@@ -258,7 +262,7 @@ class FlatAdamTrainer:
         n0, n = self.n0, self.flat_p.numel()
         opt_stream = self.opt_stream if self._overlap_update else cur
         opt_stream.wait_stream(cur)
-        with torch.cuda.stream(opt_stream):
+        with nvtx_range("optimizer"), torch.cuda.stream(opt_stream):
             if n0:
                 ops.adam_step(self.flat_p[:n0], self.flat_g[:n0], self.m[:n0], self.v[:n0], self.lr, b1, b2, self.eps,
                               self.step_count, grad_scale=1.0 / (LOSS_SCALE * self.world), zero_grad=True)

@@ -390,6 +390,8 @@ def stack_backward(eng: EncoderEngine, tw: TrainWeights, S: dict, dh: torch.Tens
     # transformer layers in reverse: one native schedule call per layer; the scratch arena is shared by all
     # layers, the two terms of the input gradient ping-pong between two buffer pairs
     scr = sched.Arena(sched.bwd_scratch_sizes(B, T, H, FF), dev)
+    # 1: the layer schedule adds the q/k/v data gradient into dx1_32 (w2v2_gemm_f16_accum): one term, not two
+    accum = bool(ops._lib.load().w2v2_dgrad_accumulates())
     gbase = G.flat.data_ptr()
     pa, pb, pp = dy_a.data_ptr(), None, 0
     ran = False
@@ -424,16 +426,19 @@ def stack_backward(eng: EncoderEngine, tw: TrainWeights, S: dict, dh: torch.Tens
             setattr(b, k, scr.ptr(k))
         b.dx1_32, b.dh_in32 = scr.ptr(f"dx1_32.{pp}"), scr.ptr(f"dh_in32.{pp}")
         sched.run_layer_bwd(b)
-        pa, pb = b.dh_in32, b.dx1_32
+        pa, pb = (b.dx1_32, None) if accum else (b.dh_in32, b.dx1_32)
         ran, last_pp = True, pp
         pp ^= 1
         layer_done(l)
-    if ran:
+    if ran and accum:
+        dy_a, dy_b = scr.tensor(f"dx1_32.{last_pp}", F32, (M, H)), None          # residual path + q/k/v term, already summed
+    elif ran:
         dy_a = scr.tensor(f"dh_in32.{last_pp}", F32, (M, H))                     # d h_in via qkv
         dy_b = scr.tensor(f"dx1_32.{last_pp}", F32, (M, H))                      # + residual path
     # encoder top:  h_e = drop(LN(pos + h0)),  pos = GELU(zpos),  zpos = posconv(h0) + b
     if ph > 0:
-        dy_a, _ = ops.add2_cast(dy_a, dy_b, want16=False)
+        if dy_b is not None or dy_a.data_ptr() == dh.data_ptr():         # (never drop in place in the caller's tensor)
+            dy_a, _ = ops.add2_cast(dy_a, dy_b, want16=False)
         dy_b = None
         ops.dropout_(dy_a, ph, seed + 2)
     dxe32, dxe16 = ops.layernorm_bwd(dy_a, S["pos"], w.enc_ln_g, a.eps, dy_b=dy_b, residual=S["h0"],
