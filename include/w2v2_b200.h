@@ -256,6 +256,27 @@ int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stre
 /* out32[M, N] += A[M, K] (f16) W[N, K]^T (f16): the data-gradient GEMMs of the backward add straight into the gradient of
  * the residual stream (every tile is written with TMA reduce-add, partial tiles of the stream-K schedule included), so the
  * LayerNorm backward that follows reads ONE fp32 gradient stream instead of two (HF:596-607 residual adds, backward). */
+/* ---- ragged evaluation batches (the reference embeds test utterances one at a time,
+ * R:src/lightning_modules/speaker/speaker_recognition_module.py:462-500, R:src/predict.py:132-170) --------------------
+ * Utterances of different length are zero-padded to a common [B, N] and carried with their lengths so that every
+ * utterance gets exactly what a batch of one would give it: GroupNorm statistics of conv layer 0 over its own frames
+ * (lens = samples), zeros behind its end for the positional conv (w2v2_cast_f16_rowmask, lens = frames), attention
+ * over its own keys (w2v2_attention_lens; every query row is still computed so that padding rows stay finite), pooling
+ * over its own frames.  lens: int32 device vectors of B entries. */
+int w2v2_conv0_gn_lens(const float* wav, int B, int N, const int* lens, const float* w, const float* gamma, const float* beta,
+                       float eps, void* workspace, void* out_f16, int C, int act, void* stream);
+int w2v2_cast_f16_rowmask(const float* x, void* y16, int B, int T, int H, const int* lens, void* stream);
+int w2v2_attention_lens(const void* qkv16, void* out16, int B, int T, int H, int heads, const int* lens, void* stream);
+int w2v2_stat_pool_lens(const float* x, float* out, int B, int T, int H, int mode, const int* lens, void* stream);
+int w2v2_asp_concat_split3_lens(const float* x, void* cat16x3, int B, int T, int H, const int* lens, void* stream);
+int w2v2_asp_concat_lens(const float* x, void* cat16, int B, int T, int H, const int* lens, void* stream);
+int w2v2_asp_pool_lens(const float* x, const float* logits, float* out, int B, int T, int H, const int* lens, void* stream);
+/* Sum all-reduce of multicast_base[lo, hi) (fp32) over `world` ranks through the NVSwitch: two-shot, rank r pulls the
+ * switch-reduced sum of its 1/world slice (multimem.ld_reduce) and broadcasts it (multimem.st).  multicast_base: this
+ * rank's address of the multicast mapping of a symmetric buffer (the same offsets on every rank); lo / hi multiples of
+ * 4 elements.  The caller orders the ranks with barriers on `stream` before (every replica written) and after (every
+ * slice broadcast).  Replaces the ncclAllReduce DDP issues for the gradient buckets (R:config/trainer/trainer.yaml:6-9). */
+int w2v2_nvls_allreduce_f32(void* multicast_base, int64_t lo, int64_t hi, int rank, int world, int ctas, void* stream);
 int w2v2_dgrad_accumulates(void);   /* 1: w2v2_encoder_layer_bwd leaves the whole input gradient in dx1_32 (dh_in32 unused) */
 int w2v2_gemm_f16_accum(const void* A, int64_t M, int64_t lda, int K, const void* W, int64_t ldw, int N, float* out32,
                         int64_t ldo, void* stream);
@@ -337,6 +358,7 @@ typedef struct {
   void* h2_16;
   float* rstd1;        /* f32 [B*T] 1/sigma of LayerNorm 1 / 2 (training; NULL in inference) */
   float* rstd2;
+  const int* key_lens; /* inference of a ragged batch: int32 [B] frames per utterance (NULL = all T frames are real) */
 } w2v2_layer_fwd_args;
 int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* args, void* stream);
 

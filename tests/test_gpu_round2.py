@@ -235,7 +235,9 @@ def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(base_param
     em = ((got["m"].double() - ref_m).norm() / ref_m.norm()).item()
     ep = ((got["p"].double() - ref_p).norm() / ref_p.norm()).item()
     assert em < 2e-3, em            # gradients: fp16 operands see batches of 16 vs 32 (other tile counts / atomics order)
-    assert ep < 1e-6, ep
+    # parameters: two Adam steps of size lr * m / (sqrt(v) + eps) -- where a gradient element is rounding noise its sign,
+    # hence a whole step of 1e-4, may differ; measured 2.4e-5 of the parameter norm
+    assert ep < 1e-4, ep
 
 
 def test_large_architecture_training_gradients_match_oracle_autograd():

@@ -229,3 +229,22 @@ def test_eval_metrics_match_the_reference_functions():
         assert abs(e - float(g[key + ".eer"])) < 1e-6, key
         assert abs(et - float(g[key + ".eer_threshold"])) < 1e-5, key
         assert abs(m - float(g[key + ".mdc"])) < 1e-6 and abs(mt - float(g[key + ".mdc_threshold"])) < 1e-5, key
+
+
+def test_bucket_planner_covers_every_utterance_once():
+    """ragged.plan_buckets: every index exactly once, batch size / padding / memory limits respected."""
+    import random
+    from w2v2_speaker_b200.ragged import plan_buckets
+    random.seed(1)
+    lengths = [random.randint(16000, 400000) for _ in range(300)] + [48000] * 40
+    for max_batch, pad in ((32, 0.15), (8, 0.0), (64, 0.5)):
+        buckets = plan_buckets(lengths, max_batch, pad, max_batch_samples=32 * 160000)
+        assert sorted(i for b in buckets for i in b) == list(range(len(lengths)))
+        for b in buckets:
+            longest = max(lengths[i] for i in b)
+            assert len(b) <= max_batch
+            assert min(lengths[i] for i in b) >= (1.0 - pad) * longest - 1e-9
+            assert len(b) == 1 or len(b) * longest <= 32 * 160000
+    assert plan_buckets([], 4) == []
+    with pytest.raises(ValueError):
+        plan_buckets([100, 0], 4)

@@ -27,6 +27,15 @@ SIGNATURES = {
                                         c_void_p, c_int64, c_void_p]),
     "w2v2_scale_copy_f32": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "w2v2_dgrad_accumulates": (c_int, []),
+    "w2v2_nvls_allreduce_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "w2v2_conv0_gn_lens": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                   c_int, c_int, c_void_p]),
+    "w2v2_cast_f16_rowmask": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "w2v2_attention_lens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "w2v2_stat_pool_lens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "w2v2_asp_concat_split3_lens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "w2v2_asp_concat_lens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "w2v2_asp_pool_lens": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "w2v2_gemm_f16_accum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "w2v2_grad_entry_scale": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
     "w2v2_scale_f32_dev": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),

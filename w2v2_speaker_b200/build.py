@@ -59,7 +59,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and out:
                     print(out)
     if jobs or force or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        # link next to the target and rename: the library in the tree is always a complete file (a gpurun snapshot
+        # taken while a build is running must never ship a half-written .so)
+        tmp = LIB + ".tmp%d" % os.getpid()
+        run([NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -26,6 +26,7 @@ struct alignas(64) AttnParams {
   CUtensorMap tmKV;   // box {64, TK, 1}
   __half* out;
   float* lse;         // [B, heads, T] or nullptr
+  const int* lens;    // [B] valid keys per utterance (ragged evaluation batches) or nullptr
   int T, TK, H, heads;
   int tmem_cols, o_col;
   uint32_t drop_thr;  // attention dropout (HF:456): keep <=> 16 random bits >= thr; 0 = off
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, cg = warp >> 2;
   pdl_trigger();
+  const int Tk = p.lens != nullptr ? __ldg(p.lens + b) : p.T;       // keys that exist for this utterance
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&p.tmQ);
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (c * 16 + j < p.T) mx = fmaxf(mx, __uint_as_float(r[j]));
+        if (c * 16 + j < Tk) mx = fmaxf(mx, __uint_as_float(r[j]));
     }
   }
   red_max[cg * 128 + row] = mx;
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
       for (int j = 0; j < 8; ++j) {
         float e0 = fast_ex2(fmaf(__uint_as_float(r[2 * j]), 1.4426950408889634f, -mxl));
         float e1 = fast_ex2(fmaf(__uint_as_float(r[2 * j + 1]), 1.4426950408889634f, -mxl));
-        if (c * 16 + 2 * j >= p.T) e0 = 0.f;
-        if (c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
+        if (c * 16 + 2 * j >= Tk) e0 = 0.f;
+        if (c * 16 + 2 * j + 1 >= Tk) e1 = 0.f;
         // the value the tensor core will see is the fp16-rounded one: sum those for a consistent normaliser
         __half2 hh = __floats2half2_rn(e0, e1);
         const float2 f = __half22float2(hh);
@@ -213,23 +215,40 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
   }
 }
 
-int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, cudaStream_t stream);
+int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, const int* lens,
+                          cudaStream_t stream);
 int attention_persist_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, uint32_t drop_thr,
-                             float drop_inv_keep, uint64_t drop_seed, cudaStream_t stream);
+                             float drop_inv_keep, uint64_t drop_seed, const int* lens, cudaStream_t stream);
 
 }  // namespace w2v2
 
 using namespace w2v2;
 
+static int attention_dispatch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, float drop_p,
+                              uint64_t drop_seed, const int* lens, void* stream_);
+
 extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, float drop_p,
                                  uint64_t drop_seed, void* stream_) {
+  return attention_dispatch(qkv16, out16, lse, B, T, H, heads, drop_p, drop_seed, nullptr, stream_);
+}
+
+// Ragged evaluation batches (utterances zero-padded to a common length): lens[b] = frames of utterance b.  Keys
+// >= lens[b] are excluded from the softmax; every query row is still computed (padding rows stay finite).
+extern "C" int w2v2_attention_lens(const void* qkv16, void* out16, int B, int T, int H, int heads, const int* lens,
+                                   void* stream_) {
+  W2V2_REQUIRE(lens != nullptr, "w2v2_attention_lens: lens is required (use w2v2_attention for full batches)");
+  return attention_dispatch(qkv16, out16, nullptr, B, T, H, heads, 0.f, 0, lens, stream_);
+}
+
+static int attention_dispatch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, float drop_p,
+                              uint64_t drop_seed, const int* lens, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * ATT_D, "w2v2_attention: head dim must be 64 (H=%d heads=%d)", H, heads);
   W2V2_REQUIRE(T >= 1, "w2v2_attention: empty sequence");
   W2V2_REQUIRE(B >= 1 && B <= 65535, "w2v2_attention: bad batch %d", B);
   if (T > 256) {       // full-utterance evaluation: key-tiled two-pass kernel (attention_long.cu), no dropout
     W2V2_REQUIRE(drop_p == 0.f, "w2v2_attention: attention dropout is only built for T <= 256 (training crops)");
-    return attention_long_launch(qkv16, out16, lse, B, T, H, heads, stream);
+    return attention_long_launch(qkv16, out16, lse, B, T, H, heads, lens, stream);
   }
   AttnParams p;
   const int TK = (T + 15) / 16 * 16;
@@ -239,6 +258,7 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
   if (rc) return rc;
   p.out = static_cast<__half*>(out16);
   p.lse = lse;
+  p.lens = lens;
   W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention: dropout p=%f out of [0,1)", drop_p);
   p.drop_thr = uint32_t(drop_p * 65536.0f + 0.5f);
   p.drop_inv_keep = 1.0f / (1.0f - float(p.drop_thr) / 65536.0f);
@@ -246,7 +266,7 @@ extern "C" int w2v2_attention_ex(const void* qkv16, void* out16, float* lse, int
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   W2V2_REQUIRE(uint64_t(B) * heads * T * (TK / 2) < (1ull << 32), "w2v2_attention: dropout mask index exceeds 32 bits");
   {     // T <= 160 (training crops): the persistent kernel (attention_persist.cu); 1 = not applicable
-    const int prc = attention_persist_launch(qkv16, out16, lse, B, T, H, heads, p.drop_thr, p.drop_inv_keep, drop_seed, stream);
+    const int prc = attention_persist_launch(qkv16, out16, lse, B, T, H, heads, p.drop_thr, p.drop_inv_keep, drop_seed, lens, stream);
     if (prc <= 0) return prc;
   }
   if (TK <= 192) { p.tmem_cols = 256; p.o_col = 192; } else { p.tmem_cols = 512; p.o_col = 256; }

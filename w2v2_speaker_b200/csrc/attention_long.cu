@@ -34,6 +34,7 @@ struct alignas(64) AttnLongParams {
   CUtensorMap tm;      // qkv [B, T, 3H]: box {64, 128, 1}
   __half* out;         // [B*T, H]
   float* lse;          // [B, heads, T] or nullptr
+  const int* lens;     // [B] valid keys per utterance (ragged evaluation batches) or nullptr
   int T, H, heads, kblocks;
 };
 
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
   const int row = quarter * 32 + lane;
   const int t_q = mt * 128 + row;
   const bool warp_valid = mt * 128 + quarter * 32 < p.T;      // warp-uniform
+  const int Tk = p.lens != nullptr ? __ldg(p.lens + b) : p.T;  // keys that exist for this utterance (>= 1)
   pdl_trigger();
 
   if (threadIdx.x == 0) {
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const bool ok = key0 + (c_lo + c) * 16 + j < p.T;
+            const bool ok = key0 + (c_lo + c) * 16 + j < Tk;
             sv[c * 16 + j] = ok ? __uint_as_float(r[j]) : -INFINITY;
             mx = fmaxf(mx, sv[c * 16 + j]);
           }
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
           for (int j = 0; j < 8; ++j) {
             float e0 = fast_ex2(fmaf(__uint_as_float(r[2 * j]), 1.4426950408889634f, -ml));
             float e1 = fast_ex2(fmaf(__uint_as_float(r[2 * j + 1]), 1.4426950408889634f, -ml));
-            if (key0 + c * 16 + 2 * j >= p.T) e0 = 0.f;
-            if (key0 + c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
+            if (key0 + c * 16 + 2 * j >= Tk) e0 = 0.f;
+            if (key0 + c * 16 + 2 * j + 1 >= Tk) e1 = 0.f;
             pk[j] = pack_half2(e0, e1);
           }
           const int col = c * 16;
@@ -243,12 +245,14 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
   }
 }
 
-int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, cudaStream_t stream) {
+int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, const int* lens,
+                          cudaStream_t stream) {
   AttnLongParams p;
   int rc = make_tmap_3d(&p.tm, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AL_D, 128, 1, 128);
   if (rc) return rc;
   p.out = static_cast<__half*>(out16);
   p.lse = lse;
+  p.lens = lens;
   p.T = T; p.H = H; p.heads = heads;
   p.kblocks = (T + AL_BK - 1) / AL_BK;
   static bool configured = false;

@@ -50,6 +50,7 @@ struct alignas(64) AttnPersistParams {
   CUtensorMap tmKV;   // qkv: box {64, TK, 1}
   __half* out;
   float* lse;         // [B, heads, T] or nullptr
+  const int* lens;    // [B] valid KEYS per utterance (ragged evaluation batches: frames >= lens[b] are padding) or nullptr
   int T, TK, H, heads, nprob, ntiles, kvb;
   uint32_t drop_thr;
   float drop_inv_keep;
@@ -197,6 +198,8 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_persist_kernel(const 
     const int b = prob / p.heads, h = prob - b * p.heads;
     const uint32_t bh = uint32_t(b) * p.heads + h;
     const int tq1 = 128 + lane;
+    // keys that exist for this utterance: every query row (padding rows included -- they must stay finite) attends to them
+    const int Tk = p.lens != nullptr ? __ldg(p.lens + b) : T;
 
     mbar_wait(bar_s, k & 1);
     __syncwarp();
@@ -217,15 +220,15 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_persist_kernel(const 
       for (int i = 0; i < AP_MAXCH; ++i) {
         const int c = c_begin + i;
         if (c < c_end) {
-          const int nv = T - c * 8;
+          const int nv = Tk - c * 8;
           mx0 = nv >= 8 ? max_chunk<true>(v0[i], 8, mx0) : max_chunk<false>(v0[i], nv, mx0);
         }
       }
       red_max0[cg * 128 + row] = mx0;
     }
     if (two) {
-      if (has1a) { const int nv = T - c1a * 8; mx1 = nv >= 8 ? max_chunk<true>(v1[0], 8, mx1) : max_chunk<false>(v1[0], nv, mx1); }
-      if (has1b) { const int nv = T - c1b * 8; mx1 = nv >= 8 ? max_chunk<true>(v1[1], 8, mx1) : max_chunk<false>(v1[1], nv, mx1); }
+      if (has1a) { const int nv = Tk - c1a * 8; mx1 = nv >= 8 ? max_chunk<true>(v1[0], 8, mx1) : max_chunk<false>(v1[0], nv, mx1); }
+      if (has1b) { const int nv = Tk - c1b * 8; mx1 = nv >= 8 ? max_chunk<true>(v1[1], 8, mx1) : max_chunk<false>(v1[1], nv, mx1); }
       red_max1[warp * 32 + lane] = mx1;
     }
     __syncthreads();
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_persist_kernel(const 
       for (int i = 0; i < AP_MAXCH; ++i) {
         const int c = c_begin + i;
         if (c < c_end) {
-          const int nv = T - c * 8;
+          const int nv = Tk - c * 8;
           uint4 o;
           sum += nv >= 8 ? exp_chunk<true, DROP>(v0[i], mxl, 8, dkeys, pair_row + c * 4, thr_hi, inv_keep, o)
                          : exp_chunk<false, DROP>(v0[i], mxl, nv, dkeys, pair_row + c * 4, thr_hi, inv_keep, o);
@@ -257,14 +260,14 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_persist_kernel(const 
       uint8_t* prow = smem + oP1 + lane * 128;
       float sum = 0.f;
       if (has1a) {
-        const int nv = T - c1a * 8;
+        const int nv = Tk - c1a * 8;
         uint4 o;
         sum += nv >= 8 ? exp_chunk<true, DROP>(v1[0], mxl, 8, dkeys, pair_row + c1a * 4, thr_hi, inv_keep, o)
                        : exp_chunk<false, DROP>(v1[0], mxl, nv, dkeys, pair_row + c1a * 4, thr_hi, inv_keep, o);
         *reinterpret_cast<uint4*>(prow + (c1a >> 3) * 4096 + (((c1a & 7) ^ (lane & 7)) << 4)) = o;
       }
       if (has1b) {
-        const int nv = T - c1b * 8;
+        const int nv = Tk - c1b * 8;
         uint4 o;
         sum += nv >= 8 ? exp_chunk<true, DROP>(v1[1], mxl, 8, dkeys, pair_row + c1b * 4, thr_hi, inv_keep, o)
                        : exp_chunk<false, DROP>(v1[1], mxl, nv, dkeys, pair_row + c1b * 4, thr_hi, inv_keep, o);
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attention_persist_kernel(const 
 
 // -> 0 launched, 1 not applicable (caller falls back to attention.cu), < 0 error
 int attention_persist_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, uint32_t drop_thr,
-                             float drop_inv_keep, uint64_t drop_seed, cudaStream_t stream) {
+                             float drop_inv_keep, uint64_t drop_seed, const int* lens, cudaStream_t stream) {
   static const bool on = []() { const char* e = getenv("W2V2_ATTN_PERSIST"); return !(e != nullptr && e[0] == '0'); }();
   const int TK = (T + 15) / 16 * 16;
   if (!on || TK > AP_MAX_TK) return 1;
@@ -363,6 +366,7 @@ int attention_persist_launch(const void* qkv16, void* out16, float* lse, int B, 
   if (rc) return rc;
   p.out = static_cast<__half*>(out16);
   p.lse = lse;
+  p.lens = lens;
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   p.nprob = B * heads;
   p.ntiles = T > 128 ? 2 : 1;

@@ -46,18 +46,19 @@ __device__ __forceinline__ float ap_max(float v, float (*sm)[AP_CH], int ts, int
 // percent of gradient accuracy in the TDNN (measured against the fp32 oracle); the hi block alone is the fp16
 // cat the weight-gradient GEMM consumes.
 __global__ void __launch_bounds__(AP_TS* AP_CH) asp_concat_split3_kernel(const float* __restrict__ x, __half* __restrict__ cat,
-                                                                          int T, int H) {
+                                                                          int T, int H, const int* __restrict__ lens) {
   __shared__ float sm[AP_TS][AP_CH];
   const int ch = threadIdx.x % AP_CH, ts = threadIdx.x / AP_CH;
   const int c = blockIdx.x * AP_CH + ch;
   const int b = blockIdx.y;
   const float* xb = x + int64_t(b) * T * H + c;
-  const float w = 1.0f / float(T);
+  const int Tv = lens != nullptr ? lens[b] : T;      // ragged batch: statistics over the utterance's own frames
+  const float w = 1.0f / float(Tv);
   float s = 0.f;
-  for (int t = ts; t < T; t += AP_TS) s = fmaf(w, xb[int64_t(t) * H], s);
+  for (int t = ts; t < Tv; t += AP_TS) s = fmaf(w, xb[int64_t(t) * H], s);
   const float mean = ap_sum(s, sm, ts, ch);
   float q = 0.f;
-  for (int t = ts; t < T; t += AP_TS) {
+  for (int t = ts; t < Tv; t += AP_TS) {
     const float d = xb[int64_t(t) * H] - mean;
     q = fmaf(w * d, d, q);
   }
@@ -256,9 +257,12 @@ extern "C" int w2v2_asp_bn_batch_stats(const float* z, int64_t rows, int A, cons
 }
 
 extern "C" int w2v2_asp_concat_split3(const float* x, void* cat16x3, int B, int T, int H, void* stream) {
+  return w2v2_asp_concat_split3_lens(x, cat16x3, B, T, H, nullptr, stream);
+}
+extern "C" int w2v2_asp_concat_split3_lens(const float* x, void* cat16x3, int B, int T, int H, const int* lens, void* stream) {
   W2V2_REQUIRE(H % AP_CH == 0, "w2v2_asp_concat_split3: H=%d must be a multiple of %d", H, AP_CH);
   dim3 g(H / AP_CH, B);
-  asp_concat_split3_kernel<<<g, AP_TS * AP_CH, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(cat16x3), T, H);
+  asp_concat_split3_kernel<<<g, AP_TS * AP_CH, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(cat16x3), T, H, lens);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

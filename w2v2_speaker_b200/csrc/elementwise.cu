@@ -45,6 +45,22 @@ __global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict_
   }
 }
 
+// y16[b, t, :] = t < lens[b] ? x[b, t, :] : 0 -- the positional conv of a padded ragged batch must see zeros behind the
+// end of each utterance (its own zero padding in a batch of one, HF:326-379)
+__global__ void cast_f16_rowmask_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t n4, int T, int H4,
+                                        const int* __restrict__ lens) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / H4;
+    const int b = int(r / T), t = int(r - int64_t(b) * T);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < lens[b]) v = reinterpret_cast<const float4*>(x)[i];
+    uint2 q;
+    q.x = pack_half2(v.x, v.y);
+    q.y = pack_half2(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = q;
+  }
+}
+
 __global__ void conv_weight_tapmajor_kernel(const float* __restrict__ w, __half* __restrict__ o, int cout, int cin,
                                             int k) {
   // o[co][j][ci] = w[co][ci][j]
@@ -70,8 +86,12 @@ __global__ void conv_weight_tapmajor_kernel(const float* __restrict__ w, __half*
 
 constexpr int C0_K = 10, C0_S = 5, C0_NMOM = 10 + 55;
 
-__global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L, double* __restrict__ mom) {
+// lens (optional): samples of utterance b in a zero-padded ragged batch -- its GroupNorm statistics cover its own
+// L_b = (lens[b] - 10) / 5 + 1 frames only, exactly what a batch of one would see.
+__global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L, double* __restrict__ mom,
+                                     const int* __restrict__ lens) {
   const int b = blockIdx.y;
+  if (lens != nullptr) L = (lens[b] - C0_K) / C0_S + 1;
   const float* x = wav + int64_t(b) * N;
   double acc[C0_NMOM];
 #pragma unroll
@@ -107,9 +127,11 @@ __global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L
 
 __global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int C, int L,
-                                   float eps, float* __restrict__ scale, float* __restrict__ shift) {
+                                   float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                   const int* __restrict__ lens) {
   // GroupNorm affine folded to y = conv * scale + shift  (scale = gamma * rstd, shift = beta - mean * scale)
   const int b = blockIdx.y;
+  if (lens != nullptr) L = (lens[b] - C0_K) / C0_S + 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double* m = mom + int64_t(b) * C0_NMOM;
@@ -282,13 +304,15 @@ __device__ __forceinline__ float block_slices_max(float v, float (*sm)[POOL_CH],
   return s;
 }
 
+// lens (optional, all three pooling kernels): valid frames of utterance b in a padded ragged batch; the row pitch stays T
 __global__ void __launch_bounds__(POOL_TS* POOL_CH) stat_pool_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                                      int T, int H, int mode) {
+                                                                      int T, int H, int mode, const int* __restrict__ lens) {
   __shared__ float sm[POOL_TS][POOL_CH];
   const int ch = threadIdx.x % POOL_CH, ts = threadIdx.x / POOL_CH;
   const int c = blockIdx.x * POOL_CH + ch;
   const int b = blockIdx.y;
   const float* xb = x + int64_t(b) * T * H + c;
+  if (lens != nullptr) T = lens[b];                  // (xb already points at the utterance)
   if (mode == 2) {
     float m = -INFINITY;
     for (int t = ts; t < T; t += POOL_TS) m = fmaxf(m, xb[int64_t(t) * H]);
@@ -317,18 +341,20 @@ __global__ void __launch_bounds__(POOL_TS* POOL_CH) stat_pool_kernel(const float
 
 // ASP front: uniform-weight mean/std (eps-clamped) + concatenated fp16 operand [x | mean | std]
 __global__ void __launch_bounds__(POOL_TS* POOL_CH) asp_concat_kernel(const float* __restrict__ x,
-                                                                       __half* __restrict__ cat, int T, int H) {
+                                                                       __half* __restrict__ cat, int T, int H,
+                                                                       const int* __restrict__ lens) {
   __shared__ float sm[POOL_TS][POOL_CH];
   const int ch = threadIdx.x % POOL_CH, ts = threadIdx.x / POOL_CH;
   const int c = blockIdx.x * POOL_CH + ch;
   const int b = blockIdx.y;
   const float* xb = x + int64_t(b) * T * H + c;
-  const float m = 1.0f / float(T);
+  const int Tv = lens != nullptr ? lens[b] : T;      // statistics over the valid frames; every row of `cat` is written
+  const float m = 1.0f / float(Tv);
   float s = 0.f;
-  for (int t = ts; t < T; t += POOL_TS) s = fmaf(m, xb[int64_t(t) * H], s);
+  for (int t = ts; t < Tv; t += POOL_TS) s = fmaf(m, xb[int64_t(t) * H], s);
   const float mean = block_slices_sum(s, sm, ts, ch);
   float q = 0.f;
-  for (int t = ts; t < T; t += POOL_TS) {
+  for (int t = ts; t < Tv; t += POOL_TS) {
     const float d = xb[int64_t(t) * H] - mean;
     q = fmaf(m * d, d, q);
   }
@@ -355,13 +381,14 @@ __global__ void asp_relu_bn_tanh_kernel(const float* __restrict__ z, const float
 // ASP tail: softmax over T per (b,c) of the attention logits, weighted mean / std
 __global__ void __launch_bounds__(POOL_TS* POOL_CH) asp_pool_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ lg, float* __restrict__ out,
-                                                                     int T, int H) {
+                                                                     int T, int H, const int* __restrict__ lens) {
   __shared__ float sm[POOL_TS][POOL_CH];
   const int ch = threadIdx.x % POOL_CH, ts = threadIdx.x / POOL_CH;
   const int c = blockIdx.x * POOL_CH + ch;
   const int b = blockIdx.y;
   const float* xb = x + int64_t(b) * T * H + c;
   const float* lb = lg + int64_t(b) * T * H + c;
+  if (lens != nullptr) T = lens[b];                  // softmax over the valid frames only (speechbrain's length mask)
   float mx = -INFINITY;
   for (int t = ts; t < T; t += POOL_TS) mx = fmaxf(mx, lb[int64_t(t) * H]);
   mx = block_slices_max(mx, sm, ts, ch);
@@ -672,6 +699,16 @@ int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* strea
   return 0;
 }
 
+int w2v2_cast_f16_rowmask(const float* x, void* y16, int B, int T, int H, const int* lens, void* stream) {
+  W2V2_REQUIRE(H % 4 == 0 && lens != nullptr, "w2v2_cast_f16_rowmask: H %% 4 == 0 and lens are required");
+  const int64_t n4 = int64_t(B) * T * (H / 4);
+  if (n4 == 0) return 0;
+  cast_f16_rowmask_kernel<<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)y16, n4, T, H / 4, lens);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int k, void* stream) {
   const int64_t n = int64_t(cout) * cin * k;
   conv_weight_tapmajor_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)w16, cout, cin, k);
@@ -712,6 +749,11 @@ int w2v2_conv0_gn_gelu(const float* wav, int B, int N, const float* w, const flo
 
 int w2v2_conv0_gn_ex(const float* wav, int B, int N, const float* w, const float* gamma, const float* beta, float eps,
                      void* workspace, void* out_f16, int C, int act, void* stream_) {
+  return w2v2_conv0_gn_lens(wav, B, N, nullptr, w, gamma, beta, eps, workspace, out_f16, C, act, stream_);
+}
+
+int w2v2_conv0_gn_lens(const float* wav, int B, int N, const int* lens, const float* w, const float* gamma, const float* beta,
+                       float eps, void* workspace, void* out_f16, int C, int act, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   W2V2_REQUIRE(act == 0 || act == 1, "w2v2_conv0_gn_ex: act must be 0 (GroupNorm output) or 1 (+ GELU)");
   W2V2_REQUIRE(B > 0 && N >= C0_K, "w2v2_conv0_gn_gelu: need B>0 and N>=10 (got B=%d N=%d)", B, N);
@@ -727,9 +769,9 @@ int w2v2_conv0_gn_ex(const float* wav, int B, int N, const float* w, const float
   __half* a16 = reinterpret_cast<__half*>(base + ws.a);
   W2V2_CHECK_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * B * C0_NMOM, stream));
   dim3 g1((L + 256 * 8 - 1) / (256 * 8), B);
-  conv0_moments_kernel<<<g1, 256, 0, stream>>>(wav, N, L, mom);
+  conv0_moments_kernel<<<g1, 256, 0, stream>>>(wav, N, L, mom, lens);
   dim3 g2((C + 127) / 128, B);
-  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, gamma, beta, C, L, eps, scale, shift);
+  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, gamma, beta, C, L, eps, scale, shift, lens);
   conv0_weight_split_kernel<<<(C + 127) / 128, 128, 0, stream>>>(w, w16, C);
   dim3 g3((L + 255) / 256, B);
   conv0_im2col_kernel<<<g3, 256, 0, stream>>>(wav, N, L, a16);
@@ -776,20 +818,26 @@ int w2v2_layernorm_ex2(const void* x, int x_dtype, const float* bias, const floa
 }
 
 int w2v2_stat_pool(const float* x, float* out, int B, int T, int H, int mode, void* stream) {
+  return w2v2_stat_pool_lens(x, out, B, T, H, mode, nullptr, stream);
+}
+int w2v2_stat_pool_lens(const float* x, float* out, int B, int T, int H, int mode, const int* lens, void* stream) {
   W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_stat_pool: H=%d must be a multiple of %d", H, POOL_CH);
   W2V2_REQUIRE(mode >= 0 && mode <= 2, "w2v2_stat_pool: unknown mode %d", mode);
   W2V2_REQUIRE(T >= 1 && (mode != 1 || T >= 2), "w2v2_stat_pool: T=%d too short", T);
   dim3 g(H / POOL_CH, B);
-  stat_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, out, T, H, mode);
+  stat_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, out, T, H, mode, lens);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int w2v2_asp_concat(const float* x, void* cat16, int B, int T, int H, void* stream) {
+  return w2v2_asp_concat_lens(x, cat16, B, T, H, nullptr, stream);
+}
+int w2v2_asp_concat_lens(const float* x, void* cat16, int B, int T, int H, const int* lens, void* stream) {
   W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_asp_concat: H=%d must be a multiple of %d", H, POOL_CH);
   dim3 g(H / POOL_CH, B);
-  asp_concat_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, (__half*)cat16, T, H);
+  asp_concat_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, (__half*)cat16, T, H, lens);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -805,9 +853,12 @@ int w2v2_asp_relu_bn_tanh(const float* z, const float* scale, const float* shift
 }
 
 int w2v2_asp_pool(const float* x, const float* logits, float* out, int B, int T, int H, void* stream) {
+  return w2v2_asp_pool_lens(x, logits, out, B, T, H, nullptr, stream);
+}
+int w2v2_asp_pool_lens(const float* x, const float* logits, float* out, int B, int T, int H, const int* lens, void* stream) {
   W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_asp_pool: H=%d must be a multiple of %d", H, POOL_CH);
   dim3 g(H / POOL_CH, B);
-  asp_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, logits, out, T, H);
+  asp_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, logits, out, T, H, lens);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -53,7 +53,12 @@ extern "C" int w2v2_encoder_layer_fwd(const w2v2_layer_fwd_args* a, void* stream
   const int l = a->layer;
   // attention block
   W2V2_TRY(w2v2_gemm_f16(a->h_in16, M, H, 0, 1, 1, 0, H, a->wqkv, H, 3 * H, a->bqkv, 0, a->qkv16, 0, 3 * H, 0, stream));
-  W2V2_TRY(w2v2_attention_ex(a->qkv16, a->att16, a->lse, a->B, a->T, H, a->heads, a->p_attn, seed + 100 + l, stream));
+  if (a->key_lens != nullptr) {   // ragged evaluation batch: keys of each utterance's own frames only
+    W2V2_REQUIRE(a->z16 == nullptr && a->lse == nullptr, "w2v2_encoder_layer_fwd: key_lens is an inference-only option");
+    W2V2_TRY(w2v2_attention_lens(a->qkv16, a->att16, a->B, a->T, H, a->heads, a->key_lens, stream));
+  } else {
+    W2V2_TRY(w2v2_attention_ex(a->qkv16, a->att16, a->lse, a->B, a->T, H, a->heads, a->p_attn, seed + 100 + l, stream));
+  }
   W2V2_TRY(w2v2_gemm_f16(a->att16, M, H, 0, 1, 1, 0, H, a->wo, H, H, nullptr, 0, a->o32, 1, H, 0, stream));
   W2V2_TRY(w2v2_layernorm_ex2(a->o32, 1, a->bo, a->h_in32, a->ln1_g, a->ln1_b, a->eps, a->h1_32, a->h1_16, a->rstd1, M, H,
                               a->p_hidden, seed + 200 + l, stream));

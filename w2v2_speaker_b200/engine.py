@@ -213,8 +213,10 @@ class EncoderEngine:
         self.arch = weights.arch
 
     # -- HF:409-419 ----------------------------------------------------------------------------
-    def feature_extractor(self, wav: torch.Tensor, stages: Optional[list] = None) -> torch.Tensor:
-        """wav f32 [B,N] -> channels-last f32 [B,T,C] (HF returns its transpose [B,C,T])."""
+    def feature_extractor(self, wav: torch.Tensor, stages: Optional[list] = None,
+                          lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """wav f32 [B,N] -> channels-last f32 [B,T,C] (HF returns its transpose [B,C,T]).  lens: int32 [B] sample counts
+        of a zero-padded ragged batch (frames behind an utterance's end are computed but meaningless)."""
         a, w = self.arch, self.w
         if wav.dim() != 2:
             raise ValueError(f"expected wav_input of shape [BATCH_SIZE, NUM_SAMPLES], got {tuple(wav.shape)}")
@@ -222,7 +224,7 @@ class EncoderEngine:
             # HF fails inside the conv stack here ("kernel size can't be greater than actual input size")
             raise ValueError(f"utterances of {wav.shape[1]} samples are shorter than the receptive field of the feature "
                              f"extractor (no output frame)")
-        h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps)
+        h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps, lens)
         if stages is not None:
             stages.append(h)
         n = len(a.conv_kernel)
@@ -261,13 +263,16 @@ class EncoderEngine:
         return out.view(B, n, tc + K, H)[:, :, halo:halo + tc].reshape(B, n * tc, H)[:, :T].contiguous()
 
     # -- HF:668-727 ----------------------------------------------------------------------------
-    def encoder(self, h0: torch.Tensor, hidden_states: Optional[list] = None) -> torch.Tensor:
-        """h0 f32 [B,T',H] (any sequence, e.g. with a CLS frame prepended) -> last_hidden_state f32."""
+    def encoder(self, h0: torch.Tensor, hidden_states: Optional[list] = None,
+                frame_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """h0 f32 [B,T',H] (any sequence, e.g. with a CLS frame prepended) -> last_hidden_state f32.
+        frame_lens: int32 [B] frames per utterance of a padded ragged batch -- the positional conv sees zeros behind each
+        utterance's end and attention only its own keys, so the valid rows equal what a batch of one computes."""
         a, w = self.arch, self.w
         B, T, H = h0.shape
         M = B * T
         h0 = h0.contiguous()
-        x16 = ops.cast_f16(h0)
+        x16 = ops.cast_f16(h0) if frame_lens is None else ops.cast_f16_rowmask(h0, frame_lens)
         if T <= self.POS_SINGLE_SLAB:
             pos = ops.posconv(x16, w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel)
         else:
@@ -290,7 +295,8 @@ class EncoderEngine:
         for l, lw in enumerate(w.layers):
             i = l if keep else (l & 1)
             sched.run_layer_fwd(sched.fwd_args(a, B, T, l, lw, p32, p16, ar, False,
-                                               out32=ar.ptr(f"h32.{i}"), out16=ar.ptr(f"h16.{i}")))
+                                               out32=ar.ptr(f"h32.{i}"), out16=ar.ptr(f"h16.{i}"),
+                                               key_lens=frame_lens.data_ptr() if frame_lens is not None else None))
             p32, p16 = ar.ptr(f"h32.{i}"), ar.ptr(f"h16.{i}")
             out = ar.tensor(f"h32.{i}", F32, (B, T, H))
             if keep:
@@ -298,13 +304,25 @@ class EncoderEngine:
         return out
 
     # -- HF:1327-1383 --------------------------------------------------------------------------
-    def forward(self, wav: torch.Tensor, trace: Optional[dict] = None) -> torch.Tensor:
-        """wav f32 [B,N] -> last_hidden_state f32 [B,T,H]."""
+    def frame_lengths(self, sample_lengths) -> List[int]:
+        return [self.arch.conv_lengths(int(n))[-1] for n in sample_lengths]
+
+    def forward(self, wav: torch.Tensor, trace: Optional[dict] = None, lengths=None) -> torch.Tensor:
+        """wav f32 [B,N] -> last_hidden_state f32 [B,T,H].  lengths: host sequence of B sample counts when `wav` is a
+        zero-padded ragged batch; rows t >= frame_lengths(lengths)[b] of the result are padding."""
         stages = [] if trace is not None else None
-        feat = self.feature_extractor(wav, stages)
+        lens_s = lens_f = None
+        if lengths is not None:
+            lengths = [int(n) for n in lengths]
+            if len(lengths) != wav.shape[0] or max(lengths) > wav.shape[1] or min(self.frame_lengths(lengths)) < 1:
+                raise ValueError("lengths must hold one sample count per utterance, each within the padded length and "
+                                 "long enough for one output frame")
+            lens_s = torch.tensor(lengths, dtype=torch.int32).to(wav.device, non_blocking=True)
+            lens_f = torch.tensor(self.frame_lengths(lengths), dtype=torch.int32).to(wav.device, non_blocking=True)
+        feat = self.feature_extractor(wav, stages, lens_s)
         h0 = self.feature_projection(feat)
         hs = [] if trace is not None else None
-        out = self.encoder(h0, hs)
+        out = self.encoder(h0, hs, lens_f)
         if trace is not None:
             trace["conv"] = stages
             trace["proj"] = h0

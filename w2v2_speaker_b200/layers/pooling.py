@@ -34,8 +34,12 @@ class MeanStatPool1D(nn.Module):
         super().__init__()
         self.dim_to_reduce = dim_to_reduce
 
-    def forward(self, tensor: torch.Tensor):
+    def forward(self, tensor: torch.Tensor, lengths=None):
+        """lengths (this package's extension, evaluation only): int32 CUDA vector of valid frames per utterance of a
+        zero-padded ragged batch -- the statistic then covers each utterance's own frames."""
         x = _as_btc(tensor, self.dim_to_reduce)
+        if lengths is not None:
+            return ops.stat_pool(x.detach(), 0, lengths)
         if torch.is_grad_enabled() and x.requires_grad:
             from ..training import MeanPoolFn
             return MeanPoolFn.apply(x)
@@ -49,8 +53,10 @@ class MeanStdStatPool1D(nn.Module):
         super().__init__()
         self.dim_to_reduce = dim_to_reduce
 
-    def forward(self, tensor: torch.Tensor):
+    def forward(self, tensor: torch.Tensor, lengths=None):
         x = _as_btc(tensor, self.dim_to_reduce)
+        if lengths is not None:                     # ragged evaluation batch (see MeanStatPool1D.forward)
+            return ops.stat_pool(x.detach(), 1, lengths)
         if torch.is_grad_enabled() and x.requires_grad:
             from ..training import MeanStdPoolFn
             return MeanStdPoolFn.apply(x)
@@ -64,8 +70,10 @@ class MaxPool1D(nn.Module):
         super().__init__()
         self.dim_to_reduce = dim_to_reduce
 
-    def forward(self, tensor: torch.Tensor):
+    def forward(self, tensor: torch.Tensor, lengths=None):
         x = _as_btc(tensor, self.dim_to_reduce)
+        if lengths is not None:
+            return ops.stat_pool(x.detach(), 2, lengths)
         if torch.is_grad_enabled() and x.requires_grad:
             # training: torch's differentiable reduction (same values; max pooling is on no measured configuration and
             # its backward is a scatter of B*C numbers -- the kernel below has no autograd node)
@@ -108,16 +116,18 @@ class _AttentiveStatisticsPooling(nn.Module):
     def forward(self, x_ncl: torch.Tensor) -> torch.Tensor:
         return self.forward_btc(x_ncl.transpose(1, 2).contiguous()).unsqueeze(2)
 
-    def forward_btc(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_btc(self, x: torch.Tensor, lengths=None) -> torch.Tensor:
         c1, bn, c2 = self.tdnn.conv.conv, self.tdnn.norm.norm, self.conv.conv
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(q.requires_grad for q in self.parameters()))
+        if lengths is not None and (self.training or needs_grad):
+            raise NotImplementedError("ragged batches (lengths=...) are an evaluation feature: call .eval() under no_grad")
         if self.training or needs_grad:
             # batch-statistics BatchNorm and / or a backward pass: the autograd Function over the same kernels
             from ..training import AspPoolFn
             return AspPoolFn.apply(x.float().contiguous(), c1.weight, c1.bias, bn.weight, bn.bias, c2.weight, c2.bias, self)
         B, T, C = x.shape
         x = x.float().contiguous()
-        cat3 = ops.asp_concat_split3(x)                                      # [B*T, 9C] fp16: [hi | lo | hi]
+        cat3 = ops.asp_concat_split3(x, lengths)                             # [B*T, 9C] fp16: [hi | lo | hi]
         w1 = c1.weight.detach().float().reshape(self.attention_channels, 3 * C).contiguous()
         z = ops.gemm_f16(cat3, ops.split3_rows(w1, 1), c1.bias.detach().float(), 0, torch.float32)    # Conv1d k=1
         scale = (bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
@@ -125,7 +135,7 @@ class _AttentiveStatisticsPooling(nn.Module):
         y16 = ops.asp_relu_bn_tanh(z.contiguous(), scale, shift)             # tanh(BN(ReLU(.)))
         logits = ops.gemm_f16(y16, ops.cast_f16(c2.weight.detach().view(C, self.attention_channels)),
                               c2.bias.detach().float(), 0, torch.float32)
-        return ops.asp_pool(x, logits.contiguous().view(B, T, C))            # [B, 2C] = [mean || std]
+        return ops.asp_pool(x, logits.contiguous().view(B, T, C), lengths)   # [B, 2C] = [mean || std]
 
 
 class AttentiveStatPool1D(nn.Module):
@@ -136,11 +146,11 @@ class AttentiveStatPool1D(nn.Module):
         self.pooling_layer = _AttentiveStatisticsPooling(embedding_size)
         self.dim_to_reduce = dim_to_reduce
 
-    def forward(self, tensor: torch.Tensor):
+    def forward(self, tensor: torch.Tensor, lengths=None):
         if self.dim_to_reduce == 2:
-            pooled_embedding = self.pooling_layer.forward_btc(tensor.transpose(1, 2).contiguous())
+            pooled_embedding = self.pooling_layer.forward_btc(tensor.transpose(1, 2).contiguous(), lengths)
         elif self.dim_to_reduce == 1:
-            pooled_embedding = self.pooling_layer.forward_btc(tensor)
+            pooled_embedding = self.pooling_layer.forward_btc(tensor, lengths)
         else:
             raise ValueError("can only pool dimension 1 or 2")
         pooled_embedding = pooled_embedding.squeeze()

@@ -258,10 +258,17 @@ class Wav2Vec2ModelB200(nn.Module):
             raise NotImplementedError("feature-axis SpecAugment (mask_feature_prob > 0) is not implemented "
                                       "(the reference configurations keep it at 0)")
 
-    def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, **_):
+    def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, lengths=None, **_):
         """HF:1327-1383.  input_values f32 [B,N].  With gradients enabled the forward keeps what the
-        hand-written backward needs (training.EncoderFn) so that loss.backward() works."""
+        hand-written backward needs (training.EncoderFn) so that loss.backward() works.
+        lengths (extension, evaluation only): host sequence of sample counts of a zero-padded ragged batch
+        (w2v2_speaker_b200/ragged.py); rows behind an utterance's last frame are padding."""
         self._check_mode()
+        if lengths is not None:
+            if self._needs_grad() or (self.training and self._stochastic()):
+                raise NotImplementedError("ragged batches (lengths=...) are an evaluation feature: call .eval() under no_grad")
+            out = self._engine().forward(input_values.float(), None, lengths)
+            return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         if self._needs_grad():
             if output_hidden_states:
                 raise NotImplementedError("output_hidden_states is only available without gradients")
@@ -338,9 +345,9 @@ def load_base_wav2vec2_model(huggingface_id: str, reg_cfg: Optional[Wav2Vec2Regu
     return Wav2Vec2ModelB200(arch_from_id(huggingface_id), reg_cfg).to(device)
 
 
-def wav2vec2_embed_raw_audio(input_tensor: torch.Tensor, model: Wav2Vec2ModelB200) -> torch.Tensor:
+def wav2vec2_embed_raw_audio(input_tensor: torch.Tensor, model: Wav2Vec2ModelB200, lengths=None) -> torch.Tensor:
     """R:src/models/wav2vec2.py:62-76: [B, num_samples] -> [B, H, num_frames]."""
-    output = model(input_tensor)
+    output = model(input_tensor, lengths=lengths) if lengths is not None else model(input_tensor)
     return output.last_hidden_state.transpose(1, 2)
 
 
@@ -376,8 +383,12 @@ class Wav2Vec2WrapperModule(_Base):
     def num_embedding_features(self):
         return self.num_features
 
-    def forward(self, wav_input: torch.Tensor):
+    def forward(self, wav_input: torch.Tensor, lengths=None):
         # wav_input has shape [BATCH_SIZE, NUM_SAMPLES]
+        if lengths is not None:
+            if self.insert_cls_token:
+                raise NotImplementedError("ragged batches are not built for the CLS-token path")
+            return wav2vec2_embed_raw_audio(wav_input, self.model, lengths)
         if self.insert_cls_token:
             # R:src/models/wav2vec2.py:128-140 (the reference hard-codes the CLS width to 768)
             features = self.model.feature_extractor(wav_input).transpose(1, 2)

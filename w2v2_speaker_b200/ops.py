@@ -118,9 +118,16 @@ def cast_f16(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     return y
 
 
+def _chk_lens(lens: torch.Tensor, B: int) -> torch.Tensor:
+    if not lens.is_cuda or lens.dtype != torch.int32 or lens.numel() != B or not lens.is_contiguous():
+        raise _lib.W2V2Error(f"lens must be a contiguous CUDA int32 vector of {B} entries")
+    return lens
+
+
 def conv0_gn_gelu(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
-                  eps: float = 1e-5) -> torch.Tensor:
-    """HF:302-323.  wav f32 [B,N] -> f16 channels-last [B, L0, C]."""
+                  eps: float = 1e-5, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """HF:302-323.  wav f32 [B,N] -> f16 channels-last [B, L0, C].  lens (int32 [B], samples): zero-padded ragged
+    batch, the GroupNorm statistics of utterance b cover its own frames only."""
     _chk(wav, F32, "wav")
     B, N = wav.shape
     C = w.shape[0]
@@ -128,9 +135,22 @@ def conv0_gn_gelu(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta:
     lib = _lib.load()
     ws = torch.empty(lib.w2v2_conv0_workspace_bytes(B, N, C), dtype=torch.uint8, device=wav.device)
     out = torch.empty(B, L0, C, dtype=F16, device=wav.device)
-    call("w2v2_conv0_gn_gelu", ptr(wav.contiguous()), B, N, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps,
-         ptr(ws), ptr(out), C, stream_ptr())
+    if lens is None:
+        call("w2v2_conv0_gn_gelu", ptr(wav.contiguous()), B, N, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps,
+             ptr(ws), ptr(out), C, stream_ptr())
+    else:
+        call("w2v2_conv0_gn_lens", ptr(wav.contiguous()), B, N, ptr(_chk_lens(lens, B)), ptr(w.contiguous()), ptr(gamma),
+             ptr(beta), eps, ptr(ws), ptr(out), C, 1, stream_ptr())
     return out
+
+
+def cast_f16_rowmask(x: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+    """f32 [B, T, H] -> f16 with the rows t >= lens[b] zeroed."""
+    _chk(x, F32, "x")
+    B, T, H = x.shape
+    y = torch.empty(x.shape, dtype=F16, device=x.device)
+    call("w2v2_cast_f16_rowmask", ptr(x.contiguous()), ptr(y), B, T, H, ptr(_chk_lens(lens, B)), stream_ptr())
+    return y
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
@@ -336,11 +356,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step: int, grad_scale: float = 
          int(step), float(grad_scale), int(zero_grad), stream_ptr())
 
 
-def stat_pool(x: torch.Tensor, mode: int) -> torch.Tensor:
+def stat_pool(x: torch.Tensor, mode: int, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(x, F32, "x")
     B, T, H = x.shape
     out = torch.empty(B, H * (2 if mode == 1 else 1), dtype=F32, device=x.device)
-    call("w2v2_stat_pool", ptr(x.contiguous()), ptr(out), B, T, H, mode, stream_ptr())
+    call("w2v2_stat_pool_lens", ptr(x.contiguous()), ptr(out), B, T, H, mode,
+         ptr(_chk_lens(lens, B)) if lens is not None else None, stream_ptr())
     return out
 
 
@@ -351,11 +372,12 @@ def asp_concat(x: torch.Tensor) -> torch.Tensor:
     return cat
 
 
-def asp_concat_split3(x: torch.Tensor) -> torch.Tensor:
+def asp_concat_split3(x: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[x | mean | std] as error-compensated operand [hi | lo | hi], f16 [B*T, 9H] (pairs with split3_rows(W, 1))."""
     B, T, H = x.shape
     cat = torch.empty(B * T, 9 * H, dtype=F16, device=x.device)
-    call("w2v2_asp_concat_split3", ptr(x), ptr(cat), B, T, H, stream_ptr())
+    call("w2v2_asp_concat_split3_lens", ptr(x), ptr(cat), B, T, H, ptr(_chk_lens(lens, B)) if lens is not None else None,
+         stream_ptr())
     return cat
 
 
@@ -366,10 +388,11 @@ def asp_relu_bn_tanh(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) 
     return y
 
 
-def asp_pool(x: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+def asp_pool(x: torch.Tensor, logits: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, T, H = x.shape
     out = torch.empty(B, 2 * H, dtype=F32, device=x.device)
-    call("w2v2_asp_pool", ptr(x), ptr(logits), ptr(out), B, T, H, stream_ptr())
+    call("w2v2_asp_pool_lens", ptr(x), ptr(logits), ptr(out), B, T, H, ptr(_chk_lens(lens, B)) if lens is not None else None,
+         stream_ptr())
     return out
 
 

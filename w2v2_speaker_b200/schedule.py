@@ -24,7 +24,7 @@ class LayerFwdArgs(ctypes.Structure):
                 [("seed", c_uint64)] +
                 [(n, c_void_p) for n in ("wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g", "ln2_b",
                                          "h_in32", "h_in16", "qkv16", "att16", "lse", "o32", "h1_32", "h1_16", "z16", "g16",
-                                         "f2_32", "h2_32", "h2_16", "rstd1", "rstd2")])
+                                         "f2_32", "h2_32", "h2_16", "rstd1", "rstd2", "key_lens")])
 
 
 class LayerBwdArgs(ctypes.Structure):
@@ -103,7 +103,7 @@ def run_layer_bwd(args: LayerBwdArgs) -> None:
 
 def fwd_args(arch, B: int, T: int, layer: int, lw: dict, h_in32: int, h_in16: int, arena: Arena, train: bool,
              p_hidden: float = 0.0, p_attn: float = 0.0, p_act: float = 0.0, seed: int = 0,
-             out32: Optional[int] = None, out16: Optional[int] = None) -> LayerFwdArgs:
+             out32: Optional[int] = None, out16: Optional[int] = None, key_lens: Optional[int] = None) -> LayerFwdArgs:
     """Argument block of one layer.  `lw`: engine.PreparedWeights.layers[layer]; h_in*: device pointers;
     out32 / out16 override where the layer output goes (inference ping-pong buffers)."""
     a = LayerFwdArgs()
@@ -122,4 +122,5 @@ def fwd_args(arch, B: int, T: int, layer: int, lw: dict, h_in32: int, h_in16: in
     a.rstd2 = arena.ptr("rstd2") if train else None
     a.h2_32 = out32 if out32 is not None else arena.ptr("h2_32")
     a.h2_16 = out16 if out16 is not None else arena.ptr("h2_16")
+    a.key_lens = key_lens          # device pointer of int32 [B] (ragged evaluation batch) or None
     return a

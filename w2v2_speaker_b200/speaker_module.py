@@ -206,6 +206,42 @@ class Wav2vec2FCModule(nn.Module):
         wav2vec_embeddings = torch.transpose(wav2vec_embeddings, 2, 1)        # [BS, T, C]
         return self._fc_head_ops_pre_spk_embedding(wav2vec_embeddings)
 
+    def compute_speaker_embeddings_ragged(self, utterances, max_batch: int = 32, max_pad_fraction: float = 0.15):
+        """Speaker embeddings of full-length utterances of DIFFERENT lengths (evaluation; this package's extension of
+        the reference's one-utterance-per-step test loop, R:src/lightning_modules/speaker/speaker_recognition_module.py:462-500).
+        utterances: sequence of 1-D waveforms (already normalised, any device).  They are sorted into length buckets
+        (ragged.plan_buckets), zero-padded per bucket and run with per-utterance length masks, so each row equals
+        `compute_speaker_embedding(u[None])` of that utterance alone.  -> [len(utterances), E] in the input order."""
+        from .ragged import plan_buckets
+        if self.training or torch.is_grad_enabled():
+            raise RuntimeError("compute_speaker_embeddings_ragged is an evaluation call: use .eval() under torch.no_grad()")
+        pool = self.test_stat_pooling
+        if isinstance(pool, (IndexPool1D, NoPooling, QuantilePool1D)) or isinstance(self.wav2vec, Wav2vecLiteWrapperModule):
+            raise NotImplementedError("ragged batches are built for mean / mean+std / max / attentive pooling")
+        dev = next(self.parameters()).device
+        lengths = [int(u.numel()) for u in utterances]
+        eng = self.wav2vec.model._engine()
+        out = None
+        for bucket in plan_buckets(lengths, max_batch, max_pad_fraction):
+            n_max = max(lengths[i] for i in bucket)
+            wav = torch.zeros(len(bucket), n_max, dtype=torch.float32, device=dev)
+            for r, i in enumerate(bucket):
+                wav[r, :lengths[i]] = utterances[i].reshape(-1).to(dev, torch.float32)
+            lens = [lengths[i] for i in bucket]
+            hidden = self.wav2vec(wav, lengths=lens)                              # [B, C, T]
+            frames = torch.tensor(eng.frame_lengths(lens), dtype=torch.int32, device=dev)
+            pooled = pool(torch.transpose(hidden, 2, 1), lengths=frames)
+            x = torch.squeeze(self.embedding_masker(pooled[:, :, None]), 2)
+            if self.cfg.embedding_layer_idx >= 0:
+                for idx, fc_layer in enumerate(self.fc_list):
+                    x = fc_layer(x)
+                    if self.cfg.embedding_layer_idx == idx:
+                        break
+            if out is None:
+                out = torch.empty(len(utterances), x.shape[1], dtype=x.dtype, device=dev)
+            out[torch.tensor(bucket, device=dev)] = x
+        return out
+
     # R:.../wav2vec2_fc.py:433-438
     def compute_speaker_prediction(self, embedding_tensor: torch.Tensor) -> torch.Tensor:
         return self._fc_head_ops_post_spk_embedding(embedding_tensor).squeeze()
