@@ -316,7 +316,7 @@ def instrumented(step_fn, lib):
     orig_call = ops.call
 
     def traced(name, *a):
-        if name == "w2v2_conv0_gn_gelu":
+        if name in ("w2v2_conv0_gn_gelu", "w2v2_conv0_raw", "w2v2_conv0_gn_lens", "w2v2_conv0_gn_ex"):
             s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
             s.record()
             r = orig_call(name, *a)
@@ -349,6 +349,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reg", action="store_true", help="train mode without dropout / LayerDrop / SpecAugment")
+    ap.add_argument("--input", default="f32", choices=["f32", "int16"],
+                    help="f32: normalised float waveforms (what the reference's data pipeline hands the model); int16: raw 16-bit "
+                         "PCM, the input normaliser folded into conv layer 0 on the device (half the H2D bytes, SURVEY 8f-2)")
     ap.add_argument("--train-cnn", action="store_true",
                     help="train mode with the CNN feature extractor unfrozen (completely_freeze_feature_extractor: false)")
     args = ap.parse_args()
@@ -383,6 +386,8 @@ def main():
         from w2v2_speaker_b200.trainer import FlatAdamTrainer
         trainer = FlatAdamTrainer(module, lr=1e-4)
     wav_cpu, labels_cpu = make_inputs(B, WL["samples"], NUM_SPEAKERS, seed=1234 + rank)
+    if args.input == "int16":        # raw PCM: the synthetic waveform at a speech-like level, quantised to 16 bits
+        wav_cpu = (wav_cpu * 3000.0).round().clamp(-32768, 32767).to(torch.int16)
     wav_pin = wav_cpu[:, None, :].contiguous().pin_memory()          # [B,1,N] as the reference batches
     labels_pin = labels_cpu.pin_memory()
     wav_dev = wav_pin.to(dev)
@@ -523,12 +528,14 @@ def main():
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate+statistics+master weights", "data": "synthetic",
-            "config": {"workload": workload_name(args.mode, not args.no_reg), "mode": args.mode, "global_batch": world * B,
-                       "parallelism": f"dp{world}" + (" (NCCL all-reduce of the flat fp32 gradient)" if train else
+            "config": {"workload": workload_name(args.mode, not args.no_reg) +
+                       (", raw int16 PCM input (normaliser folded into conv 0)" if args.input == "int16" else ""),
+                       "mode": args.mode, "global_batch": world * B,
+                       "parallelism": f"dp{world}" + (f" ({trainer.collective} of the flat fp32 gradient)" if train else
                                                        " (independent utterances, no collective)"),
                        "l2": "per-step working set (> 1.5 GB activations + 0.19 GB fp16 weights) >> 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": B * WL["samples"] * 4 + B * 8,
+                    "h2d_bytes_per_step": B * WL["samples"] * (2 if args.input == "int16" else 4) + B * 8,
                     "d2h_bytes_per_step": (0 if train else B * emb_dim * 4) + 4 + B * 8},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
             "cpu_baseline": cpu,

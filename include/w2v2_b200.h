@@ -265,6 +265,13 @@ int w2v2_scale_copy_f32(const float* x, float* y, int64_t n, float s, void* stre
  * over its own frames.  lens: int32 device vectors of B entries. */
 int w2v2_conv0_gn_lens(const float* wav, int B, int N, const int* lens, const float* w, const float* gamma, const float* beta,
                        float eps, void* workspace, void* out_f16, int C, int act, void* stream);
+/* conv layer 0 + GroupNorm (+ GELU) straight from the RAW waveform: wav is 16-bit PCM (in_dtype 0,
+ * x = pcm / 32768) or float32 (1); normalize = 1 folds the reference's input normaliser, x' = (x - mean) / (std + 1e-5)
+ * per utterance (R:src/data/preprocess/input_normalisation.py:53-67), into the GroupNorm affine -- no normalised copy
+ * of the waveform is ever written, the host uploads half the bytes and runs no arithmetic.  lens as above (may be NULL). */
+int w2v2_conv0_raw(const void* wav, int in_dtype, int normalize, int B, int N, const int* lens, const float* w,
+                   const float* gamma, const float* beta, float eps, void* workspace, void* out_f16, int C, int act,
+                   void* stream);
 int w2v2_cast_f16_rowmask(const float* x, void* y16, int B, int T, int H, const int* lens, void* stream);
 int w2v2_attention_lens(const void* qkv16, void* out16, int B, int T, int H, int heads, const int* lens, void* stream);
 int w2v2_stat_pool_lens(const float* x, float* out, int B, int T, int H, int mode, const int* lens, void* stream);

@@ -312,3 +312,48 @@ def test_ensemble_embedding_matches_oracle_hidden_states(base_params):
     for e, h in zip(got, ref[9:13]):
         assert e.shape == (2, 768)
         assert rows(e, h.mean(1)) < 1e-3
+
+
+def test_raw_int16_input_with_the_normaliser_folded_into_conv0(base_params):
+    """16-bit PCM goes in, the reference's InputNormalizer2D ((x - mean) / (std + 1e-5) per utterance,
+    R:src/data/preprocess/input_normalisation.py:53-67) is folded into conv layer 0's GroupNorm affine.  Must equal the
+    float path fed with the waveform normalised the reference's way -- evaluation embeddings, and a training step (CNN
+    frozen, regularisation off) through the same autograd path."""
+    _need_cuda()
+    g = torch.Generator().manual_seed(11)
+    pcm = (torch.randn(3, 24000, generator=g) * 3000).round().clamp(-32768, 32767).to(torch.int16)
+    pcm[1] = (pcm[1].float() * 0.05 + 700).to(torch.int16)                   # a quiet utterance with a DC offset
+    x = pcm.float() / 32768.0
+    std, mean = torch.std_mean(x, dim=1, keepdim=True)
+    x_norm = (x - mean) / (std + 1e-5)
+    labels = torch.tensor([5, 17, 4000])
+    m = _module("mean", "ce", base_params).eval()
+    with torch.no_grad():
+        e_ref = m.compute_speaker_embedding(x_norm[:, None, :].cuda())
+        e_raw = m.compute_speaker_embedding(pcm[:, None, :].cuda())
+        e_f32 = m.wav2vec.model(x.cuda(), normalize_input=True).last_hidden_state.mean(1)   # float, not yet normalised
+    assert rows(e_raw, e_ref) < 3e-4, rows(e_raw, e_ref)
+    assert rows(e_f32, e_ref) < 3e-4, rows(e_f32, e_ref)
+
+    m.train()
+    m.wav2vec.model.feature_extractor.requires_grad_(False)
+
+    def grads(inp):
+        m.zero_grad(set_to_none=True)
+        emb, pred = m(inp)
+        loss, _ = m.loss_fn(pred, labels.cuda())
+        loss.backward()
+        return loss.item(), {k: q.grad.detach().double().cpu() for k, q in m.named_parameters() if q.grad is not None}
+
+    l_ref, g_ref = grads(x_norm[:, None, :].cuda())
+    l_raw, g_raw = grads(pcm[:, None, :].cuda())
+    assert abs(l_raw - l_ref) < 1e-4 * abs(l_ref)
+    assert set(g_raw) == set(g_ref)
+    for k, gr in g_ref.items():
+        if k.endswith("k_proj.bias"):
+            continue
+        err = ((g_raw[k] - gr).norm() / gr.norm().clamp_min(1e-30)).item()
+        assert err < 3e-3, (k, err)
+    m.wav2vec.model.feature_extractor.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        m(pcm[:, None, :].cuda())

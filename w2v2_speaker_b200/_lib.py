@@ -30,6 +30,8 @@ SIGNATURES = {
     "w2v2_nvls_allreduce_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "w2v2_conv0_gn_lens": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                    c_int, c_int, c_void_p]),
+    "w2v2_conv0_raw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                               c_void_p, c_int, c_int, c_void_p]),
     "w2v2_cast_f16_rowmask": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "w2v2_attention_lens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "w2v2_stat_pool_lens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -31,7 +31,7 @@ __device__ __forceinline__ void multimem_st_f32x4(float4* mc, float4 v) {
 
 // mc: multicast address of element 0 of the span (16-byte aligned); n4: float4 elements of the span.
 constexpr int NVLS_UNROLL = 4;
-__global__ void __launch_bounds__(256) nvls_allreduce_kernel(float4* __restrict__ mc, int64_t n4, int rank, int world) {
+__global__ void __launch_bounds__(256, 6) nvls_allreduce_kernel(float4* __restrict__ mc, int64_t n4, int rank, int world) {
   const int64_t per = (n4 + world - 1) / world;
   const int64_t lo = per * rank, hi = (lo + per < n4) ? lo + per : n4;
   const int64_t nth = int64_t(gridDim.x) * blockDim.x;
@@ -58,7 +58,7 @@ extern "C" int w2v2_nvls_allreduce_f32(void* multicast_base, int64_t lo, int64_t
   W2V2_REQUIRE(world >= 1 && rank >= 0 && rank < world, "w2v2_nvls_allreduce_f32: bad rank %d of %d", rank, world);
   W2V2_REQUIRE((reinterpret_cast<uintptr_t>(multicast_base) & 15) == 0, "w2v2_nvls_allreduce_f32: base must be 16-byte aligned");
   if (hi == lo) return 0;
-  if (ctas < 1) ctas = 16;
+  if (ctas < 1) ctas = 128;
   float4* mc = reinterpret_cast<float4*>(static_cast<float*>(multicast_base) + lo);
   nvls_allreduce_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(mc, (hi - lo) / 4, rank, world);
   count_launches(1);

@@ -85,21 +85,32 @@ __global__ void conv_weight_tapmajor_kernel(const float* __restrict__ w, __half*
 // writes fp16 channels-last with 16-byte stores.
 
 constexpr int C0_K = 10, C0_S = 5, C0_NMOM = 10 + 55;
+constexpr int C0_MOMS = C0_NMOM + 2;      // per-utterance record: 65 window moments, sum(x), sum(x^2)
 
 // lens (optional): samples of utterance b in a zero-padded ragged batch -- its GroupNorm statistics cover its own
 // L_b = (lens[b] - 10) / 5 + 1 frames only, exactly what a batch of one would see.
-__global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L, double* __restrict__ mom,
+// PCM16: the waveform is raw 16-bit PCM (x = pcm / 32768, what torchaudio.load returns for a 16-bit file).
+// SUMS: additionally accumulate sum(x) and sum(x^2) over the utterance's samples (mom[65], mom[66]): the input
+// normaliser (R:src/data/preprocess/input_normalisation.py:53-67) is then folded into the GroupNorm affine below.
+template <bool PCM16>
+__device__ __forceinline__ float c0_load(const void* wav, int64_t i) {
+  if constexpr (PCM16) return float(__ldg(static_cast<const int16_t*>(wav) + i)) * (1.0f / 32768.0f);
+  else return __ldg(static_cast<const float*>(wav) + i);
+}
+template <bool PCM16, bool SUMS>
+__global__ void conv0_moments_kernel(const void* __restrict__ wav, int N, int L, double* __restrict__ mom,
                                      const int* __restrict__ lens) {
   const int b = blockIdx.y;
-  if (lens != nullptr) L = (lens[b] - C0_K) / C0_S + 1;
-  const float* x = wav + int64_t(b) * N;
+  const int n_b = lens != nullptr ? lens[b] : N;
+  if (lens != nullptr) L = (n_b - C0_K) / C0_S + 1;
+  const int64_t x0 = int64_t(b) * N;
   double acc[C0_NMOM];
 #pragma unroll
   for (int i = 0; i < C0_NMOM; ++i) acc[i] = 0.0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L; t += gridDim.x * blockDim.x) {
     float v[C0_K];
 #pragma unroll
-    for (int k = 0; k < C0_K; ++k) v[k] = __ldg(x + t * C0_S + k);
+    for (int k = 0; k < C0_K; ++k) v[k] = c0_load<PCM16>(wav, x0 + t * C0_S + k);
     int idx = C0_K;
 #pragma unroll
     for (int k = 0; k < C0_K; ++k) {
@@ -108,33 +119,54 @@ __global__ void conv0_moments_kernel(const float* __restrict__ wav, int N, int L
       for (int k2 = k; k2 < C0_K; ++k2) acc[idx++] += double(v[k]) * double(v[k2]);
     }
   }
-  __shared__ double red[8][C0_NMOM];
+  double s1 = 0.0, s2 = 0.0;
+  if constexpr (SUMS) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_b; i += gridDim.x * blockDim.x) {
+      const double v = double(c0_load<PCM16>(wav, x0 + i));
+      s1 += v;
+      s2 += v * v;
+    }
+  }
+  __shared__ double red[8][C0_NMOM + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int i = 0; i < C0_NMOM; ++i) {
-    double a = acc[i];
+  for (int i = 0; i < C0_NMOM + (SUMS ? 2 : 0); ++i) {
+    double a = i < C0_NMOM ? acc[i < C0_NMOM ? i : 0] : (i == C0_NMOM ? s1 : s2);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) red[warp][i] = a;
   }
   __syncthreads();
-  if (threadIdx.x < C0_NMOM) {
+  if (threadIdx.x < C0_NMOM + (SUMS ? 2 : 0)) {
     double a = 0.0;
     for (int w = 0; w < int(blockDim.x >> 5); ++w) a += red[w][threadIdx.x];
-    atomicAdd(mom + int64_t(b) * C0_NMOM + threadIdx.x, a);
+    atomicAdd(mom + int64_t(b) * C0_MOMS + threadIdx.x, a);
   }
 }
 
 __global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int C, int L,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift,
-                                   const int* __restrict__ lens) {
+                                   const int* __restrict__ lens, int N, int normalize) {
   // GroupNorm affine folded to y = conv * scale + shift  (scale = gamma * rstd, shift = beta - mean * scale)
+  // normalize: the network input is x' = (x - mu) * s with the utterance's mu and s = 1 / (std_unbiased + 1e-5), but the
+  // GEMM convolves the RAW x.  conv(x') = s (conv(x) - mu sum_k w_k), so mean' = s (mean - mu W), var' = s^2 var and
+  //     y = gamma (conv(x') - mean') / sqrt(var' + eps) + beta = [gamma s / sqrt(s^2 var + eps)] (conv(x) - mean) + beta:
+  // the normaliser costs nothing but a different scale.
   const int b = blockIdx.y;
-  if (lens != nullptr) L = (lens[b] - C0_K) / C0_S + 1;
+  const int n_b = lens != nullptr ? lens[b] : N;
+  if (lens != nullptr) L = (n_b - C0_K) / C0_S + 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double* m = mom + int64_t(b) * C0_NMOM;
+  const double* m = mom + int64_t(b) * C0_MOMS;
+  double s_in = 1.0;
+  if (normalize) {
+    const double ts = m[C0_NMOM], tq = m[C0_NMOM + 1];
+    const double mu = ts / double(n_b);
+    double var_x = n_b > 1 ? (tq - ts * mu) / double(n_b - 1) : 0.0;       // unbiased, like torch.std_mean
+    if (var_x < 0.0) var_x = 0.0;
+    s_in = 1.0 / (double(float(sqrt(var_x))) + 1e-5);                        // (std rounded to fp32 like the reference's tensor)
+  }
   const double invL = 1.0 / double(L);
   double wk[C0_K];
 #pragma unroll
@@ -153,7 +185,7 @@ __global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* 
     }
   }
   if (var < 0.0) var = 0.0;
-  const double sc = double(gamma[c]) / sqrt(var + double(eps));
+  const double sc = double(gamma[c]) * s_in / sqrt(s_in * s_in * var + double(eps));
   scale[int64_t(b) * C + c] = float(sc);
   shift[int64_t(b) * C + c] = float(double(beta[c]) - mean * sc);
 }
@@ -162,15 +194,16 @@ __global__ void conv0_stats_kernel(const double* __restrict__ mom, const float* 
 // error-compensated fp16 (v = hi + lo) over K = 64:  A' = [x_hi(10) | x_lo(10) | x_hi(10) | 0...],
 // W' = [w_hi | w_hi | w_lo | 0...]  ->  the fp32 TMEM accumulator holds x.w to ~2^-20 relative.
 constexpr int C0_KP = 64;
-__global__ void conv0_im2col_kernel(const float* __restrict__ wav, int N, int L, __half* __restrict__ a) {
+template <bool PCM16>
+__global__ void conv0_im2col_kernel(const void* __restrict__ wav, int N, int L, __half* __restrict__ a) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L) return;
-  const float* x = wav + int64_t(b) * N + int64_t(t) * C0_S;
+  const int64_t x0 = int64_t(b) * N + int64_t(t) * C0_S;
   __half hi[C0_K], lo[C0_K];
 #pragma unroll
   for (int k = 0; k < C0_K; ++k) {
-    const float v = __ldg(x + k);
+    const float v = c0_load<PCM16>(wav, x0 + k);
     hi[k] = __float2half_rn(v);
     lo[k] = __float2half_rn(v - __half2float(hi[k]));
   }
@@ -725,7 +758,7 @@ static Conv0Ws conv0_ws(int B, int N, int C) {
   o.scale = 0;
   o.shift = align_up(o.scale + int64_t(B) * C * 4, 256);
   o.mom = align_up(o.shift + int64_t(B) * C * 4, 256);
-  o.w = align_up(o.mom + int64_t(B) * C0_NMOM * 8, 256);
+  o.w = align_up(o.mom + int64_t(B) * C0_MOMS * 8, 256);
   o.a = align_up(o.w + int64_t(C) * C0_KP * 2, 256);
   o.total = align_up(o.a + int64_t(B) * L * C0_KP * 2, 256);
   return o;
@@ -754,7 +787,14 @@ int w2v2_conv0_gn_ex(const float* wav, int B, int N, const float* w, const float
 
 int w2v2_conv0_gn_lens(const float* wav, int B, int N, const int* lens, const float* w, const float* gamma, const float* beta,
                        float eps, void* workspace, void* out_f16, int C, int act, void* stream_) {
+  return w2v2_conv0_raw(wav, 1, 0, B, N, lens, w, gamma, beta, eps, workspace, out_f16, C, act, stream_);
+}
+
+int w2v2_conv0_raw(const void* wav, int in_dtype, int normalize, int B, int N, const int* lens, const float* w,
+                   const float* gamma, const float* beta, float eps, void* workspace, void* out_f16, int C, int act,
+                   void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  W2V2_REQUIRE(in_dtype == 0 || in_dtype == 1, "w2v2_conv0_raw: in_dtype 0 = int16 PCM, 1 = float32");
   W2V2_REQUIRE(act == 0 || act == 1, "w2v2_conv0_gn_ex: act must be 0 (GroupNorm output) or 1 (+ GELU)");
   W2V2_REQUIRE(B > 0 && N >= C0_K, "w2v2_conv0_gn_gelu: need B>0 and N>=10 (got B=%d N=%d)", B, N);
   W2V2_REQUIRE(C > 128 && C % 8 == 0, "w2v2_conv0_gn_gelu: C=%d must be a multiple of 8 and > 128", C);
@@ -767,14 +807,21 @@ int w2v2_conv0_gn_lens(const float* wav, int B, int N, const int* lens, const fl
   double* mom = reinterpret_cast<double*>(base + ws.mom);
   __half* w16 = reinterpret_cast<__half*>(base + ws.w);
   __half* a16 = reinterpret_cast<__half*>(base + ws.a);
-  W2V2_CHECK_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * B * C0_NMOM, stream));
+  W2V2_CHECK_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * B * C0_MOMS, stream));
   dim3 g1((L + 256 * 8 - 1) / (256 * 8), B);
-  conv0_moments_kernel<<<g1, 256, 0, stream>>>(wav, N, L, mom, lens);
+  if (in_dtype == 0) {
+    if (normalize) conv0_moments_kernel<true, true><<<g1, 256, 0, stream>>>(wav, N, L, mom, lens);
+    else conv0_moments_kernel<true, false><<<g1, 256, 0, stream>>>(wav, N, L, mom, lens);
+  } else {
+    if (normalize) conv0_moments_kernel<false, true><<<g1, 256, 0, stream>>>(wav, N, L, mom, lens);
+    else conv0_moments_kernel<false, false><<<g1, 256, 0, stream>>>(wav, N, L, mom, lens);
+  }
   dim3 g2((C + 127) / 128, B);
-  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, gamma, beta, C, L, eps, scale, shift, lens);
+  conv0_stats_kernel<<<g2, 128, 0, stream>>>(mom, w, gamma, beta, C, L, eps, scale, shift, lens, N, normalize);
   conv0_weight_split_kernel<<<(C + 127) / 128, 128, 0, stream>>>(w, w16, C);
   dim3 g3((L + 255) / 256, B);
-  conv0_im2col_kernel<<<g3, 256, 0, stream>>>(wav, N, L, a16);
+  if (in_dtype == 0) conv0_im2col_kernel<true><<<g3, 256, 0, stream>>>(wav, N, L, a16);
+  else conv0_im2col_kernel<false><<<g3, 256, 0, stream>>>(wav, N, L, a16);
   count_launches(4);
   W2V2_CHECK_CUDA(cudaGetLastError());
   // y = GELU(conv * scale[b,c] + shift[b,c]) on the tensor cores, fp16 channels-last out

@@ -214,9 +214,10 @@ class EncoderEngine:
 
     # -- HF:409-419 ----------------------------------------------------------------------------
     def feature_extractor(self, wav: torch.Tensor, stages: Optional[list] = None,
-                          lens: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """wav f32 [B,N] -> channels-last f32 [B,T,C] (HF returns its transpose [B,C,T]).  lens: int32 [B] sample counts
-        of a zero-padded ragged batch (frames behind an utterance's end are computed but meaningless)."""
+                          lens: Optional[torch.Tensor] = None, normalize: bool = False) -> torch.Tensor:
+        """wav [B,N] (f32, or raw int16 PCM) -> channels-last f32 [B,T,C] (HF returns its transpose [B,C,T]).  lens: int32
+        [B] sample counts of a zero-padded ragged batch (frames behind an utterance's end are computed but meaningless).
+        normalize: the waveform is NOT yet standardised -- the reference's input normaliser is folded into conv layer 0."""
         a, w = self.arch, self.w
         if wav.dim() != 2:
             raise ValueError(f"expected wav_input of shape [BATCH_SIZE, NUM_SAMPLES], got {tuple(wav.shape)}")
@@ -224,7 +225,7 @@ class EncoderEngine:
             # HF fails inside the conv stack here ("kernel size can't be greater than actual input size")
             raise ValueError(f"utterances of {wav.shape[1]} samples are shorter than the receptive field of the feature "
                              f"extractor (no output frame)")
-        h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps, lens)
+        h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps, lens, normalize)
         if stages is not None:
             stages.append(h)
         n = len(a.conv_kernel)
@@ -307,7 +308,7 @@ class EncoderEngine:
     def frame_lengths(self, sample_lengths) -> List[int]:
         return [self.arch.conv_lengths(int(n))[-1] for n in sample_lengths]
 
-    def forward(self, wav: torch.Tensor, trace: Optional[dict] = None, lengths=None) -> torch.Tensor:
+    def forward(self, wav: torch.Tensor, trace: Optional[dict] = None, lengths=None, normalize: bool = False) -> torch.Tensor:
         """wav f32 [B,N] -> last_hidden_state f32 [B,T,H].  lengths: host sequence of B sample counts when `wav` is a
         zero-padded ragged batch; rows t >= frame_lengths(lengths)[b] of the result are padding."""
         stages = [] if trace is not None else None
@@ -319,7 +320,7 @@ class EncoderEngine:
                                  "long enough for one output frame")
             lens_s = torch.tensor(lengths, dtype=torch.int32).to(wav.device, non_blocking=True)
             lens_f = torch.tensor(self.frame_lengths(lengths), dtype=torch.int32).to(wav.device, non_blocking=True)
-        feat = self.feature_extractor(wav, stages, lens_s)
+        feat = self.feature_extractor(wav, stages, lens_s, normalize)
         h0 = self.feature_projection(feat)
         hs = [] if trace is not None else None
         out = self.encoder(h0, hs, lens_f)

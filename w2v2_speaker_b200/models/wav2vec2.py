@@ -258,23 +258,35 @@ class Wav2Vec2ModelB200(nn.Module):
             raise NotImplementedError("feature-axis SpecAugment (mask_feature_prob > 0) is not implemented "
                                       "(the reference configurations keep it at 0)")
 
-    def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, lengths=None, **_):
+    def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, lengths=None,
+                normalize_input: Optional[bool] = None, **_):
         """HF:1327-1383.  input_values f32 [B,N].  With gradients enabled the forward keeps what the
         hand-written backward needs (training.EncoderFn) so that loss.backward() works.
         lengths (extension, evaluation only): host sequence of sample counts of a zero-padded ragged batch
         (w2v2_speaker_b200/ragged.py); rows behind an utterance's last frame are padding."""
         self._check_mode()
+        raw = input_values.dtype == torch.int16 or bool(normalize_input)
+        if raw:
+            # this package's extension of the boundary (SURVEY 8f-2): raw 16-bit PCM (or an un-normalised float waveform)
+            # comes in, the reference's InputNormalizer2D is folded into conv layer 0 on the device.  Evaluation, or
+            # training with the feature extractor frozen (its backward would need the normalised waveform).
+            if any(q.requires_grad for q in self._items()[3]) and torch.is_grad_enabled():
+                raise NotImplementedError("raw / int16 input needs the feature extractor frozen "
+                                          "(completely_freeze_feature_extractor: true, the reference default)")
+        else:
+            input_values = input_values.float()
         if lengths is not None:
             if self._needs_grad() or (self.training and self._stochastic()):
                 raise NotImplementedError("ragged batches (lengths=...) are an evaluation feature: call .eval() under no_grad")
-            out = self._engine().forward(input_values.float(), None, lengths)
+            out = self._engine().forward(input_values, None, lengths, normalize=raw)
             return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         if self._needs_grad():
             if output_hidden_states:
                 raise NotImplementedError("output_hidden_states is only available without gradients")
             from ..training import EncoderFn
             names, params = self._items()[:2]
-            out = EncoderFn.apply(input_values.float(), self, names, *params)
+            self._raw_next = raw                      # (read by EncoderFn.forward: fold the input normaliser into conv 0)
+            out = EncoderFn.apply(input_values, self, names, *params)
             return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         eng = self._engine()
         if self.training and self._stochastic():
@@ -286,12 +298,12 @@ class Wav2Vec2ModelB200(nn.Module):
                 raise NotImplementedError("output_hidden_states is only available in eval mode")
             from ..training import encoder_forward_train
             with torch.no_grad():
-                out, _ = encoder_forward_train(eng, input_values.float(), self._draw_reg_plan(input_values, eng),
+                out, _ = encoder_forward_train(eng, input_values, self._draw_reg_plan(input_values, eng),
                                                self.masked_spec_embed.detach(), False,
-                                               getattr(self, "_pre_encoder_hook", None))
+                                               getattr(self, "_pre_encoder_hook", None), normalize=raw)
             return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         trace = {} if output_hidden_states else None
-        out = eng.forward(input_values.float(), trace)
+        out = eng.forward(input_values, trace, None, normalize=raw)
         hs = tuple(trace["hidden_states"]) if trace is not None else None
         return Wav2Vec2BaseModelOutput(last_hidden_state=out, hidden_states=hs)
 

@@ -125,22 +125,21 @@ def _chk_lens(lens: torch.Tensor, B: int) -> torch.Tensor:
 
 
 def conv0_gn_gelu(wav: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
-                  eps: float = 1e-5, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """HF:302-323.  wav f32 [B,N] -> f16 channels-last [B, L0, C].  lens (int32 [B], samples): zero-padded ragged
-    batch, the GroupNorm statistics of utterance b cover its own frames only."""
-    _chk(wav, F32, "wav")
+                  eps: float = 1e-5, lens: Optional[torch.Tensor] = None, normalize: bool = False) -> torch.Tensor:
+    """HF:302-323.  wav [B,N] -> f16 channels-last [B, L0, C].  wav: float32, or int16 PCM (x = pcm / 32768).
+    lens (int32 [B], samples): zero-padded ragged batch, the GroupNorm statistics of utterance b cover its own frames only.
+    normalize: fold the reference's per-utterance input normaliser (x - mean) / (std + 1e-5) into the GroupNorm affine."""
+    if wav.dtype not in (F32, torch.int16) or not wav.is_cuda:
+        raise _lib.W2V2Error(f"wav: expected a CUDA float32 or int16 tensor, got {wav.dtype} on {wav.device}")
     B, N = wav.shape
     C = w.shape[0]
     L0 = (N - 10) // 5 + 1
     lib = _lib.load()
     ws = torch.empty(lib.w2v2_conv0_workspace_bytes(B, N, C), dtype=torch.uint8, device=wav.device)
     out = torch.empty(B, L0, C, dtype=F16, device=wav.device)
-    if lens is None:
-        call("w2v2_conv0_gn_gelu", ptr(wav.contiguous()), B, N, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps,
-             ptr(ws), ptr(out), C, stream_ptr())
-    else:
-        call("w2v2_conv0_gn_lens", ptr(wav.contiguous()), B, N, ptr(_chk_lens(lens, B)), ptr(w.contiguous()), ptr(gamma),
-             ptr(beta), eps, ptr(ws), ptr(out), C, 1, stream_ptr())
+    call("w2v2_conv0_raw", ptr(wav.contiguous()), 1 if wav.dtype == F32 else 0, int(bool(normalize)), B, N,
+         ptr(_chk_lens(lens, B)) if lens is not None else None, ptr(w.contiguous()), ptr(gamma), ptr(beta), eps, ptr(ws),
+         ptr(out), C, 1, stream_ptr())
     return out
 
 

@@ -26,7 +26,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
 from ._lib import nvtx_range
 from .dist_utils import remaining_spans
 from .models.wav2vec2 import Wav2Vec2ModelB200
@@ -106,7 +106,7 @@ class FlatAdamTrainer:
         self.n0 = sum(p.numel() for p in seg0)
         n = sum(p.numel() for p in self.params)
         flat_p = torch.empty(n, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_g = self._alloc_gradient(n, dev)
         m = torch.zeros(n, dtype=torch.float32, device=dev)
         v = torch.zeros(n, dtype=torch.float32, device=dev)
         o = 0
@@ -144,6 +144,39 @@ class FlatAdamTrainer:
         self._sig = self._trainable_signature()
         if self.model is not None:
             self.model.refresh()          # parameter storage moved: re-derive the operand copies on next use
+
+    def _alloc_gradient(self, n: int, dev) -> torch.Tensor:
+        """The flat gradient.  With several ranks on one NVSwitch domain it is allocated as SYMMETRIC memory with a
+        multicast mapping (torch.distributed._symmetric_memory: allocation + rendezvous + barriers are plumbing), so that
+        the exchange step can be this package's NVLS kernel (csrc/allreduce.cu) instead of ncclAllReduce; anything
+        missing (no multicast support, a torch without symmetric memory, W2V2_NVLS=0) falls back to NCCL, loudly."""
+        self._symm, self._mc_ptr = None, 0
+        # light CTAs (256 threads, ~24 registers, no shared memory: they fit next to a GEMM CTA), one per SM at most: what
+        # limits the kernel is bytes in flight towards the switch (128 x 256 x 4 x 16 B = 2 MB)
+        self._nvls_ctas = int(os.environ.get("W2V2_NVLS_CTAS", "128"))
+        if self.world > 1 and os.environ.get("W2V2_NVLS", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = dist.group.WORLD
+                try:
+                    symm_mem.enable_symm_mem_for_group(group.group_name)
+                except Exception:
+                    pass                                   # newer torch: enabled implicitly
+                n_pad = (n + 3) // 4 * 4                   # the kernel moves 16-byte vectors
+                buf = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, group)
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                if mc == 0:
+                    raise RuntimeError("the symmetric allocation has no multicast mapping (NVLS not available)")
+                buf.zero_()
+                self._symm, self._mc_ptr, self._symm_buf = hdl, mc, buf
+                self.collective = f"NVLS two-shot all-reduce (own kernel, {self._nvls_ctas} CTAs, symmetric memory)"
+                return buf[:n]
+            except Exception as e:                         # pragma: no cover - depends on the machine
+                if dist.get_rank() == 0:
+                    print(f"[w2v2_speaker_b200] NVLS all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+        self.collective = "NCCL all-reduce" if self.world > 1 else "none (single rank)"
+        return torch.zeros(n, dtype=torch.float32, device=dev)
 
     def _broadcast_initial_state(self):
         """What DistributedDataParallel does at construction (R:config/trainer/trainer.yaml:6-9 `accelerator: ddp`): every
@@ -207,6 +240,14 @@ class FlatAdamTrainer:
         self._overlapped.append((lo, hi))
         self.comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
+            if self._symm is not None:
+                # every rank's replica of the span is complete -> pull / broadcast through the switch -> every slice landed
+                lo4, hi4 = lo // 4 * 4, (hi + 3) // 4 * 4          # (span edges are parameter boundaries: multiples of 4
+                self._symm.barrier(channel=0)                      #  except the padded end of the buffer)
+                _lib.call("w2v2_nvls_allreduce_f32", _lib.c_void_p(self._mc_ptr), lo4, hi4, dist.get_rank(), self.world,
+                          self._nvls_ctas, _lib.stream_ptr())
+                self._symm.barrier(channel=0)
+                return
             for s in range(lo, hi, self.bucket_elems):
                 dist.all_reduce(self.flat_g[s:min(hi, s + self.bucket_elems)], op=dist.ReduceOp.SUM)
 

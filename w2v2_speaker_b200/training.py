@@ -215,14 +215,16 @@ def cnn_backward(eng: EncoderEngine, params: Dict[str, torch.Tensor], S: dict, d
 
 
 def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[RegPlan] = None,
-                          mask_embed: Optional[torch.Tensor] = None, train_cnn: bool = False, pre_encoder_hook=None):
+                          mask_embed: Optional[torch.Tensor] = None, train_cnn: bool = False, pre_encoder_hook=None,
+                          normalize: bool = False):
     """Same arithmetic as EncoderEngine.forward (the GELUs run as separate passes so the pre-activations
     can be kept) plus the train-mode regularisation of `plan`; returns (last_hidden_state f32 [B,T,H], saved)."""
     S = {"plan": plan}
     if train_cnn:
         feat, S["cnn"] = cnn_forward_train(eng, wav)          # unfrozen CNN: pre-activations kept
     else:
-        feat = eng.feature_extractor(wav)                     # frozen CNN: nothing saved from inside
+        feat = eng.feature_extractor(wav, None, None, normalize)   # frozen CNN: nothing saved from inside (raw input: the
+                                                                   # normaliser is folded into conv layer 0)
     if pre_encoder_hook is not None:
         pre_encoder_hook()                                    # e.g. join the optimizer stream (trainer.py)
     B, T, C = feat.shape
@@ -468,8 +470,9 @@ class EncoderFn(torch.autograd.Function):
         eng = model._engine()
         plan = model._draw_reg_plan(wav, eng)
         train_cnn = any(q.requires_grad for q in model._items()[3])
+        raw = bool(getattr(model, "_raw_next", False))
         out, saved = encoder_forward_train(eng, wav, plan, model.masked_spec_embed.detach(), train_cnn,
-                                           getattr(model, "_pre_encoder_hook", None))
+                                           getattr(model, "_pre_encoder_hook", None), normalize=raw)
         ctx.model, ctx.names, ctx.saved, ctx.eng = model, names, saved, eng
         return out
 
