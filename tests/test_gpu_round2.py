@@ -357,3 +357,34 @@ def test_raw_int16_input_with_the_normaliser_folded_into_conv0(base_params):
     m.wav2vec.model.feature_extractor.requires_grad_(True)
     with pytest.raises(NotImplementedError):
         m(pcm[:, None, :].cuda())
+
+
+def test_paired_model_at_the_reference_crop_length_evaluates_and_refuses_to_train(base_params):
+    """the paired-input model at the reference's own pipeline (two 3 s crops -> 1 + 149 + 1 + 149 + 1 = 301
+    frames, R:config/experiment/speaker_wav2vec2_pairs.yaml:5) exceeds the 256-frame limit of the training kernels.  The
+    documented behaviour: it evaluates (key-tiled attention, chunked positional conv), training raises
+    loudly instead of computing something else, and 2 x 2.5 s (251 frames) trains."""
+    _need_cuda()
+    from oracle.params import make_inputs
+    from w2v2_speaker_b200._lib import W2V2Error
+    from w2v2_speaker_b200.optim.loss import BinaryCrossEntropyLoss
+    from w2v2_speaker_b200.paired_speaker_module import Wav2vec2PairedSpeakerModule, Wav2vec2PairedSpeakerModuleConfig
+    m = Wav2vec2PairedSpeakerModule(Wav2vec2PairedSpeakerModuleConfig(**ZERO_REG), BinaryCrossEntropyLoss)
+    m.wav2vec.model.load_state_dict(base_params)
+    m = m.cuda().eval()
+    a, _ = make_inputs(2, 48000, seed=41)
+    b, _ = make_inputs(2, 48000, seed=42)
+    with torch.no_grad():
+        s = m(a.cuda(), b.cuda())
+    assert s.shape == (2, 1) and torch.isfinite(s).all()
+    m.train()
+    m.on_train_start()
+    with pytest.raises((W2V2Error, NotImplementedError, ValueError)):
+        out = m(a.cuda(), b.cuda())
+        out.sum().backward()
+    m.zero_grad(set_to_none=True)
+    out = m(a[:, :40000].cuda(), b[:, :40000].cuda())          # 124 + 124 + 3 = 251 frames
+    loss, _ = m.loss_fn(out, torch.tensor([1, 0]).cuda())
+    loss.backward()
+    q = dict(m.named_parameters())["wav2vec.model.encoder.layers.0.attention.q_proj.weight"]
+    assert q.grad is not None and torch.isfinite(q.grad).all() and q.grad.abs().max().item() > 0

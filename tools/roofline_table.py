@@ -60,12 +60,18 @@ def classify(rows):
             role, fl = "fwd QKV projection (+bias, f16 out)", gemm(M, 3 * H, H)
         elif "gemm_tc_kernel<256, 0, 1, 1, 2, 1, 1>" in name:
             role, fl = "fwd FFN1, dual epilogue (z and gelu(z))", gemm(M, FF, H)
+        elif "gemm_tc_kernel<256, 0, 1, 1, 2, 1, 2>" in name:
+            role, fl = "fwd FFN1, dual epilogue (gelu(z) and gelu'(z))", gemm(M, FF, H)
         elif "gemm_tc_kernel<256, 0, 2, 0, 2" in name:
             role, fl = "bwd FFN2 data gradient, GELU-backward + bias-gradient epilogue", gemm(M, FF, H)
+        elif "gemm_tc_kernel<256, 0, 3, 0, 2" in name:
+            role, fl = "bwd FFN2 data gradient, multiply-by-gelu' + bias-gradient epilogue", gemm(M, FF, H)
         elif "gemm_tc_kernel<256, 0, 0, 0, 2" in name:
             role, fl = "bwd out_proj data gradient (f16 out)", gemm(M, H, H)
         elif "gemm_tc_kernel<256, 1, 0, 0, 2" in name and us > 12:
-            if not bwd:
+            if "attention_bwd" in prev:
+                role, fl = "bwd QKV data gradient (f32, accumulating)", gemm(M, H, 3 * H)
+            elif not bwd:
                 role, fl = ("fwd out_proj (f32 out, stream-K)", gemm(M, H, H)) if "attention" in prev else \
                            ("fwd FFN2 (f32 out, stream-K)", gemm(M, H, FF))
             elif "wgrad" in prev and wg == 2:
@@ -79,12 +85,18 @@ def classify(rows):
             wg = (wg + 1) % 4
         elif name.endswith("attention_kernel"):
             role, fl, by = "attention forward (dropout on)", 4.0 * B * HEADS * T * T * D, act * 3 * 2 + act * 2 + B * HEADS * T * 4
-        elif "attention_bwd_fused_kernel" in name:
-            role, fl, by = "attention backward", 10.0 * B * HEADS * T * T * D, act * 3 * 2 * 2 + act * 2 * 2
+        elif "attention_persist_kernel" in name:
+            role, fl, by = "attention forward, persistent (dropout on)", 4.0 * B * HEADS * T * T * D, act * 3 * 2 + act * 2 + B * HEADS * T * 4
+        elif "attention_bwd_fused_kernel" in name or "attention_bwd_persist_kernel" in name:
+            role, fl, by = "attention backward" + (", persistent" if "persist" in name else ""), 10.0 * B * HEADS * T * T * D, act * 3 * 2 * 2 + act * 2 * 2
         elif "layernorm_kernel<1, 6, 1>" in name:
             role, by = "LayerNorm forward (+bias +residual, f32 + f16 out)", act * (4 + 4 + 4 + 2)
         elif "layernorm_bwd_kernel<1, 6, 1, 1>" in name:
-            role, by = "LayerNorm backward from the output (two gradient branches in, f32 + f16 out)", act * (4 + 4 + 4 + 4 + 2)
+            # round 2: the data-gradient GEMMs accumulate into the residual gradient -> ONE gradient stream in (14 B / element);
+            # pass "two" as argv[4] for launch lists taken with W2V2_DGRAD_ACCUM=0 (18 B / element)
+            two = len(sys.argv) > 4 and sys.argv[4] == "two"
+            role = "LayerNorm backward from the output (%s in, f32 + f16 out)" % ("two gradient branches" if two else "one gradient stream")
+            by = act * ((4 + 4 + 4 + 4 + 2) if two else (4 + 4 + 4 + 2))
         elif name.endswith("posconv_kernel"):
             role, fl = "positional conv (forward / data gradient)", gemm(M, H, 128 * (H // 16))
         elif "posconv_wgrad_kernel" in name:
@@ -93,7 +105,7 @@ def classify(rows):
             # p, g, m, v read + p, m, v written + g cleared = 32 B per parameter; the two launches (encoder behind the
             # frozen CNN, heads) are modelled together: bytes go to the role, split evenly over its launches
             role, by = "Adam (fused update + gradient clear), encoder + head parameters", 32.0 * (N_ENC + N_HEAD) / 2
-        elif "prepare_weights_kernel" in name:
+        elif "prepare_weights_kernel" in name or "prepare_weights_v2_kernel" in name:
             # fp32 master read once, fp16 operand copy + transposed fp16 copy (data-gradient operand) written
             role, by = "re-derivation of the fp16 operand copies (one batched launch)", N_ENC * (4 + 2 + 2)
         out.append((role or "other: " + name.replace("w2v2::", "")[:40], us, fl, by))

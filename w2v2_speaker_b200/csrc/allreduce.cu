@@ -31,7 +31,7 @@ __device__ __forceinline__ void multimem_st_f32x4(float4* mc, float4 v) {
 
 // mc: multicast address of element 0 of the span (16-byte aligned); n4: float4 elements of the span.
 constexpr int NVLS_UNROLL = 4;
-__global__ void __launch_bounds__(256, 6) nvls_allreduce_kernel(float4* __restrict__ mc, int64_t n4, int rank, int world) {
+__global__ void __launch_bounds__(256, 5) nvls_allreduce_kernel(float4* __restrict__ mc, int64_t n4, int rank, int world) {
   const int64_t per = (n4 + world - 1) / world;
   const int64_t lo = per * rank, hi = (lo + per < n4) ? lo + per : n4;
   const int64_t nth = int64_t(gridDim.x) * blockDim.x;
