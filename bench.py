@@ -493,17 +493,20 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json: cuBLAS bf16 sustained; fp16 runs at the same tensor rate)" \
             if peaks else "fallback (B200_PROFILING.md)"
         roof = None
+        try:        # DRAM traffic per launch comes from committed ncu captures (it cannot be counted inside this run)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        except Exception:
+            traffic = {}
         if t["gemm_launches"]:
             g_ms = t["gemm_ms"]
             fl = t["gemm_flops"]
             ach = fl / (g_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel + gemm_wgrad_kernel (tcgen05), all launches of one step",
                     "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s", "frac": ach / tens_peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of the largest single instance (FFN2: M=9536, N=768,
-                    # K=3072, f32 out; algorithmic 92.6 MB, part of the output still sits in L2 when the kernel ends),
-                    # ncu --set full capture in profiles/r01_e_gemm_pair_full.txt
-                    "traffic": 76.79e6 if WL is WORKLOADS["cfg1"] else None,
-                    "traffic_note": "bytes per launch of the FFN2 GEMM instance (profiles/r01_e_gemm_pair_full.txt)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the largest single f32-output instance
+                    "traffic": traffic.get("gemm", {}).get("bytes") if WL is WORKLOADS["cfg1"] else None,
+                    "traffic_note": "FROM PROFILE, not this run: " + traffic.get("gemm", {}).get("kernel", "-") + " (" +
+                                    traffic.get("gemm", {}).get("source", "-") + ")",
                     "peak_source": peak_src, "launches": t["gemm_launches"], "ms_per_step": g_ms, "tflop_per_step": fl / 1e12,
                     # train mode: the FFN2 data-gradient launches carry the GELU backward and the bias-gradient sums in
                     # their epilogue (counted in the time, not in the FLOPs); per-role rates: profiles/r01_g_kernel_roofline_table.txt
@@ -515,7 +518,9 @@ def main():
             ach = c0_bytes / (c_ms * 1e-3) / 1e9
             roof_hbm = {"bound": "hbm", "kernel": "conv0+GroupNorm+GELU stage (moments, stats, im2col, tensor-core GEMM "
                         "with GN+GELU epilogue)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None, "ms_per_step": c_ms}
+                        "traffic": traffic.get("conv0_stage", {}).get("bytes") if WL is WORKLOADS["cfg1"] else None,
+                        "traffic_note": "FROM PROFILE, not this run (" + traffic.get("conv0_stage", {}).get("source", "-") + ")",
+                        "algorithmic_bytes": c0_bytes, "ms_per_step": c_ms}
         cpu = None
         if not args.no_cpu_baseline:
             cb = 4 if train else 8

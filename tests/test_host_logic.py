@@ -185,9 +185,15 @@ def test_profile_tools_reproduce_the_committed_tables():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     csv_path = os.path.join(root, "profiles", "r01_g_train_launches.csv")
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "roofline_table.py"), csv_path], check=True,
-                         capture_output=True, text=True).stdout
+    # (round 1's LayerNorm backward read two gradient streams: the "two" argument selects its byte model)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "roofline_table.py"), csv_path, "1373.2", "6549.0", "two"],
+                         check=True, capture_output=True, text=True).stdout
     assert out == open(os.path.join(root, "profiles", "r01_g_kernel_roofline_table.txt")).read()
+    # round 2's list (persistent attention, accumulating data-gradient GEMMs, one gradient stream into the LayerNorm backward)
+    out2 = subprocess.run([sys.executable, os.path.join(root, "tools", "roofline_table.py"),
+                           os.path.join(root, "profiles", "r02_c_train_launches.csv")], check=True, capture_output=True, text=True).stdout
+    assert out2 == open(os.path.join(root, "profiles", "r02_c_kernel_roofline_table.txt")).read()
+    assert "attention backward, persistent" in out2 and "one gradient stream in" in out2
     lines = out.splitlines()
     assert "270 launches" in lines[1]
     shares = [float(l.split("%")[0].split()[-1]) for l in lines[3:]]

@@ -105,14 +105,18 @@ struct WorkIter {
 // DUAL: 1 = the epilogue stores the pre-activation next to the activated output (training keeps both), 2 = it stores
 // gelu'(pre-activation) instead (all the backward needs of it; experimental, see schedule.cu): twice the
 // staging, one pipeline stage less
-template <int BN, int CL = 1, int MINB = 1, int DUAL = 0>
+constexpr int EPI2_MAX_N = 512;
+template <int BN, int CL = 1, int MINB = 1, int DUAL = 0, bool AFFINE = false>
 struct GemmCfg {
   static constexpr int B_BYTES = (BN / CL) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = MINB == 2 ? 2 : ((BN == 256 && CL == 1) ? (DUAL ? 3 : 4) : (DUAL ? 5 : 6));
+  static constexpr int STAGES = (MINB == 2 ? 2 : ((BN == 256 && CL == 1) ? (DUAL ? 3 : 4) : (DUAL ? 5 : 6))) -
+                                ((AFFINE && BN == 256) ? 1 : 0);     // (the wide affine staging costs the A/B variants a stage)
   static constexpr int WSTAGE = WSTAGE_BYTES * (DUAL ? 2 : 1);
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int BIAS_BYTES = 2 * BN * 4;        // double-buffered bias tile
+  // double-buffered bias tile; the per-(batch, column) affine of conv layer 0 (EPI 2) keeps scale and shift of ALL
+  // its columns (<= EPI2_MAX_N each) so that the n-tiles of one m-tile can run back to back
+  static constexpr int BIAS_BYTES = AFFINE ? 2 * EPI2_MAX_N * 4 : 2 * BN * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE + BIAS_BYTES + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
   static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area too small");
@@ -123,7 +127,7 @@ struct GemmCfg {
 //      gradient of FFN2 fused with the GELU backward and the FFN1 bias gradient (f16 output, EPI 0, one batch)
 template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, int DUAL = 0>
 __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
+  using Cfg = GemmCfg<BN, CL, MINB, DUAL, EPI == 2>;
   static_assert(!DUAL || (!OUT_F32 && ACT == 1), "the dual-output epilogue is the fp16 pre-activation + GELU pair");
   static_assert(ACT < 2 || (!OUT_F32 && EPI == 0 && !DUAL), "the gelu'-multiply epilogue writes f16 and takes no bias");
   constexpr bool GRAD = (ACT == 2 || ACT == 3);      // 3: aux already holds gelu'(z), the epilogue only multiplies
@@ -171,10 +175,12 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
   }
   auto decode = [&](int tile, int& nt, int& mt, int& b) {
     if constexpr (CHUNKED) {
-      mt = tile % p.m_tiles;
-      const int rest = tile / p.m_tiles;
-      nt = rest % p.n_tiles;
-      b = rest / p.n_tiles;
+      // contiguous chunk per CTA, n fastest inside it: the n-tiles of one m-tile run back to back on the same CTA, so the
+      // A tile (conv layer 0: the 16 KB window operand) is read from DRAM once instead of once per n-tile
+      nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      mt = rest % p.m_tiles;
+      b = rest / p.m_tiles;
     } else {
       nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
       const bool sk_trail = SK_OK && !acc_out && k_begin != 0;
       const bool use_red = SK_OK && (k_begin != 0 || acc_out);
       const bool add_bias = k_begin == 0;
-      const float* bias_tile = sbias + (EPI == 1 ? (tcount & 1) * BN : 0);
+      const float* bias_tile = sbias + (EPI == 1 ? (tcount & 1) * BN : (EPI == 2 ? nt * BN : 0));
       if constexpr (EPI == 1) {
         // stage this tile's bias slice once (the previous user of this buffer was two tiles ago and
         // every epilogue warp has passed the barrier of the tile in between)
@@ -348,12 +354,11 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
       } else if constexpr (EPI == 2) {
         // scale in sbias[0:BN], shift in sbias[BN:2BN]; single-buffered -> fence both sides.  With the
         // chunked schedule (b, nt) changes at most a couple of times per CTA.
-        if (b != prev_b || nt != prev_nt) {
+        if (b != prev_b) {
           named_bar_sync(1, EPI_WARPS * 32);
-          if (epi_tid < BN) {
-            const int n = nt * BN + epi_tid;
-            sbias[epi_tid] = (n < p.N) ? __ldg(p.bias + (long long)b * p.N + n) : 0.f;
-            sbias[BN + epi_tid] = (n < p.N) ? __ldg(p.shift + (long long)b * p.N + n) : 0.f;
+          for (int n = epi_tid; n < EPI2_MAX_N; n += EPI_WARPS * 32) {
+            sbias[n] = (n < p.N) ? __ldg(p.bias + (long long)b * p.N + n) : 0.f;
+            sbias[EPI2_MAX_N + n] = (n < p.N) ? __ldg(p.shift + (long long)b * p.N + n) : 0.f;
           }
           named_bar_sync(1, EPI_WARPS * 32);
           prev_b = b; prev_nt = nt;
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
         for (int j = 0; j < 32; j += 4) {
           if constexpr (EPI == 2) {
             const float4 sc = *reinterpret_cast<const float4*>(bsrc + j);
-            const float4 sh = *reinterpret_cast<const float4*>(bsrc + BN + j);
+            const float4 sh = *reinterpret_cast<const float4*>(bsrc + EPI2_MAX_N + j);
             v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
             v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
             v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
@@ -650,7 +655,7 @@ static bool pair_enabled() {
 
 template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, int DUAL = 0>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL, MINB, DUAL>;
+  using Cfg = GemmCfg<BN, CL, MINB, DUAL, EPI == 2>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, OUT_F32, ACT, EPI, CL, MINB, DUAL>;
   if (!configured) {
@@ -739,6 +744,7 @@ int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* t
   W2V2_REQUIRE(!accumulate || (out_dtype == 1 && act == 0 && shift == nullptr),
                "w2v2_gemm_f16: accumulate needs fp32 output without activation / affine epilogue");
   W2V2_REQUIRE(ntaps >= 1 && ntaps <= 3, "w2v2_gemm_f16: ntaps=%d not in [1,3]", ntaps);
+  W2V2_REQUIRE(shift == nullptr || N <= EPI2_MAX_N, "w2v2_gemm_f16: the per-batch affine epilogue holds at most %d columns", EPI2_MAX_N);
   W2V2_REQUIRE(cin % BK == 0, "w2v2_gemm_f16: cin=%d must be a multiple of %d", cin, BK);
   W2V2_REQUIRE(out_dtype == 0 || out_dtype == 1, "w2v2_gemm_f16: out_dtype must be 0 (f16) or 1 (f32)");
   W2V2_REQUIRE(act == 0 || act == 1, "w2v2_gemm_f16: act must be 0 (none) or 1 (gelu)");

@@ -65,14 +65,22 @@ __global__ void __launch_bounds__(256) time_mask_bwd_kernel(float* __restrict__ 
   const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = int64_t(blockIdx.x) * per, r1 = (r0 + per < rows) ? r0 + per : rows;
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t r = r0; r < r1; ++r) {
-    if (mask[r] == 0) continue;                      // block-uniform
-    for (int cc = c; cc < H; cc += blockDim.x * 4) {
+  // the chunk's mask bytes in one parallel load (a serial walk pays a dependent global load per row)
+  __shared__ uint8_t flags[256];
+  for (int64_t rb = r0; rb < r1; rb += 256) {
+    __syncthreads();
+    if (rb + threadIdx.x < r1) flags[threadIdx.x] = mask[rb + threadIdx.x];
+    __syncthreads();
+    const int64_t re = (rb + 256 < r1) ? rb + 256 : r1;
+    for (int64_t r = rb; r < re; ++r) {
+      if (flags[r - rb] == 0) continue;              // block-uniform
+      for (int cc = c; cc < H; cc += blockDim.x * 4) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (cc + j < H) {
-          s[j] += dh[r * H + cc + j];
-          dh[r * H + cc + j] = 0.f;
+        for (int j = 0; j < 4; ++j) {
+          if (cc + j < H) {
+            s[j] += dh[r * H + cc + j];
+            dh[r * H + cc + j] = 0.f;
+          }
         }
       }
     }
