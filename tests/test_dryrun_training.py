@@ -230,3 +230,16 @@ def test_flat_trainer_follows_the_freeze_protocol():
         assert torch.all(tr.m[tr.n0:] == 0.5) and torch.all(tr.m[:tr.n0] == 0)          # heads kept, encoder fresh
         q = dict(m.wav2vec.model.named_parameters())["encoder.layers.0.attention.q_proj.weight"]
         assert q.data_ptr() >= tr.flat_p.data_ptr() and q.data_ptr() < tr.flat_p.data_ptr() + 4 * tr.flat_p.numel()
+
+
+def test_hidden_states_under_grad_are_returned_detached():
+    """`model(x, output_hidden_states=True)` used to raise with gradients enabled; it now returns the
+    13 per-layer outputs the training forward keeps anyway (detached: gradients flow through last_hidden_state)."""
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2RegularisationConfig, Wav2Vec2WrapperModule
+    with dry_library():
+        w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False, reg_cfg=Wav2Vec2RegularisationConfig(layerdrop=0.5)).train()
+        w.model.feature_extractor.requires_grad_(False)
+        out = w.model(torch.randn(2, 16000), output_hidden_states=True)
+        assert out.last_hidden_state.requires_grad and out.last_hidden_state.shape == (2, 49, 768)
+        assert len(out.hidden_states) == 13 and all(h.shape == (2, 49, 768) and not h.requires_grad for h in out.hidden_states)
+        out.last_hidden_state.sum().backward()

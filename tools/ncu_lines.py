@@ -11,7 +11,8 @@ import os
 
 rep, kre, obj, mangled = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+sel = ["--kernel-id", kre[3:]] if kre.startswith("id:") else ["--kernel-name", "regex:" + kre]      # id:::::N = N-th launch
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 # first kernel only
 start = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]

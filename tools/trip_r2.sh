@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_engine.py tests/test_gpu_modules.py tests/test_gpu_round2.py tests/test_gpu_ragged.py -m gpu -x -q > gpurun_out/r2n_tests.log 2>&1; tail -4 gpurun_out/r2n_tests.log
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2n_train.log 2>&1; tail -c 420 gpurun_out/r2n_train.log
-python bench.py --mode forward --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2n_fwd.log 2>&1; tail -c 200 gpurun_out/r2n_fwd.log
-# memcheck of the small-shape kernel tests (race / memory checking)
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ops.py tests/test_gpu_backward.py tests/test_gpu_regularise.py -m gpu -x -q -k "not 9536 and not 64-149 and not persistent and not full_size and not large" > gpurun_out/r2n_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -6 gpurun_out/r2n_sanitizer_memcheck.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2o_tests_all.log 2>&1; tail -4 gpurun_out/r2o_tests_all.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2o_smoke.log 2>&1; tail -1 gpurun_out/r2o_smoke.log
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:"gemm_tc_kernel|conv0_" -s 12 -c 12 -o gpurun_out/r2o_kernels python tools/ncu_kernels.py > gpurun_out/r2o_ncu_kernels.log 2>&1; tail -1 gpurun_out/r2o_ncu_kernels.log
+# shared-memory race check of the persistent attention kernels and the small-shape kernel tests
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_attention_persist.py -m gpu -x -q -k "20-96 or 160-17 or 31-129" > gpurun_out/r2o_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 gpurun_out/r2o_sanitizer_racecheck.log

@@ -97,25 +97,6 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&rs)[8], const uint32_
   ds_out = make_uint4(dsk[0], dsk[1], dsk[2], dsk[3]);
 }
 
-// lane = row, v[j] = column j of that row (N = 16 or 32).  Returns, in lane L, the sum of column (L mod N) over the
-// warp's 32 rows: at each step a lane keeps one half of its columns and trades the other half with its partner.
-template <int N>
-__device__ __forceinline__ float warp_colsum_bfly(float (&v)[N]) {
-  const uint32_t lane = threadIdx.x & 31;
-#pragma unroll
-  for (int h = N / 2; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      const float keep = up ? v[i + h] : v[i], send = up ? v[i] : v[i + h];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  float r = v[0];
-  if (N == 16) r += __shfl_xor_sync(0xffffffffu, r, 16);
-  return r;
-}
-
 __device__ __forceinline__ void store_row_f16x16_bp(__half* dst, const float (&v)[16]) {
   uint4 a, b;
   a.x = pack_half2(v[0], v[1]);   a.y = pack_half2(v[2], v[3]);   a.z = pack_half2(v[4], v[5]);   a.w = pack_half2(v[6], v[7]);

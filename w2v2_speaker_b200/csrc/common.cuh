@@ -511,6 +511,25 @@ __device__ __forceinline__ void warp_colsum_atomic(const float (&v)[N], bool row
   if (lane < N) atomicAdd(dst + lane, mine * scale);
 }
 
+// lane = row, v[j] = column j of that row (N = 16 or 32).  Returns, in lane L, the sum of column (L mod N) over the
+// warp's 32 rows: at each step a lane keeps one half of its columns and trades the other half with its partner.
+template <int N>
+__device__ __forceinline__ float warp_colsum_bfly(float (&v)[N]) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = N / 2; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? v[i + h] : v[i], send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  float r = v[0];
+  if (N == 16) r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -281,13 +281,25 @@ class Wav2Vec2ModelB200(nn.Module):
             out = self._engine().forward(input_values, None, lengths, normalize=raw)
             return Wav2Vec2BaseModelOutput(last_hidden_state=out)
         if self._needs_grad():
-            if output_hidden_states:
-                raise NotImplementedError("output_hidden_states is only available without gradients")
             from ..training import EncoderFn
             names, params = self._items()[:2]
             self._raw_next = raw                      # (read by EncoderFn.forward: fold the input normaliser into conv 0)
+            self._keep_saved = bool(output_hidden_states)
             out = EncoderFn.apply(input_values, self, names, *params)
-            return Wav2Vec2BaseModelOutput(last_hidden_state=out)
+            hs = None
+            if output_hidden_states:
+                # the per-layer outputs the training forward keeps anyway, as DETACHED views: gradients flow through
+                # last_hidden_state only (what the reference differentiates; its hidden-state consumer, the test-time
+                # ensemble of R:src/lightning_modules/speaker/wav2vec2_fc.py:440-463, runs without gradients)
+                S = self.__dict__.pop("_last_saved")
+                B, T, H = out.shape
+                hs, cur = [S["top"][0].view(B, T, H)], S["top"][0].view(B, T, H)
+                for L in S["layers"]:
+                    if L is not None:                 # (a LayerDrop-skipped layer passes its input on, HF:701-713)
+                        cur = L["arena"].tensor("h2_32", torch.float32, (B, T, H))
+                    hs.append(cur)
+                hs = tuple(h.detach() for h in hs)
+            return Wav2Vec2BaseModelOutput(last_hidden_state=out, hidden_states=hs)
         eng = self._engine()
         if self.training and self._stochastic():
             # train mode without gradients: the reference reaches this routinely (`wav2vec_initially_frozen`: freeze() calls

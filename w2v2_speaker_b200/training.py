@@ -474,6 +474,8 @@ class EncoderFn(torch.autograd.Function):
         out, saved = encoder_forward_train(eng, wav, plan, model.masked_spec_embed.detach(), train_cnn,
                                            getattr(model, "_pre_encoder_hook", None), normalize=raw)
         ctx.model, ctx.names, ctx.saved, ctx.eng = model, names, saved, eng
+        if getattr(model, "_keep_saved", False):      # output_hidden_states=True under grad (models/wav2vec2.py)
+            model.__dict__["_last_saved"] = saved
         return out
 
     @staticmethod
