@@ -55,6 +55,7 @@ struct alignas(64) GemmParams {
   long long ld_aux;
   float* colsum;                 // ACT 2: colsum[n] += sum over rows of the (fp16-rounded) output
   int accumulate;                // fp32 output without activation: out += A W^T (every store is a TMA reduce-add)
+  int no_tail_skip;              // W2V2_GEMM_TAIL_SKIP=0 (A/B): epilogue warps whose rows are all out of range still run
 };
 
 // Stream-K (fp32 output, no activation): the (tile, k-block) iteration space is cut into gridDim.x equal
@@ -381,8 +382,12 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
         }
         __syncwarp();
       }
+      // A warp whose 32 rows lie entirely behind the last valid row (the m tail: 9536 rows leave 64 of the last 256-row
+      // pair tile, so six of its eight row groups are empty) has nothing to compute or store: it hands the accumulator
+      // back at once.  For the epilogue-bound variants that makes the tail tiles of the last scheduling round cheap.
+      const bool rows_live = row0 < p.rows || p.no_tail_skip;      // warp-uniform
       uint32_t ra[32], rb[32];
-      tmem_ld_32x32b_x32(t_addr, ra);
+      if (rows_live) tmem_ld_32x32b_x32(t_addr, ra);
 
       auto process = [&](uint32_t (&r)[32], int c, const uint4 (&zz)[4]) {
         // c: chunk index within this warp's half; 32 consecutive columns of one row per thread
@@ -506,8 +511,16 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) gemm_tc_kernel(const __grid
         }
       };
 
+      if (!rows_live) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+      }
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; c += 2) {
+      for (int c = 0; rows_live && c < NCHUNK; c += 2) {
         tmem_ld_wait();
         tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rb);
         process(ra, c, za);
@@ -653,6 +666,12 @@ static bool pair_enabled() {
   return v == 1;
 }
 
+// W2V2_GEMM_TAIL_SKIP=0 (A/B measurements): epilogue warps whose rows all lie behind the last valid row still run
+static int no_tail_skip() {
+  static const int v = []() { const char* e = getenv("W2V2_GEMM_TAIL_SKIP"); return (e != nullptr && e[0] == '0') ? 1 : 0; }();
+  return v;
+}
+
 template <int BN, bool OUT_F32, int ACT, int EPI, int CL, int MINB = 1, int DUAL = 0>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL, MINB, DUAL, EPI == 2>;
@@ -780,6 +799,7 @@ int gemm_f16_impl2(const void* A, int64_t a_rows, int64_t a_extent, const int* t
   p.N = N;
   p.rows = a_rows;
   p.accumulate = accumulate;
+  p.no_tail_skip = no_tail_skip();
   const int slot = gemm_prof_begin(2.0 * double(a_rows) * batch * ntaps * cin * N, stream);
   if (CL == 2) rc = out_dtype == 1 ? dispatch_epilogue<256, true, 2>(p, act, stream) : dispatch_epilogue<256, false, 2>(p, act, stream);
   else if (BN == 256) rc = out_dtype == 1 ? dispatch_epilogue<256, true, 1>(p, act, stream) : dispatch_epilogue<256, false, 1>(p, act, stream);
@@ -828,6 +848,7 @@ static int gemm_dual_gelu(const void* A, int64_t M, int64_t lda, int K, const vo
   W2V2_REQUIRE(K % BK == 0 && N > 128 && bias != nullptr && M > 0, "w2v2_gemm_f16_dual_gelu: needs K %% 64 == 0, N > 128, a bias");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.no_tail_skip = no_tail_skip();
   const int CL = pair_enabled() ? 2 : 1;
   int rc = make_tmap_3d(&p.tmA[0], A, 2, K, M, 1, uint64_t(lda) * 2, uint64_t(M) * lda * 2, BK, BM, 1, 128);
   if (rc) return rc;
@@ -877,6 +898,7 @@ static int gemm_mul_epilogue(const void* A, int64_t M, int64_t lda, int K, const
                "w2v2_gemm_f16_gelu_bwd: z must be 16-byte aligned with ldz %% 8 == 0, dbias is required");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.no_tail_skip = no_tail_skip();
   const int CL = pair_enabled() ? 2 : 1;
   int rc = make_tmap_3d(&p.tmA[0], A, 2, K, M, 1, uint64_t(lda) * 2, uint64_t(M) * lda * 2, BK, BM, 1, 128);
   if (rc) return rc;

@@ -69,7 +69,10 @@ class FlatAdamTrainer:
 
     # ---- flat buffers -------------------------------------------------------------------------------------------
     def _trainable_signature(self):
-        return tuple(p.requires_grad for p in self.module.parameters())
+        ps = self.__dict__.get("_all_params")
+        if ps is None:                     # the Parameter objects never change after construction: walk the tree once
+            ps = self._all_params = list(self.module.parameters())
+        return tuple(p.requires_grad for p in ps)
 
     def _layout(self):
         """(Re)build the flat parameter / gradient / Adam-state buffers for the CURRENT set of trainable parameters.

@@ -27,6 +27,8 @@ from .engine import ArchConfig, EncoderEngine, PreparedWeights
 
 F16, F32 = torch.float16, torch.float32
 
+_PLAN_EARLY = __import__("os").environ.get("W2V2_PLAN_EARLY", "0") == "1"      # A/B: draw the regularisation before the CNN
+
 LOSS_SCALE = 4096.0          # static scale of the activation gradients (fp16 operands of dgrad / wgrad)
 
 
@@ -121,19 +123,24 @@ class RegPlan:
 def compute_time_mask(B: int, T: int, mask_prob: float, mask_length: int, min_masks: int, rng):
     """uint8 [B*T]; own restatement of HF `_compute_mask_indices` (HF:101-217) for full-length inputs:
     num_spans = max(min_masks, int(mask_prob*T/mask_length + U[0,1))), clipped so the spans fit; span starts
-    drawn without replacement from [0, T - mask_length]."""
+    drawn without replacement from [0, T - mask_length].  Vectorised over the batch (no per-utterance python loop: the
+    draw sits on the host's critical path of a step): the first n_b entries of a random permutation of the admissible
+    starts are n_b starts drawn uniformly without replacement."""
     import numpy as np
     mask = np.zeros((B, T), dtype=np.uint8)
     if mask_length < 1 or mask_length > T:
         return mask.reshape(-1)
-    for b in range(B):
-        n = int(mask_prob * T / mask_length + rng.random())
-        n = max(n, min_masks)
-        if n * mask_length > T:
-            n = T // mask_length
-        starts = rng.choice(T - (mask_length - 1), size=n, replace=False)
-        for s in starts:
-            mask[b, s:s + mask_length] = 1
+    n = (mask_prob * T / mask_length + rng.random(B)).astype(np.int64)
+    n = np.maximum(n, min_masks)
+    n = np.where(n * mask_length > T, T // mask_length, n)
+    nmax = int(n.max())
+    if nmax == 0:
+        return mask.reshape(-1)
+    starts = np.argsort(rng.random((B, T - (mask_length - 1))), axis=1)[:, :nmax]        # [B, nmax] distinct per row
+    live = np.arange(nmax)[None, :] < n[:, None]
+    rows = np.repeat(np.arange(B), nmax).reshape(B, nmax)
+    for off in range(mask_length):
+        mask[rows[live], starts[live] + off] = 1
     return mask.reshape(-1)
 
 
@@ -218,13 +225,19 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
                           mask_embed: Optional[torch.Tensor] = None, train_cnn: bool = False, pre_encoder_hook=None,
                           normalize: bool = False):
     """Same arithmetic as EncoderEngine.forward (the GELUs run as separate passes so the pre-activations
-    can be kept) plus the train-mode regularisation of `plan`; returns (last_hidden_state f32 [B,T,H], saved)."""
-    S = {"plan": plan}
+    can be kept) plus the train-mode regularisation of `plan`; returns (last_hidden_state f32 [B,T,H], saved).
+    `plan` may be a zero-argument callable: it is then drawn AFTER the feature extractor's kernels have been enqueued, so
+    the host-side draw (seeds, LayerDrop, SpecAugment spans: ~0.3 ms) runs under ~1 ms of CNN work instead of in front of
+    the step's first launch -- what a loop that synchronises every step (bench.py's e2e) would otherwise wait for."""
+    S = {}
     if train_cnn:
         feat, S["cnn"] = cnn_forward_train(eng, wav)          # unfrozen CNN: pre-activations kept
     else:
         feat = eng.feature_extractor(wav, None, None, normalize)   # frozen CNN: nothing saved from inside (raw input: the
                                                                    # normaliser is folded into conv layer 0)
+    if callable(plan):
+        plan = plan()
+    S["plan"] = plan
     if pre_encoder_hook is not None:
         pre_encoder_hook()                                    # e.g. join the optimizer stream (trainer.py)
     B, T, C = feat.shape
@@ -468,7 +481,9 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wav, model, names, *params):
         eng = model._engine()
-        plan = model._draw_reg_plan(wav, eng)
+        plan = lambda: model._draw_reg_plan(wav, eng)          # drawn once the CNN forward is in flight
+        if _PLAN_EARLY:
+            plan = plan()
         train_cnn = any(q.requires_grad for q in model._items()[3])
         raw = bool(getattr(model, "_raw_next", False))
         out, saved = encoder_forward_train(eng, wav, plan, model.masked_spec_embed.detach(), train_cnn,
