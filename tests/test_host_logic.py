@@ -254,3 +254,30 @@ def test_bucket_planner_covers_every_utterance_once():
     assert plan_buckets([], 4) == []
     with pytest.raises(ValueError):
         plan_buckets([100, 0], 4)
+
+
+def test_accelerate_heads_retypes_plain_linears_in_place():
+    """integration.accelerate_heads: the classifier layers the reference builds itself (nn.Linear, R:src/lightning_modules/
+    speaker/wav2vec2_fc.py:176-210) become SpeakerLinear without touching parameters or state_dict keys; idempotent."""
+    import torch.nn as nn
+    from w2v2_speaker_b200.integration import accelerate_heads
+    from w2v2_speaker_b200.layers.linear import SpeakerLinear
+
+    class Holder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc_list = nn.ModuleList([nn.Sequential(nn.Linear(8, 4), nn.ReLU()), nn.Sequential(nn.Linear(4, 3))])
+            self.other = nn.Linear(2, 2)
+    m = Holder()
+    keys, w = list(m.state_dict().keys()), m.fc_list[0][0].weight
+    assert accelerate_heads(m) == 2 and accelerate_heads(m) == 0
+    assert all(isinstance(seq[0], SpeakerLinear) for seq in m.fc_list) and type(m.other) is nn.Linear
+    assert list(m.state_dict().keys()) == keys and m.fc_list[0][0].weight is w
+
+
+def test_synthetic_batch_is_standardised_and_reproducible():
+    from w2v2_speaker_b200.synthetic import synthetic_batch
+    x, y = synthetic_batch(4, 16000, 100, seed=3)
+    x2, y2 = synthetic_batch(4, 16000, 100, seed=3)
+    assert torch.equal(x, x2) and torch.equal(y, y2) and x.shape == (4, 16000) and y.dtype == torch.int64
+    assert x.mean(1).abs().max() < 1e-5 and (x.std(1) - 1).abs().max() < 1e-3 and int(y.max()) < 100

@@ -187,7 +187,10 @@ class PreparedWeights:
         if not self._aliased:
             return False
         self.prep.run()
-        self._pos_w.clear()
+        # the folded positional-conv weights that were in use are re-derived right here (the caller runs this on the
+        # optimizer stream, under the next step's CNN forward) instead of lazily inside the next forward
+        for u in list(self._pos_w.keys()):
+            self._pos_w[u] = ops.posconv_fold_weight(self._pos_v, self._pos_g, self._groups, u)
         if self._cnn_sources is not None:      # unfrozen feature extractor: its tap-major fp16 weights change too
             for i, src in enumerate(self._cnn_sources):
                 if src is not None:

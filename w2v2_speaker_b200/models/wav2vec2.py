@@ -180,8 +180,10 @@ class Wav2Vec2ModelB200(nn.Module):
         eng = self._prepared
         if eng is not None and self._prepared_sig == self._signature() and eng.w.update():
             tw = getattr(eng, "_train_weights", None)
-            if tw is not None:
-                tw._pos_dgrad.clear()
+            if tw is not None:              # same for the data-gradient form of the folded positional-conv weight
+                from .. import ops
+                for u in list(tw._pos_dgrad.keys()):
+                    tw._pos_dgrad[u] = ops.posconv_fold_weight(eng.w._pos_v, eng.w._pos_g, eng.w._groups, u, mode=1)
             return
         self._prepared = None
 
