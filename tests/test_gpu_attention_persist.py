@@ -85,3 +85,77 @@ def test_persistent_attention_dropout_and_bias_gradients(ops, B, T, H, heads):
     ref_b = gref.double().sum(0)
     assert ((dbias.double() - ref_b).norm() / ref_b.norm()).item() < 5e-3
     assert abs(float(np.mean(keep)) - (1 - p)) < 5e-3
+
+
+@pytest.mark.parametrize("B,T,H,heads,p", [(6, 301, 768, 12, 0.0), (6, 301, 768, 12, 0.1), (3, 400, 1024, 16, 0.1),
+                                           (2, 600, 768, 12, 0.1), (4, 257, 768, 12, 0.0)])
+def test_attention_trains_beyond_256_frames(ops, B, T, H, heads, p):
+    """Training on sequences longer than one key tile set (the paired-input model at two 3 s crops has 301 frames,
+    R:src/lightning_modules/speaker/wav2vec2_paired_input.py:163-207): the key-tiled forward with attention dropout
+    (csrc/attention_long.cu) and the backward launched once per key block (csrc/attention_bwd.cu), against torch fp32
+    with the mask replayed in numpy; the bias gradient is the sum over the blocks."""
+    g = torch.Generator().manual_seed(T * 7 + B)
+    qkv = torch.randn(B * T, 3 * H, generator=g).cuda().half()
+    qkv[:, :H] *= 0.35
+    d_o = (torch.randn(B * T, H, generator=g) * 0.7).cuda().half()
+    seed = 1234567
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True, drop_p=p, drop_seed=seed)
+    dbias = torch.zeros(3 * H, device="cuda")
+    dqkv = ops.attention_bwd(qkv, out, d_o, lse, B, T, H, heads, drop_p=p, drop_seed=seed, qscale=0.125, dbias=dbias)
+    torch.cuda.synchronize()
+    m, inv = None, 1.0
+    if p > 0:
+        TK = (T + 15) // 16 * 16
+        keep, inv = keep_mask(seed, B * heads * T * TK, p)
+        m = torch.from_numpy(keep).view(B, heads, T, TK)[..., :T].cuda()
+    o, lse_ref, gref = _reference(qkv, d_o, B, T, H, heads, m, inv)
+    gref = gref.clone()
+    gref[:, :H] *= 0.125
+    assert torch.isfinite(out.float()).all() and torch.isfinite(dqkv.float()).all()
+    eo = (out.float() - o).view(B, T, heads, -1).norm(dim=(1, 3)) / o.view(B, T, heads, -1).norm(dim=(1, 3))
+    assert eo.max().item() < 2e-3, eo.max().item()
+    assert rel(lse, lse_ref) < 1e-3
+    for i in range(3):
+        a, r = dqkv[:, i * H:(i + 1) * H].float(), gref[:, i * H:(i + 1) * H]
+        e = (a - r).view(B, T, heads, -1).norm(dim=(1, 3)) / r.view(B, T, heads, -1).norm(dim=(1, 3))
+        assert e.max().item() < 6e-3, ("qkv"[i], e.max().item())
+    ref_b = gref.double().sum(0)
+    assert ((dbias.double() - ref_b).norm() / ref_b.norm()).item() < 5e-3
+
+
+_TWO_CTA_DRIVER = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from w2v2_speaker_b200 import ops
+from test_gpu_regularise import keep_mask
+from test_gpu_attention_persist import _reference, rel
+for B, T, H, heads, p in ((64, 149, 768, 12, 0.1), (33, 160, 768, 12, 0.0), (40, 100, 768, 12, 0.1), (29, 145, 1024, 16, 0.0)):
+    g = torch.Generator().manual_seed(B + T)
+    qkv = torch.randn(B * T, 3 * H, generator=g).cuda().half()
+    qkv[:, :H] *= 0.35
+    out, lse = ops.attention(qkv, B, T, H, heads, want_lse=True, drop_p=p, drop_seed=99)
+    torch.cuda.synchronize()
+    m, inv = None, 1.0
+    if p > 0:
+        TK = (T + 15) // 16 * 16
+        keep, inv = keep_mask(99, B * heads * T * TK, p)
+        m = torch.from_numpy(keep).view(B, heads, T, TK)[..., :T].cuda()
+    o, lse_ref, _ = _reference(qkv, None, B, T, H, heads, m, inv)
+    eo = (out.float() - o).view(B, T, heads, -1).norm(dim=(1, 3)) / o.view(B, T, heads, -1).norm(dim=(1, 3))
+    assert eo.max().item() < 2e-3, (B, T, eo.max().item())
+    assert rel(lse, lse_ref) < 1e-3
+print("TWO_CTA_OK")
+"""
+
+
+def test_two_cta_variant(ops):
+    """csrc/attention_persist2.cu (two resident CTAs per SM; an experiment that tied with the default kernel and stays
+    behind W2V2_ATTN_2CTA=1): same parity bar, in a child process because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, W2V2_ATTN_2CTA="1")
+    r = subprocess.run([sys.executable, "-c", _TWO_CTA_DRIVER.format(root=root)], env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "TWO_CTA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -105,21 +105,30 @@ def test_wrapper_cls_token_and_lite_paths(base_params):
     assert ((f.cpu().double() - feat.transpose(1, 2).double()).norm() / feat.double().norm()).item() < 2e-3
 
 
-def test_long_utterance_evaluates_and_training_on_it_fails_loudly(base_params):
-    """Utterances longer than 256 frames: the evaluation forward handles any length (full-utterance test_step);
-    TRAINING on them is not built (the reference trains on 3 s crops) and must raise, not fall back."""
+def test_long_utterance_evaluates_and_trains_and_very_long_training_fails_loudly(base_params):
+    """Utterances longer than 256 frames: the evaluation forward handles any length (full-utterance test_step).
+    TRAINING runs the key-tiled attention kernels up to what the single-slab positional conv holds (about 1150 frames
+    at wav2vec2-base; parity at 301 frames: tests/test_gpu_round2.py::test_paired_model_trains_at_the_reference_crop_length);
+    beyond that it must raise, not fall back."""
     _need_cuda()
     from w2v2_speaker_b200._lib import W2V2Error
-    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
-    w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False).cuda().eval()
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2RegularisationConfig, Wav2Vec2WrapperModule
+    # dropout / SpecAugment at the reference's defaults, LayerDrop off so that every layer must see a gradient
+    w = Wav2Vec2WrapperModule("facebook/wav2vec2-base", False,
+                              reg_cfg=Wav2Vec2RegularisationConfig(layerdrop=0.0)).cuda().eval()
     with torch.no_grad():
         out = w(torch.randn(1, 16000 * 6, device="cuda"))           # 299 frames > 256
     assert out.shape == (1, 768, 299) and torch.isfinite(out).all()
     w.train()
     w.model.feature_extractor.requires_grad_(False)
+    out = w(torch.randn(2, 16000 * 6, device="cuda"))
+    # (a random readout: sum(out) and sum(out^2) are constants of the final LayerNorm -- their gradients vanish)
+    (out * torch.randn(out.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(1))).mean().backward()
+    amax = [dict(w.model.named_parameters())[f"encoder.layers.{i}.attention.q_proj.weight"].grad.abs().max().item()
+            for i in range(12)]
+    assert all(0 < a < float("inf") for a in amax), amax
     with pytest.raises(W2V2Error):
-        w(torch.randn(1, 16000 * 6, device="cuda")).sum().backward()
-
+        w(torch.randn(1, 16000 * 40, device="cuda")).sum().backward()      # 1999 frames
 
 
 @pytest.mark.parametrize("center", [False, True])

@@ -216,9 +216,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __grid_con
 }
 
 int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, const int* lens,
-                          cudaStream_t stream);
+                          uint32_t drop_thr, float drop_inv_keep, uint64_t drop_seed, cudaStream_t stream);
 int attention_persist_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, uint32_t drop_thr,
                              float drop_inv_keep, uint64_t drop_seed, const int* lens, cudaStream_t stream);
+int attention_persist2_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, uint32_t drop_thr,
+                              float drop_inv_keep, uint64_t drop_seed, const int* lens, cudaStream_t stream);
 
 }  // namespace w2v2
 
@@ -246,9 +248,13 @@ static int attention_dispatch(const void* qkv16, void* out16, float* lse, int B,
   W2V2_REQUIRE(heads > 0 && H == heads * ATT_D, "w2v2_attention: head dim must be 64 (H=%d heads=%d)", H, heads);
   W2V2_REQUIRE(T >= 1, "w2v2_attention: empty sequence");
   W2V2_REQUIRE(B >= 1 && B <= 65535, "w2v2_attention: bad batch %d", B);
-  if (T > 256) {       // full-utterance evaluation: key-tiled two-pass kernel (attention_long.cu), no dropout
-    W2V2_REQUIRE(drop_p == 0.f, "w2v2_attention: attention dropout is only built for T <= 256 (training crops)");
-    return attention_long_launch(qkv16, out16, lse, B, T, H, heads, lens, stream);
+  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention: dropout p=%f out of [0,1)", drop_p);
+  if (T > 256) {       // full-utterance evaluation, training on paired crops: key-tiled two-pass kernel (attention_long.cu)
+    const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
+    W2V2_REQUIRE(thr == 0 || uint64_t(B) * heads * T * ((T + 15) / 16 * 8) < (1ull << 32),
+                 "w2v2_attention: dropout mask index exceeds 32 bits");
+    return attention_long_launch(qkv16, out16, lse, B, T, H, heads, lens, thr, 1.0f / (1.0f - float(thr) / 65536.0f),
+                                 drop_seed, stream);
   }
   AttnParams p;
   const int TK = (T + 15) / 16 * 16;
@@ -265,7 +271,10 @@ static int attention_dispatch(const void* qkv16, void* out16, float* lse, int B,
   p.drop_seed = drop_seed;
   p.T = T; p.TK = TK; p.H = H; p.heads = heads;
   W2V2_REQUIRE(uint64_t(B) * heads * T * (TK / 2) < (1ull << 32), "w2v2_attention: dropout mask index exceeds 32 bits");
-  {     // T <= 160 (training crops): the persistent kernel (attention_persist.cu); 1 = not applicable
+  {     // T <= 160 (training crops): the persistent kernels -- two CTAs per SM (attention_persist2.cu), else one
+        // (attention_persist.cu); 1 = not applicable / switched off
+    const int prc2 = attention_persist2_launch(qkv16, out16, lse, B, T, H, heads, p.drop_thr, p.drop_inv_keep, drop_seed, lens, stream);
+    if (prc2 <= 0) return prc2;
     const int prc = attention_persist_launch(qkv16, out16, lse, B, T, H, heads, p.drop_thr, p.drop_inv_keep, drop_seed, lens, stream);
     if (prc <= 0) return prc;
   }

@@ -13,6 +13,10 @@
 // (dV, dK) stop at the last 16-query step that holds a valid row, so unwritten rows are never read.
 // T <= 192: both Q / dO tiles stay resident; longer sequences reload the 128-row tile per iteration
 // (the P / dS buffers then need the space).
+// T > 256 (the paired-input model at two 3 s crops: 301 frames): the key axis is cut into blocks of <= 256 keys and
+// the kernel is launched once per block (k0 = first key of the block) over ALL query tiles -- with lse and
+// delta = rowsum(dO * O) given per row, every (query tile, key block) pair is independent: dK / dV of a key block are
+// complete after its launch, dQ is the sum over the blocks (launches after the first add to the fp16 rows in place).
 #include "common.cuh"
 #include "w2v2_b200.h"
 
@@ -34,7 +38,10 @@ struct alignas(64) AttnBwdParams {
   const __half* d_o;   // [B*T, H]
   const float* lse;    // [B, heads, T]
   __half* dqkv;        // [B*T, 3H]
-  int T, TK, H, heads, qtiles;
+  int T, TK, H, heads, qtiles;   // TK: keys of this launch's block, rounded up to 16
+  int k0;              // first key of the block (multiple of 64)
+  int tk_pairs;        // dropout mask row pitch: (T rounded up to 16) / 2
+  int dq_accum;        // 1: dQ rows are added to what dqkv holds (key blocks after the first)
   int pblocks;         // 64-key blocks of P / dS
   int resident;        // 1: every Q / dO tile stays in smem; 0: one tile buffer, reloaded per query tile
   int col_dq;          // TMEM column of dQ
@@ -98,8 +105,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
         tma_load_3d(sdO + i * 16384, &p.tmDO, bar_tma, h * AB_D, i * 128, b);
       }
     }
-    tma_load_3d(sK, &p.tmKV, bar_tma, p.H + h * AB_D, 0, b);
-    tma_load_3d(sV, &p.tmKV, bar_tma, 2 * p.H + h * AB_D, 0, b);
+    tma_load_3d(sK, &p.tmKV, bar_tma, p.H + h * AB_D, p.k0, b);
+    tma_load_3d(sV, &p.tmKV, bar_tma, 2 * p.H + h * AB_D, p.k0, b);
   }
   mbar_wait(bar_tma, 0);
   __syncwarp();
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
         }
       }
     }
-    const uint32_t pair_row = ((uint32_t(b) * p.heads + h) * p.T + (valid ? t : 0)) * uint32_t(TK / 2);
+    const uint32_t pair_row = ((uint32_t(b) * p.heads + h) * p.T + (valid ? t : 0)) * uint32_t(p.tk_pairs) + uint32_t(p.k0 >> 1);
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
     __syncwarp();
@@ -180,8 +187,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
         for (int j = 0; j < 8; ++j) {
           float e0 = fast_ex2(fmaf(__uint_as_float(r[2 * j]), 1.4426950408889634f, -lse2));
           float e1 = fast_ex2(fmaf(__uint_as_float(r[2 * j + 1]), 1.4426950408889634f, -lse2));
-          if (!valid || c * 16 + 2 * j >= p.T) e0 = 0.f;
-          if (!valid || c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
+          if (!valid || p.k0 + c * 16 + 2 * j >= p.T) e0 = 0.f;
+          if (!valid || p.k0 + c * 16 + 2 * j + 1 >= p.T) e1 = 0.f;
           pk[j] = pack_half2(e0, e1);
           if (drop_thr != 0) {
             const uint32_t hb = dropout_hash32(dkeys, pair_row + uint32_t(c * 8 + j));
@@ -300,14 +307,28 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
       if (valid) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = v[8 * c + j];
+          if (p.dq_accum) {                 // the earlier key blocks' share of this row (written by the previous launch)
+            const uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * c);
+            const __half2* oh = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(oh[j]);
+              a[2 * j] += f.x;
+              a[2 * j + 1] += f.y;
+            }
+          }
           uint4 q;
-          q.x = pack_half2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]));
-          q.y = pack_half2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-          q.z = pack_half2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-          q.w = pack_half2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+          q.x = pack_half2(a[0], a[1]);
+          q.y = pack_half2(a[2], a[3]);
+          q.z = pack_half2(a[4], a[5]);
+          q.w = pack_half2(a[6], a[7]);
           *reinterpret_cast<uint4*>(dst + 8 * c) = q;
         }
       }
+      // the bias gradient is linear in the blocks: each launch adds the column sums of its own share
       if (p.dbias != nullptr) warp_colsum_atomic<32>(v, valid, 1.0f, p.dbias + h * AB_D + cg * 32);
     }
     // all threads must be done with S/dP and dQ columns before the next tile's MMAs overwrite them
@@ -318,9 +339,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
 
   // ---- dK (column half 0 warps), dV (column half 1 warps) rows (keys) -> global
   for (int kt = 0; kt < ktiles; ++kt) {
-    const int key = kt * 128 + row;
-    const bool kvalid = key < p.T;
-    if (kt * 128 + quarter * 32 >= p.T) continue;             // warp-uniform
+    const int key = p.k0 + kt * 128 + row;
+    const bool kvalid = key < p.T && kt * 128 + row < TK;
+    if (p.k0 + kt * 128 + quarter * 32 >= p.T || kt * 128 + quarter * 32 >= TK) continue;      // warp-uniform
     const uint32_t col = (cg == 0 ? AB_COL_DK : AB_COL_DV) + kt * AB_D;
     __half* dst = p.dqkv + (int64_t(b) * p.T + (kvalid ? key : 0)) * 3 * p.H + h * AB_D + (cg == 0 ? p.H : 2 * p.H);
 #pragma unroll
@@ -376,8 +397,7 @@ extern "C" int w2v2_attention_bwd_ex2(const void* qkv16, const void* o16, const 
                                       float* dbias, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   W2V2_REQUIRE(heads > 0 && H == heads * AB_D, "w2v2_attention_bwd: head dim must be 64 (H=%d heads=%d)", H, heads);
-  W2V2_REQUIRE(T >= 1 && T <= 256,
-               "w2v2_attention_bwd: T=%d frames not supported (the single-pass backward handles T <= 256)", T);
+  W2V2_REQUIRE(T >= 1, "w2v2_attention_bwd: empty sequence");
   W2V2_REQUIRE(B >= 1 && B <= 65535, "w2v2_attention_bwd: bad batch %d", B);
   AttnBwdParams p;
   const int TK = (T + 15) / 16 * 16;
@@ -394,40 +414,49 @@ extern "C" int w2v2_attention_bwd_ex2(const void* qkv16, const void* o16, const 
   }
   int rc = make_tmap_3d(&p.tmQ, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AB_D, 128, 1, 128);
   if (rc) return rc;
-  rc = make_tmap_3d(&p.tmKV, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AB_D, TK, 1, 128);
-  if (rc) return rc;
   rc = make_tmap_3d(&p.tmDO, do16, 2, H, T, B, uint64_t(H) * 2, uint64_t(T) * H * 2, AB_D, 128, 1, 128);
   if (rc) return rc;
   p.o = static_cast<const __half*>(o16);
   p.d_o = static_cast<const __half*>(do16);
   p.lse = lse;
   p.dqkv = static_cast<__half*>(dqkv16);
-  p.T = T; p.TK = TK; p.H = H; p.heads = heads;
+  p.T = T; p.H = H; p.heads = heads;
   p.qtiles = (T + 127) / 128;
-  p.pblocks = (TK + 63) / 64;
-  p.resident = TK <= 192 ? 1 : 0;
-  p.col_dq = TK <= 192 ? 192 : 0;
+  p.tk_pairs = TK / 2;
   p.qscale = qscale;
   p.dbias = dbias;
-  W2V2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "w2v2_attention_bwd: dropout p=%f out of [0,1)", drop_p);
   p.drop_thr = uint32_t(drop_p * 65536.0f + 0.5f);
   p.drop_inv_keep = 1.0f / (1.0f - float(p.drop_thr) / 65536.0f);
   p.drop_seed = drop_seed;
-  const int kvb = (TK * 128 + 1023) & ~1023;
-  const int nq = p.resident ? p.qtiles : 1;
-  // the MMAs over 128-row operand windows may read (never use) up to one 16 KB block past sP / sdS: keep
-  // at least that much behind them inside the allocation
-  const int smem = 2 * p.pblocks * 16384 + 2 * nq * 16384 + 2 * kvb + 64;
-  W2V2_REQUIRE(smem <= 227 * 1024, "w2v2_attention_bwd: shared memory budget exceeded (%d bytes)", smem);
-  static int configured = 0;
-  if (smem > configured) {
-    W2V2_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+  // key blocks: one launch when the whole key axis fits (T <= 256), else equal blocks rounded up to 64 keys
+  const int nblk = (TK + 255) / 256;
+  const int kblk = nblk == 1 ? TK : ((TK + nblk - 1) / nblk + 63) / 64 * 64;
+  for (int k0 = 0; k0 < TK; k0 += kblk) {
+    const int tkb = TK - k0 < kblk ? TK - k0 : kblk;
+    rc = make_tmap_3d(&p.tmKV, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AB_D, tkb, 1, 128);
+    if (rc) return rc;
+    p.TK = tkb;
+    p.k0 = k0;
+    p.dq_accum = k0 != 0;
+    p.pblocks = (tkb + 63) / 64;
+    p.resident = (nblk == 1 && tkb <= 192) ? 1 : 0;
+    p.col_dq = tkb <= 192 ? 192 : 0;
+    const int kvb = (tkb * 128 + 1023) & ~1023;
+    const int nq = p.resident ? p.qtiles : 1;
+    // the MMAs over 128-row operand windows may read (never use) up to one 16 KB block past sP / sdS: keep
+    // at least that much behind them inside the allocation
+    const int smem = 2 * p.pblocks * 16384 + 2 * nq * 16384 + 2 * kvb + 64;
+    W2V2_REQUIRE(smem <= 227 * 1024, "w2v2_attention_bwd: shared memory budget exceeded (%d bytes)", smem);
+    static int configured = 0;
+    if (smem > configured) {
+      W2V2_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = smem;
+    }
+    dim3 grid(heads, B);
+    W2V2_CHECK_CUDA(launch_k(attention_bwd_kernel, grid, dim3(AB_THREADS), smem, stream, 1, p));
+    count_launches(1);
+    W2V2_CHECK_CUDA(cudaGetLastError());
   }
-  dim3 grid(heads, B);
-  W2V2_CHECK_CUDA(launch_k(attention_bwd_kernel, grid, dim3(AB_THREADS), smem, stream, 1, p));
-  count_launches(1);
-  W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -6,7 +6,8 @@
 //   pass 2: S_blk again, P_blk = exp(S_blk - max) (fp16, K-major swizzled smem), O += P_blk V_blk.
 // Two passes instead of an online rescale of the O accumulator: the extra Q K^T is a few percent of the work
 // and O never has to leave TMEM; this is the evaluation path, not the training hot loop (T <= 256 there uses
-// the single-tile kernels of attention.cu).  K / V blocks are double-buffered: the TMA load of block j+1 is
+// the single-tile kernels of attention.cu; training on longer sequences -- the paired-input model at two 3 s crops has
+// 301 frames -- comes through here with attention dropout applied to P in pass 2).  K / V blocks are double-buffered: the TMA load of block j+1 is
 // in flight while block j is processed.  8 warps: warp & 3 = TMEM lane quarter, warp >> 2 = column half; the
 // two threads of a row combine their (max, sum) through shared memory once, after pass 1.
 #include "common.cuh"
@@ -36,6 +37,9 @@ struct alignas(64) AttnLongParams {
   float* lse;          // [B, heads, T] or nullptr
   const int* lens;     // [B] valid keys per utterance (ragged evaluation batches) or nullptr
   int T, H, heads, kblocks;
+  uint32_t drop_thr;   // attention dropout (training on sequences beyond 256 frames): same mask convention as attention.cu
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
 __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid_constant__ AttnLongParams p) {
@@ -103,6 +107,11 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
   float m_run = -INFINITY, l_run = 0.f;          // this thread's column half: running max (raw scores) and sum
   float m_row = 0.f, inv_l = 0.f;                // combined, available after pass 1
   const int c_lo = cg * 4, c_hi = c_lo + 4;      // 16-column chunks of this thread within a 128-key block
+  const DropKeys dkeys = drop_keys(p.drop_seed);
+  const uint32_t drop_thr = p.drop_thr;
+  const float inv_keep = p.drop_inv_keep;
+  // dropout mask index of (row, key pair): the numbering of attention.cu, TK = T rounded up to 16
+  const uint32_t pair_row = ((uint32_t(b) * p.heads + h) * p.T + (t_q < p.T ? t_q : 0)) * uint32_t(((p.T + 15) / 16 * 16) / 2);
 
   for (int i = 0; i < 2 * nb; ++i) {
     const int kb = i < nb ? i : i - nb;
@@ -187,6 +196,11 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
             float e1 = fast_ex2(fmaf(__uint_as_float(r[2 * j + 1]), 1.4426950408889634f, -ml));
             if (key0 + c * 16 + 2 * j >= Tk) e0 = 0.f;
             if (key0 + c * 16 + 2 * j + 1 >= Tk) e1 = 0.f;
+            if (drop_thr != 0) {               // the row sum (pass 1) is that of the undropped probabilities
+              const uint32_t hb = dropout_hash32(dkeys, pair_row + uint32_t((key0 + c * 16) / 2 + j));
+              e0 = (hb & 0xffffu) >= drop_thr ? e0 * inv_keep : 0.f;
+              e1 = (hb >> 16) >= drop_thr ? e1 * inv_keep : 0.f;
+            }
             pk[j] = pack_half2(e0, e1);
           }
           const int col = c * 16;
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(AL_THREADS) attention_long_kernel(const __grid
 }
 
 int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int T, int H, int heads, const int* lens,
-                          cudaStream_t stream) {
+                          uint32_t drop_thr, float drop_inv_keep, uint64_t drop_seed, cudaStream_t stream) {
   AttnLongParams p;
   int rc = make_tmap_3d(&p.tm, qkv16, 2, 3 * H, T, B, uint64_t(3 * H) * 2, uint64_t(T) * 3 * H * 2, AL_D, 128, 1, 128);
   if (rc) return rc;
@@ -255,6 +269,9 @@ int attention_long_launch(const void* qkv16, void* out16, float* lse, int B, int
   p.lens = lens;
   p.T = T; p.H = H; p.heads = heads;
   p.kblocks = (T + AL_BK - 1) / AL_BK;
+  p.drop_thr = drop_thr;
+  p.drop_inv_keep = drop_inv_keep;
+  p.drop_seed = drop_seed;
   static bool configured = false;
   if (!configured) {
     W2V2_CHECK_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM));
