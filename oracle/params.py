@@ -33,6 +33,10 @@ class ArchConfig:
     pos_kernel: int = 128
     pos_groups: int = 16
     eps: float = 1e-5
+    # the "-lv60" / XLSR family (HF configs with feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True):
+    feat_extract_norm: str = "group"      # "layer": every conv layer is Conv1d(+bias) -> LayerNorm(C) -> GELU (HF:275-299)
+    conv_bias: bool = False
+    stable_layer_norm: bool = False       # pre-LN encoder layers + final encoder LayerNorm (HF:632-655, HF:731-799)
 
     def conv_lengths(self, n: int):
         out = []
@@ -44,6 +48,8 @@ class ArchConfig:
 
 BASE = ArchConfig()
 LARGE = ArchConfig(name="large", hidden=1024, layers=24, heads=16, ffn=4096)
+LARGE_LV60 = ArchConfig(name="large-lv60", hidden=1024, layers=24, heads=16, ffn=4096, feat_extract_norm="layer",
+                        conv_bias=True, stable_layer_norm=True)
 # a tiny architecture for fast CPU tests of host logic (same structure, fewer/lighter layers)
 TINY = ArchConfig(name="tiny", hidden=128, layers=2, heads=2, ffn=256, conv_dim=64,
                   pos_kernel=16, pos_groups=4)
@@ -54,7 +60,7 @@ def arch_from_id(huggingface_id: str) -> ArchConfig:
     if "base" in huggingface_id:
         return BASE
     if "large" in huggingface_id:
-        return LARGE
+        return LARGE_LV60 if ("lv60" in huggingface_id or "xlsr" in huggingface_id) else LARGE
     if "tiny" in huggingface_id:
         return TINY
     raise ValueError("cannot determine num features")
@@ -76,9 +82,11 @@ def make_params(arch: ArchConfig = BASE, seed: int = 0) -> Dict[str, torch.Tenso
     for i, k in enumerate(arch.conv_kernel):
         # kaiming_normal_, fan_in, gain sqrt(2)  (HF:998-1003)
         p[f"feature_extractor.conv_layers.{i}.conv.weight"] = randn(C, cin, k, std=math.sqrt(2.0 / (cin * k)))
-        if i == 0:
-            p["feature_extractor.conv_layers.0.layer_norm.weight"] = 1.0 + randn(C, std=0.1)
-            p["feature_extractor.conv_layers.0.layer_norm.bias"] = randn(C, std=0.1)
+        if arch.conv_bias:
+            p[f"feature_extractor.conv_layers.{i}.conv.bias"] = randn(C, std=0.05)
+        if i == 0 or arch.feat_extract_norm == "layer":
+            p[f"feature_extractor.conv_layers.{i}.layer_norm.weight"] = 1.0 + randn(C, std=0.1)
+            p[f"feature_extractor.conv_layers.{i}.layer_norm.bias"] = randn(C, std=0.1)
         cin = C
     p["feature_projection.layer_norm.weight"] = 1.0 + randn(C, std=0.1)
     p["feature_projection.layer_norm.bias"] = randn(C, std=0.1)

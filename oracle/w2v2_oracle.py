@@ -54,13 +54,24 @@ def conv_layer(h: torch.Tensor, i: int, p: P, arch: ArchConfig = BASE) -> torch.
     return F.gelu(h)
 
 
+def conv_layer_ln(h: torch.Tensor, i: int, p: P, arch: ArchConfig) -> torch.Tensor:
+    """Wav2Vec2LayerNormConvLayer (HF:275-299; the "-lv60" / XLSR feature extractor, every layer): Conv1d(+bias) ->
+    LayerNorm over the channels (transpose, LayerNorm(C), transpose back) -> exact GELU."""
+    pre = f"feature_extractor.conv_layers.{i}."
+    h = F.conv1d(h, p[pre + "conv.weight"], p.get(pre + "conv.bias"), stride=arch.conv_stride[i])
+    h = F.layer_norm(h.transpose(1, 2), (arch.conv_dim,), p[pre + "layer_norm.weight"], p[pre + "layer_norm.bias"],
+                     arch.eps).transpose(1, 2)
+    return F.gelu(h)
+
+
 def feature_extractor(wav: torch.Tensor, p: P, arch: ArchConfig = BASE,
                       stages: Optional[list] = None) -> torch.Tensor:
-    h = conv_layer0(wav, p, arch)
+    layer_mode = arch.feat_extract_norm == "layer"
+    h = conv_layer_ln(wav[:, None, :], 0, p, arch) if layer_mode else conv_layer0(wav, p, arch)
     if stages is not None:
         stages.append(h)
     for i in range(1, len(arch.conv_kernel)):
-        h = conv_layer(h, i, p, arch)
+        h = conv_layer_ln(h, i, p, arch) if layer_mode else conv_layer(h, i, p, arch)
         if stages is not None:
             stages.append(h)
     return h  # [B, C, T]
@@ -130,8 +141,39 @@ def encoder_layer(h: torch.Tensor, l: int, p: P, arch: ArchConfig = BASE) -> tor
     return h
 
 
+def encoder_layer_stable(h: torch.Tensor, l: int, p: P, arch: ArchConfig) -> torch.Tensor:
+    """Pre-LN block of the stable-layer-norm models (Wav2Vec2EncoderLayerStableLayerNorm, HF:632-655):
+    h = h + attn(LN1(h)); h = h + FFN(LN2(h))."""
+    pre = f"encoder.layers.{l}."
+    a = F.layer_norm(h, (arch.hidden,), p[pre + "layer_norm.weight"], p[pre + "layer_norm.bias"], arch.eps)
+    h = h + _drop(attention(a, l, p, arch), "hidden")
+    c = F.layer_norm(h, (arch.hidden,), p[pre + "final_layer_norm.weight"], p[pre + "final_layer_norm.bias"], arch.eps)
+    f = F.gelu(F.linear(c, p[pre + "feed_forward.intermediate_dense.weight"],
+                        p[pre + "feed_forward.intermediate_dense.bias"]))
+    f = F.linear(f, p[pre + "feed_forward.output_dense.weight"], p[pre + "feed_forward.output_dense.bias"])
+    return h + _drop(f, "hidden")
+
+
+def encoder_stable(h: torch.Tensor, p: P, arch: ArchConfig, hidden_states: Optional[list] = None) -> torch.Tensor:
+    """Wav2Vec2EncoderStableLayerNorm.forward (HF:731-799), eval mode: h = h + pos_conv(h); L x pre-LN layer; final
+    LayerNorm.  hidden_states collects the input of every layer and the normalised output, as HF does."""
+    h = _drop(h + pos_conv_embed(h, p, arch), "hidden")
+    for l in range(arch.layers):
+        if hidden_states is not None:
+            hidden_states.append(h)
+        if TRAIN_REG is not None and torch.rand([]).item() < TRAIN_REG.get("layerdrop", 0.0):
+            continue
+        h = encoder_layer_stable(h, l, p, arch)
+    h = F.layer_norm(h, (arch.hidden,), p["encoder.layer_norm.weight"], p["encoder.layer_norm.bias"], arch.eps)
+    if hidden_states is not None:
+        hidden_states.append(h)
+    return h
+
+
 def encoder(h: torch.Tensor, p: P, arch: ArchConfig = BASE, hidden_states: Optional[list] = None) -> torch.Tensor:
     """Wav2Vec2Encoder.forward (HF:668-727), eval mode: h = LN(h + pos_conv(h)); 12 x layer."""
+    if arch.stable_layer_norm:
+        return encoder_stable(h, p, arch, hidden_states)
     h = h + pos_conv_embed(h, p, arch)
     h = _drop(F.layer_norm(h, (arch.hidden,), p["encoder.layer_norm.weight"], p["encoder.layer_norm.bias"], arch.eps),
               "hidden")

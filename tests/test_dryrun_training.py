@@ -243,3 +243,47 @@ def test_hidden_states_under_grad_are_returned_detached():
         assert out.last_hidden_state.requires_grad and out.last_hidden_state.shape == (2, 49, 768)
         assert len(out.hidden_states) == 13 and all(h.shape == (2, 49, 768) and not h.requires_grad for h in out.hidden_states)
         out.last_hidden_state.sum().backward()
+
+
+def test_stable_layer_norm_variant_evaluation_control_flow():
+    """-lv60 / XLSR architecture (2 layers of it): the evaluation forward composes, per conv layer, tap-GEMM -> LayerNorm
+    (+ conv bias) -> GELU, and per encoder layer LN -> QKV -> attention -> out_proj -> add -> LN -> FFN1 -> FFN2 -> add;
+    hidden_states has layers + 1 entries (the input of every layer and the normalised output, as HF returns them)."""
+    import dataclasses
+    from w2v2_speaker_b200.engine import LARGE_LV60
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2ModelB200
+    with dry_library() as lib:
+        m = Wav2Vec2ModelB200(dataclasses.replace(LARGE_LV60, layers=2)).eval()
+        with torch.no_grad():
+            out = m(torch.zeros(2, 12000), output_hidden_states=True)
+        assert tuple(out.last_hidden_state.shape) == (2, 37, 1024) and len(out.hidden_states) == 3
+        c = collections.Counter(lib.calls)
+        assert c["w2v2_gelu_fwd"] == 7 and c["w2v2_attention_ex"] == 2 and c["w2v2_add2_cast"] == 1 + 2 * 2
+        assert c["w2v2_layernorm_ex"] == 7 + 1 + 2 * 2 + 1               # conv layers, projection, two per layer, final
+        assert c["w2v2_gemm_f16"] == 7 + 1 + 2 * 4
+        assert "w2v2_encoder_layer_fwd" not in c                         # (the post-LN schedule is not used)
+
+
+def test_stable_layer_norm_variant_training_control_flow():
+    """The pre-LN training path (training_stable.py) on 2 layers of the -lv60 architecture, default regularisation, CNN
+    frozen: forward + backward drive the kernels launch by launch (no native layer schedule); every parameter behind the
+    CNN gets a gradient, the CNN gets none."""
+    import dataclasses
+    from w2v2_speaker_b200.engine import LARGE_LV60
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2ModelB200, Wav2Vec2RegularisationConfig
+    with dry_library() as lib:
+        m = Wav2Vec2ModelB200(dataclasses.replace(LARGE_LV60, layers=2), Wav2Vec2RegularisationConfig(layerdrop=0.0)).train()
+        m.feature_extractor.requires_grad_(False)
+        out = m(torch.zeros(2, 16000)).last_hidden_state
+        assert tuple(out.shape) == (2, 49, 1024)
+        out.sum().backward()
+        c = collections.Counter(lib.calls)
+        assert "w2v2_encoder_layer_fwd" not in c and "w2v2_encoder_layer_bwd" not in c
+        assert c["w2v2_attention_ex"] == 2 and c["w2v2_attention_bwd_ex2"] == 2
+        assert c["w2v2_gemm_wgrad_f16"] == 2 * 4 + 1                    # four per layer + the feature projection
+        assert c["w2v2_layernorm_bwd_ex"] == 2 * 2 + 1 + 1              # two per layer, final LayerNorm, projection
+        for n, q in m.named_parameters():
+            if n.startswith("feature_extractor"):
+                assert q.grad is None, n
+            elif n != "masked_spec_embed":
+                assert q.grad is not None, n

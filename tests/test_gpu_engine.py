@@ -70,6 +70,46 @@ def test_large_architecture_forward_matches_oracle():
     assert r < 3e-3, r
 
 
+def test_stable_layer_norm_variant_forward_matches_oracle():
+    """wav2vec2-large-lv60 / XLSR architecture: LayerNorm conv layers with bias (HF:275-299), pre-LN
+    encoder layers and the final encoder LayerNorm (HF:632-655, HF:731-799) -- the evaluation forward through the mirror
+    (what ``compute_speaker_embedding`` runs), every conv stage and hidden state against the oracle (itself pinned to
+    the live HF model, tests/test_oracle_golden.py)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle import w2v2_oracle as O
+    from oracle.params import LARGE_LV60 as O_LV60, make_inputs, make_params
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2WrapperModule
+    torch.set_num_threads(8)
+    p = make_params(O_LV60, seed=4)
+    w = Wav2Vec2WrapperModule("facebook/wav2vec2-large-lv60", False)
+    w.model.load_state_dict(p)
+    w = w.cuda().eval()
+    wav, _ = make_inputs(2, 12000, seed=5)
+    with torch.no_grad():
+        out = w.model(wav.cuda(), output_hidden_states=True)
+        trace = {}
+        ref = O.wav2vec2_forward(wav, p, O_LV60, trace)
+        feat = w.model.feature_extractor(wav.cuda())                                  # [B, C, T] like HF
+    torch.cuda.synchronize()
+    h = out.last_hidden_state
+    assert h.shape == ref.shape == (2, 37, 1024)
+    assert rel_rows(h.mean(1), ref.mean(1)) < 1.5e-3
+    r = ((h.cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+    assert r < 3e-3, r
+    fr = trace["conv"][-1]
+    assert ((feat.cpu().double() - fr.double()).norm() / fr.double().norm()).item() < 2e-3
+    assert len(out.hidden_states) == len(trace["hidden_states"]) == 25
+    for i in (0, 1, 12, 24):
+        a, b = out.hidden_states[i].cpu().double(), trace["hidden_states"][i].double()
+        assert ((a - b).norm() / b.norm()).item() < 3e-3, i
+    # pooled embedding through the wrapper ([B, H, T] like the reference's wav2vec2_embed_raw_audio)
+    with torch.no_grad():
+        emb = w(wav.cuda()).mean(dim=2)
+    assert rel_rows(emb, ref.mean(1)) < 1.5e-3
+    # (its training step: tests/test_gpu_round2.py::test_large_architecture_training_gradients_match_oracle_autograd)
+
+
 def test_five_second_utterances_use_the_wide_tiles(engine, base_params):
     """5 s -> 249 frames: attention TK = 256 (512 TMEM columns), two positional-conv row tiles."""
     from oracle import w2v2_oracle as O

@@ -240,18 +240,22 @@ def test_two_rank_step_equals_one_rank_step_on_the_concatenated_batch(base_param
     assert ep < 1e-4, ep
 
 
-def test_large_architecture_training_gradients_match_oracle_autograd():
+@pytest.mark.parametrize("hf_id", ["facebook/wav2vec2-large", "facebook/wav2vec2-large-lv60"])
+def test_large_architecture_training_gradients_match_oracle_autograd(hf_id):
     """BASELINE.json configs[4] architecture (wav2vec2-large: 24 layers, H = 1024, 16 heads, FFN 4096) + mean+std pooling +
     CE: one training step (B = 2, 1 s, regularisation off, CNN frozen) against autograd of the CPU oracle -- loss within
-    1e-3, every parameter gradient within 1.5e-2 norm-wise (24 layers of fp16-operand arithmetic)."""
+    1e-3, every parameter gradient within 1.5e-2 norm-wise (24 layers of fp16-operand arithmetic).  Also for the
+    stable-layer-norm sibling (-lv60 / XLSR: LayerNorm conv layers, pre-LN encoder layers; training_stable.py)."""
     _need_cuda()
     from oracle import w2v2_oracle as O
-    from oracle.params import LARGE, make_head_params, make_inputs, make_params
+    from oracle.params import arch_from_id, make_head_params, make_inputs, make_params
     from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
     from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    LARGE = arch_from_id(hf_id)
+    assert LARGE.stable_layer_norm == ("lv60" in hf_id)
     params = make_params(LARGE, seed=3)
     head = make_head_params(2048, S, seed=1)
-    cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id="facebook/wav2vec2-large", stat_pooling_type="mean+std",
+    cfg = Wav2vec2FCModuleConfig(wav2vec_hunggingface_id=hf_id, stat_pooling_type="mean+std",
                                  test_stat_pooling_type="mean+std", **ZERO_REG)
     m = Wav2vec2FCModule(cfg, S, CrossEntropyLoss)
     res = m.wav2vec.model.load_state_dict(params, strict=False)
@@ -291,7 +295,21 @@ def test_large_architecture_training_gradients_match_oracle_autograd():
         assert err < 1.5e-2, (k, err)
     lin = m.fc_list[-1][0]
     assert ((lin.weight.grad.cpu().double() - fw.grad.double()).norm() / fw.grad.double().norm()).item() < 1e-2
-    print("worst LARGE parameter-gradient error", worst)
+    print("worst LARGE parameter-gradient error", hf_id, worst)
+    if LARGE.stable_layer_norm:
+        # the same module with the reference's default regularisation (dropouts, LayerDrop, SpecAugment): finite, non-zero
+        m2 = Wav2vec2FCModule(Wav2vec2FCModuleConfig(wav2vec_hunggingface_id=hf_id, layerdrop=0.1), S, CrossEntropyLoss)
+        m2.wav2vec.model.load_state_dict(params, strict=False)
+        m2 = m2.cuda().train()
+        m2.wav2vec.model.feature_extractor.requires_grad_(False)
+        _, pred2 = m2(wav[:, None, :].cuda())
+        loss2, _ = m2.loss_fn(pred2, labels.cuda())
+        loss2.backward()
+        q = dict(m2.named_parameters())["wav2vec.model.encoder.layers.23.attention.q_proj.weight"]
+        assert torch.isfinite(loss2) and q.grad is not None and torch.isfinite(q.grad).all()
+        m2.wav2vec.model.feature_extractor.requires_grad_(True)
+        with pytest.raises(NotImplementedError, match="CNN frozen"):
+            m2(wav[:, None, :].cuda())
 
 
 def test_ensemble_embedding_matches_oracle_hidden_states(base_params):

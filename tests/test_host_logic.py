@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from w2v2_speaker_b200.engine import BASE, LARGE, arch_from_id
+from w2v2_speaker_b200.engine import BASE, LARGE, LARGE_LV60, arch_from_id
 from w2v2_speaker_b200.models.wav2vec2 import (Wav2Vec2RegularisationConfig, Wav2Vec2WrapperModule,
                                                Wav2vecLiteWrapperModule)
 from w2v2_speaker_b200.optim.loss import AngularAdditiveMarginSoftMaxLoss, CrossEntropyLoss
@@ -11,7 +11,11 @@ from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleC
 
 def test_arch_detection_follows_reference_substring_rule():
     assert arch_from_id("facebook/wav2vec2-base") is BASE
-    assert arch_from_id("facebook/wav2vec2-large-lv60") is LARGE
+    assert arch_from_id("facebook/wav2vec2-large") is LARGE
+    # the stable-layer-norm checkpoints (HF configs: feat_extract_norm="layer", conv_bias, do_stable_layer_norm)
+    assert arch_from_id("facebook/wav2vec2-large-lv60") is LARGE_LV60
+    assert arch_from_id("facebook/wav2vec2-large-xlsr-53") is LARGE_LV60
+    assert LARGE_LV60.stable_layer_norm and LARGE_LV60.conv_bias and LARGE_LV60.feat_extract_norm == "layer"
     with pytest.raises(ValueError):
         arch_from_id("facebook/hubert")
     assert BASE.conv_lengths(48000) == [9599, 4799, 2399, 1199, 599, 299, 149]
@@ -281,3 +285,22 @@ def test_synthetic_batch_is_standardised_and_reproducible():
     x2, y2 = synthetic_batch(4, 16000, 100, seed=3)
     assert torch.equal(x, x2) and torch.equal(y, y2) and x.shape == (4, 16000) and y.dtype == torch.int64
     assert x.mean(1).abs().max() < 1e-5 and (x.std(1) - 1).abs().max() < 1e-3 and int(y.max()) < 100
+
+
+def test_stable_layer_norm_variant_has_hf_parameter_names_and_is_evaluation_only():
+    """-lv60 / XLSR mirror: the parameter names are those of the HF model with feat_extract_norm="layer", conv_bias,
+    do_stable_layer_norm (checked against a 2-layer HF instance of that configuration); training with the CNN unfrozen
+    raises (the layer-norm feature extractor has no backward here)."""
+    import dataclasses
+    import transformers as tr
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2ModelB200, init_hf_parameters
+    arch = dataclasses.replace(LARGE_LV60, layers=2)
+    cfg = tr.Wav2Vec2Config(hidden_size=1024, num_hidden_layers=2, num_attention_heads=16, intermediate_size=4096,
+                            feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True)
+    hf = tr.Wav2Vec2Model(cfg).state_dict()
+    mine = init_hf_parameters(arch)
+    assert set(mine) == set(hf)
+    assert all(tuple(mine[k].shape) == tuple(hf[k].shape) for k in hf)
+    m = Wav2Vec2ModelB200(arch).train()
+    with pytest.raises(NotImplementedError, match="CNN frozen"):
+        m(torch.zeros(1, 16000))

@@ -82,6 +82,33 @@ def test_oracle_matches_live_hf_model(base_params):
     assert rel(got, ref) < 1e-5
 
 
+def test_stable_layer_norm_restatement_matches_live_hf_model():
+    """The -lv60 / XLSR variant of the oracle (LayerNorm conv layers with bias, HF:275-299; pre-LN encoder layers and
+    the final encoder LayerNorm, HF:632-655 / HF:731-799) against the live HF model of that configuration: last hidden
+    state and every entry of ``hidden_states``."""
+    tr = pytest.importorskip("transformers")
+    from oracle import w2v2_oracle as O
+    from oracle.params import ArchConfig, make_params
+    arch = ArchConfig(name="small-lv60", hidden=256, layers=3, heads=4, ffn=512, conv_dim=64, feat_extract_norm="layer",
+                      conv_bias=True, stable_layer_norm=True)
+    p = make_params(arch, seed=3)
+    cfg = tr.Wav2Vec2Config(hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=512,
+                            conv_dim=(64,) * 7, feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True,
+                            mask_time_prob=0.0)
+    m = tr.Wav2Vec2Model(cfg).eval()
+    missing, unexpected = m.load_state_dict(p, strict=False)
+    assert not missing and unexpected == ["masked_spec_embed"]
+    wav = torch.randn(2, 8000, generator=torch.Generator().manual_seed(1))
+    trace = {}
+    with torch.no_grad():
+        out = m(wav, output_hidden_states=True)
+        ref = O.wav2vec2_forward(wav, p, arch, trace)
+    assert (out.last_hidden_state - ref).abs().max().item() < 1e-5
+    assert len(out.hidden_states) == len(trace["hidden_states"]) == 4
+    for a, b in zip(out.hidden_states, trace["hidden_states"]):
+        assert (a - b).abs().max().item() < 1e-5
+
+
 def test_pos_conv_weight_norm_formula(base_params):
     w = O.pos_conv_weight(base_params)
     v = base_params["encoder.pos_conv_embed.conv.parametrizations.weight.original1"]

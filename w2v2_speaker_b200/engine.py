@@ -93,6 +93,10 @@ class ArchConfig:
     pos_kernel: int = 128
     pos_groups: int = 16
     eps: float = 1e-5
+    # the "-lv60" / XLSR checkpoints (HF: feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True)
+    feat_extract_norm: str = "group"      # "layer": every conv layer is Conv1d(+bias) -> LayerNorm(C) -> GELU (HF:275-299)
+    conv_bias: bool = False
+    stable_layer_norm: bool = False       # pre-LN encoder layers + final encoder LayerNorm (HF:632-655, HF:731-799)
 
     def conv_lengths(self, n: int) -> List[int]:
         out = []
@@ -104,14 +108,18 @@ class ArchConfig:
 
 BASE = ArchConfig()
 LARGE = ArchConfig(name="large", hidden=1024, layers=24, heads=16, ffn=4096)
+LARGE_LV60 = ArchConfig(name="large-lv60", hidden=1024, layers=24, heads=16, ffn=4096, feat_extract_norm="layer",
+                        conv_bias=True, stable_layer_norm=True)
 
 
 def arch_from_id(huggingface_id: str) -> ArchConfig:
-    """Size detection by substring of the HF id, as the reference does (R:src/models/wav2vec2.py:112-117)."""
+    """Size detection by substring of the HF id, as the reference does (R:src/models/wav2vec2.py:112-117: 768 / 1024
+    features); among the large checkpoints the "-lv60" and XLSR ones are the stable-layer-norm variant (their HF
+    configs: feat_extract_norm="layer", conv_bias, do_stable_layer_norm), which ``from_pretrained`` would build."""
     if "base" in huggingface_id:
         return BASE
     if "large" in huggingface_id:
-        return LARGE
+        return LARGE_LV60 if ("lv60" in huggingface_id or "xlsr" in huggingface_id) else LARGE
     raise ValueError("cannot determine num features")
 
 
@@ -128,6 +136,21 @@ class PreparedWeights:
         self.conv0_w = f("feature_extractor.conv_layers.0.conv.weight").view(arch.conv_dim, arch.conv_kernel[0])
         self.gn_g = f("feature_extractor.conv_layers.0.layer_norm.weight")
         self.gn_b = f("feature_extractor.conv_layers.0.layer_norm.bias")
+        self.layer_mode = arch.feat_extract_norm == "layer"
+        if self.layer_mode:
+            # LayerNorm conv layers (HF:275-299): per-layer conv bias and LayerNorm affine; conv layer 0 (1 -> C, k, stride s
+            # with k = 2s) runs on the same tap-GEMM as the others by viewing the waveform as [N / s, s] "channels": a k = 2,
+            # stride-1 conv over s input channels, zero-padded to the 64-channel granule of the GEMM's operand tiles
+            k0, s0 = arch.conv_kernel[0], arch.conv_stride[0]
+            if k0 != 2 * s0 or s0 > 64:
+                raise NotImplementedError("layer-norm feature extractor: conv layer 0 must have kernel = 2 x stride")
+            w0 = torch.zeros(arch.conv_dim, 64, 2, dtype=F32, device=self.conv0_w.device)
+            w0[:, :s0, :] = self.conv0_w.view(arch.conv_dim, 2, s0).transpose(1, 2)
+            self.conv0_w_taps = ops.conv_weight_tapmajor(w0)
+            n = len(arch.conv_kernel)
+            self.conv_b = [f(f"feature_extractor.conv_layers.{i}.conv.bias") if arch.conv_bias else None for i in range(n)]
+            self.conv_ln_g = [f(f"feature_extractor.conv_layers.{i}.layer_norm.weight") for i in range(n)]
+            self.conv_ln_b = [f(f"feature_extractor.conv_layers.{i}.layer_norm.bias") for i in range(n)]
         self.conv_w = [None] + [ops.conv_weight_tapmajor(f(f"feature_extractor.conv_layers.{i}.conv.weight"))
                                 for i in range(1, len(arch.conv_kernel))]
         # trainable feature extractor: remember the live fp32 sources so update() can re-derive conv_w
@@ -228,6 +251,11 @@ class EncoderEngine:
             # HF fails inside the conv stack here ("kernel size can't be greater than actual input size")
             raise ValueError(f"utterances of {wav.shape[1]} samples are shorter than the receptive field of the feature "
                              f"extractor (no output frame)")
+        if w.layer_mode:
+            if lens is not None or normalize:
+                raise NotImplementedError("ragged batches / raw PCM input are not built for the layer-norm feature "
+                                          "extractor (-lv60 / XLSR checkpoints)")
+            return self._feature_extractor_layer_norm(wav.float(), stages)
         h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps, lens, normalize)
         if stages is not None:
             stages.append(h)
@@ -235,6 +263,30 @@ class EncoderEngine:
         for i in range(1, n):
             h = ops.conv1d_cl_f16(h, w.conv_w[i], a.conv_kernel[i], a.conv_stride[i], act=1,
                                   out_dtype=F32 if i == n - 1 else F16)
+            if stages is not None:
+                stages.append(h)
+        return h
+
+    def _feature_extractor_layer_norm(self, wav: torch.Tensor, stages: Optional[list]) -> torch.Tensor:
+        """The "-lv60" / XLSR feature extractor (HF:275-299, every layer): Conv1d(+bias) -> LayerNorm over the channels ->
+        GELU.  Each layer is the tap-GEMM (fp32 out), the row LayerNorm kernel (which adds the conv bias on its way in)
+        and the GELU pass: three launches per layer instead of one -- this variant is built for coverage (no reference
+        configuration names it), not tuned."""
+        a, w = self.arch, self.w
+        B, N = wav.shape
+        s0 = a.conv_stride[0]
+        rows = N // s0
+        x = torch.zeros(B, rows, 64, dtype=F16, device=wav.device)
+        x[:, :, :s0] = wav[:, :rows * s0].view(B, rows, s0)
+        n = len(a.conv_kernel)
+        h = x
+        for i in range(n):
+            if i == 0:
+                z = ops.conv1d_cl_f16(h, w.conv0_w_taps, 2, 1, act=0, out_dtype=F32)                # [B, rows - 1, C]
+            else:
+                z = ops.conv1d_cl_f16(h, w.conv_w[i], a.conv_kernel[i], a.conv_stride[i], act=0, out_dtype=F32)
+            y32, _ = ops.layernorm(z, w.conv_ln_g[i], w.conv_ln_b[i], a.eps, bias=w.conv_b[i], want16=False)
+            h, _ = ops.gelu_fwd(y32, F32 if i == n - 1 else F16)
             if stages is not None:
                 stages.append(h)
         return h
@@ -281,6 +333,8 @@ class EncoderEngine:
             pos = ops.posconv(x16, w.pos_w(T), w.pos_b, a.pos_groups, a.pos_kernel)
         else:
             pos = self._posconv_long(x16)
+        if a.stable_layer_norm:
+            return self._encoder_stable(h0, pos, hidden_states, frame_lens)
         h32, h16 = ops.layernorm(pos.view(M, H), w.enc_ln_g, w.enc_ln_b, a.eps, residual=h0.view(M, H))
         if hidden_states is not None:
             hidden_states.append(h32.view(B, T, H))
@@ -305,6 +359,37 @@ class EncoderEngine:
             out = ar.tensor(f"h32.{i}", F32, (B, T, H))
             if keep:
                 hidden_states.append(out)
+        return out
+
+    def _encoder_stable(self, h0: torch.Tensor, pos: torch.Tensor, hidden_states: Optional[list],
+                        frame_lens: Optional[torch.Tensor]) -> torch.Tensor:
+        """Stable-layer-norm encoder (HF:731-799 / HF:632-655), eval mode:  h = h0 + pos;  per layer
+        h = h + attn(LN1(h)), h = h + FFN(LN2(h));  out = LN(h).  The same GEMM / attention / LayerNorm kernels as the
+        post-LN schedule, composed per layer from here (the residual sums are their own fp32 passes): built for
+        coverage of the -lv60 / XLSR checkpoints, not tuned."""
+        a, w = self.arch, self.w
+        B, T, H = h0.shape
+        M = B * T
+        h, _ = ops.add2_cast(h0.view(M, H), pos.view(M, H), want16=False)
+        for lw in w.layers:
+            if hidden_states is not None:
+                hidden_states.append(h.view(B, T, H))
+            _, a16 = ops.layernorm(h, lw["ln1_g"], lw["ln1_b"], a.eps, want32=False)
+            qkv = ops.gemm_f16(a16, lw["wqkv"], lw["bqkv"], 0, F16)
+            if frame_lens is not None:
+                att = ops.attention_lens(qkv, B, T, H, a.heads, frame_lens)
+            else:
+                att = ops.attention(qkv, B, T, H, a.heads)
+            o = ops.gemm_f16(att, lw["wo"], lw["bo"], 0, F32)
+            h, _ = ops.add2_cast(o, h, want16=False)
+            _, c16 = ops.layernorm(h, lw["ln2_g"], lw["ln2_b"], a.eps, want32=False)
+            g16 = ops.gemm_f16(c16, lw["w1"], lw["b1"], 1, F16)
+            f2 = ops.gemm_f16(g16, lw["w2"], lw["b2"], 0, F32)
+            h, _ = ops.add2_cast(f2, h, want16=False)
+        out, _ = ops.layernorm(h, w.enc_ln_g, w.enc_ln_b, a.eps, want16=False)
+        out = out.view(B, T, H)
+        if hidden_states is not None:
+            hidden_states.append(out)
         return out
 
     # -- HF:1327-1383 --------------------------------------------------------------------------

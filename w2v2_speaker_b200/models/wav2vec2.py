@@ -86,6 +86,7 @@ class _FeatureExtractor(_Holder):
 
     def forward(self, input_values: torch.Tensor) -> torch.Tensor:
         model = self._owner()
+        model._check_mode()
         cnn = model._items()[3]
         if torch.is_grad_enabled() and any(q.requires_grad for q in cnn):
             from ..training import FeatureExtractorFn
@@ -256,6 +257,11 @@ class Wav2Vec2ModelB200(nn.Module):
         return RegPlan(dataclasses.replace(self.reg_cfg, mask_time_prob=0.0), self.arch.layers, B, T, self._rng, device)
 
     def _check_mode(self):
+        if self.arch.feat_extract_norm == "layer" and torch.is_grad_enabled() and any(
+                q.requires_grad for q in self._items()[3]):
+            raise NotImplementedError(
+                "the layer-norm feature extractor (-lv60, XLSR checkpoints) trains with its CNN frozen only "
+                "(completely_freeze_feature_extractor: true, the reference default): its backward is not built")
         if self.reg_cfg.mask_feature_prob > 0 and self.training:
             raise NotImplementedError("feature-axis SpecAugment (mask_feature_prob > 0) is not implemented "
                                       "(the reference configurations keep it at 0)")
@@ -286,6 +292,9 @@ class Wav2Vec2ModelB200(nn.Module):
             from ..training import EncoderFn
             names, params = self._items()[:2]
             self._raw_next = raw                      # (read by EncoderFn.forward: fold the input normaliser into conv 0)
+            if output_hidden_states and self.arch.stable_layer_norm:
+                raise NotImplementedError("output_hidden_states under gradients is not built for the stable-layer-norm "
+                                          "variant: call it in eval mode under no_grad")
             self._keep_saved = bool(output_hidden_states)
             out = EncoderFn.apply(input_values, self, names, *params)
             hs = None
@@ -332,9 +341,12 @@ def init_hf_parameters(arch: ArchConfig) -> dict:
         w = torch.empty(C, cin, k)
         nn.init.kaiming_normal_(w)
         p[f"feature_extractor.conv_layers.{i}.conv.weight"] = w
-        if i == 0:
-            p["feature_extractor.conv_layers.0.layer_norm.weight"] = torch.ones(C)
-            p["feature_extractor.conv_layers.0.layer_norm.bias"] = torch.zeros(C)
+        if arch.conv_bias:                                   # (-lv60 / XLSR: HF:275-299)
+            bound = math.sqrt(1.0 / (cin * k))
+            p[f"feature_extractor.conv_layers.{i}.conv.bias"] = torch.empty(C).uniform_(-bound, bound)
+        if i == 0 or arch.feat_extract_norm == "layer":
+            p[f"feature_extractor.conv_layers.{i}.layer_norm.weight"] = torch.ones(C)
+            p[f"feature_extractor.conv_layers.{i}.layer_norm.bias"] = torch.zeros(C)
         cin = C
     p["feature_projection.layer_norm.weight"] = torch.ones(C)
     p["feature_projection.layer_norm.bias"] = torch.zeros(C)

@@ -266,6 +266,14 @@ def attention(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, want_lse:
     return (out, lse) if want_lse else out
 
 
+def attention_lens(qkv16: torch.Tensor, B: int, T: int, H: int, heads: int, lens: torch.Tensor) -> torch.Tensor:
+    """Attention over a zero-padded ragged batch: keys t >= lens[b] are excluded (evaluation) -> out f16 [B*T, H]."""
+    _chk(qkv16, F16, "qkv16")
+    out = torch.empty(B * T, H, dtype=F16, device=qkv16.device)
+    call("w2v2_attention_lens", ptr(qkv16), ptr(out), B, T, H, heads, ptr(_chk_lens(lens, B)), stream_ptr())
+    return out
+
+
 # ---- backward ------------------------------------------------------------------------------------
 
 

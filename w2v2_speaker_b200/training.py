@@ -265,6 +265,9 @@ def stack_forward_train(eng: EncoderEngine, h0: torch.Tensor, B: int, T: int, pl
     positional conv + GELU, LayerNorm, dropout, the encoder layers.  Fills `S` with what stack_backward needs;
     -> last_hidden_state f32 [B, T, H]."""
     a, w = eng.arch, eng.w
+    if a.stable_layer_norm:                      # -lv60 / XLSR checkpoints: pre-LN layers (training_stable.py)
+        from .training_stable import stack_forward_train_stable
+        return stack_forward_train_stable(eng, h0, B, T, plan, S)
     H, M = a.hidden, B * T
     ph = plan.p_hidden if plan is not None else 0.0
     seed = plan.seed if plan is not None else 0
@@ -386,6 +389,9 @@ def stack_backward(eng: EncoderEngine, tw: TrainWeights, S: dict, dh: torch.Tens
     conv, the encoder LayerNorm and every layer into G; -> the two (loss-scaled, f32 [M, H]) terms of d h0:
     through the LayerNorm residual and through the positional conv."""
     a, w = eng.arch, eng.w
+    if a.stable_layer_norm:
+        from .training_stable import stack_backward_stable
+        return stack_backward_stable(eng, tw, S, dh, G, on_layer_done)
     B, T = S["B"], S["T"]
     H, M, FF = a.hidden, B * T, a.ffn
     dev = dh.device
