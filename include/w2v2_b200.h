@@ -493,7 +493,8 @@ int w2v2_cast_f16(const float* x, void* y16, int64_t n, float scale, void* strea
 /* Batched weight preparation after an optimizer step (one launch for all trainable matrices):
  * per job, v = src[r, c] * scale is written to any of  dst16[r*ld + c] (f16),  dst32[r*ld + c] (f32),
  * dstT16[c*ldt + r] (f16, transposed; point it at a column offset to assemble fused W^T operands).
- * The table lives in device memory; tile_begin is the exclusive prefix sum of ceil(R/32)*ceil(C/32).
+ * The table lives in device memory; tile_begin is the exclusive prefix sum of ceil(R/E)*ceil(C/E), E =
+ * w2v2_prepare_tile_edge() (host-only query: 64, or 32 with W2V2_PREP_V3=0).
  * (replaces the per-step .half() / .t() / torch.cat the reference's AMP autocast does implicitly) */
 typedef struct {
   const void* src;      /* f32 [R, C] row-major */
@@ -507,6 +508,7 @@ typedef struct {
   int64_t tile_begin;
 } w2v2_prep_job;
 int w2v2_prepare_weights(const w2v2_prep_job* jobs_dev, int njobs, int64_t total_tiles, void* stream);
+int w2v2_prepare_tile_edge(void);
 /* Conv1d weight [Cout, Cin, K] f32 -> tap-major fp16 [Cout, K, Cin] (the W operand of w2v2_gemm_f16). */
 int w2v2_conv_weight_tapmajor(const float* w, void* w16, int cout, int cin, int k, void* stream);
 

@@ -11,7 +11,8 @@ import torch
 
 # entry points that run on the host only (no kernel launch, no CUDA context)
 HOST_ONLY = {"w2v2_last_error", "w2v2_abi_version", "w2v2_conv0_workspace_bytes", "w2v2_conv0_workspace_offsets",
-             "w2v2_posconv_taps_per_mma", "w2v2_launch_count", "w2v2_reset_launch_count", "w2v2_dgrad_accumulates"}
+             "w2v2_posconv_taps_per_mma", "w2v2_launch_count", "w2v2_reset_launch_count", "w2v2_dgrad_accumulates",
+             "w2v2_prepare_tile_edge"}
 
 
 class DryLib:

@@ -105,7 +105,7 @@ def classify(rows):
             # p, g, m, v read + p, m, v written + g cleared = 32 B per parameter; the two launches (encoder behind the
             # frozen CNN, heads) are modelled together: bytes go to the role, split evenly over its launches
             role, by = "Adam (fused update + gradient clear), encoder + head parameters", 32.0 * (N_ENC + N_HEAD) / 2
-        elif "prepare_weights_kernel" in name or "prepare_weights_v2_kernel" in name:
+        elif "prepare_weights_kernel" in name or "prepare_weights_v2_kernel" in name or "prepare_weights_v3_kernel" in name:
             # fp32 master read once, fp16 operand copy + transposed fp16 copy (data-gradient operand) written
             role, by = "re-derivation of the fp16 operand copies (one batched launch)", N_ENC * (4 + 2 + 2)
         out.append((role or "other: " + name.replace("w2v2::", "")[:40], us, fl, by))

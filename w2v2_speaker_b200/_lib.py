@@ -90,6 +90,7 @@ SIGNATURES = {
                                 c_void_p]),
     "w2v2_gelu_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "w2v2_prepare_weights": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    "w2v2_prepare_tile_edge": (c_int, []),
     "w2v2_posconv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_posconv_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "w2v2_weight_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int,

@@ -166,9 +166,124 @@ __global__ void __launch_bounds__(256) prepare_weights_v2_kernel(const w2v2_prep
   }
 }
 
+// Third form (default; W2V2_PREP_V3=0 restores the second).  The second form moves ~0.76 GB in 337 us -- a third of the
+// copy bandwidth: 4-byte loads, 2-byte stores (64-byte segments), two block barriers and a one-thread search per group of
+// four 4 KB tiles.  Here a block owns one 64 x 64 tile per iteration: every thread issues four 16-byte loads (a warp reads
+// two full 256-byte row segments) before anything is used, the plain copies leave as 8-byte (fp16) / 16-byte (fp32)
+// stores, the transposed copy goes through an fp32 shared-memory tile and leaves as 16-byte stores (8 consecutive source
+// rows of one column), the job search runs in every thread on the shared-memory copy of the table (no barrier), and four
+// blocks per SM keep 64 KB of loads in flight per SM.  Same multiplies, same round-to-nearest conversions: bit-identical
+// outputs.  tile_begin counts 64 x 64 tiles for this form (w2v2_prepare_tile_edge() tells the host which).
+constexpr int PV3_EDGE = 64;
+constexpr int PV3_PITCH = 65;
+
+__device__ __forceinline__ uint32_t pv3_pack(float a, float b) {
+  const __half2 h = __halves2half2(__float2half_rn(a), __float2half_rn(b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256, 4) prepare_weights_v3_kernel(const w2v2_prep_job* __restrict__ jobs, int njobs,
+                                                                    long long total_tiles) {
+  extern __shared__ __align__(16) unsigned char pv3_smem[];
+  float* tile = reinterpret_cast<float*>(pv3_smem);                                       // [64][65]
+  w2v2_prep_job* sjobs = reinterpret_cast<w2v2_prep_job*>(pv3_smem + sizeof(float) * PV3_EDGE * PV3_PITCH + 16);
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(jobs);
+    uint4* d = reinterpret_cast<uint4*>(sjobs);
+    for (int i = threadIdx.x; i < njobs * 4; i += blockDim.x) d[i] = g[i];      // 64-byte records = 4 x uint4
+  }
+  __syncthreads();
+  const int c4 = threadIdx.x & 15, rr = threadIdx.x >> 4;      // load map: 16 float4 per row, 16 rows per pass
+  const int r8 = threadIdx.x & 7, cc = threadIdx.x >> 3;       // transposed-store map: 8 chunks of 8 rows, 32 columns per pass
+  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sjobs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const w2v2_prep_job& j = sjobs[lo];
+    const int R = j.R, C = j.C;
+    const int tiles_c = (C + PV3_EDGE - 1) / PV3_EDGE;
+    const int local = int(t - j.tile_begin);
+    const int r0 = (local / tiles_c) * PV3_EDGE, c0 = (local % tiles_c) * PV3_EDGE;
+    const float* src = static_cast<const float*>(j.src);
+    __half* d16 = static_cast<__half*>(j.dst16);
+    float* d32 = static_cast<float*>(j.dst32);
+    __half* dT = static_cast<__half*>(j.dstT16);
+    const bool vec = (C & 3) == 0 && (j.ld & 3) == 0;            // 16-byte source rows / 8-byte fp16 destination rows
+    const int c = c0 + 4 * c4;
+    float4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + rr + 16 * k;
+      raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < R) {
+        const float* s = src + int64_t(r) * C + c;
+        if (vec && c + 3 < C) raw[k] = __ldg(reinterpret_cast<const float4*>(s));
+        else {
+          if (c < C) raw[k].x = __ldg(s);
+          if (c + 1 < C) raw[k].y = __ldg(s + 1);
+          if (c + 2 < C) raw[k].z = __ldg(s + 2);
+          if (c + 3 < C) raw[k].w = __ldg(s + 3);
+        }
+      }
+    }
+    if (dT != nullptr) __syncthreads();          // the previous tile's transposed reads are done with `tile` (block-uniform)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = rr + 16 * k, r = r0 + i;
+      if (r < R && c < C) {
+        const float v0 = raw[k].x * j.scale, v1 = raw[k].y * j.scale, v2 = raw[k].z * j.scale, v3 = raw[k].w * j.scale;
+        if (vec && c + 3 < C) {
+          if (d16 != nullptr) *reinterpret_cast<uint2*>(d16 + int64_t(r) * j.ld + c) = make_uint2(pv3_pack(v0, v1), pv3_pack(v2, v3));
+          if (d32 != nullptr) *reinterpret_cast<float4*>(d32 + int64_t(r) * j.ld + c) = make_float4(v0, v1, v2, v3);
+        } else {
+          const float vv[4] = {v0, v1, v2, v3};
+          for (int e = 0; e < 4 && c + e < C; ++e) {
+            if (d16 != nullptr) d16[int64_t(r) * j.ld + c + e] = __float2half_rn(vv[e]);
+            if (d32 != nullptr) d32[int64_t(r) * j.ld + c + e] = vv[e];
+          }
+        }
+      }
+      if (dT != nullptr) {
+        float* trow = tile + i * PV3_PITCH + 4 * c4;
+        trow[0] = raw[k].x * j.scale_t;
+        trow[1] = raw[k].y * j.scale_t;
+        trow[2] = raw[k].z * j.scale_t;
+        trow[3] = raw[k].w * j.scale_t;
+      }
+    }
+    if (dT == nullptr) continue;                 // block-uniform
+    __syncthreads();
+    const bool vec_t = (j.ldt & 7) == 0 && (reinterpret_cast<uintptr_t>(dT) & 15) == 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int ci = cc + 32 * k, col = c0 + ci, row = r0 + 8 * r8;
+      if (col >= C || row >= R) continue;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tile[(8 * r8 + e) * PV3_PITCH + ci];
+      __half* dst = dT + int64_t(col) * j.ldt + row;
+      if (vec_t && row + 7 < R) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pv3_pack(v[0], v[1]), pv3_pack(v[2], v[3]), pv3_pack(v[4], v[5]), pv3_pack(v[6], v[7]));
+      } else {
+        for (int e = 0; e < 8 && row + e < R; ++e) dst[e] = __float2half_rn(v[e]);
+      }
+    }
+  }
+}
+
+static bool prep_v3() {
+  static const bool on = []() { const char* e = getenv("W2V2_PREP_V3"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+
 }  // namespace w2v2
 
 using namespace w2v2;
+
+// Edge of the square tiles `tile_begin` of the job table counts (the host builds the table with it).
+extern "C" int w2v2_prepare_tile_edge(void) { return prep_v3() ? PV3_EDGE : 32; }
 
 extern "C" int w2v2_prepare_weights(const w2v2_prep_job* jobs_dev, int njobs, int64_t total_tiles, void* stream) {
   W2V2_REQUIRE(njobs >= 0 && total_tiles >= 0 && total_tiles < (int64_t(1) << 31), "w2v2_prepare_weights: bad job table");
@@ -177,6 +292,21 @@ extern "C" int w2v2_prepare_weights(const w2v2_prep_job* jobs_dev, int njobs, in
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t cap = int64_t(sms > 0 ? sms : 148) * 3;
+  if (prep_v3()) {
+    W2V2_REQUIRE(njobs <= PV2_MAX_JOBS, "w2v2_prepare_weights: %d jobs exceed the shared-memory table (%d)", njobs, PV2_MAX_JOBS);
+    const size_t smem3 = sizeof(float) * PV3_EDGE * PV3_PITCH + 16 + sizeof(w2v2_prep_job) * size_t(njobs);
+    static size_t configured3 = 0;
+    if (smem3 > configured3) {
+      W2V2_CHECK_CUDA(cudaFuncSetAttribute(prepare_weights_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem3)));
+      configured3 = smem3;
+    }
+    const int64_t cap3 = int64_t(sms > 0 ? sms : 148) * 4;
+    prepare_weights_v3_kernel<<<unsigned(total_tiles < cap3 ? total_tiles : cap3), 256, smem3, static_cast<cudaStream_t>(stream)>>>(
+        jobs_dev, njobs, total_tiles);
+    count_launches(1);
+    W2V2_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   static const bool v2 = []() { const char* e = getenv("W2V2_PREP_V2"); return !(e != nullptr && e[0] == '0'); }();
   if (v2 && njobs <= PV2_MAX_JOBS) {
     const size_t smem = sizeof(w2v2_prep_job) * size_t(njobs) + sizeof(float) * PV2_GROUP * 32 * 33;

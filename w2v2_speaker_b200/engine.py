@@ -64,6 +64,7 @@ class WeightPrep:
     def run(self):
         if self._table is None:
             rec = np.zeros(len(self.jobs), dtype=self.DT)
+            edge = ops.prepare_tile_edge()                # tiles the kernel walks: 64 x 64 (32 x 32 for the older forms)
             t = 0
             for i, j in enumerate(self.jobs.values()):
                 R, C = j["src"].shape
@@ -72,7 +73,7 @@ class WeightPrep:
                           j["dst32"].data_ptr() if j["dst32"] is not None else 0, R, C,
                           (j["dst16"] if j["dst16"] is not None else j["dst32"]).stride(0) if R > 1 else C,
                           j["dstT"].stride(0) if j["dstT"] is not None else 0, j["scale"], j["scale_t"], t)
-                t += ((R + 31) // 32) * ((C + 31) // 32)
+                t += ((R + edge - 1) // edge) * ((C + edge - 1) // edge)
             dev = next(iter(self.jobs.values()))["src"].device
             self._table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
             self._tiles = t

@@ -297,6 +297,11 @@ def gemm_wgrad_f16(dy16: torch.Tensor, x16: torch.Tensor, dw: torch.Tensor) -> t
     return dw
 
 
+def prepare_tile_edge() -> int:
+    """Edge of the square tiles the job table's `tile_begin` counts (host-only query)."""
+    return int(_lib.load().w2v2_prepare_tile_edge())
+
+
 def prepare_weights(table_u8: torch.Tensor, njobs: int, tiles: int):
     """table_u8: device copy of an array of w2v2_prep_job records (see engine.WeightPrep)."""
     assert table_u8.dtype == torch.uint8 and table_u8.numel() == 64 * njobs
