@@ -223,6 +223,169 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, MAXV <= 6 ? 4 : 3) layernorm_b
 }
 
 // =================================================================================================
+// LayerNorm backward from the LayerNorm output with the rows STREAMED through shared memory (the form the encoder layers
+// use; default, W2V2_LNB_RING=0 restores the register-resident kernel above).  The ncu capture of that kernel
+// (profiles/r02_d_hot_kernels_ncu.txt, r02_h_layernorm_bwd.txt) shows what holds it at 63 % of the copy bandwidth: a warp
+// loads its row (y, dy: 6 KB at H = 768) into 48 registers, waits, computes, and only then issues the next row's loads --
+// 45 % of the warp stalls are the L1TEX scoreboard, DRAM is 33 % busy, and with 128 registers per thread only 13 warps
+// per SM take turns.  (Two warps per row -- half the registers, twice the warps -- was tried first: 27.7 us against
+// 24.6 us; the bytes in flight per SM stay the same and a barrier per row is added.)
+// Here every warp owns a two-stage ring of row buffers in shared memory, filled by 1-D bulk copies (cp.async.bulk +
+// mbarrier transaction count) that its lane 0 issues one row AHEAD of the arithmetic: loads are in flight all the time,
+// the arithmetic reads the row from shared memory, and the registers go to the dgamma / dbeta / dbias column sums instead
+// (no shared-memory read-modify-write per row).  Same arithmetic per element in the same order.
+constexpr int LNR_WARPS = 4, LNR_ST = 2;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(LNR_WARPS * 32, 3) layernorm_bwd_ring_kernel(
+    const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ beta,
+    const float* __restrict__ rstd_saved, const float* __restrict__ gamma, float* __restrict__ dx32, __half* __restrict__ dx16,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int64_t rows, uint32_t thr,
+    float inv_keep, uint64_t seed) {
+  constexpr int H = MAXV * 128;
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(128) unsigned char lnr_smem[];
+  float* ring = reinterpret_cast<float*>(lnr_smem);                            // [warps][stages][y | dy][H]
+  float4* sconst = reinterpret_cast<float4*>(ring + LNR_WARPS * LNR_ST * 2 * H);       // [3][H / 4]: beta, 1 / gamma, gamma
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sconst + 3 * (H / 4));          // [warps][stages]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int v = threadIdx.x; v < H / 4; v += LNR_WARPS * 32) {
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + v * 4));
+    sconst[v] = __ldg(reinterpret_cast<const float4*>(beta + v * 4));
+    sconst[H / 4 + v] = make_float4(ln_safe_inv(gm.x), ln_safe_inv(gm.y), ln_safe_inv(gm.z), ln_safe_inv(gm.w));
+    sconst[2 * (H / 4) + v] = gm;
+  }
+  if (threadIdx.x < LNR_WARPS * LNR_ST) mbar_init(bars + threadIdx.x, 1);
+  fence_barrier_init();
+  __syncthreads();
+  float* my_ring = ring + warp * LNR_ST * 2 * H;
+  uint64_t* my_bars = bars + warp * LNR_ST;
+  const int64_t wstride = int64_t(gridDim.x) * LNR_WARPS;
+  const int64_t row0 = int64_t(blockIdx.x) * LNR_WARPS + warp;
+  auto issue = [&](int64_t row, int st) {                       // lane 0: both halves of the stage are free
+    mbar_arrive_expect_tx(my_bars + st, 2 * H * 4);
+    bulk_load_1d(my_ring + st * 2 * H, y + row * H, H * 4, my_bars + st);
+    bulk_load_1d(my_ring + st * 2 * H + H, dy + row * H, H * 4, my_bars + st);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < LNR_ST; ++st)
+      if (row0 + st * wstride < rows) issue(row0 + st * wstride, st);
+  }
+  float4 ag[MAXV], ab[MAXV], ad[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const DropKeys dkeys = drop_keys(seed);
+  int it = 0;
+  for (int64_t row = row0; row < rows; row += wstride, ++it) {
+    const int st = it % LNR_ST;
+    const float rstd = __ldg(rstd_saved + row);
+    mbar_wait(my_bars + st, (it / LNR_ST) & 1);
+    const float4* ybuf = reinterpret_cast<const float4*>(my_ring + st * 2 * H);
+    const float4* dbuf = ybuf + H / 4;
+    float4 x[MAXV], g[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = i * 32 + lane;
+      float4 a = ybuf[v];
+      const float4 d = dbuf[v];
+      const float4 bb = sconst[v], ig = sconst[H / 4 + v], gm = sconst[2 * (H / 4) + v];
+      a.x = (a.x - bb.x) * ig.x; a.y = (a.y - bb.y) * ig.y; a.z = (a.z - bb.z) * ig.z; a.w = (a.w - bb.w) * ig.w;
+      ag[i].x += d.x * a.x; ag[i].y += d.y * a.y; ag[i].z += d.z * a.z; ag[i].w += d.w * a.w;
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      float4 q = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += (q.x + q.y) + (q.z + q.w);
+      s2 += (q.x * a.x + q.y * a.y) + (q.z * a.z + q.w * a.w);
+      x[i] = a;
+      g[i] = q;
+    }
+    // this warp is done with the stage: refill it with the row LNR_ST iterations ahead
+    __syncwarp();
+    if (lane == 0 && row + LNR_ST * wstride < rows) issue(row + LNR_ST * wstride, st);
+    s1 = warp_sum(s1) / float(H);
+    s2 = warp_sum(s2) / float(H);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rstd * (g[i].x - s1 - x[i].x * s2);
+      o.y = rstd * (g[i].y - s1 - x[i].y * s2);
+      o.z = rstd * (g[i].z - s1 - x[i].z * s2);
+      o.w = rstd * (g[i].w - s1 - x[i].w * s2);
+      if (dx32 != nullptr) *reinterpret_cast<float4*>(dx32 + row * H + c) = o;
+      if (dx16 != nullptr || dbias != nullptr) {
+        if (thr != 0) dropout4(o, dkeys, row * H + c, thr, inv_keep);
+        if (dx16 != nullptr) {
+          uint2 q;
+          q.x = pack_half2(o.x, o.y);
+          q.y = pack_half2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx16 + row * H + c) = q;
+        }
+        ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w;
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr && dbias == nullptr) return;
+  // block reduction of the per-warp column sums through the (now idle) ring, one vector atomic per 4 columns per block
+  __syncthreads();                              // every warp has consumed its last stage: the ring is free
+  float4* red = reinterpret_cast<float4*>(lnr_smem);                           // [warps][3][H / 4]
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = i * 32 + lane;
+    red[(warp * 3 + 0) * (H / 4) + v] = ag[i];
+    red[(warp * 3 + 1) * (H / 4) + v] = ab[i];
+    red[(warp * 3 + 2) * (H / 4) + v] = ad[i];
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < H / 4; v += LNR_WARPS * 32) {
+    float4 tg = red[v], tb = red[(H / 4) + v], td = red[2 * (H / 4) + v];
+#pragma unroll
+    for (int w = 1; w < LNR_WARPS; ++w) {
+      const float4 a = red[(w * 3 + 0) * (H / 4) + v], b = red[(w * 3 + 1) * (H / 4) + v], d = red[(w * 3 + 2) * (H / 4) + v];
+      tg.x += a.x; tg.y += a.y; tg.z += a.z; tg.w += a.w;
+      tb.x += b.x; tb.y += b.y; tb.z += b.z; tb.w += b.w;
+      td.x += d.x; td.y += d.y; td.z += d.z; td.w += d.w;
+    }
+    if (dbias != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias + 4 * v), "f"(td.x), "f"(td.y), "f"(td.z), "f"(td.w) : "memory");
+    if (dgamma != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + 4 * v), "f"(tg.x), "f"(tg.y), "f"(tg.z), "f"(tg.w) : "memory");
+    if (dbeta != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + 4 * v), "f"(tb.x), "f"(tb.y), "f"(tb.z), "f"(tb.w) : "memory");
+  }
+}
+
+template <int MAXV>
+static int launch_lnb_ring(const float* dy, const float* y32, const float* rstd, const float* gamma, const float* beta,
+                           float* dx32, void* dx16, float* dgamma, float* dbeta, float* dbias, int64_t rows, uint32_t thr,
+                           float inv_keep, uint64_t drop_seed, cudaStream_t st) {
+  constexpr int H = MAXV * 128;
+  constexpr int smem = LNR_WARPS * LNR_ST * 2 * H * 4 + 3 * H * 4 + LNR_WARPS * LNR_ST * 8;
+  static_assert(LNR_WARPS * 3 * H * 4 <= LNR_WARPS * LNR_ST * 2 * H * 4, "the final reduction borrows the ring");
+  static bool configured = false;
+  if (!configured) {
+    W2V2_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_ring_kernel<MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  // one wave of resident blocks, every warp the same number of rows (+-1)
+  constexpr int per_sm = 3 * (smem + 1024) <= 227 * 1024 ? 3 : 2;           // H = 1024: two 78 KB blocks per SM
+  const int64_t want = (rows + LNR_WARPS - 1) / LNR_WARPS, slots = int64_t(device_sm_count()) * per_sm;
+  const int64_t per_warp = (want + slots - 1) / slots;
+  const int grid = int((want + per_warp - 1) / per_warp);
+  W2V2_CHECK_CUDA(launch_k(layernorm_bwd_ring_kernel<MAXV>, dim3(grid), dim3(LNR_WARPS * 32), size_t(smem), st, 1, dy, y32, beta,
+                           rstd, gamma, dx32, (__half*)dx16, dgamma, dbeta, dbias, rows, thr, inv_keep, drop_seed));
+  return 0;
+}
+
+// =================================================================================================
 // dz = dg * gelu'(z)  (f16 in / f16 out), gelu'(z) = Phi(z) + z * phi(z)
 __device__ __forceinline__ float gelu_grad(float z) {
   const float a = fabsf(z);
@@ -473,10 +636,21 @@ int w2v2_layernorm_bwd_from_output(const float* dy_a, const float* dy_b, const f
   if (rows == 0) return 0;
   const uint32_t thr = uint32_t(drop_p * 65536.0f + 0.5f);
   const float inv_keep = 1.0f / (1.0f - float(thr) / 65536.0f);
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool ring = []() { const char* e = getenv("W2V2_LNB_RING"); return !(e != nullptr && e[0] == '0'); }();
+  if (ring && dy_b == nullptr) {      // (one gradient stream: what the accumulating data-gradient GEMMs leave)
+    int rc;
+    if (H == 512) rc = launch_lnb_ring<4>(dy_a, y32, rstd, gamma, beta, dx32, dx16, dgamma, dbeta, dbias, rows, thr, inv_keep, drop_seed, st);
+    else if (H == 768) rc = launch_lnb_ring<6>(dy_a, y32, rstd, gamma, beta, dx32, dx16, dgamma, dbeta, dbias, rows, thr, inv_keep, drop_seed, st);
+    else rc = launch_lnb_ring<8>(dy_a, y32, rstd, gamma, beta, dx32, dx16, dgamma, dbeta, dbias, rows, thr, inv_keep, drop_seed, st);
+    if (rc) return rc;
+    count_launches(1);
+    W2V2_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int64_t want = (rows + LNB_WARPS - 1) / LNB_WARPS, slots = int64_t(device_sm_count()) * (H <= 768 ? 4 : 3);
   const int64_t per_warp = (want + slots - 1) / slots;
   const int grid = int((want + per_warp - 1) / per_warp);
-  cudaStream_t st = (cudaStream_t)stream;
 #define W2V2_LNY(NV) \
   launch_k(layernorm_bwd_kernel<true, NV, true, true>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, 1, dy_a, dy_b, (const void*)y32, beta, rstd, gamma, 0.f, dx32, (__half*)dx16, dgamma, dbeta, dbias, rows, H, thr, inv_keep, drop_seed)
   if (H == 512) W2V2_LNY(4); else if (H == 768) W2V2_LNY(6); else W2V2_LNY(8);
