@@ -91,7 +91,7 @@ def classify(rows):
             role, fl, by = "attention backward" + (", persistent" if "persist" in name else ""), 10.0 * B * HEADS * T * T * D, act * 3 * 2 * 2 + act * 2 * 2
         elif "layernorm_kernel<1, 6, 1>" in name:
             role, by = "LayerNorm forward (+bias +residual, f32 + f16 out)", act * (4 + 4 + 4 + 2)
-        elif "layernorm_bwd_kernel<1, 6, 1, 1>" in name:
+        elif "layernorm_bwd_kernel<1, 6, 1, 1>" in name or "layernorm_bwd_ring_kernel<6>" in name:
             # round 2: the data-gradient GEMMs accumulate into the residual gradient -> ONE gradient stream in (14 B / element);
             # pass "two" as argv[4] for launch lists taken with W2V2_DGRAD_ACCUM=0 (18 B / element)
             two = len(sys.argv) > 4 and sys.argv[4] == "two"
