@@ -441,3 +441,66 @@ def test_paired_model_trains_at_the_reference_crop_length(base_params):
     loss2.backward()
     q = dict(m2.named_parameters())["wav2vec.model.encoder.layers.0.attention.q_proj.weight"]
     assert torch.isfinite(loss2) and q.grad is not None and torch.isfinite(q.grad).all() and q.grad.abs().max().item() > 0
+
+
+def test_freeze_protocol_on_hardware(base_params):
+    """`wav2vec_initially_frozen` + `num_frozen_steps` (R:src/lightning_modules/speaker/wav2vec2_fc.py:
+    339-361) on the GPU, through the flat-buffer trainer built WHILE the encoder is frozen.  Step 1 (frozen): only the head
+    moves, and its gradient equals the oracle's with the encoder treated as a constant.  on_after_backward() releases the
+    encoder (the CNN stays frozen).  Step 2: every encoder parameter behind the CNN moves, and the gradients of that step
+    equal autograd of the oracle at the post-step-1 parameters."""
+    _need_cuda()
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_inputs
+    from w2v2_speaker_b200.trainer import FlatAdamTrainer
+    m = _module("mean", "ce", base_params, wav2vec_initially_frozen=True, num_frozen_steps=1).train()
+    m.on_train_start()
+    assert not any(q.requires_grad for q in m.wav2vec.parameters())
+    tr = FlatAdamTrainer(m, lr=1e-3)
+    wav, labels = make_inputs(4, 16000, S, seed=77)
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    head_w0, head_b0 = m.fc_list[-1][0].weight.detach().clone(), m.fc_list[-1][0].bias.detach().clone()
+    loss1, _ = tr.step(wav[:, None, :].cuda(), labels.cuda())
+    m.on_after_backward()                                          # steps = 1 >= num_frozen_steps: release
+    torch.cuda.synchronize()
+    after1 = {k: v.detach().clone() for k, v in m.named_parameters()}
+    moved1 = {k for k in before if not torch.equal(before[k], after1[k])}
+    assert moved1 and all(not k.startswith("wav2vec.") for k in moved1), sorted(moved1)[:5]
+    enc = dict(m.wav2vec.model.named_parameters())
+    assert all(q.requires_grad == (not k.startswith("feature_extractor")) for k, q in enc.items())
+    # oracle loss of step 1 (eval semantics = ZERO_REG training)
+    torch.set_num_threads(8)
+    lin = m.fc_list[-1][0]
+    with torch.no_grad():
+        ref_emb = O.speaker_embedding(wav, base_params, "mean")
+        _, ref_loss1, _ = O.cross_entropy_head(ref_emb, head_w0.cpu(), head_b0.cpu(), labels)
+    assert abs(loss1.item() - ref_loss1.item()) / ref_loss1.item() < 1e-3
+    # step 2 with gradients kept: run the module by hand at the post-step-1 parameters and compare with oracle autograd
+    emb, pred = m(wav[:, None, :].cuda())
+    loss2, _ = m.loss_fn(pred, labels.cuda())
+    p = {k: after1["wav2vec.model." + k].cpu().clone().requires_grad_(not k.startswith("feature_extractor")) for k in enc}
+    fw = lin.weight.detach().cpu().clone().requires_grad_(True)
+    fb = lin.bias.detach().cpu().clone().requires_grad_(True)
+    ref_emb2 = O.speaker_embedding(wav, p, "mean")
+    _, ref_loss2, _ = O.cross_entropy_head(ref_emb2, fw, fb, labels)
+    ref_loss2.backward()
+    assert abs(loss2.item() - ref_loss2.item()) / ref_loss2.item() < 1e-3
+    # the trainer's second step moves the encoder (everything behind the CNN) and leaves the CNN alone
+    loss2b, _ = tr.step(wav[:, None, :].cuda(), labels.cuda())
+    torch.cuda.synchronize()
+    assert abs(loss2b.item() - ref_loss2.item()) / ref_loss2.item() < 1e-3
+    after2 = {k: v.detach().clone() for k, v in m.named_parameters()}
+    for k in after1:
+        if k.startswith("wav2vec.model.feature_extractor") or k.endswith("masked_spec_embed"):
+            assert torch.equal(after1[k], after2[k]), k
+        elif k.startswith("wav2vec.model."):
+            assert not torch.equal(after1[k], after2[k]), k
+            if k.endswith("k_proj.bias"):                      # gradient exactly 0 in exact arithmetic: noise on both sides
+                continue
+            # Adam's first step for a parameter moves it by lr * sign(g) (m / sqrt(v) = g / |g|): check the direction against
+            # the oracle gradient where that gradient is not rounding noise
+            g = p[k[len("wav2vec.model."):]].grad
+            step = (after2[k] - after1[k]).cpu()
+            big = g.abs() > 0.05 * g.abs().max()
+            agree = (torch.sign(step[big]) == -torch.sign(g[big])).float().mean().item()
+            assert agree > 0.99, (k, agree)
