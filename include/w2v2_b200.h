@@ -237,6 +237,9 @@ int w2v2_attention_bwd_ex2(const void* qkv16, const void* o16, const void* do16,
                            int T, int H, int heads, float drop_p, uint64_t drop_seed, float qscale, float* dbias,
                            void* stream);
 int w2v2_time_mask_apply(float* h, const uint8_t* mask, const float* embed, int64_t rows, int H, void* stream);
+/* SpecAugment along the feature axis (HF:1312-1322, mask_feature_prob): h[b, t, c] = 0 where mask[b * H + c] != 0, in place
+ * (h f32 [B, T, H], H % 4 == 0, mask 4-byte aligned); the same call masks the gradient in the backward. */
+int w2v2_feature_mask(float* h, const uint8_t* mask, int B, int T, int H, void* stream);
 int w2v2_time_mask_bwd(float* dh, const uint8_t* mask, float* dembed, int64_t rows, int H, float scale, void* stream);
 /* Gradient plumbing: out = a + b (b may be NULL) as f32 and/or f16 (n % 4 == 0); row-wise f32 -> f16 cast
  * with zero padding to ldy and a scale; in-place scale; f32 CE gradient (prob - onehot) * coef * dloss[0]

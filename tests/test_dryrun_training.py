@@ -287,3 +287,15 @@ def test_stable_layer_norm_variant_training_control_flow():
                 assert q.grad is None, n
             elif n != "masked_spec_embed":
                 assert q.grad is not None, n
+
+
+def test_feature_axis_specaugment_control_flow():
+    """mask_feature_prob > 0 (HF:1312-1322): the feature mask is drawn per step on the [B, hidden] grid and applied once in
+    the forward and once to the gradient in the backward (fused call path only, like HF)."""
+    with dry_library() as lib:
+        m = _fc_module("mean", "ce", layerdrop=0.0, mask_feature_prob=0.2).train()
+        m.on_train_start()
+        emb, pred = m(torch.randn(2, 1, 16000))
+        out, _ = m.loss_fn(pred, torch.tensor([1, 2]))
+        out.backward()
+        assert lib.calls.count("w2v2_feature_mask") == 2

@@ -119,6 +119,66 @@ def test_time_mask_apply_and_backward(ops):
     assert rel(dembed, 0.5 * dh[mask.bool()].sum(0)) < 1e-5
 
 
+def test_feature_axis_specaugment_kernel_and_training_step(ops, base_params):
+    """SpecAugment along the feature axis (HF:1312-1322, `mask_feature_prob`; off in every reference configuration, built
+    for completeness): the masking kernel against torch, then one training step with ONLY that regularisation on against
+    autograd of the oracle with the same mask applied between the feature projection and the encoder."""
+    import torch.nn.functional as F
+    from oracle import w2v2_oracle as O
+    from oracle.params import make_head_params, make_inputs
+    from w2v2_speaker_b200.optim.loss import CrossEntropyLoss
+    from w2v2_speaker_b200.speaker_module import Wav2vec2FCModule, Wav2vec2FCModuleConfig
+    from w2v2_speaker_b200.training import compute_time_mask
+    B, T, H = 3, 49, 768
+    rng = np.random.default_rng(5)
+    fm = torch.from_numpy(compute_time_mask(B, H, 0.3, 10, 0, rng)).cuda()
+    assert 0.1 < fm.float().mean().item() < 0.4
+    h = torch.randn(B, T, H, generator=torch.Generator().manual_seed(1)).cuda()
+    out = ops.feature_mask_(h.clone(), fm, B, T)
+    assert torch.equal(out, torch.where(fm.view(B, 1, H).bool(), torch.zeros_like(h), h))
+
+    zero = dict(activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, hidden_dropout=0.0, layerdrop=0.0,
+                mask_time_prob=0.0)
+    m = Wav2vec2FCModule(Wav2vec2FCModuleConfig(mask_feature_prob=0.3, mask_feature_length=10, **zero), S, CrossEntropyLoss)
+    m.wav2vec.model.load_state_dict(base_params, strict=False)
+    head = make_head_params(768, S, seed=1)
+    with torch.no_grad():
+        m.fc_list[-1][0].weight.copy_(head["fc.weight"]); m.fc_list[-1][0].bias.copy_(head["fc.bias"])
+    m = m.cuda().train()
+    m.on_train_start()
+    model = m.wav2vec.model
+    plans = []
+    draw = model._draw_reg_plan
+    model._draw_reg_plan = lambda *a, **k: (plans.append(draw(*a, **k)), plans[-1])[1]
+    wav, labels = make_inputs(B, 16000, S, seed=9)
+    emb, pred = m(wav[:, None, :].cuda())
+    loss, _ = m.loss_fn(pred, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert len(plans) == 1 and plans[0].fmask is not None and plans[0].mask is None
+    keep = 1.0 - plans[0].fmask.view(B, 1, H).float().cpu()
+
+    torch.set_num_threads(8)
+    p = {k: v.clone().requires_grad_(not k.startswith("feature_extractor")) for k, v in base_params.items()}
+    fw, fb = head["fc.weight"].clone().requires_grad_(True), head["fc.bias"].clone().requires_grad_(True)
+    proj = O.feature_projection(O.feature_extractor(wav, p).transpose(1, 2), p) * keep
+    ref_emb = O.encoder(proj, p).mean(1)
+    ref_loss = F.cross_entropy(F.linear(ref_emb, fw, fb), labels)
+    ref_loss.backward()
+    assert rel(emb.detach().cpu(), ref_emb.detach()) < 1.5e-3
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-3
+    got = dict(model.named_parameters())
+    for k in ("feature_projection.projection.weight", "feature_projection.projection.bias", "feature_projection.layer_norm.weight",
+              "encoder.layers.0.attention.q_proj.weight", "encoder.layers.11.feed_forward.output_dense.weight",
+              "encoder.pos_conv_embed.conv.bias"):
+        assert rel(got[k].grad.cpu(), p[k].grad) < 1e-2, k
+    # the masked hidden units see no gradient through the projection: their bias gradient is exactly zero for an
+    # utterance-independent check only where EVERY utterance masks the unit
+    allm = plans[0].fmask.view(B, H).bool().all(0).cpu()
+    if allm.any():
+        assert got["feature_projection.projection.bias"].grad.cpu()[allm].abs().max().item() == 0.0
+
+
 def test_training_step_with_reference_default_regularisation(base_params):
     """dropout 0.1 x3, LayerDrop 0.05, SpecAugment 0.05 (the reference defaults): the step runs, every
     gradient is finite, LayerDrop-skipped layers get exactly zero gradient, masked_spec_embed trains."""

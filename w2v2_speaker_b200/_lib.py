@@ -119,6 +119,7 @@ SIGNATURES = {
     "w2v2_attention_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_float, c_uint64, c_void_p]),
     "w2v2_time_mask_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "w2v2_feature_mask": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_time_mask_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "w2v2_add2_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "w2v2_cast_f16_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]),

@@ -46,6 +46,24 @@ __global__ void dropout_kernel(const void* __restrict__ x_, const float* __restr
   }
 }
 
+// SpecAugment along the feature axis (HF:1312-1322): columns with mask[b, c] != 0 are zeroed in every frame of utterance b.
+// Only masked columns are written (a few percent of the tensor): the pass reads the mask and stores zeros.
+__global__ void feature_mask_kernel(float4* __restrict__ h, const uint8_t* __restrict__ mask, int T, int H4, int64_t n4) {
+  const int64_t per_utt = int64_t(T) * H4;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = i / per_utt;
+    const int c4 = int(i % H4);
+    const uint32_t m = *reinterpret_cast<const uint32_t*>(mask + (b * H4 + c4) * 4);
+    if (m == 0) continue;
+    float4 v = h[i];
+    if (m & 0x000000ffu) v.x = 0.f;
+    if (m & 0x0000ff00u) v.y = 0.f;
+    if (m & 0x00ff0000u) v.z = 0.f;
+    if (m & 0xff000000u) v.w = 0.f;
+    h[i] = v;
+  }
+}
+
 // SpecAugment: rows with mask != 0 are overwritten by the learned embedding (HF:1301-1310)
 __global__ void time_mask_apply_kernel(float* __restrict__ h, const uint8_t* __restrict__ mask,
                                        const float* __restrict__ embed, int64_t rows, int H) {
@@ -109,6 +127,18 @@ int w2v2_dropout(const void* x, int dtype, const float* bias, int H, void* y, vo
   const int grid = rgrid(n / 2, 256, 8);
   if (dtype == 1) launch_k(dropout_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
   else launch_k(dropout_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, x, bias, H, y, (__half*)y16, n, thr, inv_keep, seed);
+  count_launches(1);
+  W2V2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// SpecAugment along the feature axis (HF:1312-1322, `mask_feature_prob`): h[b, t, c] = 0 where mask[b, c]; the same
+// call zeroes the gradient of those columns in the backward.  One float4 per thread, mask bytes read as one word.
+int w2v2_feature_mask(float* h, const uint8_t* mask, int B, int T, int H, void* stream) {
+  W2V2_REQUIRE(H % 4 == 0, "w2v2_feature_mask: H=%d must be a multiple of 4", H);
+  const int64_t n4 = int64_t(B) * T * (H / 4);
+  if (n4 == 0) return 0;
+  feature_mask_kernel<<<rgrid(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(h), mask, T, H / 4, n4);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

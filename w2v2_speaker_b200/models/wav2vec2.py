@@ -223,7 +223,7 @@ class Wav2Vec2ModelB200(nn.Module):
             self._rng = np.random.default_rng(torch.initial_seed() % (1 << 63))
         T = self.arch.conv_lengths(wav.shape[1])[-1]
         if self.reg_cfg.mask_time_prob <= 0:
-            return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device)
+            return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device, hidden=self.arch.hidden)
         # ring of pinned staging buffers for the SpecAugment mask (the host may run a few steps ahead of the device)
         ring = self.__dict__.setdefault("_mask_ring", {})
         key = (wav.shape[0], T)
@@ -232,7 +232,8 @@ class Wav2Vec2ModelB200(nn.Module):
             ring[key] = [[torch.empty(wav.shape[0] * T, dtype=torch.uint8, pin_memory=pin) for _ in range(8)], 0]
         bufs, i = ring[key]
         ring[key][1] = (i + 1) % len(bufs)
-        return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device, bufs[i])
+        return RegPlan(self.reg_cfg, self.arch.layers, wav.shape[0], T, self._rng, wav.device, bufs[i],
+                       hidden=self.arch.hidden)
 
     def _split_params(self, prefix: str):
         """(names, parameters) of one part of the model, in registration order (cached)."""
@@ -262,9 +263,6 @@ class Wav2Vec2ModelB200(nn.Module):
             raise NotImplementedError(
                 "the layer-norm feature extractor (-lv60, XLSR checkpoints) trains with its CNN frozen only "
                 "(completely_freeze_feature_extractor: true, the reference default): its backward is not built")
-        if self.reg_cfg.mask_feature_prob > 0 and self.training:
-            raise NotImplementedError("feature-axis SpecAugment (mask_feature_prob > 0) is not implemented "
-                                      "(the reference configurations keep it at 0)")
 
     def forward(self, input_values: torch.Tensor, output_hidden_states: bool = False, lengths=None,
                 normalize_input: Optional[bool] = None, **_):

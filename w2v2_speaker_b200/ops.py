@@ -540,6 +540,15 @@ def time_mask_apply_(h: torch.Tensor, mask_u8: torch.Tensor, embed: torch.Tensor
     return h
 
 
+def feature_mask_(h: torch.Tensor, mask_u8: torch.Tensor, B: int, T: int):
+    """In place: h[b, t, c] = 0 where mask_u8[b * H + c] (SpecAugment along the feature axis; also its backward)."""
+    _chk(h, F32, "h")
+    H = h.shape[-1]
+    assert h.is_contiguous() and h.numel() == B * T * H and mask_u8.dtype == torch.uint8 and mask_u8.numel() == B * H
+    call("w2v2_feature_mask", ptr(h), ptr(mask_u8), B, T, H, stream_ptr())
+    return h
+
+
 def time_mask_bwd_(dh: torch.Tensor, mask_u8: torch.Tensor, dembed: torch.Tensor, scale: float = 1.0):
     rows, H = dh.shape
     call("w2v2_time_mask_bwd", ptr(dh), ptr(mask_u8), ptr(dembed), rows, H, float(scale), stream_ptr())

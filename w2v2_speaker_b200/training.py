@@ -99,7 +99,8 @@ class RegPlan:
     (HF:701-713) and the SpecAugment time mask (HF:101-217, 1280-1324; spans of `mask_time_length`
     frames, at least two per utterance), all drawn on the host like the reference does."""
 
-    def __init__(self, reg, layers: int, B: int, T: int, rng, device, pinned: Optional[torch.Tensor] = None):
+    def __init__(self, reg, layers: int, B: int, T: int, rng, device, pinned: Optional[torch.Tensor] = None,
+                 hidden: int = 0):
         self.p_feat = float(reg.feat_proj_dropout)
         self.p_hidden = float(reg.hidden_dropout)
         self.p_attn = float(reg.attention_dropout)
@@ -114,10 +115,18 @@ class RegPlan:
                 self.mask = pinned.to(device, non_blocking=True)
             else:
                 self.mask = m.to(device)
+        # SpecAugment along the feature axis (HF:1312-1322; off in every reference configuration): spans of
+        # `mask_feature_length` hidden units per utterance, drawn like the time spans over the [B, hidden] grid, no minimum
+        # (`hidden` = 0: the split call path, where HF applies no SpecAugment at all)
+        self.fmask = None
+        if getattr(reg, "mask_feature_prob", 0.0) > 0 and hidden > 0:
+            f = compute_time_mask(B, hidden, reg.mask_feature_prob, reg.mask_feature_length, 0, rng)
+            self.fmask = torch.from_numpy(f).to(device)
 
     @property
     def any(self) -> bool:
-        return (self.p_feat + self.p_hidden + self.p_attn + self.p_act) > 0 or any(self.skip) or self.mask is not None
+        return ((self.p_feat + self.p_hidden + self.p_attn + self.p_act) > 0 or any(self.skip) or self.mask is not None
+                or self.fmask is not None)
 
 
 def compute_time_mask(B: int, T: int, mask_prob: float, mask_length: int, min_masks: int, rng):
@@ -245,6 +254,8 @@ def encoder_forward_train(eng: EncoderEngine, wav: torch.Tensor, plan: Optional[
     h0, n16 = projection_forward_train(eng, feat2, plan)
     if plan is not None and plan.mask is not None:
         ops.time_mask_apply_(h0, plan.mask, mask_embed)                  # HF:1301-1310
+    if plan is not None and plan.fmask is not None:
+        ops.feature_mask_(h0, plan.fmask, B, T)                          # HF:1312-1322
     S.update(feat=feat2, n16=n16)
     return stack_forward_train(eng, h0, B, T, plan, S), S
 
@@ -359,7 +370,9 @@ def encoder_backward(eng: EncoderEngine, tw: TrainWeights, params: Dict[str, tor
     dxe32, dx_pos = stack_backward(eng, tw, S, dh, G, on_layer_done)
     # feature projection:  h0 = timemask(drop(LN512(feat) Wp^T + bp))
     dh0_32, dh0_16 = ops.add2_cast(dxe32, dx_pos, want32=True, want16=True)
-    if plan is not None and (plan.mask is not None or plan.p_feat > 0):
+    if plan is not None and (plan.mask is not None or plan.fmask is not None or plan.p_feat > 0):
+        if plan.fmask is not None:
+            ops.feature_mask_(dh0_32, plan.fmask, S["B"], S["T"])
         if plan.mask is not None:
             ops.time_mask_bwd_(dh0_32, plan.mask, G.view("masked_spec_embed"))
         if plan.p_feat > 0:
