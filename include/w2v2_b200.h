@@ -102,7 +102,8 @@ int w2v2_attention(const void* qkv16, void* out16, float* lse, int B, int T, int
 
 /* ---- pooling (R:src/layers/pooling.py) -------------------------------------------------------- */
 /* mode 0: mean -> [B,H] (:24-30); mode 1: [std_unbiased || mean] -> [B,2H] (:38-44);
- * mode 2: max -> [B,H] (:74-80).  x f32 [B,T,H]. */
+ * mode 2: max -> [B,H] (:74-80); mode 3: the ASP front statistics [mean || sqrt(clamp(var_population, 1e-12))] -> [B,2H].
+ * x f32 [B,T,H]. */
 int w2v2_stat_pool(const float* x, float* out, int B, int T, int H, int mode, void* stream);
 /* attentive statistics pooling tail (speechbrain ASP as used at :87-106): given x f32 [B,T,H] and
  * attention logits a f32 [B,T,H]: softmax over T per (b,c), weighted mean and
@@ -115,6 +116,11 @@ int w2v2_asp_concat(const float* x, void* cat16, int B, int T, int H, void* stre
  * stats); z f32 [rows, A] -> y16 f16 [rows, A]. */
 int w2v2_asp_relu_bn_tanh(const float* z, const float* scale, const float* shift, void* y16, int64_t rows, int A,
                           void* stream);
+/* Same with a per-utterance bias added to z first: ubias f32 [rows / rows_per_utt, A].  The evaluation path feeds the
+ * TDNN's 1x1 conv with the frames only (K = H) and adds the product of its mean / std columns with the utterance's
+ * statistics here, instead of materialising [x | mean | std] for every frame (K = 3H). */
+int w2v2_asp_relu_bn_tanh_ubias(const float* z, const float* scale, const float* shift, const float* ubias, int rows_per_utt,
+                                void* y16, int64_t rows, int A, void* stream);
 
 /* ---- heads / losses --------------------------------------------------------------------------- */
 /* Row-wise softmax + cross entropy + argmax over logits f32 [B, ldl] (first S valid):

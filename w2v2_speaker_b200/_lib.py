@@ -132,6 +132,7 @@ SIGNATURES = {
     "w2v2_asp_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_asp_concat_split3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "w2v2_asp_relu_bn_tanh": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "w2v2_asp_relu_bn_tanh_ubias": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "w2v2_softmax_ce": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "w2v2_aam_softmax_ce": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
                                     c_void_p, c_int, c_int, c_void_p]),

@@ -367,8 +367,13 @@ __global__ void __launch_bounds__(POOL_TS* POOL_CH) stat_pool_kernel(const float
   }
   q = block_slices_sum(q, sm, ts, ch);
   if (ts == 0) {
-    out[int64_t(b) * 2 * H + c] = sqrtf(q / float(T - 1));        // [std (unbiased) || mean]
-    out[int64_t(b) * 2 * H + H + c] = mean;
+    if (mode == 3) {                                                // ASP front statistics: [mean || std (population, clamped)]
+      out[int64_t(b) * 2 * H + c] = mean;
+      out[int64_t(b) * 2 * H + H + c] = sqrtf(fmaxf(q / float(T), 1e-12f));
+    } else {
+      out[int64_t(b) * 2 * H + c] = sqrtf(q / float(T - 1));      // [std (unbiased) || mean]
+      out[int64_t(b) * 2 * H + H + c] = mean;
+    }
   }
 }
 
@@ -402,11 +407,16 @@ __global__ void __launch_bounds__(POOL_TS* POOL_CH) asp_concat_kernel(const floa
   }
 }
 
+// ubias (optional, f32 [rows / rows_per_utt, A]): a per-utterance bias added to z first -- the share of the TDNN's 1x1 conv
+// that multiplies the utterance's mean / std columns, which are constant over its frames
 __global__ void asp_relu_bn_tanh_kernel(const float* __restrict__ z, const float* __restrict__ scale,
-                                        const float* __restrict__ shift, __half* __restrict__ y, int64_t n, int A) {
+                                        const float* __restrict__ shift, __half* __restrict__ y, int64_t n, int A,
+                                        const float* __restrict__ ubias, int64_t per_utt) {
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int a = i % A;
-    const float r = fmaxf(z[i], 0.f);
+    float zi = z[i];
+    if (ubias != nullptr) zi += __ldg(ubias + (i / per_utt) * A + a);
+    const float r = fmaxf(zi, 0.f);
     y[i] = __float2half_rn(tanhf(fmaf(r, __ldg(scale + a), __ldg(shift + a))));
   }
 }
@@ -869,7 +879,7 @@ int w2v2_stat_pool(const float* x, float* out, int B, int T, int H, int mode, vo
 }
 int w2v2_stat_pool_lens(const float* x, float* out, int B, int T, int H, int mode, const int* lens, void* stream) {
   W2V2_REQUIRE(H % POOL_CH == 0, "w2v2_stat_pool: H=%d must be a multiple of %d", H, POOL_CH);
-  W2V2_REQUIRE(mode >= 0 && mode <= 2, "w2v2_stat_pool: unknown mode %d", mode);
+  W2V2_REQUIRE(mode >= 0 && mode <= 3, "w2v2_stat_pool: unknown mode %d", mode);
   W2V2_REQUIRE(T >= 1 && (mode != 1 || T >= 2), "w2v2_stat_pool: T=%d too short", T);
   dim3 g(H / POOL_CH, B);
   stat_pool_kernel<<<g, POOL_TS * POOL_CH, 0, (cudaStream_t)stream>>>(x, out, T, H, mode, lens);
@@ -892,8 +902,15 @@ int w2v2_asp_concat_lens(const float* x, void* cat16, int B, int T, int H, const
 
 int w2v2_asp_relu_bn_tanh(const float* z, const float* scale, const float* shift, void* y16, int64_t rows, int A,
                           void* stream) {
+  return w2v2_asp_relu_bn_tanh_ubias(z, scale, shift, nullptr, 1, y16, rows, A, stream);
+}
+int w2v2_asp_relu_bn_tanh_ubias(const float* z, const float* scale, const float* shift, const float* ubias, int rows_per_utt,
+                                void* y16, int64_t rows, int A, void* stream) {
+  W2V2_REQUIRE(rows_per_utt >= 1 && rows % rows_per_utt == 0, "w2v2_asp_relu_bn_tanh: rows=%lld not a multiple of %d",
+               (long long)rows, rows_per_utt);
   const int64_t n = rows * A;
-  asp_relu_bn_tanh_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, scale, shift, (__half*)y16, n, A);
+  asp_relu_bn_tanh_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(z, scale, shift, (__half*)y16, n, A, ubias,
+                                                                              int64_t(rows_per_utt) * A);
   count_launches(1);
   W2V2_CHECK_CUDA(cudaGetLastError());
   return 0;

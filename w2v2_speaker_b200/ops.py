@@ -371,7 +371,7 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step: int, grad_scale: float = 
 def stat_pool(x: torch.Tensor, mode: int, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(x, F32, "x")
     B, T, H = x.shape
-    out = torch.empty(B, H * (2 if mode == 1 else 1), dtype=F32, device=x.device)
+    out = torch.empty(B, H * (2 if mode in (1, 3) else 1), dtype=F32, device=x.device)
     call("w2v2_stat_pool_lens", ptr(x.contiguous()), ptr(out), B, T, H, mode,
          ptr(_chk_lens(lens, B)) if lens is not None else None, stream_ptr())
     return out
@@ -393,10 +393,18 @@ def asp_concat_split3(x: torch.Tensor, lens: Optional[torch.Tensor] = None) -> t
     return cat
 
 
-def asp_relu_bn_tanh(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+def asp_relu_bn_tanh(z: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, ubias: Optional[torch.Tensor] = None,
+                     rows_per_utt: int = 1) -> torch.Tensor:
+    """tanh(BN(ReLU(z (+ ubias[utterance])))) -> f16 [rows, A]; ubias f32 [rows / rows_per_utt, A]."""
     rows, A = z.shape
     y = torch.empty(rows, A, dtype=F16, device=z.device)
-    call("w2v2_asp_relu_bn_tanh", ptr(z), ptr(scale), ptr(shift), ptr(y), rows, A, stream_ptr())
+    if ubias is None:
+        call("w2v2_asp_relu_bn_tanh", ptr(z), ptr(scale), ptr(shift), ptr(y), rows, A, stream_ptr())
+    else:
+        _chk(ubias, F32, "ubias")
+        assert ubias.is_contiguous() and ubias.shape == (rows // rows_per_utt, A)
+        call("w2v2_asp_relu_bn_tanh_ubias", ptr(z), ptr(scale), ptr(shift), ptr(ubias), rows_per_utt, ptr(y), rows, A,
+             stream_ptr())
     return y
 
 
