@@ -278,6 +278,13 @@ def test_stable_layer_norm_variant_training_control_flow():
         assert tuple(out.shape) == (2, 49, 1024)
         out.sum().backward()
         c = collections.Counter(lib.calls)
+        # (activation dropout, off by default, takes the two-pass GELU backward: same argument-list check)
+        m2 = Wav2Vec2ModelB200(dataclasses.replace(LARGE_LV60, layers=1),
+                               Wav2Vec2RegularisationConfig(layerdrop=0.0, activation_dropout=0.1)).train()
+        m2.feature_extractor.requires_grad_(False)
+        n0 = lib.calls.count("w2v2_gelu_bwd_colsum")
+        m2(torch.zeros(2, 16000)).last_hidden_state.sum().backward()
+        assert lib.calls.count("w2v2_gelu_bwd_colsum") == n0 + 2      # positional conv + the layer's FFN
         assert "w2v2_encoder_layer_fwd" not in c and "w2v2_encoder_layer_bwd" not in c
         assert c["w2v2_attention_ex"] == 2 and c["w2v2_attention_bwd_ex2"] == 2
         assert c["w2v2_gemm_wgrad_f16"] == 2 * 4 + 1                    # four per layer + the feature projection
