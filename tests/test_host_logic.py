@@ -198,6 +198,11 @@ def test_profile_tools_reproduce_the_committed_tables():
                            os.path.join(root, "profiles", "r02_c_train_launches.csv")], check=True, capture_output=True, text=True).stdout
     assert out2 == open(os.path.join(root, "profiles", "r02_c_kernel_roofline_table.txt")).read()
     assert "attention backward, persistent" in out2 and "one gradient stream in" in out2
+    # the launch list of the final bench command of round 2 (ring LayerNorm backward, 64 x 64-tile weight preparation)
+    out3 = subprocess.run([sys.executable, os.path.join(root, "tools", "roofline_table.py"),
+                           os.path.join(root, "profiles", "r02_i_train_launches.csv")], check=True, capture_output=True, text=True).stdout
+    assert out3 == open(os.path.join(root, "profiles", "r02_i_kernel_roofline_table.txt")).read()
+    assert "290 launches" in out3.splitlines()[1] and "re-derivation of the fp16 operand copies" in out3
     lines = out.splitlines()
     assert "270 launches" in lines[1]
     shares = [float(l.split("%")[0].split()[-1]) for l in lines[3:]]
