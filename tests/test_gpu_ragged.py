@@ -77,3 +77,39 @@ def test_ragged_rejects_training_mode(base_params):
         m.compute_speaker_embeddings_ragged(_utterances([16000, 17000]))          # gradients enabled
     with torch.no_grad(), pytest.raises(ValueError):
         m.wav2vec.model(torch.zeros(2, 16000, device="cuda"), lengths=[16000, 300])   # shorter than the receptive field
+
+
+def test_ragged_and_raw_input_with_the_layer_norm_feature_extractor():
+    """-lv60 / XLSR variant (LayerNorm conv layers, pre-LN encoder): a zero-padded ragged batch gives every utterance the
+    embedding it gets alone (no length-aware statistics are needed in front: every frame is normalised on its own), and raw
+    16-bit PCM input equals the standardised float waveform."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import dataclasses
+    from oracle.params import LARGE_LV60 as O_LV60, make_inputs, make_params
+    from w2v2_speaker_b200.engine import LARGE_LV60
+    from w2v2_speaker_b200.models.wav2vec2 import Wav2Vec2ModelB200
+    arch = dataclasses.replace(LARGE_LV60, layers=3)
+    p = make_params(dataclasses.replace(O_LV60, layers=3), seed=6)
+    m = Wav2Vec2ModelB200(arch)
+    m.load_state_dict(p)
+    m = m.cuda().eval()
+    lens = [16000, 11283, 24000]
+    wavs = [make_inputs(1, n, seed=50 + i)[0][0] for i, n in enumerate(lens)]
+    batch = torch.zeros(3, max(lens))
+    for i, w in enumerate(wavs):
+        batch[i, :len(w)] = w
+    with torch.no_grad():
+        rag = m(batch.cuda(), lengths=lens).last_hidden_state
+        for i, w in enumerate(wavs):
+            one = m(w[None, :].cuda()).last_hidden_state[0]
+            T = one.shape[0]
+            err = ((rag[i, :T] - one).norm() / one.norm()).item()
+            assert err < 2e-3, (i, err)
+        pcm = (wavs[0] * 3000.0).round().clamp(-32768, 32767).to(torch.int16)
+        raw = m(pcm[None, :].cuda()).last_hidden_state
+        x = pcm.float()
+        ref = m(((x - x.mean()) / (x.std() + 1e-5))[None, :].cuda()).last_hidden_state
+        assert ((raw - ref).norm() / ref.norm()).item() < 2e-3
+        with pytest.raises(NotImplementedError):
+            m(batch.cuda().mul(3000).to(torch.int16), lengths=lens)

@@ -253,9 +253,14 @@ class EncoderEngine:
             raise ValueError(f"utterances of {wav.shape[1]} samples are shorter than the receptive field of the feature "
                              f"extractor (no output frame)")
         if w.layer_mode:
-            if lens is not None or normalize:
-                raise NotImplementedError("ragged batches / raw PCM input are not built for the layer-norm feature "
-                                          "extractor (-lv60 / XLSR checkpoints)")
+            # LayerNorm conv layers normalise every frame on its own: a zero-padded ragged batch needs no length-aware
+            # statistics here (frames of an utterance that exist see only its own samples; the others are never used).
+            # Raw PCM / un-normalised input: the standardisation is its own pass (nothing to fold it into).
+            if normalize:
+                if lens is not None:
+                    raise NotImplementedError("raw / un-normalised input of a RAGGED batch is not built for the layer-norm "
+                                              "feature extractor (-lv60 / XLSR checkpoints): normalise per utterance first")
+                wav = ops.normalize_wav(wav)[0]
             return self._feature_extractor_layer_norm(wav.float(), stages)
         h = ops.conv0_gn_gelu(wav, w.conv0_w, w.gn_g, w.gn_b, a.eps, lens, normalize)
         if stages is not None:
